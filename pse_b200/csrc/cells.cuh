@@ -1,0 +1,225 @@
+// Cell binning, spatial ordering and the real-space neighbour list.
+//
+// Replaces HOOMD's CellListGPU + NeighborListGPUBinned (not in /root/reference; used at
+// PSEv1/integrate.py:58-83 and consumed at PSEv1/Stokes.cc:433-438, PSEv1/Mobility.cu:624-641).
+// Contract: per-particle neighbour SET == brute-force minimum-image set with
+// |r|^2 < r_list^2, stored as a full list (both directions), rows ascending.
+//
+// Layout in HBM: particles are permuted into cell order ("slots"); cells are boxes of the
+// fractional (sheared) coordinate space, raster order with z fastest, so the particles of a run of
+// z-adjacent cells are contiguous.  perm[slot] = particle id.  Neighbour list is CSR over slots:
+// head[slot], nn[slot], nl[head .. head+nn) ascending slot numbers.
+#pragma once
+#include "box.cuh"
+#include "common.cuh"
+
+struct CellGrid {
+    int ncx, ncy, ncz;  // cells per dimension
+    int ncell;
+    // search reach in fractional units (already includes the shear widening for x)
+    float reach_fx, reach_fy, reach_fz;
+};
+
+__device__ __forceinline__ int cell_coord(float frac, int nc) {
+    // fractional coordinate nominally in [0,1); particles exactly on / slightly outside the
+    // boundary are clamped into the edge cells (the search below uses the same function)
+    int c = (int)floorf(frac * (float)nc);
+    return c < 0 ? 0 : (c >= nc ? nc - 1 : c);
+}
+
+__global__ void cell_id_kernel(const float4* __restrict__ pos, uint32_t N, PseBox box, CellGrid cg,
+                               uint32_t* __restrict__ cell_of, uint32_t* __restrict__ cell_count) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    float4 p = __ldg(pos + i);
+    float3 f = box.make_fraction(p.x, p.y, p.z);
+    // positions may sit a hair outside the box: wrap the fraction into [0,1)
+    f.x -= floorf(f.x); f.y -= floorf(f.y); f.z -= floorf(f.z);
+    int cx = cell_coord(f.x, cg.ncx), cy = cell_coord(f.y, cg.ncy), cz = cell_coord(f.z, cg.ncz);
+    uint32_t c = ((uint32_t)cx * cg.ncy + cy) * cg.ncz + cz;
+    cell_of[i] = c;
+    atomicAdd(cell_count + c, 1u);
+}
+
+// ---- exclusive scan (three-phase, uint32) ------------------------------------------------
+#define SCAN_BLOCK 1024
+__global__ void scan_block_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+                                  uint32_t* __restrict__ block_sums, uint32_t n) {
+    __shared__ uint32_t warp_tot[32];
+    uint32_t i = blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    uint32_t v = i < n ? in[i] : 0u;
+    uint32_t x = v;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_tot[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t t = warp_tot[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, t, o);
+            if (lane >= o) t += y;
+        }
+        warp_tot[lane] = t;
+    }
+    __syncthreads();
+    uint32_t incl = x + (wid > 0 ? warp_tot[wid - 1] : 0u);
+    if (i < n) out[i] = incl - v;
+    if (threadIdx.x == SCAN_BLOCK - 1) block_sums[blockIdx.x] = incl;
+}
+__global__ void scan_add_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ block_offs, uint32_t n,
+                                uint32_t* __restrict__ total_out) {
+    uint32_t i = blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    if (i < n) out[i] += block_offs[blockIdx.x];
+    if (total_out && i == n - 1) total_out[0] = 0;  // placeholder, real total written by caller kernel
+}
+
+// place particles into their cells (slot order inside a cell is made canonical afterwards)
+__global__ void cell_fill_kernel(const uint32_t* __restrict__ cell_of, uint32_t N, const uint32_t* __restrict__ cell_start,
+                                 uint32_t* __restrict__ cell_fill, uint32_t* __restrict__ perm) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    uint32_t c = cell_of[i];
+    uint32_t k = atomicAdd(cell_fill + c, 1u);
+    perm[cell_start[c] + k] = i;
+}
+
+// canonical order: ascending particle id inside each cell (insertion sort; cells hold O(10))
+__global__ void cell_sort_kernel(const uint32_t* __restrict__ cell_start, uint32_t ncell, uint32_t* __restrict__ perm) {
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    uint32_t b = cell_start[c], e = cell_start[c + 1];
+    for (uint32_t i = b + 1; i < e; ++i) {
+        uint32_t v = perm[i];
+        uint32_t j = i;
+        while (j > b && perm[j - 1] > v) { perm[j] = perm[j - 1]; --j; }
+        perm[j] = v;
+    }
+}
+
+__global__ void invert_perm_kernel(const uint32_t* __restrict__ perm, uint32_t N, uint32_t* __restrict__ slot_of) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < N) slot_of[perm[s]] = s;
+}
+
+// out[slot] = in[perm[slot]]  (float4 payload)
+__global__ void gather4_kernel(const float4* __restrict__ in, const uint32_t* __restrict__ perm, uint32_t N,
+                               float4* __restrict__ out) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < N) out[s] = __ldg(in + perm[s]);
+}
+// two payloads at once (positions and forces)
+__global__ void gather4x2_kernel(const float4* __restrict__ a, const float4* __restrict__ b,
+                                 const uint32_t* __restrict__ perm, uint32_t N, float4* __restrict__ oa,
+                                 float4* __restrict__ ob) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < N) {
+        uint32_t p = perm[s];
+        oa[s] = __ldg(a + p);
+        ob[s] = __ldg(b + p);
+    }
+}
+
+// ---- neighbour search ---------------------------------------------------------------------
+// Sorted enumeration of a periodic cell range: cells {lo, lo+1, ..., lo+len-1} mod nc, visited
+// in ascending cell number so that rows come out ascending in slot number.
+struct CellRange {
+    int lo, len, wrapped;  // wrapped = how many of the len cells wrap past nc
+    __device__ __forceinline__ int at(int t) const { return t < wrapped ? t : lo + (t - wrapped); }
+};
+__device__ __forceinline__ CellRange make_range(float f, float reach, int nc) {
+    // cells overlapped by [f - reach, f + reach] in fractional units
+    int c0 = (int)floorf((f - reach) * (float)nc);
+    int c1 = (int)floorf((f + reach) * (float)nc);
+    int len = c1 - c0 + 1;
+    if (len > nc) len = nc;
+    int lo = c0 % nc;
+    if (lo < 0) lo += nc;
+    CellRange r;
+    r.lo = lo; r.len = len;
+    r.wrapped = lo + len > nc ? lo + len - nc : 0;
+    return r;
+}
+
+// MODE 0: count neighbours; MODE 1: fill rows.  One thread per slot.
+template <int MODE>
+__global__ void nlist_kernel(const float4* __restrict__ spos, uint32_t N, PseBox box, CellGrid cg,
+                             const uint32_t* __restrict__ cell_start, float rlist_sq, uint32_t* __restrict__ nn,
+                             const uint32_t* __restrict__ head, uint32_t* __restrict__ nl) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    float4 pi = __ldg(spos + i);
+    float3 f = box.make_fraction(pi.x, pi.y, pi.z);
+    f.x -= floorf(f.x); f.y -= floorf(f.y); f.z -= floorf(f.z);
+    // a fraction that rounds to exactly 1.0 was clamped into the last cell by cell_id_kernel
+    CellRange rx = make_range(f.x, cg.reach_fx, cg.ncx);
+    CellRange ry = make_range(f.y, cg.reach_fy, cg.ncy);
+    CellRange rz = make_range(f.z, cg.reach_fz, cg.ncz);
+    uint32_t count = 0;
+    uint32_t w = MODE == 1 ? head[i] : 0u;
+    for (int tx = 0; tx < rx.len; ++tx) {
+        int cx = rx.at(tx);
+        for (int ty = 0; ty < ry.len; ++ty) {
+            int cy = ry.at(ty);
+            uint32_t rowbase = ((uint32_t)cx * cg.ncy + cy) * cg.ncz;
+            // z cells: at most two contiguous runs [0, wrapped) and [lo, lo + len - wrapped)
+            for (int part = 0; part < 2; ++part) {
+                int z0 = part == 0 ? 0 : rz.lo;
+                int zn = part == 0 ? rz.wrapped : rz.len - rz.wrapped;
+                if (zn <= 0) continue;
+                uint32_t b = __ldg(cell_start + rowbase + z0), e = __ldg(cell_start + rowbase + z0 + zn);
+                for (uint32_t j = b; j < e; ++j) {
+                    if (j == i) continue;
+                    float4 pj = __ldg(spos + j);
+                    float3 d = box.min_image(make_float3(PSE_SUB(pi.x, pj.x), PSE_SUB(pi.y, pj.y), PSE_SUB(pi.z, pj.z)));
+                    float r2 = pse_norm2_rn(d);
+                    if (r2 < rlist_sq) {
+                        if (MODE == 1) nl[w + count] = j;
+                        ++count;
+                    }
+                }
+            }
+        }
+    }
+    if (MODE == 0) nn[i] = count;
+}
+
+// largest squared displacement since the list was built (staleness test); result via atomicMax on bits
+__global__ void max_disp_kernel(const float4* __restrict__ pos, const float4* __restrict__ pos_build, uint32_t N,
+                                PseBox box, uint32_t* __restrict__ max_bits) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    float r2 = 0.f;
+    if (i < N) {
+        float4 a = __ldg(pos + i), b = __ldg(pos_build + i);
+        float3 d = box.min_image(make_float3(a.x - b.x, a.y - b.y, a.z - b.z));
+        r2 = d.x * d.x + d.y * d.y + d.z * d.z;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) r2 = fmaxf(r2, __shfl_xor_sync(0xffffffffu, r2, o));
+    if ((threadIdx.x & 31) == 0 && r2 > 0.f) atomicMax(max_bits, __float_as_uint(r2));
+}
+
+// ---- export in the reference layout (particle ids, rows ascending by id) --------------------
+__global__ void export_counts_kernel(const uint32_t* __restrict__ nn, const uint32_t* __restrict__ perm, uint32_t N,
+                                     uint32_t* __restrict__ nn_by_id) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < N) nn_by_id[perm[s]] = nn[s];
+}
+__global__ void export_rows_kernel(const uint32_t* __restrict__ nn, const uint32_t* __restrict__ head,
+                                   const uint32_t* __restrict__ nl, const uint32_t* __restrict__ perm, uint32_t N,
+                                   const uint32_t* __restrict__ head_by_id, uint32_t* __restrict__ out) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= N) return;
+    uint32_t n = nn[s], h = head[s];
+    uint32_t* row = out + head_by_id[perm[s]];
+    for (uint32_t k = 0; k < n; ++k) {  // insertion sort by particle id
+        uint32_t v = perm[nl[h + k]];
+        uint32_t j = k;
+        while (j > 0 && row[j - 1] > v) { row[j] = row[j - 1]; --j; }
+        row[j] = v;
+    }
+}

@@ -1,0 +1,620 @@
+// Engine: owns the workspaces and sequences the kernels of one PSE Brownian-dynamics step.
+//
+// Replaces the host drivers of the reference: gpu_stokes_step_one (PSEv1/Stokes.cu:234-365),
+// gpu_stokes_CombinedMobilityBrownian_wrap (PSEv1/Brownian.cu:772-923),
+// gpu_stokes_BrealLanczos_wrap (:357-765), gpu_stokes_Mobility_wrap / Mwave_wrap
+// (PSEv1/Mobility.cu:729-782, :515-575) and the per-step array plumbing of
+// Stokes::integrateStepOne (PSEv1/Stokes.cc:429-523).
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <vector>
+
+#include "../../include/pse_b200.h"
+#include "box.cuh"
+#include "cells.cuh"
+#include "common.cuh"
+#include "real.cuh"
+#include "rng.cuh"
+#include "wave.cuh"
+
+int pse_tridiag_sqrt_e1(int m, const double* diag, const double* off, double* c, double* lambda_min_out);
+
+#define LANCZOS_M_MAX 100  // PSEv1/Brownian.cu:397
+
+static char g_create_error[512] = "no error";
+
+struct pse_engine {
+    pse_config cfg;
+    pse_params prm;
+    PseBox box;
+    WaveParams wp;
+    RealParams rp;
+    CellGrid cg;
+    cudaStream_t stream;
+    uint32_t N;
+    size_t G, Gh;
+    char err[512];
+    float rlist;
+
+    // real-space table
+    float4* d_table;
+    // cells / ordering
+    uint32_t *d_cell_of, *d_cell_count, *d_cell_start, *d_scan_tmp, *d_perm, *d_slot_of;
+    size_t cell_cap;
+    float4 *d_spos, *d_sx, *d_sy;
+    // neighbour list (slot numbering)
+    uint32_t *d_nn, *d_head, *d_nl;
+    size_t nl_cap;
+    uint64_t nnz;
+    float4* d_pos_build;
+    float xy_build;
+    bool nlist_valid;
+    uint32_t* d_flag;
+    uint32_t* h_flag;  // pinned
+    cudaEvent_t flag_event;
+    bool flag_pending;
+    // wave space
+    float* d_grid;
+    float2* d_spec;
+    cufftHandle plan_f, plan_b;
+    bool plans_ok;
+    // Lanczos
+    float4 *d_V, *d_u, *d_y;
+    float *d_alpha, *d_beta, *d_coef, *d_partials;
+    unsigned int* d_counter;
+    float* h_ab;  // pinned: alpha[m_max] | beta[m_max+1]
+    int m_lanczos;
+    float last_stepnorm;
+    // step scratch
+    float4* d_vel_work;
+    float4 *d_hpos, *d_hF;  // device staging for pse_step_host
+    int3* d_himage;
+    // stats
+    uint64_t launches, fft_execs, nlist_builds;
+};
+
+static int fail(pse_engine* e, int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(e ? e->err : g_create_error, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t _e = (call);                                                                        \
+        if (_e != cudaSuccess) return fail(e, PSE_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+    } while (0)
+#define CKFFT(call)                                                                                     \
+    do {                                                                                                \
+        cufftResult _r = (call);                                                                        \
+        if (_r != CUFFT_SUCCESS) return fail(e, PSE_ECUDA, "%s:%d %s: cufft error %d", __FILE__, __LINE__, #call, (int)_r); \
+    } while (0)
+#define LAUNCHED(e) ((e)->launches++)
+#define CKRC(call)              \
+    do {                        \
+        int _rc = (call);       \
+        if (_rc != PSE_OK) return _rc; \
+    } while (0)
+
+static inline unsigned int nblk(size_t n, int b) { return (unsigned int)((n + b - 1) / b); }
+
+// ---- exclusive scan driver -------------------------------------------------------------------
+static int exclusive_scan(pse_engine* e, const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* tmp) {
+    unsigned int nb = nblk(n, SCAN_BLOCK);
+    scan_block_kernel<<<nb, SCAN_BLOCK, 0, e->stream>>>(in, out, tmp, n);
+    LAUNCHED(e);
+    if (nb > 1) {
+        uint32_t* next = tmp + ((nb + 31) / 32) * 32;
+        CKRC(exclusive_scan(e, tmp, tmp, nb, next));
+        scan_add_kernel<<<nb, SCAN_BLOCK, 0, e->stream>>>(out, tmp, n, nullptr);
+        LAUNCHED(e);
+    }
+    return PSE_OK;
+}
+
+// ---- parameter blocks --------------------------------------------------------------------------
+static void refresh_box(pse_engine* e, const pse_box& b) {
+    e->cfg.box = b;
+    e->box = pse_make_box(b.Lx, b.Ly, b.Lz, b.xy);
+}
+
+static void setup_cell_grid(pse_engine* e) {
+    // cells of about half the list radius; the fractional x reach is widened by the tilt
+    const float target = e->rlist * 0.5f;
+    CellGrid& cg = e->cg;
+    cg.ncx = (int)fmaxf(1.f, floorf(e->box.Lx / target));
+    cg.ncy = (int)fmaxf(1.f, floorf(e->box.Ly / target));
+    cg.ncz = (int)fmaxf(1.f, floorf(e->box.Lz / target));
+    // bound the cell count by the number of particles (sparse systems) and by memory
+    while ((size_t)cg.ncx * cg.ncy * cg.ncz > e->cell_cap) {
+        if (cg.ncx >= cg.ncy && cg.ncx >= cg.ncz) cg.ncx = (cg.ncx + 1) / 2;
+        else if (cg.ncy >= cg.ncz) cg.ncy = (cg.ncy + 1) / 2;
+        else cg.ncz = (cg.ncz + 1) / 2;
+    }
+    cg.ncell = cg.ncx * cg.ncy * cg.ncz;
+    const float xy = fabsf(e->box.xy);
+    const float safety = 1.0001f;
+    cg.reach_fx = e->rlist * sqrtf(1.f + xy * xy) / e->box.Lx * safety + 1e-6f;
+    cg.reach_fy = e->rlist / e->box.Ly * safety + 1e-6f;
+    cg.reach_fz = e->rlist / e->box.Lz * safety + 1e-6f;
+}
+
+// ---- create / destroy ---------------------------------------------------------------------------
+extern "C" const char* pse_last_error(const pse_engine* e) { return e ? e->err : g_create_error; }
+
+static int alloc_all(pse_engine* e) {
+    const size_t N = e->N;
+    const pse_params& p = e->prm;
+    CK(cudaMalloc(&e->d_table, sizeof(float4) * (p.ewald_n + 1)));
+    e->cell_cap = std::max<size_t>(4096, 4 * N);
+    CK(cudaMalloc(&e->d_cell_of, sizeof(uint32_t) * N));
+    CK(cudaMalloc(&e->d_cell_count, sizeof(uint32_t) * (e->cell_cap + 1)));
+    CK(cudaMalloc(&e->d_cell_start, sizeof(uint32_t) * (e->cell_cap + 1)));
+    size_t scan_n = std::max(e->cell_cap + 1, N + 1);
+    CK(cudaMalloc(&e->d_scan_tmp, sizeof(uint32_t) * (scan_n / SCAN_BLOCK + 4096)));
+    CK(cudaMalloc(&e->d_perm, sizeof(uint32_t) * N));
+    CK(cudaMalloc(&e->d_slot_of, sizeof(uint32_t) * N));
+    CK(cudaMalloc(&e->d_spos, sizeof(float4) * N));
+    CK(cudaMalloc(&e->d_sx, sizeof(float4) * N));
+    CK(cudaMalloc(&e->d_sy, sizeof(float4) * N));
+    CK(cudaMalloc(&e->d_nn, sizeof(uint32_t) * (N + 1)));
+    CK(cudaMalloc(&e->d_head, sizeof(uint32_t) * (N + 1)));
+    e->d_nl = nullptr; e->nl_cap = 0;
+    CK(cudaMalloc(&e->d_pos_build, sizeof(float4) * N));
+    CK(cudaMalloc(&e->d_flag, sizeof(uint32_t)));
+    CK(cudaMallocHost(&e->h_flag, sizeof(uint32_t)));
+    CK(cudaEventCreateWithFlags(&e->flag_event, cudaEventDisableTiming));
+    CK(cudaMalloc(&e->d_grid, sizeof(float) * 3 * e->G));
+    CK(cudaMalloc(&e->d_spec, sizeof(float2) * 3 * e->Gh));
+    CK(cudaMalloc(&e->d_V, sizeof(float4) * N * LANCZOS_M_MAX));
+    CK(cudaMalloc(&e->d_u, sizeof(float4) * N));
+    CK(cudaMalloc(&e->d_y, sizeof(float4) * N));
+    CK(cudaMalloc(&e->d_alpha, sizeof(float) * (LANCZOS_M_MAX + 2)));
+    CK(cudaMalloc(&e->d_beta, sizeof(float) * (LANCZOS_M_MAX + 2)));
+    CK(cudaMalloc(&e->d_coef, sizeof(float) * (LANCZOS_M_MAX + 2)));
+    CK(cudaMalloc(&e->d_partials, sizeof(float) * (N / 8 + 1024)));
+    CK(cudaMalloc(&e->d_counter, sizeof(unsigned int)));
+    CK(cudaMemset(e->d_counter, 0, sizeof(unsigned int)));
+    CK(cudaMallocHost(&e->h_ab, sizeof(float) * (2 * LANCZOS_M_MAX + 4)));
+    CK(cudaMalloc(&e->d_vel_work, sizeof(float4) * N));
+    e->d_hpos = e->d_hF = nullptr; e->d_himage = nullptr;
+    return PSE_OK;
+}
+
+extern "C" int pse_create(const pse_config* cfg, void* stream, pse_engine** out) {
+    pse_engine* e = nullptr;
+    if (!cfg || !out) return fail(e, PSE_EINVAL, "pse_create: null argument");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(e, PSE_ENODEVICE, "pse_create: no CUDA device (there is no CPU fallback)");
+    }
+    pse_params prm;
+    int rc = pse_derive_params(cfg, &prm);
+    if (rc != PSE_OK) return fail(e, rc, "pse_create: parameter derivation failed (%d)%s", rc,
+                                  rc == PSE_EGRID ? ": Fourier grid above 512^3, reduce xi (PSEv1/Stokes.cc:203)" : "");
+    pse_config c = *cfg;
+    if (!(c.r_buff >= 0.f)) c.r_buff = 0.4f;
+    const float rlist = prm.rcut + c.r_buff;
+    const float plane_x = c.box.Lx / sqrtf(1.f + c.max_strain * c.max_strain);
+    if (2.f * rlist > fminf(plane_x, fminf(c.box.Ly, c.box.Lz)))
+        return fail(e, PSE_EINVAL, "pse_create: box too small for the minimum-image real-space sum (2*(rcut+r_buff) = %g)",
+                    2.f * rlist);
+    if (c.dt <= 0.f) return fail(e, PSE_EINVAL, "pse_create: dt must be positive");
+
+    pse_engine* eng = new pse_engine();
+    memset(eng, 0, sizeof(*eng));
+    e = eng;
+    strcpy(e->err, "no error");
+    e->cfg = c; e->prm = prm; e->N = c.N;
+    e->stream = (cudaStream_t)stream;
+    e->rlist = rlist;
+    refresh_box(e, c.box);
+    e->G = (size_t)prm.Nx * prm.Ny * prm.Nz;
+    WaveParams& wp = e->wp;
+    wp.Nx = prm.Nx; wp.Ny = prm.Ny; wp.Nz = prm.Nz; wp.Nzh = prm.Nz / 2 + 1; wp.P = prm.P;
+    wp.hx = prm.hx; wp.hy = prm.hy; wp.hz = prm.hz;
+    wp.prefac = prm.prefac; wp.expfac = prm.expfac; wp.quadW = prm.quadW;
+    wp.xi = c.xi; wp.eta = prm.eta;
+    wp.two_pi_k = (c.flags & PSE_FLAG_REF_PI) ? (float)(2.0 * 3.1416926536) : (float)(2.0 * 3.14159265358979323846);
+    e->Gh = (size_t)prm.Nx * prm.Ny * wp.Nzh;
+    RealParams& rp = e->rp;
+    rp.self = prm.self; rp.rcut = prm.rcut; rp.rcut_sq = prm.rcut * prm.rcut; rp.dr = prm.dr; rp.dr_sq = prm.dr * prm.dr;
+    rp.ewald_n = prm.ewald_n;
+    e->m_lanczos = 2;  // PSEv1/Stokes.cc:132
+
+    rc = alloc_all(e);
+    if (rc != PSE_OK) { strncpy(g_create_error, e->err, 511); pse_destroy(e); return rc; }
+    setup_cell_grid(e);
+
+    std::vector<float> tab(4 * (size_t)(prm.ewald_n + 1));
+    pse_ewald_table(&c, tab.data());
+    if (cudaMemcpy(e->d_table, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+        fail(nullptr, PSE_ECUDA, "pse_create: table upload failed");
+        pse_destroy(e);
+        return PSE_ECUDA;
+    }
+    int n[3] = {prm.Nx, prm.Ny, prm.Nz};
+    if (cufftPlanMany(&e->plan_f, 3, n, nullptr, 1, 0, nullptr, 1, 0, CUFFT_R2C, 3) != CUFFT_SUCCESS ||
+        cufftPlanMany(&e->plan_b, 3, n, nullptr, 1, 0, nullptr, 1, 0, CUFFT_C2R, 3) != CUFFT_SUCCESS) {
+        fail(nullptr, PSE_ECUDA, "pse_create: cufftPlanMany failed for %dx%dx%d", n[0], n[1], n[2]);
+        pse_destroy(e);
+        return PSE_ECUDA;
+    }
+    e->plans_ok = true;
+    cufftSetStream(e->plan_f, e->stream);
+    cufftSetStream(e->plan_b, e->stream);
+    *out = e;
+    return PSE_OK;
+}
+
+extern "C" void pse_destroy(pse_engine* e) {
+    if (!e) return;
+    if (e->plans_ok) { cufftDestroy(e->plan_f); cufftDestroy(e->plan_b); }
+    void* bufs[] = {e->d_table, e->d_cell_of, e->d_cell_count, e->d_cell_start, e->d_scan_tmp, e->d_perm, e->d_slot_of,
+                    e->d_spos, e->d_sx, e->d_sy, e->d_nn, e->d_head, e->d_nl, e->d_pos_build, e->d_flag, e->d_grid,
+                    e->d_spec, e->d_V, e->d_u, e->d_y, e->d_alpha, e->d_beta, e->d_coef, e->d_partials, e->d_counter,
+                    e->d_vel_work, e->d_hpos, e->d_hF, e->d_himage};
+    for (void* b : bufs)
+        if (b) cudaFree(b);
+    if (e->h_flag) cudaFreeHost(e->h_flag);
+    if (e->h_ab) cudaFreeHost(e->h_ab);
+    if (e->flag_event) cudaEventDestroy(e->flag_event);
+    delete e;
+}
+
+extern "C" int pse_get_params(const pse_engine* e, pse_params* out) {
+    if (!e || !out) return PSE_EINVAL;
+    *out = e->prm;
+    return PSE_OK;
+}
+extern "C" int pse_set_box(pse_engine* e, const pse_box* b) {
+    if (!e || !b) return PSE_EINVAL;
+    if (b->Lx != e->cfg.box.Lx || b->Ly != e->cfg.box.Ly || b->Lz != e->cfg.box.Lz)
+        return fail(e, PSE_EINVAL, "pse_set_box: only the tilt may change (the reference sizes the grid once, Stokes.cc:139)");
+    refresh_box(e, *b);
+    return PSE_OK;
+}
+extern "C" int pse_set_temperature(pse_engine* e, float T) {
+    if (!e || T < 0.f) return PSE_EINVAL;
+    e->cfg.T = T;
+    return PSE_OK;
+}
+extern "C" int pse_set_lanczos_m(pse_engine* e, int m) {
+    if (!e || m < 1 || m > LANCZOS_M_MAX) return PSE_EINVAL;
+    e->m_lanczos = m;
+    return PSE_OK;
+}
+extern "C" int pse_get_lanczos_m(const pse_engine* e) { return e ? e->m_lanczos : PSE_EINVAL; }
+extern "C" int pse_get_stats(const pse_engine* e, pse_stats* out) {
+    if (!e || !out) return PSE_EINVAL;
+    out->nnz = e->nnz; out->kernel_launches = e->launches; out->fft_execs = e->fft_execs;
+    out->nlist_builds = e->nlist_builds; out->lanczos_m = e->m_lanczos; out->lanczos_stepnorm = e->last_stepnorm;
+    return PSE_OK;
+}
+
+// ---- binning + neighbour list ------------------------------------------------------------------
+extern "C" int pse_build_neighbors(pse_engine* e, const float4* d_pos) {
+    if (!e || !d_pos) return PSE_EINVAL;
+    const uint32_t N = e->N;
+    cudaStream_t st = e->stream;
+    setup_cell_grid(e);
+    const CellGrid cg = e->cg;
+    const uint32_t ncell = cg.ncell;
+    CK(cudaMemsetAsync(e->d_cell_count, 0, sizeof(uint32_t) * (ncell + 1), st));
+    cell_id_kernel<<<nblk(N, 256), 256, 0, st>>>(d_pos, N, e->box, cg, e->d_cell_of, e->d_cell_count); LAUNCHED(e);
+    CKRC(exclusive_scan(e, e->d_cell_count, e->d_cell_start, ncell + 1, e->d_scan_tmp));
+    CK(cudaMemsetAsync(e->d_cell_count, 0, sizeof(uint32_t) * (ncell + 1), st));
+    cell_fill_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_cell_of, N, e->d_cell_start, e->d_cell_count, e->d_perm); LAUNCHED(e);
+    cell_sort_kernel<<<nblk(ncell, 128), 128, 0, st>>>(e->d_cell_start, ncell, e->d_perm); LAUNCHED(e);
+    invert_perm_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_perm, N, e->d_slot_of); LAUNCHED(e);
+    gather4_kernel<<<nblk(N, 256), 256, 0, st>>>(d_pos, e->d_perm, N, e->d_spos); LAUNCHED(e);
+
+    const float rl2 = e->rlist * e->rlist;
+    CK(cudaMemsetAsync(e->d_nn + N, 0, sizeof(uint32_t), st));
+    nlist_kernel<0><<<nblk(N, 128), 128, 0, st>>>(e->d_spos, N, e->box, cg, e->d_cell_start, rl2, e->d_nn, nullptr, nullptr); LAUNCHED(e);
+    CKRC(exclusive_scan(e, e->d_nn, e->d_head, N + 1, e->d_scan_tmp));
+    uint32_t total = 0;
+    CK(cudaMemcpyAsync(&total, e->d_head + N, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (total > e->nl_cap) {
+        if (e->d_nl) cudaFree(e->d_nl);
+        e->d_nl = nullptr;
+        e->nl_cap = (size_t)(total * 1.2) + 1024;
+        CK(cudaMalloc(&e->d_nl, sizeof(uint32_t) * e->nl_cap));
+    }
+    e->nnz = total;
+    nlist_kernel<1><<<nblk(N, 128), 128, 0, st>>>(e->d_spos, N, e->box, cg, e->d_cell_start, rl2, e->d_nn, e->d_head, e->d_nl); LAUNCHED(e);
+    CK(cudaMemcpyAsync(e->d_pos_build, d_pos, sizeof(float4) * N, cudaMemcpyDeviceToDevice, st));
+    e->xy_build = e->box.xy;
+    e->nlist_valid = true;
+    e->flag_pending = false;
+    e->nlist_builds++;
+    CK(cudaGetLastError());
+    return PSE_OK;
+}
+
+// list still valid for positions d_pos?  2*max displacement + tilt drift must stay inside the buffer
+static bool stale_from_bits(const pse_engine* e, uint32_t bits) {
+    float r2;
+    memcpy(&r2, &bits, 4);
+    const float drift = fabsf(e->box.xy - e->xy_build) * e->rlist;
+    return 2.f * sqrtf(r2) + drift > e->cfg.r_buff;
+}
+static int launch_disp_check(pse_engine* e, const float4* d_pos) {
+    CK(cudaMemsetAsync(e->d_flag, 0, sizeof(uint32_t), e->stream));
+    max_disp_kernel<<<nblk(e->N, 256), 256, 0, e->stream>>>(d_pos, e->d_pos_build, e->N, e->box, e->d_flag); LAUNCHED(e);
+    CK(cudaMemcpyAsync(e->h_flag, e->d_flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaEventRecord(e->flag_event, e->stream));
+    e->flag_pending = true;
+    return PSE_OK;
+}
+// make cells / list / slot-ordered positions current for d_pos
+static int ensure_neighbors(pse_engine* e, const float4* d_pos) {
+    bool rebuild = !e->nlist_valid;
+    if (!rebuild) {
+        CKRC(launch_disp_check(e, d_pos));
+        CK(cudaEventSynchronize(e->flag_event));
+        e->flag_pending = false;
+        rebuild = stale_from_bits(e, *e->h_flag);
+    }
+    if (rebuild) return pse_build_neighbors(e, d_pos);
+    gather4_kernel<<<nblk(e->N, 256), 256, 0, e->stream>>>(d_pos, e->d_perm, e->N, e->d_spos); LAUNCHED(e);
+    return PSE_OK;
+}
+
+extern "C" int pse_neighbor_list(pse_engine* e, uint32_t* d_n_neigh, uint32_t* d_headlist, uint32_t* d_nlist,
+                                 size_t cap, size_t* nnz_out) {
+    if (!e) return PSE_EINVAL;
+    if (!e->nlist_valid) return fail(e, PSE_EINVAL, "pse_neighbor_list: no list built yet");
+    if (nnz_out) *nnz_out = e->nnz;
+    if (!d_n_neigh && !d_headlist && !d_nlist) return PSE_OK;
+    const uint32_t N = e->N;
+    uint32_t *nn_id = nullptr, *head_id = nullptr;
+    CK(cudaMalloc(&nn_id, sizeof(uint32_t) * (N + 1)));
+    CK(cudaMalloc(&head_id, sizeof(uint32_t) * (N + 1)));
+    CK(cudaMemsetAsync(nn_id + N, 0, sizeof(uint32_t), e->stream));
+    export_counts_kernel<<<nblk(N, 256), 256, 0, e->stream>>>(e->d_nn, e->d_perm, N, nn_id); LAUNCHED(e);
+    int rc = exclusive_scan(e, nn_id, head_id, N + 1, e->d_scan_tmp);
+    if (rc == PSE_OK && d_nlist) {
+        if (cap < e->nnz) rc = fail(e, PSE_ECAPACITY, "pse_neighbor_list: need %llu entries", (unsigned long long)e->nnz);
+        else { export_rows_kernel<<<nblk(N, 128), 128, 0, e->stream>>>(e->d_nn, e->d_head, e->d_nl, e->d_perm, N, head_id, d_nlist); LAUNCHED(e); }
+    }
+    if (rc == PSE_OK && d_n_neigh) cudaMemcpyAsync(d_n_neigh, nn_id, sizeof(uint32_t) * N, cudaMemcpyDeviceToDevice, e->stream);
+    if (rc == PSE_OK && d_headlist) cudaMemcpyAsync(d_headlist, head_id, sizeof(uint32_t) * N, cudaMemcpyDeviceToDevice, e->stream);
+    cudaError_t ce = cudaStreamSynchronize(e->stream);
+    cudaFree(nn_id); cudaFree(head_id);
+    if (ce != cudaSuccess) return fail(e, PSE_ECUDA, "pse_neighbor_list: %s", cudaGetErrorString(ce));
+    return rc;
+}
+
+extern "C" int pse_grid_index(pse_engine* e, const float4* d_pos, int3* d_out) {
+    if (!e || !d_pos || !d_out) return PSE_EINVAL;
+    grid_index_kernel<<<nblk(e->N, 256), 256, 0, e->stream>>>(d_pos, e->N, e->box, e->wp, d_out); LAUNCHED(e);
+    CK(cudaGetLastError());
+    return PSE_OK;
+}
+
+// ---- building blocks (slot order) -----------------------------------------------------------------
+static int run_spmv_plain(pse_engine* e, const float4* x, float4* y) {
+    constexpr int TPP = 8;
+    LanczosArgs la = {};
+    spmv_kernel<TPP, SPMV_PLAIN><<<nblk((size_t)e->N * TPP, 256), 256, 0, e->stream>>>(
+        e->d_spos, x, y, e->N, e->d_nn, e->d_head, e->d_nl, e->d_table, e->rp, e->box, la);
+    LAUNCHED(e);
+    return PSE_OK;
+}
+
+// wave-space pipeline on slot-ordered (spos, sF): result scattered into U (particle-id order)
+static int run_wave(pse_engine* e, const float4* sF, float4* U, int accumulate, bool det, bool noise, uint32_t key,
+                    const float* d_u_grid) {
+    cudaStream_t st = e->stream;
+    if (det) {
+        CK(cudaMemsetAsync(e->d_grid, 0, sizeof(float) * 3 * e->G, st));
+        spread_scatter_kernel<<<nblk((size_t)e->N * 32, 256), 256, 0, st>>>(e->d_spos, sF, e->N, e->box, e->wp, e->d_grid); LAUNCHED(e);
+        CKFFT(cufftExecR2C(e->plan_f, e->d_grid, (cufftComplex*)e->d_spec)); e->fft_execs++;
+    }
+    const float T = e->cfg.T, dt = e->cfg.dt;
+    const float noise_fac = sqrtf((float)(2.0 * T / dt / e->wp.quadW));  // PSEv1/Brownian.cu:198
+    scale_kernel<<<nblk(e->Gh, 256), 256, 0, st>>>(e->d_spec, e->wp, e->box, det ? 1 : 0, noise ? 1 : 0, noise_fac, d_u_grid, key); LAUNCHED(e);
+    CKFFT(cufftExecC2R(e->plan_b, (cufftComplex*)e->d_spec, e->d_grid)); e->fft_execs++;
+    interp_warp_kernel<<<nblk((size_t)e->N * 32, 256), 256, 0, st>>>(e->d_spos, e->N, e->box, e->wp, e->d_grid, e->d_perm, U, accumulate); LAUNCHED(e);
+    return PSE_OK;
+}
+
+// one Lanczos iteration j (two kernels)
+static void lanczos_iteration(pse_engine* e, int j) {
+    constexpr int TPP = 8;
+    const uint32_t N = e->N;
+    float4* Vj = e->d_V + (size_t)j * N;
+    LanczosArgs la;
+    la.beta_j = e->d_beta + j;
+    la.v_prev = j > 0 ? e->d_V + (size_t)(j - 1) * N : nullptr;
+    la.v_out = Vj;
+    la.alpha_out = e->d_alpha + j;
+    la.partials = e->d_partials;
+    la.counter = e->d_counter;
+    la.first = j == 0;
+    spmv_kernel<TPP, SPMV_LANCZOS><<<nblk((size_t)N * TPP, 256), 256, 0, e->stream>>>(
+        e->d_spos, e->d_u, e->d_y, N, e->d_nn, e->d_head, e->d_nl, e->d_table, e->rp, e->box, la);
+    LAUNCHED(e);
+    lanczos_update_kernel<<<nblk(N, 256), 256, 0, e->stream>>>(e->d_y, Vj, e->d_u, N, e->d_alpha + j, e->d_beta + j + 1,
+                                                               e->d_partials, e->d_counter);
+    LAUNCHED(e);
+}
+
+static int solve_coeffs(pse_engine* e, int m, const float* alpha, const float* beta, std::vector<double>& c) {
+    std::vector<double> d(m), o(m > 1 ? m - 1 : 1);
+    for (int i = 0; i < m; ++i) d[i] = alpha[i];
+    for (int i = 0; i + 1 < m; ++i) o[i] = beta[i + 1];
+    c.assign(m, 0.0);
+    double lmin = 0;
+    int rc = pse_tridiag_sqrt_e1(m, d.data(), o.data(), c.data(), &lmin);
+    if (rc != PSE_OK)
+        return fail(e, PSE_EEIGEN, "Lanczos tridiagonal matrix (m = %d) is not positive definite (lambda_min = %g)", m, lmin);
+    return PSE_OK;
+}
+
+// U[perm] (+)= sqrt(2T/dt) * M_real^{1/2} psi, psi drawn per particle id (PSEv1/Brownian.cu:357-765)
+static int run_lanczos(pse_engine* e, float4* U, int accumulate, uint32_t key, const float* d_u_particles, int* m_out) {
+    const uint32_t N = e->N;
+    cudaStream_t st = e->stream;
+    psi_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_u, e->d_perm, N, d_u_particles, key); LAUNCHED(e);
+    dot_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_u, e->d_u, N, e->d_beta, e->d_partials, e->d_counter, true); LAUNCHED(e);
+
+    float* alpha = e->h_ab;
+    float* beta = e->h_ab + LANCZOS_M_MAX + 1;
+    int m = e->m_lanczos - 1;  // PSEv1/Brownian.cu:465-466
+    if (m < 1) m = 1;
+    for (int j = 0; j < m; ++j) lanczos_iteration(e, j);
+    CK(cudaMemcpyAsync(alpha, e->d_alpha, sizeof(float) * m, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(beta, e->d_beta, sizeof(float) * (m + 1), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int j = 0; j < m; ++j)
+        if (beta[j + 1] < 1e-8f) { m = j > 0 ? j : 1; break; }  // breakdown, PSEv1/Brownian.cu:507-510
+    std::vector<double> c, c_prev;
+    CKRC(solve_coeffs(e, m, alpha, beta, c));
+    c_prev = c;
+    const double rho = alpha[0];  // psi.M.psi/|psi|^2 == alpha_0 (PSEv1/Brownian.cu:452-457 spends an extra SpMV on it)
+    double stepnorm = 1.0;
+    const bool broke = beta[m] < 1e-8f;
+    while (!broke && stepnorm > e->cfg.error && m < LANCZOS_M_MAX) {  // PSEv1/Brownian.cu:606-736
+        ++m;
+        const int j = m - 1;
+        lanczos_iteration(e, j);
+        CK(cudaMemcpyAsync(alpha + j, e->d_alpha + j, sizeof(float), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(beta + j + 1, e->d_beta + j + 1, sizeof(float), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (beta[j + 1] < 1e-8f) { m = j; break; }
+        CKRC(solve_coeffs(e, m, alpha, beta, c));
+        // ||V c_m - V c_{m-1}|| = ||c_m - [c_{m-1}; 0]|| for an orthonormal basis: no N-vector pass
+        double s = 0.0;
+        for (int i = 0; i < m; ++i) {
+            double d = c[i] - (i < (int)c_prev.size() ? c_prev[i] : 0.0);
+            s += d * d;
+        }
+        stepnorm = sqrt(s / rho);
+        c_prev = c;
+    }
+    c = c_prev;
+    m = (int)c.size();
+    float hc[LANCZOS_M_MAX + 2];
+    for (int i = 0; i < m; ++i) hc[i] = (float)c[i];
+    CK(cudaMemcpyAsync(e->d_coef, hc, sizeof(float) * m, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));  // hc lives on this stack frame
+    const float thermal = sqrtf((float)(2.0 * e->cfg.T / e->cfg.dt));  // PSEv1/Brownian.cu:739
+    basis_combine_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_V, e->d_coef, m, N, (size_t)N, e->d_beta, thermal, e->d_perm, U, accumulate); LAUNCHED(e);
+    e->m_lanczos = m;
+    e->last_stepnorm = (float)stepnorm;
+    if (m_out) *m_out = m;
+    return PSE_OK;
+}
+
+// ---- public operators -----------------------------------------------------------------------------
+extern "C" int pse_mreal(pse_engine* e, const float4* d_pos, const float4* d_F, float4* d_U) {
+    if (!e || !d_pos || !d_F || !d_U) return PSE_EINVAL;
+    CKRC(ensure_neighbors(e, d_pos));
+    gather4_kernel<<<nblk(e->N, 256), 256, 0, e->stream>>>(d_F, e->d_perm, e->N, e->d_sx); LAUNCHED(e);
+    CKRC(run_spmv_plain(e, e->d_sx, e->d_sy));
+    scatter_add_kernel<<<nblk(e->N, 256), 256, 0, e->stream>>>(e->d_sy, e->d_perm, e->N, d_U, 0); LAUNCHED(e);
+    CK(cudaGetLastError());
+    return PSE_OK;
+}
+
+extern "C" int pse_mwave(pse_engine* e, const float4* d_pos, const float4* d_F, float4* d_U) {
+    if (!e || !d_pos || !d_F || !d_U) return PSE_EINVAL;
+    CKRC(ensure_neighbors(e, d_pos));
+    gather4_kernel<<<nblk(e->N, 256), 256, 0, e->stream>>>(d_F, e->d_perm, e->N, e->d_sx); LAUNCHED(e);
+    CKRC(run_wave(e, e->d_sx, d_U, 0, true, false, 0u, nullptr));
+    CK(cudaGetLastError());
+    return PSE_OK;
+}
+
+extern "C" int pse_velocity(pse_engine* e, const float4* d_pos, const float4* d_F, float4* d_U, uint32_t timestep,
+                            const float* d_u_particles, const float* d_u_grid, uint32_t parts, int* m_out) {
+    if (!e || !d_pos || !d_F || !d_U) return PSE_EINVAL;
+    const uint32_t N = e->N;
+    cudaStream_t st = e->stream;
+    const bool det = parts & 1u;
+    const bool thermal = e->cfg.T > 0.f;  // PSEv1/Brownian.cu:855,885
+    const bool wnoise = (parts & 2u) && thermal, rnoise = (parts & 4u) && thermal;
+    const uint32_t key = timestep + e->prm.seed_hashed;  // PSEv1/Brownian.cu:117,176
+    CKRC(ensure_neighbors(e, d_pos));
+    if (det) { gather4_kernel<<<nblk(N, 256), 256, 0, st>>>(d_F, e->d_perm, N, e->d_sx); LAUNCHED(e); }
+    int acc = 0;
+    if (det || wnoise) { CKRC(run_wave(e, e->d_sx, d_U, 0, det, wnoise, key, d_u_grid)); acc = 1; }
+    if (det) {
+        CKRC(run_spmv_plain(e, e->d_sx, e->d_sy));
+        scatter_add_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_sy, e->d_perm, N, d_U, acc); LAUNCHED(e);
+        acc = 1;
+    }
+    if (m_out) *m_out = e->m_lanczos;
+    if (rnoise) { CKRC(run_lanczos(e, d_U, acc, key, d_u_particles, m_out)); acc = 1; }
+    if (!acc) CK(cudaMemsetAsync(d_U, 0, sizeof(float4) * N, st));
+    CK(cudaGetLastError());
+    return PSE_OK;
+}
+
+extern "C" int pse_mobility(pse_engine* e, const float4* d_pos, const float4* d_F, float4* d_U) {
+    return pse_velocity(e, d_pos, d_F, d_U, 0u, nullptr, nullptr, 1u, nullptr);
+}
+
+// Euler update + affine shear advection + periodic wrap: PSEv1/Stokes.cu:137-192
+__global__ void integrate_kernel(float4* __restrict__ pos, int3* __restrict__ image, const float4* __restrict__ vel, uint32_t N,
+                                 PseBox box, float dt, float shear_rate) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    float4 p = pos[i];
+    const float4 v = __ldg(vel + i);
+    float3 w = make_float3(p.x, p.y, p.z);
+    const float vx = v.x + shear_rate * p.y;
+    w.x += vx * dt; w.y += v.y * dt; w.z += v.z * dt;
+    int3 im = image ? image[i] : make_int3(0, 0, 0);
+    box.wrap(w, im);
+    pos[i] = make_float4(w.x, w.y, w.z, p.w);
+    if (image) image[i] = im;
+}
+
+extern "C" int pse_step(pse_engine* e, float4* d_pos, int3* d_image, const float4* d_F, float4* d_vel, uint32_t timestep,
+                        float shear_rate, int* m_out) {
+    if (!e || !d_pos || !d_F) return PSE_EINVAL;
+    float4* vel = d_vel ? d_vel : e->d_vel_work;
+    CKRC(pse_velocity(e, d_pos, d_F, vel, timestep, nullptr, nullptr, 7u, m_out));
+    integrate_kernel<<<nblk(e->N, 256), 256, 0, e->stream>>>(d_pos, d_image, vel, e->N, e->box, e->cfg.dt, shear_rate); LAUNCHED(e);
+    CK(cudaGetLastError());
+    return PSE_OK;
+}
+
+extern "C" int pse_step_host(pse_engine* e, float* h_pos4, int* h_image3, const float* h_F4, float* h_vel4, uint32_t timestep,
+                             float shear_rate, int* m_out) {
+    if (!e || !h_pos4 || !h_F4) return PSE_EINVAL;
+    const size_t N = e->N;
+    cudaStream_t st = e->stream;
+    if (!e->d_hpos) {
+        CK(cudaMalloc(&e->d_hpos, sizeof(float4) * N));
+        CK(cudaMalloc(&e->d_hF, sizeof(float4) * N));
+        CK(cudaMalloc(&e->d_himage, sizeof(int3) * N));
+    }
+    CK(cudaMemcpyAsync(e->d_hpos, h_pos4, sizeof(float4) * N, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(e->d_hF, h_F4, sizeof(float4) * N, cudaMemcpyHostToDevice, st));
+    if (h_image3) CK(cudaMemcpyAsync(e->d_himage, h_image3, sizeof(int3) * N, cudaMemcpyHostToDevice, st));
+    else CK(cudaMemsetAsync(e->d_himage, 0, sizeof(int3) * N, st));
+    CKRC(pse_step(e, e->d_hpos, e->d_himage, e->d_hF, h_vel4 ? e->d_vel_work : nullptr, timestep, shear_rate, m_out));
+    CK(cudaMemcpyAsync(h_pos4, e->d_hpos, sizeof(float4) * N, cudaMemcpyDeviceToHost, st));
+    if (h_image3) CK(cudaMemcpyAsync(h_image3, e->d_himage, sizeof(int3) * N, cudaMemcpyDeviceToHost, st));
+    if (h_vel4) CK(cudaMemcpyAsync(h_vel4, e->d_vel_work, sizeof(float4) * N, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return PSE_OK;
+}
+
+// test hook: host tridiagonal square root (compared against numpy in the CPU tests)
+extern "C" int pse_test_tridiag_sqrt_e1(int m, const double* diag, const double* off, double* c) {
+    return pse_tridiag_sqrt_e1(m, diag, off, c, nullptr);
+}

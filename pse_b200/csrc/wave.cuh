@@ -1,0 +1,248 @@
+// Wave-space far field: Gaussian spreading, k-space scaling (+ Hermitian random modes),
+// Gaussian interpolation.  FFTs are cuFFT R2C/C2R on three real grids (the reference runs six
+// C2C transforms on purely real data, PSEv1/Brownian.cu:844-869).
+//
+// Grid layout in HBM: real grids  g[c][x][y][z], c = 0..2, z fastest (same node order as the
+// reference's x*Ny*Nz + y*Nz + z, PSEv1/Mobility.cu:233); spectra  s[c][x][y][kz], kz in
+// [0, Nz/2].  No k-vector table is stored (the reference rewrites a 16 B/node table every step,
+// PSEv1/Stokes.cu:298): k and B(k) are recomputed per node.
+#pragma once
+#include "box.cuh"
+#include "common.cuh"
+#include "rng.cuh"
+#include <cufft.h>
+
+struct WaveParams {
+    int Nx, Ny, Nz, Nzh;  // Nzh = Nz/2 + 1
+    int P;
+    float hx, hy, hz;
+    float prefac, expfac, quadW;
+    float xi, eta;
+    float two_pi_k;  // 2*pi used for wave vectors (reference typo or exact)
+};
+
+// ---- particle -> grid assignment (bit-exact contract) ------------------------------------------
+// PSEv1/Mobility.cu:173-214: fractional position * N, truncation, centred support.
+struct Support {
+    int x0, y0, z0;  // first node of the support, NOT wrapped
+};
+__device__ __forceinline__ Support support_origin(const PseBox& box, const WaveParams& wp, float px, float py, float pz) {
+    float3 f = box.make_fraction(px, py, pz);
+    f.x = PSE_MUL(f.x, (float)wp.Nx);
+    f.y = PSE_MUL(f.y, (float)wp.Ny);
+    f.z = PSE_MUL(f.z, (float)wp.Nz);
+    const int x = (int)f.x, y = (int)f.y, z = (int)f.z;
+    const int odd = wp.P & 1, half = wp.P / 2;
+    Support s;
+    s.x0 = x - half + 1 - odd * (PSE_SUB(f.x, (float)x) < 0.5f);
+    s.y0 = y - half + 1 - odd * (PSE_SUB(f.y, (float)y) < 0.5f);
+    s.z0 = z - half + 1 - odd * (PSE_SUB(f.z, (float)z) < 0.5f);
+    return s;
+}
+__device__ __forceinline__ int wrap_node(int i, int n) { return i < 0 ? i + n : (i > n - 1 ? i - n : i); }
+
+__global__ void grid_index_kernel(const float4* __restrict__ pos, uint32_t N, PseBox box, WaveParams wp,
+                                  int3* __restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    float4 p = __ldg(pos + i);
+    Support s = support_origin(box, wp, p.x, p.y, p.z);
+    out[i] = make_int3(wrap_node(s.x0, wp.Nx), wrap_node(s.y0, wp.Ny), wrap_node(s.z0, wp.Nz));
+}
+
+// Gaussian weight of node (ix,iy,iz) for a particle, as PSEv1/Mobility.cu:222-241
+__device__ __forceinline__ float gauss_weight(const PseBox& box, const WaveParams& wp, int ix, int iy, int iz, float px,
+                                              float py, float pz, float pref) {
+    float gx = wp.hx * (float)ix - box.Lx * 0.5f;
+    float gy = wp.hy * (float)iy - box.Ly * 0.5f;
+    float gz = wp.hz * (float)iz - box.Lz * 0.5f;
+    gx = gx + box.xy * gy;
+    float3 r = box.min_image(make_float3(gx - px, gy - py, gz - pz));
+    float rsq = r.x * r.x + r.y * r.y + r.z * r.z;
+    return pref * expf(-wp.expfac * rsq);
+}
+
+// ---- spreading, scatter form ------------------------------------------------------------------
+// One warp per particle; lanes tile the (x,y) footprint and walk z.  REDG float atomics into the
+// three real grids (which must be zero on entry).
+__global__ void __launch_bounds__(256)
+spread_scatter_kernel(const float4* __restrict__ pos, const float4* __restrict__ F, uint32_t N, PseBox box, WaveParams wp,
+                      float* __restrict__ grid) {
+    const uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (p >= N) return;
+    const float4 pp = __ldg(pos + p), ff = __ldg(F + p);
+    const Support s = support_origin(box, wp, pp.x, pp.y, pp.z);
+    const size_t G = (size_t)wp.Nx * wp.Ny * wp.Nz;
+    const int P = wp.P, PP = P * P;
+    for (int t = lane; t < PP; t += 32) {
+        const int tx = t / P, ty = t - tx * P;
+        const int ix = wrap_node(s.x0 + tx, wp.Nx), iy = wrap_node(s.y0 + ty, wp.Ny);
+        for (int tz = 0; tz < P; ++tz) {
+            const int iz = wrap_node(s.z0 + tz, wp.Nz);
+            const float w = gauss_weight(box, wp, ix, iy, iz, pp.x, pp.y, pp.z, wp.prefac);
+            const size_t idx = ((size_t)ix * wp.Ny + iy) * wp.Nz + iz;
+            atomicAdd(grid + idx, w * ff.x);
+            atomicAdd(grid + G + idx, w * ff.y);
+            atomicAdd(grid + 2 * G + idx, w * ff.z);
+        }
+    }
+}
+
+// ---- interpolation, one warp per particle -----------------------------------------------------
+// U[perm[slot]] (+)= quadW*prefac * sum_nodes w * grid    (PSEv1/Mobility.cu:325-477)
+__global__ void __launch_bounds__(256)
+interp_warp_kernel(const float4* __restrict__ pos, uint32_t N, PseBox box, WaveParams wp, const float* __restrict__ grid,
+                   const uint32_t* __restrict__ perm, float4* __restrict__ U, int accumulate) {
+    const uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (p >= N) return;
+    const float4 pp = __ldg(pos + p);
+    const Support s = support_origin(box, wp, pp.x, pp.y, pp.z);
+    const size_t G = (size_t)wp.Nx * wp.Ny * wp.Nz;
+    const int P = wp.P, PP = P * P;
+    const float pref = wp.quadW * wp.prefac;
+    float3 acc = make_float3(0.f, 0.f, 0.f);
+    for (int t = lane; t < PP; t += 32) {
+        const int tx = t / P, ty = t - tx * P;
+        const int ix = wrap_node(s.x0 + tx, wp.Nx), iy = wrap_node(s.y0 + ty, wp.Ny);
+        for (int tz = 0; tz < P; ++tz) {
+            const int iz = wrap_node(s.z0 + tz, wp.Nz);
+            const float w = gauss_weight(box, wp, ix, iy, iz, pp.x, pp.y, pp.z, pref);
+            const size_t idx = ((size_t)ix * wp.Ny + iy) * wp.Nz + iz;
+            acc.x += w * __ldg(grid + idx);
+            acc.y += w * __ldg(grid + G + idx);
+            acc.z += w * __ldg(grid + 2 * G + idx);
+        }
+    }
+    acc.x = warp_sum(acc.x); acc.y = warp_sum(acc.y); acc.z = warp_sum(acc.z);
+    if (lane == 0) {
+        const uint32_t id = perm ? perm[p] : p;
+        float4 o = accumulate ? U[id] : make_float4(0.f, 0.f, 0.f, 0.f);
+        o.x += acc.x; o.y += acc.y; o.z += acc.z; o.w = 0.f;
+        U[id] = o;
+    }
+}
+
+// ---- k-space scaling + random modes, half spectrum ---------------------------------------------
+struct KVec { float kx, ky, kz, w; };  // w = B(k)/G without the sinc^2 factor, as gridk.w
+
+// wave vector and scaling of full-grid node (i,j,k): PSEv1/Helper.cu:300-329
+__device__ __forceinline__ KVec k_of_node(int i, int j, int k, const WaveParams& wp, const PseBox& box) {
+    KVec kv;
+    float fx = (float)((i < (wp.Nx + 1) / 2) ? i : i - wp.Nx);
+    float fy = ((float)((j < (wp.Ny + 1) / 2) ? j : j - wp.Ny) - box.xy * fx * box.Ly / box.Lx) / box.Ly;
+    fx = fx / box.Lx;
+    float fz = (float)((k < (wp.Nz + 1) / 2) ? k : k - wp.Nz) / box.Lz;
+    kv.kx = fx * wp.two_pi_k; kv.ky = fy * wp.two_pi_k; kv.kz = fz * wp.two_pi_k;
+    const float k2 = kv.kx * kv.kx + kv.ky * kv.ky + kv.kz * kv.kz;
+    const float xisq = wp.xi * wp.xi;
+    const float G = (float)(wp.Nx * wp.Ny * wp.Nz);
+    kv.w = (i == 0 && j == 0 && k == 0)
+               ? 0.f
+               : 6.0f * 3.1415926536f * (1.0f + k2 / 4.0f / xisq) * expf(-(1.f - wp.eta) * k2 / 4.0f / xisq) / k2 / G;
+    return kv;
+}
+
+// does the reference's selection rule process full-grid node (ii,jj,kk)?  PSEv1/Brownian.cu:210-215
+__device__ __forceinline__ bool ref_processed(int ii, int jj, int kk, const WaveParams& wp) {
+    return !(2 * kk >= wp.Nz + 1) && !((kk == 0) && (2 * jj >= wp.Ny + 1)) &&
+           !((kk == 0) && (jj == 0) && (2 * ii >= wp.Nx + 1)) && !((kk == 0) && (jj == 0) && (ii == 0));
+}
+
+// six uniforms of a node (reX,reY,reZ,imX,imY,imZ) on (-sqrt(3/2), sqrt(3/2)): PSEv1/Brownian.cu:179-189
+__device__ __forceinline__ void node_draws(uint32_t idx, const float* __restrict__ u_grid, uint32_t key, float re[3],
+                                           float im[3]) {
+    const float a = 1.2247448713915889f;
+    if (u_grid) {
+        const float* t = u_grid + (size_t)idx * 6;
+        re[0] = pse_affine(__ldg(t + 0), -a, a); re[1] = pse_affine(__ldg(t + 1), -a, a); re[2] = pse_affine(__ldg(t + 2), -a, a);
+        im[0] = pse_affine(__ldg(t + 3), -a, a); im[1] = pse_affine(__ldg(t + 4), -a, a); im[2] = pse_affine(__ldg(t + 5), -a, a);
+    } else {
+        const uint4 b0 = pse_philox(idx, 0u, PSE_RNG_DOMAIN_GRID, key), b1 = pse_philox(idx, 1u, PSE_RNG_DOMAIN_GRID, key);
+        re[0] = pse_uniform(b0.x, -a, a); re[1] = pse_uniform(b0.y, -a, a); re[2] = pse_uniform(b0.z, -a, a);
+        im[0] = pse_uniform(b0.w, -a, a); im[1] = pse_uniform(b1.x, -a, a); im[2] = pse_uniform(b1.y, -a, a);
+    }
+}
+
+// One thread per half-spectrum node.  deterministic: u = B (I - kk/k^2) f  (PSEv1/Mobility.cu:264-299);
+// stochastic: + fac * B^{1/2} (I - kk/k^2) (re + i im), Hermitian by construction
+// (PSEv1/Brownian.cu:153-345, each conjugate pair generated exactly once — SURVEY.md Q4).
+// do_det = 0 discards the incoming spectrum (pure noise field).
+__global__ void __launch_bounds__(256)
+scale_kernel(float2* __restrict__ spec, WaveParams wp, PseBox box, int do_det, int do_noise, float noise_fac,
+             const float* __restrict__ u_grid, uint32_t key) {
+    const size_t nh = (size_t)wp.Nx * wp.Ny * wp.Nzh;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= nh) return;
+    const int kk = (int)(tid % wp.Nzh);
+    const int jj = (int)((tid / wp.Nzh) % wp.Ny);
+    const int ii = (int)(tid / ((size_t)wp.Nzh * wp.Ny));
+    float2 fX = make_float2(0.f, 0.f), fY = fX, fZ = fX;
+    if (do_det) { fX = spec[tid]; fY = spec[nh + tid]; fZ = spec[2 * nh + tid]; }
+
+    const bool origin = (ii == 0 && jj == 0 && kk == 0);
+    const KVec kv = k_of_node(ii, jj, kk, wp, box);
+    const float ksq = kv.kx * kv.kx + kv.ky * kv.ky + kv.kz * kv.kz;
+    const float k = sqrtf(ksq);
+    const float sinc = origin ? 0.f : sinf(k) / k;
+    float2 oX = make_float2(0.f, 0.f), oY = oX, oZ = oX;
+    if (do_det && !origin) {
+        const float B = kv.w * sinc * sinc;
+        const float2 kdF = make_float2((kv.kx * fX.x + kv.ky * fY.x + kv.kz * fZ.x) / ksq,
+                                       (kv.kx * fX.y + kv.ky * fY.y + kv.kz * fZ.y) / ksq);
+        oX = make_float2((fX.x - kv.kx * kdF.x) * B, (fX.y - kv.kx * kdF.y) * B);
+        oY = make_float2((fY.x - kv.ky * kdF.x) * B, (fY.y - kv.ky * kdF.y) * B);
+        oZ = make_float2((fZ.x - kv.kz * kdF.x) * B, (fZ.y - kv.kz * kdF.y) * B);
+    }
+    if (do_noise && !origin) {
+        const bool ii_nyq = (ii == wp.Nx / 2) && (wp.Nx / 2 == (wp.Nx + 1) / 2);
+        const bool jj_nyq = (jj == wp.Ny / 2) && (wp.Ny / 2 == (wp.Ny + 1) / 2);
+        const bool kk_nyq = (kk == wp.Nz / 2) && (wp.Nz / 2 == (wp.Nz + 1) / 2);
+        const bool self_conj = (ii == 0 || ii_nyq) && (jj == 0 || jj_nyq) && (kk == 0 || kk_nyq);
+        const uint32_t idx = ((uint32_t)ii * wp.Ny + jj) * wp.Nz + kk;  // full-grid node index (reference numbering)
+        float re[3], im[3];
+        if (self_conj) {
+            node_draws(idx, u_grid, key, re, im);
+            const float sqrt2 = 1.4142135623730951f;
+            re[0] *= sqrt2; re[1] *= sqrt2; re[2] *= sqrt2;
+            im[0] = im[1] = im[2] = 0.f;
+        } else {
+            // the mirror node shares this node's conjugate pair; it lives in the half spectrum only on
+            // the kz = 0 and kz = Nyquist planes.  Owner of the pair = the node the reference rule
+            // processes; if the rule processes both, the smaller index owns it.
+            const int mi = ii == 0 ? 0 : wp.Nx - ii, mj = jj == 0 ? 0 : wp.Ny - jj, mk = kk == 0 ? 0 : wp.Nz - kk;
+            const uint32_t midx = ((uint32_t)mi * wp.Ny + mj) * wp.Nz + mk;
+            const bool me = ref_processed(ii, jj, kk, wp), other = ref_processed(mi, mj, mk, wp);
+            const bool own = me && (!other || idx < midx);
+            node_draws(own ? idx : midx, u_grid, key, re, im);
+            if (!own) { im[0] = -im[0]; im[1] = -im[1]; im[2] = -im[2]; }
+        }
+        const float B12 = sqrtf(kv.w) * sinc;
+        const float2 kdF = make_float2((kv.kx * re[0] + kv.ky * re[1] + kv.kz * re[2]) / ksq,
+                                       (kv.kx * im[0] + kv.ky * im[1] + kv.kz * im[2]) / ksq);
+        oX.x += noise_fac * (re[0] - kv.kx * kdF.x) * B12; oX.y += noise_fac * (im[0] - kv.kx * kdF.y) * B12;
+        oY.x += noise_fac * (re[1] - kv.ky * kdF.x) * B12; oY.y += noise_fac * (im[1] - kv.ky * kdF.y) * B12;
+        oZ.x += noise_fac * (re[2] - kv.kz * kdF.x) * B12; oZ.y += noise_fac * (im[2] - kv.kz * kdF.y) * B12;
+    }
+    spec[tid] = oX; spec[nh + tid] = oY; spec[2 * nh + tid] = oZ;
+}
+
+// particle noise psi (slot order) : 3 uniforms on (-sqrt3, sqrt3), PSEv1/Brownian.cu:99-130
+__global__ void psi_kernel(float4* __restrict__ psi, const uint32_t* __restrict__ perm, uint32_t N,
+                           const float* __restrict__ u_particles, uint32_t key) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= N) return;
+    const uint32_t id = perm[s];
+    const float a = 1.73205080757f;
+    float x, y, z;
+    if (u_particles) {
+        x = pse_affine(__ldg(u_particles + 3 * (size_t)id + 0), -a, a);
+        y = pse_affine(__ldg(u_particles + 3 * (size_t)id + 1), -a, a);
+        z = pse_affine(__ldg(u_particles + 3 * (size_t)id + 2), -a, a);
+    } else {
+        const uint4 b = pse_philox(id, 0u, PSE_RNG_DOMAIN_PARTICLE, key);
+        x = pse_uniform(b.x, -a, a); y = pse_uniform(b.y, -a, a); z = pse_uniform(b.z, -a, a);
+    }
+    psi[s] = make_float4(x, y, z, 0.f);
+}
