@@ -618,3 +618,9 @@ extern "C" int pse_step_host(pse_engine* e, float* h_pos4, int* h_image3, const 
 extern "C" int pse_test_tridiag_sqrt_e1(int m, const double* diag, const double* off, double* c) {
     return pse_tridiag_sqrt_e1(m, diag, off, c, nullptr);
 }
+
+// test hook: Philox4x32-10 known-answer vectors (host path of rng.cuh)
+extern "C" void pse_test_philox4x32(const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
+    uint4 r = pse_philox4x32(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}

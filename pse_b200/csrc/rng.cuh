@@ -23,10 +23,8 @@ PSE_HD uint32_t pse_mulhi32(uint32_t a, uint32_t b) {
 #endif
 }
 
-// ctr = (index, block, domain, 0), key = (timestep + seed, 0xB200)
-PSE_HD uint4 pse_philox(uint32_t index, uint32_t block, uint32_t domain, uint32_t key0) {
-    uint32_t c0 = index, c1 = block, c2 = domain, c3 = 0u;
-    uint32_t k0 = key0, k1 = 0xB200u;
+// Philox4x32-10 (Salmon et al., SC'11): counter (c0..c3), key (k0,k1)
+PSE_HD uint4 pse_philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         uint32_t hi0 = pse_mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
@@ -36,6 +34,11 @@ PSE_HD uint4 pse_philox(uint32_t index, uint32_t block, uint32_t domain, uint32_
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
     return make_uint4(c0, c1, c2, c3);
+}
+
+// engine streams: ctr = (index, block, domain, 0), key = (timestep + seed, 0xB200)
+PSE_HD uint4 pse_philox(uint32_t index, uint32_t block, uint32_t domain, uint32_t key0) {
+    return pse_philox4x32(index, block, domain, 0u, key0, 0xB200u);
 }
 
 // 24-bit uniform in [0,1)

@@ -165,10 +165,31 @@ __device__ __forceinline__ void node_draws(uint32_t idx, const float* __restrict
     }
 }
 
+// scaled value of one node for wave vector kv:  out += scale * (f - k (k.f)/k^2)   (complex 3-vector)
+__device__ __forceinline__ void project_add(const KVec& kv, float scale, const float2 fX, const float2 fY, const float2 fZ,
+                                            float2& oX, float2& oY, float2& oZ) {
+    const float ksq = kv.kx * kv.kx + kv.ky * kv.ky + kv.kz * kv.kz;
+    const float2 kdF = make_float2((kv.kx * fX.x + kv.ky * fY.x + kv.kz * fZ.x) / ksq,
+                                   (kv.kx * fX.y + kv.ky * fY.y + kv.kz * fZ.y) / ksq);
+    oX.x += (fX.x - kv.kx * kdF.x) * scale; oX.y += (fX.y - kv.kx * kdF.y) * scale;
+    oY.x += (fY.x - kv.ky * kdF.x) * scale; oY.y += (fY.y - kv.ky * kdF.y) * scale;
+    oZ.x += (fZ.x - kv.kz * kdF.x) * scale; oZ.y += (fZ.y - kv.kz * kdF.y) * scale;
+}
+__device__ __forceinline__ float sinc_of(const KVec& kv) {
+    const float k = sqrtf(kv.kx * kv.kx + kv.ky * kv.ky + kv.kz * kv.kz);
+    return sinf(k) / k;
+}
+
 // One thread per half-spectrum node.  deterministic: u = B (I - kk/k^2) f  (PSEv1/Mobility.cu:264-299);
 // stochastic: + fac * B^{1/2} (I - kk/k^2) (re + i im), Hermitian by construction
 // (PSEv1/Brownian.cu:153-345, each conjugate pair generated exactly once — SURVEY.md Q4).
 // do_det = 0 discards the incoming spectrum (pure noise field).
+//
+// Nyquist components (even sizes): the reference scales the full C2C spectrum node by node and keeps
+// the real part of the inverse transform, i.e. the Hermitian part (X(n) + conj X(mirror))/2 of its
+// spectrum.  A node n with a Nyquist index and its mirror carry wave vectors that are NOT negatives of
+// each other (PSEv1/Helper.cu:308-311 maps index N/2 to -N/2 for both; under shear even |k| differs), so
+// the half-spectrum C2R path evaluates both wave vectors and averages.
 __global__ void __launch_bounds__(256)
 scale_kernel(float2* __restrict__ spec, WaveParams wp, PseBox box, int do_det, int do_noise, float noise_fac,
              const float* __restrict__ u_grid, uint32_t key) {
@@ -180,50 +201,47 @@ scale_kernel(float2* __restrict__ spec, WaveParams wp, PseBox box, int do_det, i
     const int ii = (int)(tid / ((size_t)wp.Nzh * wp.Ny));
     float2 fX = make_float2(0.f, 0.f), fY = fX, fZ = fX;
     if (do_det) { fX = spec[tid]; fY = spec[nh + tid]; fZ = spec[2 * nh + tid]; }
-
-    const bool origin = (ii == 0 && jj == 0 && kk == 0);
-    const KVec kv = k_of_node(ii, jj, kk, wp, box);
-    const float ksq = kv.kx * kv.kx + kv.ky * kv.ky + kv.kz * kv.kz;
-    const float k = sqrtf(ksq);
-    const float sinc = origin ? 0.f : sinf(k) / k;
     float2 oX = make_float2(0.f, 0.f), oY = oX, oZ = oX;
-    if (do_det && !origin) {
-        const float B = kv.w * sinc * sinc;
-        const float2 kdF = make_float2((kv.kx * fX.x + kv.ky * fY.x + kv.kz * fZ.x) / ksq,
-                                       (kv.kx * fX.y + kv.ky * fY.y + kv.kz * fZ.y) / ksq);
-        oX = make_float2((fX.x - kv.kx * kdF.x) * B, (fX.y - kv.kx * kdF.y) * B);
-        oY = make_float2((fY.x - kv.ky * kdF.x) * B, (fY.y - kv.ky * kdF.y) * B);
-        oZ = make_float2((fZ.x - kv.kz * kdF.x) * B, (fZ.y - kv.kz * kdF.y) * B);
-    }
-    if (do_noise && !origin) {
+    const bool origin = (ii == 0 && jj == 0 && kk == 0);
+    if (!origin) {
         const bool ii_nyq = (ii == wp.Nx / 2) && (wp.Nx / 2 == (wp.Nx + 1) / 2);
         const bool jj_nyq = (jj == wp.Ny / 2) && (wp.Ny / 2 == (wp.Ny + 1) / 2);
         const bool kk_nyq = (kk == wp.Nz / 2) && (wp.Nz / 2 == (wp.Nz + 1) / 2);
-        const bool self_conj = (ii == 0 || ii_nyq) && (jj == 0 || jj_nyq) && (kk == 0 || kk_nyq);
+        const int mi = ii == 0 ? 0 : wp.Nx - ii, mj = jj == 0 ? 0 : wp.Ny - jj, mk = kk == 0 ? 0 : wp.Nz - kk;
         const uint32_t idx = ((uint32_t)ii * wp.Ny + jj) * wp.Nz + kk;  // full-grid node index (reference numbering)
-        float re[3], im[3];
-        if (self_conj) {
-            node_draws(idx, u_grid, key, re, im);
-            const float sqrt2 = 1.4142135623730951f;
-            re[0] *= sqrt2; re[1] *= sqrt2; re[2] *= sqrt2;
-            im[0] = im[1] = im[2] = 0.f;
-        } else {
-            // the mirror node shares this node's conjugate pair; it lives in the half spectrum only on
-            // the kz = 0 and kz = Nyquist planes.  Owner of the pair = the node the reference rule
-            // processes; if the rule processes both, the smaller index owns it.
-            const int mi = ii == 0 ? 0 : wp.Nx - ii, mj = jj == 0 ? 0 : wp.Ny - jj, mk = kk == 0 ? 0 : wp.Nz - kk;
-            const uint32_t midx = ((uint32_t)mi * wp.Ny + mj) * wp.Nz + mk;
-            const bool me = ref_processed(ii, jj, kk, wp), other = ref_processed(mi, mj, mk, wp);
-            const bool own = me && (!other || idx < midx);
-            node_draws(own ? idx : midx, u_grid, key, re, im);
-            if (!own) { im[0] = -im[0]; im[1] = -im[1]; im[2] = -im[2]; }
+        const uint32_t midx = ((uint32_t)mi * wp.Ny + mj) * wp.Nz + mk;
+        const bool self_conj = idx == midx;
+        const bool two = (ii_nyq || jj_nyq || kk_nyq) && !self_conj;  // mirror wave vector differs from -k
+        const KVec kv = k_of_node(ii, jj, kk, wp, box);
+        const float sinc = sinc_of(kv);
+        KVec kvm = kv;
+        float sincm = sinc;
+        if (two) { kvm = k_of_node(mi, mj, mk, wp, box); sincm = sinc_of(kvm); }
+        const float half = two ? 0.5f : 1.0f;
+        if (do_det) {
+            project_add(kv, half * kv.w * sinc * sinc, fX, fY, fZ, oX, oY, oZ);
+            if (two) project_add(kvm, half * kvm.w * sincm * sincm, fX, fY, fZ, oX, oY, oZ);
         }
-        const float B12 = sqrtf(kv.w) * sinc;
-        const float2 kdF = make_float2((kv.kx * re[0] + kv.ky * re[1] + kv.kz * re[2]) / ksq,
-                                       (kv.kx * im[0] + kv.ky * im[1] + kv.kz * im[2]) / ksq);
-        oX.x += noise_fac * (re[0] - kv.kx * kdF.x) * B12; oX.y += noise_fac * (im[0] - kv.kx * kdF.y) * B12;
-        oY.x += noise_fac * (re[1] - kv.ky * kdF.x) * B12; oY.y += noise_fac * (im[1] - kv.ky * kdF.y) * B12;
-        oZ.x += noise_fac * (re[2] - kv.kz * kdF.x) * B12; oZ.y += noise_fac * (im[2] - kv.kz * kdF.y) * B12;
+        if (do_noise) {
+            float re[3], im[3];
+            if (self_conj) {
+                node_draws(idx, u_grid, key, re, im);
+                const float sqrt2 = 1.4142135623730951f;
+                re[0] *= sqrt2; re[1] *= sqrt2; re[2] *= sqrt2;
+                im[0] = im[1] = im[2] = 0.f;
+            } else {
+                // the mirror node shares this node's conjugate pair; it lives in the half spectrum only on
+                // the kz = 0 and kz = Nyquist planes.  Owner of the pair = the node the reference rule
+                // processes; if the rule processes both, the smaller index owns it.
+                const bool me = ref_processed(ii, jj, kk, wp), other = ref_processed(mi, mj, mk, wp);
+                const bool own = me && (!other || idx < midx);
+                node_draws(own ? idx : midx, u_grid, key, re, im);
+                if (!own) { im[0] = -im[0]; im[1] = -im[1]; im[2] = -im[2]; }
+            }
+            const float2 dX = make_float2(re[0], im[0]), dY = make_float2(re[1], im[1]), dZ = make_float2(re[2], im[2]);
+            project_add(kv, half * noise_fac * sqrtf(kv.w) * sinc, dX, dY, dZ, oX, oY, oZ);
+            if (two) project_add(kvm, half * noise_fac * sqrtf(kvm.w) * sincm, dX, dY, dZ, oX, oY, oZ);
+        }
     }
     spec[tid] = oX; spec[nh + tid] = oY; spec[2 * nh + tid] = oZ;
 }

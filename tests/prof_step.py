@@ -1,0 +1,21 @@
+"""Profiling driver (not a test): a few BD steps at the headline config for ncu launch lists."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from pse_b200 import engine as E, _lib
+from tests import util
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
+phi = float(sys.argv[2]) if len(sys.argv) > 2 else 0.3
+steps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+L = util.box_length(N, phi)
+cfg = E.make_config(N, L, T=1.0, dt=1e-3, seed=1)
+eng = E.Engine(cfg)
+pos = torch.from_numpy(util.lattice_positions(N, L, 0)).cuda()
+F = torch.from_numpy(util.random_forces(N, 1)).cuda()
+img = torch.zeros((N, 3), dtype=torch.int32, device="cuda")
+eng.lanczos_m = 5
+for t in range(steps):
+    m = eng.step(pos, img, F, t)
+torch.cuda.synchronize()
+print("m", m, eng.stats())

@@ -1,0 +1,345 @@
+"""GPU parity suite (-m gpu): the CUDA path behind the C ABI against
+  (1) the reference's own CUDA kernels compiled unmodified (oracle/_ref/libpse_ref.so),
+  (2) the CPU restatement (oracle/pse_oracle.c) and its dense double-precision Ewald sum,
+  (3) size-independent properties at the BASELINE.json headline size (N = 1M).
+Tolerances: integer outputs (neighbour list, particle->grid index) bit-exact; deterministic M.F and
+Brownian displacements for identical random vectors 1e-5 relative (BASELINE.json north_star), measured
+as |a-b|_2/|b|_2 and max|a-b|/max|b|; accuracy vs dense Ewald 3x the requested error."""
+import math
+
+import numpy as np
+import pytest
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+class System:
+    def __init__(self, N, L, xy=0.0, seed=0, lattice=False, ref_pi=True, error=1e-3, xi=0.5, T=1.0, dt=1e-3, want_ref=True):
+        import torch
+        from oracle import oraclewrap as O
+        from oracle import refwrap
+        from pse_b200 import _lib
+        from pse_b200 import engine as E
+        self.torch, self.E = torch, E
+        self.N, self.L, self.T, self.dt = N, L, T, dt
+        self.cfg = E.make_config(N, L, xy=xy, flags=_lib.PSE_FLAG_REF_PI if ref_pi else 0, T=T, dt=dt, seed=1, error=error, xi=xi)
+        self.eng = E.Engine(self.cfg)
+        self.p = self.eng.params
+        Lx = L if np.isscalar(L) else L[0]
+        self.pos_np = util.lattice_positions(N, Lx, seed) if lattice else util.random_positions(N, Lx, seed)
+        if not np.isscalar(L):
+            self.pos_np[:, 1] *= L[1] / L[0]; self.pos_np[:, 2] *= L[2] / L[0]
+        self.F_np = util.random_forces(N, seed + 1)
+        self.pos = torch.from_numpy(self.pos_np).cuda(); self.F = torch.from_numpy(self.F_np).cuda()
+        self.eng.build_neighbors(self.pos)
+        self.nl = self.eng.neighbor_list()
+        self.orc = O.Oracle(N, L, xi=xi, error=error, xy=xy, ref_pi=ref_pi)
+        self.ref = None
+        if want_ref and refwrap.available():
+            self.ref = refwrap.Reference(self.cfg, self.p, E.ewald_table(self.cfg))
+            self.ref.set_neighbors(*self.nl)
+
+    def nl_np(self):
+        return [t.cpu().numpy().view(np.uint32) for t in self.nl]
+
+    def noise(self, seed=5, neutralise=True):
+        torch, p = self.torch, self.p
+        g = torch.Generator(device="cuda"); g.manual_seed(seed)
+        G = p.Nx * p.Ny * p.Nz
+        up = torch.rand((self.N, 3), device="cuda", generator=g); ug = torch.rand((G, 6), device="cuda", generator=g)
+        if neutralise:  # nodes the reference visits twice with a data race: u = 0.5 -> exactly 0
+            v = ug.view(p.Nx, p.Ny, p.Nz, 6)
+            if p.Nz % 2 == 0: v[:, :, p.Nz // 2, :] = 0.5
+            if p.Ny % 2 == 0: v[:, p.Ny // 2, 0, :] = 0.5
+        return up, ug
+
+
+def close(a, b, tol=TOL):
+    l2, mx = util.rel_err(a.detach().cpu().numpy() if hasattr(a, "detach") else a, b.detach().cpu().numpy() if hasattr(b, "detach") else b)
+    assert l2 < tol and mx < tol, (l2, mx)
+
+
+@pytest.fixture(scope="module", params=[0.0, 0.3], ids=["ortho", "sheared"])
+def cfg1(request, cuda):
+    """BASELINE.json config 1: N = 1000, phi = 0.1, error 1e-3 (36^3 grid), i.i.d. positions incl. overlaps."""
+    return System(1000, util.box_length(1000, 0.1), xy=request.param)
+
+
+# ---------------------------------------------------------------- bit-exact integer outputs
+def test_neighbor_list_bit_exact_vs_bruteforce(cfg1):
+    nn, head, nl = cfg1.nl_np()
+    onn, ohead, onl = cfg1.orc.neighbors(cfg1.pos_np, cfg1.p.rcut + 0.4, brute=True)
+    assert np.array_equal(nn, onn) and np.array_equal(head, ohead) and np.array_equal(nl, onl)
+
+
+def test_grid_index_bit_exact(cfg1):
+    gi = cfg1.eng.grid_index(cfg1.pos).cpu().numpy()
+    assert np.array_equal(gi, cfg1.orc.grid_index(cfg1.pos_np))
+    _check_index_against_reference_spread(cfg1, gi)
+
+
+def _check_index_against_reference_spread(s, gi):
+    """The reference has no index output; its Spread kernel with prefac = 1, expfac = 0 deposits exactly
+    F on each of the P^3 support nodes (PSEv1/Mobility.cu:241-246), i.e. an integer histogram."""
+    if s.ref is None:
+        pytest.skip("reference library not built")
+    torch, p, N = s.torch, s.p, s.N
+    ids = (np.arange(N) % 1021 + 1).astype(np.float64)
+    Fh = torch.zeros_like(s.F); Fh[:, 0] = 1.0; Fh[:, 1] = torch.from_numpy(ids).float().cuda()
+    gX, gY, _ = s.ref.spread(s.pos, Fh, P=p.P, prefac=1.0, expfac=0.0)
+    hist = np.zeros(p.Nx * p.Ny * p.Nz); hid = np.zeros_like(hist)
+    g = gi.astype(np.int64)
+    for tx in range(p.P):
+        for ty in range(p.P):
+            for tz in range(p.P):
+                lin = (((g[:, 0] + tx) % p.Nx) * p.Ny + (g[:, 1] + ty) % p.Ny) * p.Nz + (g[:, 2] + tz) % p.Nz
+                hist += np.bincount(lin, minlength=hist.size); hid += np.bincount(lin, weights=ids, minlength=hist.size)
+    assert np.array_equal(hist, gX[:, 0].cpu().numpy()) and np.array_equal(hid, gY[:, 0].cpu().numpy())
+
+
+# ---------------------------------------------------------------- deterministic operators
+def test_mreal_parity(cfg1):
+    U = cfg1.eng.mreal(cfg1.pos, cfg1.F)
+    cfg1.orc.set_neighbors(*cfg1.nl_np())
+    close(U, cfg1.orc.mreal(cfg1.pos_np, cfg1.F_np))
+    if cfg1.ref: close(U, cfg1.ref.mreal(cfg1.pos, cfg1.F))
+    assert float(U[:, 3].abs().max()) == 0.0  # .w written as 0 (PSEv1/Mobility.cu:632)
+
+
+def test_mwave_parity(cfg1):
+    U = cfg1.eng.mwave(cfg1.pos, cfg1.F)
+    close(U, cfg1.orc.mwave(cfg1.pos_np, cfg1.F_np))
+    if cfg1.ref: close(U, cfg1.ref.mwave(cfg1.pos, cfg1.F))
+
+
+def test_mobility_parity_and_repeatability(cfg1):
+    U = cfg1.eng.mobility(cfg1.pos, cfg1.F)
+    if cfg1.ref: close(U, cfg1.ref.mobility(cfg1.pos, cfg1.F))
+    close(U, cfg1.eng.mreal(cfg1.pos, cfg1.F) + cfg1.eng.mwave(cfg1.pos, cfg1.F), 2e-7)
+    close(cfg1.eng.mobility(cfg1.pos, cfg1.F), U, 1e-6)
+
+
+@pytest.mark.parametrize("xy", [0.0, 0.3])
+def test_mobility_within_ewald_error_of_dense(cuda, xy):
+    from oracle import oraclewrap as O
+    N = 400
+    L = util.box_length(N, 0.1)
+    for error in (1e-3, 1e-4):
+        s = System(N, L, xy=xy, seed=3, ref_pi=False, error=error, want_ref=False)
+        Ud = O.dense_mobility(s.pos_np[:, :3], s.F_np[:, :3], L, xy=xy)
+        U = s.eng.mobility(s.pos, s.F).cpu().numpy()[:, :3].astype(np.float64)
+        err = np.linalg.norm(U - Ud) / np.linalg.norm(Ud)
+        assert err < 3 * error, (error, err)
+        # the reference's 2*pi typo moves the answer by more than the parity tolerance but far less than `error`
+        s2 = System(N, L, xy=xy, seed=3, ref_pi=True, error=error, want_ref=False)
+        U2 = s2.eng.mobility(s2.pos, s2.F).cpu().numpy()[:, :3].astype(np.float64)
+        d = np.linalg.norm(U2 - U) / np.linalg.norm(U)
+        assert 1e-6 < d < 3e-4, d
+
+
+# ---------------------------------------------------------------- Brownian parts, identical random vectors
+def test_velocity_parity_injected_noise(cfg1):
+    s = cfg1
+    up, ug = s.noise()
+    psi = s.torch.zeros_like(s.F); psi[:, :3] = s.torch.from_numpy((up.cpu().numpy() * np.float32(2 * 1.73205080757) - np.float32(1.73205080757))).cuda()
+    s.orc.set_neighbors(*s.nl_np())
+    # real-space Brownian term alone (Lanczos), same starting m on all sides
+    s.eng.lanczos_m = 2
+    Ue, m = s.eng.velocity(s.pos, s.F, timestep=3, u_particles=up, u_grid=ug, parts=4)
+    psi_np = np.zeros((s.N, 4), dtype=np.float32); a = np.float32(1.73205080757)
+    psi_np[:, :3] = np.float32(2) * a * up.cpu().numpy() - a
+    Uo, mo, _ = s.orc.lanczos(s.pos_np, psi_np, s.T, s.dt, m_in=2)
+    assert abs(m - mo) <= 1
+    close(Ue, Uo, 1e-3 if m != mo else 2e-5)   # one extra iteration changes the result at the `error` level
+    # wave-space Brownian term alone
+    Uw, _ = s.eng.velocity(s.pos, s.F, timestep=3, u_particles=up, u_grid=ug, parts=2)
+    nf = math.sqrt(2.0 * s.T / s.dt / s.p.quadW)
+    close(Uw, s.orc.mwave(s.pos_np, s.F_np, do_det=False, u_grid=ug.cpu().numpy(), noise_fac=nf))
+    if s.ref:
+        s.ref.set_noise_tables(up, ug)
+        try:
+            s.eng.lanczos_m = 2; s.ref.m_lanczos = 2
+            Ue, m = s.eng.velocity(s.pos, s.F, timestep=3, u_particles=up, u_grid=ug, parts=7)
+            Ur = s.ref.velocity(s.pos, s.F, s.T, s.dt, 3)
+            assert m == s.ref.m_lanczos
+            close(Ue, Ur)
+        finally:
+            s.ref.set_noise_tables(None, None)
+
+
+def test_zero_temperature_skips_brownian(cfg1):
+    s = cfg1
+    s.eng.set_temperature(0.0)
+    try:
+        U, _ = s.eng.velocity(s.pos, s.F, timestep=1, parts=7)  # PSEv1/Brownian.cu:855,885
+        close(U, s.eng.mobility(s.pos, s.F), 1e-7)
+    finally:
+        s.eng.set_temperature(s.T)
+
+
+def test_step_parity_engine_rng_odd_grid(cuda):
+    """Three full BD steps with the engine's own Philox streams against gpu_stokes_step_one: 75^3 grid (odd sizes
+    have no doubly-visited nodes), steady shear rate 0.5, tilted box."""
+    import torch
+    s = System(20000, 77.0, xy=0.1, seed=2, lattice=True)
+    if s.ref is None:
+        pytest.skip("reference library not built")
+    assert s.p.Nx == 75
+    pe, pr = s.pos.clone(), s.pos.clone()
+    ie = torch.zeros((s.N, 3), dtype=torch.int32, device="cuda"); ir = ie.clone()
+    vel = torch.zeros_like(s.F); vel[:, 3] = 1.0
+    acc = torch.zeros((s.N, 3), device="cuda")
+    s.eng.lanczos_m = 2; s.ref.m_lanczos = 2
+    for t in range(3):
+        s.eng.build_neighbors(pr); s.ref.set_neighbors(*s.eng.neighbor_list())
+        s.ref.step(pr, vel, acc, ir, s.F, s.T, s.dt, t, shear_rate=0.5)
+        s.eng.step(pe, ie, s.F, t, shear_rate=0.5)
+        assert s.eng.lanczos_m == s.ref.m_lanczos
+        assert torch.equal(ie, ir)
+        assert float((pe - pr).abs().max()) < 2e-5 * 1.0   # positions O(40), per-step displacement O(0.1)
+    assert float((pe - s.pos).abs().max()) > 1e-2
+
+
+def test_brownian_covariance_is_mobility(cuda):
+    """<u u^T> dt / (2T) -> M over many seeds (fluctuation-dissipation), small system, engine RNG."""
+    import torch
+    N = 12
+    L = 13.0
+    s = System(N, L, seed=4, want_ref=False, ref_pi=False)
+    Z = torch.zeros_like(s.F)
+    M = np.zeros((3 * N, 3 * N))
+    for c in range(3 * N):
+        e = torch.zeros_like(s.F); e[c // 3, c % 3] = 1
+        M[:, c] = s.eng.mobility(s.pos, e).cpu().numpy()[:, :3].reshape(-1)
+    nsamp = 6000
+    C = np.zeros_like(M)
+    us = []
+    for t in range(nsamp):
+        U, _ = s.eng.velocity(s.pos, Z, timestep=t, parts=6)
+        us.append(U[:, :3].reshape(-1))
+    Uall = torch.stack(us).double().cpu().numpy()
+    C = Uall.T @ Uall / nsamp * s.dt / (2 * s.T)
+    assert abs(np.trace(C) / np.trace(M) - 1) < 0.03
+    assert np.linalg.norm(C - M) / np.linalg.norm(M) < 0.12   # ~ sqrt(2*dim/nsamp) sampling error
+    assert abs(Uall.mean()) < 5 * Uall.std() / math.sqrt(Uall.size)
+
+
+# ---------------------------------------------------------------- edge cases
+@pytest.mark.parametrize("error,P", [(1e-2, 4), (3e-3, 5), (1e-4, 8)])
+def test_other_support_sizes_and_noncubic_box(cuda, error, P):
+    s = System(600, (40.0, 36.0, 44.0), xy=0.2, seed=6, error=error)
+    assert s.p.P == P
+    nn, head, nl = s.nl_np()
+    onn, ohead, onl = s.orc.neighbors(s.pos_np, s.p.rcut + 0.4, brute=True)
+    assert np.array_equal(nn, onn) and np.array_equal(nl, onl)
+    gi = s.eng.grid_index(s.pos).cpu().numpy()
+    assert np.array_equal(gi, s.orc.grid_index(s.pos_np))
+    _check_index_against_reference_spread(s, gi)
+    U = s.eng.mobility(s.pos, s.F)
+    if s.ref: close(U, s.ref.mobility(s.pos, s.F))
+    s.orc.set_neighbors(nn, head, nl)
+    close(U, s.orc.mreal(s.pos_np, s.F_np) + s.orc.mwave(s.pos_np, s.F_np))
+
+
+def test_boundary_overlap_and_coincident_particles(cuda):
+    import torch
+    N, L = 64, 30.0
+    s = System(N, L, seed=8)
+    pos = s.pos_np.copy()
+    h = np.float32(L / 2)
+    pos[0, :3] = (-h, -h, -h)                    # exactly on the lower corner: fraction 0
+    pos[1, :3] = (np.nextafter(h, np.float32(0)),) * 3   # last float below the upper corner
+    pos[2, :3] = (1.0, 2.0, 3.0); pos[3, :3] = (1.0, 2.0, 3.0)          # coincident: r < dr, skipped (PSEv1/Mobility.cu:652)
+    pos[4, :3] = (5.0, 5.0, 5.0); pos[5, :3] = (5.5, 5.0, 5.0)          # overlapping: r < 2a branch of the table
+    pos[6, :3] = (h - np.float32(0.01), 0, 0); pos[7, :3] = (-h + np.float32(0.01), 0, 0)  # neighbours across the boundary
+    p = torch.from_numpy(pos).cuda()
+    s.eng.build_neighbors(p)
+    nn, head, nl = [t.cpu().numpy().view(np.uint32) for t in s.eng.neighbor_list()]
+    onn, ohead, onl = s.orc.neighbors(pos, s.p.rcut + 0.4, brute=True)
+    assert np.array_equal(nn, onn) and np.array_equal(nl, onl)
+    assert 7 in nl[head[6]: head[6] + nn[6]] and 3 in nl[head[2]: head[2] + nn[2]]
+    assert np.array_equal(s.eng.grid_index(p).cpu().numpy(), s.orc.grid_index(pos))
+    U = s.eng.mobility(p, s.F)
+    assert bool(torch.isfinite(U).all())
+    s.ref.set_neighbors(*s.eng.neighbor_list()) if s.ref else None
+    if s.ref: close(U, s.ref.mobility(p, s.F))
+
+
+def test_single_particle_periodic_self_mobility(cuda):
+    import torch
+    L = 20.0
+    s = System(1, L, ref_pi=False, want_ref=False)
+    pos = torch.zeros((1, 4), device="cuda"); F = torch.tensor([[1.0, 0, 0, 0]], device="cuda")
+    U = s.eng.mobility(pos, F)
+    assert abs(float(U[0, 0]) - (1 - 2.837297 / L + 4 * math.pi / 3 / L**3)) < 3e-3
+    assert s.eng.stats()["nnz"] == 0
+
+
+def test_stale_list_is_rebuilt_and_host_step_matches_device_step(cuda):
+    import torch
+    s = System(3000, util.box_length(3000, 0.15), seed=9, lattice=True, want_ref=False)
+    b0 = s.eng.stats()["nlist_builds"]
+    moved = s.pos.clone(); moved[:, 0] += 0.05
+    s.eng.mreal(moved, s.F)
+    assert s.eng.stats()["nlist_builds"] == b0            # within the buffer: list kept
+    moved[:, 0] += 3.0; moved[:, 0] = (moved[:, 0] + s.L / 2) % s.L - s.L / 2
+    far = moved.clone(); far[::2, 1] += 1.0; far[:, 1] = (far[:, 1] + s.L / 2) % s.L - s.L / 2
+    U = s.eng.mreal(far, s.F)
+    assert s.eng.stats()["nlist_builds"] == b0 + 1        # displaced beyond r_buff/2: rebuilt
+    s2 = System(3000, s.L, seed=9, lattice=True, want_ref=False)
+    close(U, s2.eng.mreal(far, s.F), 1e-6)
+    # host-buffer entry point == device entry point
+    pd = s.pos.clone(); im = torch.zeros((s.N, 3), dtype=torch.int32, device="cuda")
+    s.eng.lanczos_m = 2; s2.eng.lanczos_m = 2
+    s.eng.step(pd, im, s.F, 11, shear_rate=0.3)
+    ph = s.pos_np.copy(); ih = np.zeros((s.N, 3), dtype=np.int32)
+    s2.eng.step_host(ph, ih, s.F_np, 11, shear_rate=0.3)
+    assert np.array_equal(ph, pd.cpu().numpy()) and np.array_equal(ih, im.cpu().numpy())
+
+
+# ---------------------------------------------------------------- properties at the headline size
+@pytest.fixture(scope="module")
+def big(cuda):
+    """BASELINE.json config 3: N = 1,000,000, phi = 0.3, error 1e-3 (240^3 grid)."""
+    return System(1000000, util.box_length(1000000, 0.3), lattice=True, seed=0)
+
+
+def test_full_size_integer_outputs(big):
+    gi = big.eng.grid_index(big.pos).cpu().numpy()
+    assert np.array_equal(gi, big.orc.grid_index(big.pos_np))
+    _check_index_against_reference_spread(big, gi)
+    nn, head, nl = big.nl_np()
+    onn, ohead, onl = big.orc.neighbors(big.pos_np, big.p.rcut + 0.4, brute=False)
+    assert np.array_equal(nn, onn) and np.array_equal(nl, onl)
+    assert abs(nl.size / big.N - 54.3) < 1.5
+
+
+def test_full_size_properties(big):
+    torch = big.torch
+    F, G = big.F, torch.from_numpy(util.random_forces(big.N, 77)).cuda()
+    for op in (big.eng.mreal, big.eng.mwave, big.eng.mobility):
+        MF, MG = op(big.pos, F), op(big.pos, G)
+        a = float((G[:, :3].double() * MF[:, :3].double()).sum()); b = float((F[:, :3].double() * MG[:, :3].double()).sum())
+        assert abs(a - b) < 1e-4 * max(abs(a), abs(b))            # symmetry
+        assert float((F[:, :3].double() * MF[:, :3].double()).sum()) > 0   # each half positive definite
+        lin = op(big.pos, 2.0 * F - 0.5 * G)
+        close(lin, 2.0 * MF - 0.5 * MG, 2e-6)                     # linearity
+
+
+def test_full_size_parity_with_reference_kernels(big):
+    if big.ref is None:
+        pytest.skip("reference library not built")
+    close(big.eng.mobility(big.pos, big.F), big.ref.mobility(big.pos, big.F))
+    up, ug = big.noise()
+    big.ref.set_noise_tables(up, ug)
+    try:
+        big.eng.lanczos_m = 2; big.ref.m_lanczos = 2
+        Ue, m = big.eng.velocity(big.pos, big.F, timestep=3, u_particles=up, u_grid=ug, parts=7)
+        Ur = big.ref.velocity(big.pos, big.F, big.T, big.dt, 3)
+        assert m == big.ref.m_lanczos
+        close(Ue, Ur)
+    finally:
+        big.ref.set_noise_tables(None, None)
