@@ -178,6 +178,13 @@ typedef struct {
 } pse_stats;
 int pse_get_stats(const pse_engine* e, pse_stats* out);
 
+/* Optional per-phase device timing with CUDA events on the engine's stream (off by default; adds two
+ * event records per phase).  pse_get_profile synchronises the stream, returns the number of phases and
+ * fills accumulated milliseconds / span counts since pse_set_profiling(e, 1). */
+int pse_set_profiling(pse_engine* e, int on);
+int pse_get_profile(pse_engine* e, double* ms_out, uint64_t* calls_out, int n);
+const char* pse_profile_phase_name(int i);
+
 #ifdef __cplusplus
 }
 #endif

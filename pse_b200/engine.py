@@ -107,6 +107,16 @@ class Engine:
         self._ck(lib.pse_get_stats(self._h, ctypes.byref(s)))
         return {k: getattr(s, k) for k, _ in s._fields_}
 
+    def set_profiling(self, on=True):
+        self._ck(lib.pse_set_profiling(self._h, 1 if on else 0))
+
+    def profile(self):
+        """{phase: (total_ms, spans)} accumulated since set_profiling(True) (CUDA events on the engine stream)."""
+        n = lib.pse_get_profile(self._h, None, None, 0)
+        ms = (ctypes.c_double * n)(); calls = (ctypes.c_uint64 * n)()
+        lib.pse_get_profile(self._h, ms, calls, n)
+        return {lib.pse_profile_phase_name(i).decode(): (ms[i], calls[i]) for i in range(n)}
+
     # -- bit-exact outputs
     def build_neighbors(self, pos):
         _check4(pos, self.N, "pos")

@@ -1,0 +1,94 @@
+"""Minimal standalone particle / box shim that stands in for the HOOMD objects the reference plugin is
+handed (`hoomd.context.current.system_definition`, `group.all()`, `ParticleData`, `BoxDim`;
+PSEv1/integrate.py:58-86, PSEv1/Stokes.cc:436-470).  It owns the device arrays in the reference's
+layouts and a step counter; it does not try to be HOOMD."""
+import numpy as np
+
+
+class Box:
+    """Periodic box centred at the origin, sheared in xy (HOOMD BoxDim subset)."""
+
+    def __init__(self, Lx, Ly=None, Lz=None, xy=0.0):
+        self.Lx = float(Lx); self.Ly = float(Lx if Ly is None else Ly); self.Lz = float(Lx if Lz is None else Lz)
+        self.xy = float(xy)
+
+
+class Group:
+    """`hoomd.group.all()` stand-in.  The reference only works for the group of all particles."""
+
+    def __init__(self, system):
+        self.system = system
+        self.cpp_group = self
+
+
+class System:
+    """Particle data on one GPU: positions float4 (x,y,z,type), net_force float4 (F, pe), image int3."""
+
+    def __init__(self, positions, box, device="cuda"):
+        import torch
+        pos = np.asarray(positions, dtype=np.float32)
+        if pos.ndim != 2 or pos.shape[1] not in (3, 4):
+            raise ValueError("positions must be [N,3] or [N,4]")
+        N = pos.shape[0]
+        p4 = np.zeros((N, 4), dtype=np.float32); p4[:, : pos.shape[1]] = pos
+        self.N = N
+        self.box = box if isinstance(box, Box) else Box(*np.atleast_1d(box))
+        self.pos = torch.from_numpy(p4).to(device)
+        self.net_force = torch.zeros((N, 4), dtype=torch.float32, device=device)
+        self.vel = torch.zeros((N, 4), dtype=torch.float32, device=device)
+        self.image = torch.zeros((N, 3), dtype=torch.int32, device=device)
+        self.timestep = 0
+        self.dt = None          # set by integrate.mode_standard
+        self.integrator = None  # set by integrate.PSEv1
+        self.updaters = []
+
+    def all(self):
+        return Group(self)
+
+    def getCurrentTimeStep(self):
+        return self.timestep
+
+    def set_forces(self, F):
+        import torch
+        F = torch.as_tensor(F, dtype=torch.float32, device=self.pos.device)
+        self.net_force[:, : F.shape[1]] = F
+
+    def run(self, nsteps):
+        """`hoomd.run(n)`: updaters (box tilt) then the integrator, once per step."""
+        if self.integrator is None:
+            raise RuntimeError("no integration method set")
+        for _ in range(int(nsteps)):
+            for u in self.updaters:
+                u(self.timestep)
+            self.integrator.integrate_step(self.timestep)
+            self.timestep += 1
+
+
+class box_resize:
+    """`hoomd.update.box_resize(xy=variant)` stand-in: sets the box tilt from a variant every step
+    (the plugin itself never changes the tilt)."""
+
+    def __init__(self, system, xy):
+        self.system, self.xy = system, xy
+        system.updaters.append(self)
+
+    def __call__(self, timestep):
+        val = float(self.xy.get_value(timestep))
+        self.system.box.xy = val
+        if self.system.integrator is not None:
+            self.system.integrator.set_tilt(val)
+
+
+_current = None
+
+
+def set_current(system):
+    global _current
+    _current = system
+    return system
+
+
+def current():
+    if _current is None:
+        raise RuntimeError("no current system: call pse_b200.system.set_current(System(...)) first")
+    return _current

@@ -15,7 +15,17 @@ pos = torch.from_numpy(util.lattice_positions(N, L, 0)).cuda()
 F = torch.from_numpy(util.random_forces(N, 1)).cuda()
 img = torch.zeros((N, 3), dtype=torch.int32, device="cuda")
 eng.lanczos_m = 5
-for t in range(steps):
+m = eng.step(pos, img, F, 0)
+torch.cuda.synchronize()
+eng.set_profiling(True)
+import time
+t0 = time.time()
+for t in range(1, steps + 1):
     m = eng.step(pos, img, F, t)
 torch.cuda.synchronize()
-print("m", m, eng.stats())
+wall = (time.time() - t0) / steps * 1e3
+prof = eng.profile()
+tot = sum(v[0] for v in prof.values())
+print(f"N={N} steps={steps} m={m} wall/step={wall:.3f} ms  sum(phases)/step={tot/steps:.3f} ms  {eng.stats()}")
+for k, (ms, n) in sorted(prof.items(), key=lambda kv: -kv[1][0]):
+    if n: print(f"  {k:14s} {ms/steps:8.3f} ms/step  {n/steps:5.1f} spans/step  {ms/n*1e3:9.1f} us/span")

@@ -1,0 +1,109 @@
+"""Host-side mirror of the plugin API (no GPU): shear functions, variant, argument validation, and the
+multi-process replica logic over gloo (world_size 2)."""
+import math
+import os
+import subprocess
+import sys
+import textwrap
+
+import pytest
+
+import pse_b200 as PSEv1
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class _Sys:
+    def __init__(self, t=0):
+        self.timestep = t
+
+    def getCurrentTimeStep(self):
+        return self.timestep
+
+
+@pytest.fixture
+def at_step_10():
+    PSEv1.system._current = _Sys(10)
+    yield
+    PSEv1.system._current = None
+
+
+def test_shear_function_classes_mirror_reference(at_step_10):
+    sf = PSEv1.shear_function
+    dt = 1e-3
+    s = sf.steady(dt=dt, shear_rate=2.0)
+    assert s.get_offset() == 10 and s.get_shear_rate(500) == 2.0 and s.get_strain(510) == pytest.approx(2.0 * 500 * dt)
+    z = sf.steady(dt=0)                                     # "no shear" default of integrate.py:93
+    assert z.get_shear_rate(99) == 0 and z.get_strain(99) == 0
+    f = sf.sine(dt=dt, shear_rate=1.0, shear_freq=2.0, zero=4)
+    assert f.get_offset() == 4
+    assert f.get_shear_rate(4 + 125) == pytest.approx(math.cos(2 * 2 * 3.1415926536 * 0.125))
+    c = sf.chirp(dt=dt, amplitude=0.1, omega_0=1.0, omega_f=10.0, periodT=2.0)
+    assert c.get_strain(10) == 0 and abs(c.get_strain(1500)) <= 0.1
+    w = sf.tukey_window(dt=dt, periodT=2.0, tukey_param=0.5)
+    assert w.get_strain(10) == 0 and w.get_strain(10 + 1000) == 1 and 0 < w.get_strain(10 + 100) < 1
+    ww = sf.windowed(c, w)
+    t = 10 + 300
+    assert ww.get_strain(t) == pytest.approx(c.get_strain(t) * w.get_strain(t))
+    assert ww.get_shear_rate(t) == pytest.approx(c.get_shear_rate(t) * w.get_strain(t) + c.get_strain(t) * w.get_shear_rate(t))
+    assert ww.get_offset() == c.get_offset()
+
+
+def test_shear_function_validation_errors(at_step_10):
+    sf = PSEv1.shear_function
+    for bad in (lambda: sf.sine(dt=1e-3, shear_rate=0, shear_freq=1), lambda: sf.sine(dt=1e-3, shear_rate=1, shear_freq=-1),
+                lambda: sf.tukey_window(dt=1e-3, periodT=1.0, tukey_param=0), lambda: sf.tukey_window(dt=1e-3, periodT=1.0, tukey_param=1.5),
+                lambda: sf.steady(dt=1e-3, zero=-1), lambda: sf.steady(dt=1e-3, zero=11)):
+        with pytest.raises(RuntimeError):
+            bad()
+
+
+def test_shear_variant_wraps_into_max_strain(at_step_10):
+    f = PSEv1.shear_function.steady(dt=1e-2, shear_rate=1.0, zero=5)
+    v = PSEv1.variant.shear_variant(f, total_timestep=200, max_strain=0.5)
+    assert v.get_value(0) == 0 and v.get_value(30) == pytest.approx(0.25) and v.get_value(56) == pytest.approx(-0.49)
+    assert v.get_value(10**6) == pytest.approx(0.0)
+    with pytest.raises(RuntimeError):
+        PSEv1.variant.shear_variant(f, total_timestep=0)
+
+
+def test_integrator_refuses_to_run_without_cuda():
+    import numpy as np
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    s = PSEv1.system.System.__new__(PSEv1.system.System)     # no device arrays without a GPU
+    s.N, s.box, s.dt, s.timestep = 10, PSEv1.system.Box(30.0), 1e-3, 0
+    g = PSEv1.system.Group(s)
+    with pytest.raises(RuntimeError):                         # PSEv1/integrate.py:51-53
+        PSEv1.integrate.PSEv1(group=g, T=1.0)
+    assert PSEv1.integrate.PSE is PSEv1.integrate.PSEv1
+
+
+def test_replica_logic_world_size_2_gloo(tmp_path):
+    """bench.py's multi-GPU path (independent replicas): aggregate = all units / slowest rank, seeds distinct."""
+    script = tmp_path / "w.py"
+    script.write_text(textwrap.dedent(f"""
+        import os, sys
+        sys.path.insert(0, {ROOT!r})
+        import torch.distributed as dist
+        from pse_b200 import replicas as R
+        dist.init_process_group("gloo")
+        rank, world, local = R.rank_world()
+        assert world == 2 and dist.get_world_size() == 2
+        secs = 1.0 + rank                      # rank 1 is slower
+        thr = R.aggregate_throughput(10, secs)
+        assert abs(thr - 20 / 2.0) < 1e-12, thr
+        assert R.max_over_ranks(rank) == 1.0 and R.sum_over_ranks(1) == 2.0
+        seeds = R.replica_seeds(0, rank)
+        gathered = [None, None]
+        dist.all_gather_object(gathered, seeds)
+        assert len(set(gathered[0]) | set(gathered[1])) == 6 or gathered[0] != gathered[1]
+        dist.barrier(); dist.destroy_process_group()
+        print("ok", rank)
+    """))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29533", str(script)], capture_output=True, text=True, env=env, timeout=240)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "ok 0" in out.stdout and "ok 1" in out.stdout
