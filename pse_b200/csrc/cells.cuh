@@ -138,6 +138,26 @@ __global__ void gather4_kernel(const float4* __restrict__ in, const uint32_t* __
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s < N) out[s] = __ldg(in + perm[s]);
 }
+// slot-ordered positions: plain copy for the cell/wave kernels + the .p half of the packed SpMV record
+__global__ void gather_pos_kernel(const float4* __restrict__ pos, const uint32_t* __restrict__ perm, uint32_t N,
+                                  float4* __restrict__ spos, float4* __restrict__ px /* stride 2 float4 */) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < N) {
+        const float4 v = __ldg(pos + perm[s]);
+        spos[s] = v;
+        px[2 * (size_t)s] = v;
+    }
+}
+// slot-ordered vector: plain copy (wave space) + the .x half of the packed SpMV record
+__global__ void gather_vec_kernel(const float4* __restrict__ F, const uint32_t* __restrict__ perm, uint32_t N,
+                                  float4* __restrict__ sF, float4* __restrict__ px) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < N) {
+        const float4 v = __ldg(F + perm[s]);
+        if (sF) sF[s] = v;
+        px[2 * (size_t)s + 1] = v;
+    }
+}
 // two payloads at once (positions and forces)
 __global__ void gather4x2_kernel(const float4* __restrict__ a, const float4* __restrict__ b,
                                  const uint32_t* __restrict__ perm, uint32_t N, float4* __restrict__ oa,
@@ -171,47 +191,65 @@ __device__ __forceinline__ CellRange make_range(float f, float reach, int nc) {
     return r;
 }
 
-// MODE 0: count neighbours; MODE 1: fill rows.  One thread per slot.
-template <int MODE>
+// One search pass, one thread per slot: rows are first written at ell[slot * cap ...] (fixed stride);
+// nn[slot] is the true count even when it exceeds cap (the host then grows cap and rebuilds).  A scan of nn and
+// compact_rows_kernel then pack the rows into CSR, which the SpMV reads ~1.6x faster than the strided rows
+// (adjacent rows share cache lines).
 __global__ void nlist_kernel(const float4* __restrict__ spos, uint32_t N, PseBox box, CellGrid cg,
-                             const uint32_t* __restrict__ cell_start, float rlist_sq, uint32_t* __restrict__ nn,
-                             const uint32_t* __restrict__ head, uint32_t* __restrict__ nl) {
+                             const uint32_t* __restrict__ cell_start, float rlist_sq, uint32_t cap, uint32_t* __restrict__ nn,
+                             uint32_t* __restrict__ nl, uint32_t* __restrict__ max_nn) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    float4 pi = __ldg(spos + i);
-    float3 f = box.make_fraction(pi.x, pi.y, pi.z);
-    f.x -= floorf(f.x); f.y -= floorf(f.y); f.z -= floorf(f.z);
-    // a fraction that rounds to exactly 1.0 was clamped into the last cell by cell_id_kernel
-    CellRange rx = make_range(f.x, cg.reach_fx, cg.ncx);
-    CellRange ry = make_range(f.y, cg.reach_fy, cg.ncy);
-    CellRange rz = make_range(f.z, cg.reach_fz, cg.ncz);
     uint32_t count = 0;
-    uint32_t w = MODE == 1 ? head[i] : 0u;
-    for (int tx = 0; tx < rx.len; ++tx) {
-        int cx = rx.at(tx);
-        for (int ty = 0; ty < ry.len; ++ty) {
-            int cy = ry.at(ty);
-            uint32_t rowbase = ((uint32_t)cx * cg.ncy + cy) * cg.ncz;
-            // z cells: at most two contiguous runs [0, wrapped) and [lo, lo + len - wrapped)
-            for (int part = 0; part < 2; ++part) {
-                int z0 = part == 0 ? 0 : rz.lo;
-                int zn = part == 0 ? rz.wrapped : rz.len - rz.wrapped;
-                if (zn <= 0) continue;
-                uint32_t b = __ldg(cell_start + rowbase + z0), e = __ldg(cell_start + rowbase + z0 + zn);
-                for (uint32_t j = b; j < e; ++j) {
-                    if (j == i) continue;
-                    float4 pj = __ldg(spos + j);
-                    float3 d = box.min_image(make_float3(PSE_SUB(pi.x, pj.x), PSE_SUB(pi.y, pj.y), PSE_SUB(pi.z, pj.z)));
-                    float r2 = pse_norm2_rn(d);
-                    if (r2 < rlist_sq) {
-                        if (MODE == 1) nl[w + count] = j;
-                        ++count;
+    if (i < N) {
+        float4 pi = __ldg(spos + i);
+        float3 f = box.make_fraction(pi.x, pi.y, pi.z);
+        f.x -= floorf(f.x); f.y -= floorf(f.y); f.z -= floorf(f.z);
+        // a fraction that rounds to exactly 1.0 was clamped into the last cell by cell_id_kernel
+        CellRange rx = make_range(f.x, cg.reach_fx, cg.ncx);
+        CellRange ry = make_range(f.y, cg.reach_fy, cg.ncy);
+        CellRange rz = make_range(f.z, cg.reach_fz, cg.ncz);
+        uint32_t* __restrict__ row = nl + (size_t)i * cap;
+        for (int tx = 0; tx < rx.len; ++tx) {
+            int cx = rx.at(tx);
+            for (int ty = 0; ty < ry.len; ++ty) {
+                int cy = ry.at(ty);
+                uint32_t rowbase = ((uint32_t)cx * cg.ncy + cy) * cg.ncz;
+                // z cells: at most two contiguous runs [0, wrapped) and [lo, lo + len - wrapped)
+                for (int part = 0; part < 2; ++part) {
+                    int z0 = part == 0 ? 0 : rz.lo;
+                    int zn = part == 0 ? rz.wrapped : rz.len - rz.wrapped;
+                    if (zn <= 0) continue;
+                    uint32_t b = __ldg(cell_start + rowbase + z0), e = __ldg(cell_start + rowbase + z0 + zn);
+                    for (uint32_t j = b; j < e; ++j) {
+                        if (j == i) continue;
+                        float4 pj = __ldg(spos + j);
+                        float3 d = box.min_image(make_float3(PSE_SUB(pi.x, pj.x), PSE_SUB(pi.y, pj.y), PSE_SUB(pi.z, pj.z)));
+                        float r2 = pse_norm2_rn(d);
+                        if (r2 < rlist_sq) {
+                            if (count < cap) row[count] = j;
+                            ++count;
+                        }
                     }
                 }
             }
         }
+        nn[i] = count;
     }
-    if (MODE == 0) nn[i] = count;
+    uint32_t m = count;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(max_nn, m);
+}
+
+// ell[slot * cap + k] -> nl[head[slot] + k], 8 lanes per row
+__global__ void compact_rows_kernel(const uint32_t* __restrict__ ell, uint32_t cap, const uint32_t* __restrict__ nn,
+                                    const uint32_t* __restrict__ head, uint32_t N, uint32_t* __restrict__ nl) {
+    const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const uint32_t sub = threadIdx.x & 7;
+    if (row >= N) return;
+    const uint32_t n = nn[row], h = head[row];
+    const uint32_t* __restrict__ src = ell + (size_t)row * cap;
+    for (uint32_t k = sub; k < n; k += 8) nl[h + k] = __ldg(src + k);
 }
 
 // largest squared displacement since the list was built (staleness test); result via atomicMax on bits

@@ -54,9 +54,15 @@ struct pse_engine {
     uint32_t *d_cell_of, *d_cell_count, *d_cell_start, *d_scan_tmp, *d_perm, *d_slot_of;
     size_t cell_cap;
     float4 *d_spos, *d_sx, *d_sy;
+    PX* d_px;  // packed (position, vector) records for the SpMV
     // neighbour list (slot numbering)
     uint32_t *d_nn, *d_head, *d_nl;
     size_t nl_cap;
+    uint32_t nl_stride;            // row stride of the fixed-stride search output
+    uint32_t* d_ell;
+    size_t ell_cap;
+    unsigned long long* d_nlinfo;  // [0] nnz, [1] max row length
+    unsigned long long* h_nlinfo;  // pinned
     uint64_t nnz;
     float4* d_pos_build;
     float xy_build;
@@ -226,9 +232,12 @@ static int alloc_all(pse_engine* e) {
     CK(cudaMalloc(&e->d_spos, sizeof(float4) * N));
     CK(cudaMalloc(&e->d_sx, sizeof(float4) * N));
     CK(cudaMalloc(&e->d_sy, sizeof(float4) * N));
+    CK(cudaMalloc(&e->d_px, sizeof(PX) * N));
     CK(cudaMalloc(&e->d_nn, sizeof(uint32_t) * (N + 1)));
     CK(cudaMalloc(&e->d_head, sizeof(uint32_t) * (N + 1)));
-    e->d_nl = nullptr; e->nl_cap = 0;
+    e->d_nl = nullptr; e->nl_cap = 0; e->nl_stride = 0;
+    CK(cudaMalloc(&e->d_nlinfo, 2 * sizeof(unsigned long long)));
+    CK(cudaMallocHost(&e->h_nlinfo, 2 * sizeof(unsigned long long)));
     CK(cudaMalloc(&e->d_pos_build, sizeof(float4) * N));
     CK(cudaMalloc(&e->d_flag, sizeof(uint32_t)));
     CK(cudaMallocHost(&e->h_flag, sizeof(uint32_t)));
@@ -353,13 +362,15 @@ extern "C" void pse_destroy(pse_engine* e) {
     if (!e) return;
     if (e->plans_ok) { cufftDestroy(e->plan_f); cufftDestroy(e->plan_b); }
     void* bufs[] = {e->d_table, e->d_cell_of, e->d_cell_count, e->d_cell_start, e->d_scan_tmp, e->d_perm, e->d_slot_of,
-                    e->d_spos, e->d_sx, e->d_sy, e->d_nn, e->d_head, e->d_nl, e->d_pos_build, e->d_flag, e->d_grid,
+                    e->d_spos, e->d_sx, e->d_sy, e->d_px, e->d_nn, e->d_head, e->d_nl, e->d_pos_build, e->d_flag, e->d_grid,
                     e->d_spec, e->d_V, e->d_u, e->d_y, e->d_alpha, e->d_beta, e->d_coef, e->d_partials, e->d_counter,
                     e->d_vel_work, e->d_hpos, e->d_hF, e->d_himage, e->d_org, e->d_worg, e->d_wcell_of, e->d_wcount,
-                    e->d_wstart, e->d_wperm, e->d_wpos, e->d_wF, e->d_wtmp};
+                    e->d_wstart, e->d_wperm, e->d_wpos, e->d_wF, e->d_wtmp, e->d_ell};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (e->h_flag) cudaFreeHost(e->h_flag);
+    if (e->h_nlinfo) cudaFreeHost(e->h_nlinfo);
+    if (e->d_nlinfo) cudaFree(e->d_nlinfo);
     if (e->h_ab) cudaFreeHost(e->h_ab);
     if (e->flag_event) cudaEventDestroy(e->flag_event);
     if (e->prof_pool) { for (cudaEvent_t ev : *e->prof_pool) cudaEventDestroy(ev); delete e->prof_pool; }
@@ -413,25 +424,47 @@ extern "C" int pse_build_neighbors(pse_engine* e, const float4* d_pos) {
     cell_fill_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_cell_of, N, e->d_cell_start, e->d_cell_count, e->d_perm); LAUNCHED(e);
     cell_sort_kernel<<<nblk(ncell, 128), 128, 0, st>>>(e->d_cell_start, ncell, e->d_perm); LAUNCHED(e);
     invert_perm_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_perm, N, e->d_slot_of); LAUNCHED(e);
-    gather4_kernel<<<nblk(N, 256), 256, 0, st>>>(d_pos, e->d_perm, N, e->d_spos); LAUNCHED(e);
+    gather_pos_kernel<<<nblk(N, 256), 256, 0, st>>>(d_pos, e->d_perm, N, e->d_spos, (float4*)e->d_px); LAUNCHED(e);
 
     delete ps;
     ps = new ProfScope(e, PH_NLIST);
     const float rl2 = e->rlist * e->rlist;
+    if (e->nl_stride == 0) {
+        // expected neighbours per particle at uniform density, with head room for fluctuations
+        const double dens = (double)N / ((double)e->box.Lx * e->box.Ly * e->box.Lz);
+        const double expect = 4.0 / 3.0 * 3.14159265358979 * (double)e->rlist * e->rlist * e->rlist * dens;
+        e->nl_stride = (uint32_t)(((size_t)(1.5 * expect + 24.0) + 7) / 8 * 8);
+        if (e->nl_stride > N) e->nl_stride = ((N + 7) / 8) * 8;
+    }
     CK(cudaMemsetAsync(e->d_nn + N, 0, sizeof(uint32_t), st));
-    nlist_kernel<0><<<nblk(N, 128), 128, 0, st>>>(e->d_spos, N, e->box, cg, e->d_cell_start, rl2, e->d_nn, nullptr, nullptr); LAUNCHED(e);
-    CKRC(exclusive_scan(e, e->d_nn, e->d_head, N + 1, e->d_scan_tmp));
-    uint32_t total = 0;
-    CK(cudaMemcpyAsync(&total, e->d_head + N, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    if (total > e->nl_cap) {
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        const size_t need = (size_t)N * e->nl_stride;
+        if (need > e->ell_cap) {
+            if (e->d_ell) cudaFree(e->d_ell);
+            e->d_ell = nullptr;
+            e->ell_cap = need;
+            CK(cudaMalloc(&e->d_ell, sizeof(uint32_t) * e->ell_cap));
+        }
+        CK(cudaMemsetAsync(e->d_nlinfo, 0, 2 * sizeof(unsigned long long), st));
+        nlist_kernel<<<nblk(N, 128), 128, 0, st>>>(e->d_spos, N, e->box, cg, e->d_cell_start, rl2, e->nl_stride, e->d_nn, e->d_ell,
+                                                   (uint32_t*)(e->d_nlinfo + 1)); LAUNCHED(e);
+        CKRC(exclusive_scan(e, e->d_nn, e->d_head, N + 1, e->d_scan_tmp));
+        CK(cudaMemcpyAsync(e->h_nlinfo, e->d_nlinfo, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(e->h_flag, e->d_head + N, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const uint32_t max_nn = (uint32_t)e->h_nlinfo[1];
+        e->nnz = *e->h_flag;
+        if (max_nn <= e->nl_stride) break;
+        e->nl_stride = ((max_nn + 16 + 7) / 8) * 8;  // a row overflowed its stride: grow and search again
+        if (attempt == 2) return fail(e, PSE_ENOMEM, "neighbour rows keep overflowing (max %u)", max_nn);
+    }
+    if (e->nnz > e->nl_cap) {
         if (e->d_nl) cudaFree(e->d_nl);
         e->d_nl = nullptr;
-        e->nl_cap = (size_t)(total * 1.2) + 1024;
+        e->nl_cap = (size_t)(e->nnz * 1.2) + 1024;
         CK(cudaMalloc(&e->d_nl, sizeof(uint32_t) * e->nl_cap));
     }
-    e->nnz = total;
-    nlist_kernel<1><<<nblk(N, 128), 128, 0, st>>>(e->d_spos, N, e->box, cg, e->d_cell_start, rl2, e->d_nn, e->d_head, e->d_nl); LAUNCHED(e);
+    compact_rows_kernel<<<nblk((size_t)N * 8, 256), 256, 0, st>>>(e->d_ell, e->nl_stride, e->d_nn, e->d_head, N, e->d_nl); LAUNCHED(e);
     CK(cudaMemcpyAsync(e->d_pos_build, d_pos, sizeof(float4) * N, cudaMemcpyDeviceToDevice, st));
     delete ps;
     e->xy_build = e->box.xy;
@@ -469,7 +502,7 @@ static int ensure_neighbors(pse_engine* e, const float4* d_pos) {
     }
     if (rebuild) return pse_build_neighbors(e, d_pos);
     ProfScope ps(e, PH_REORDER);
-    gather4_kernel<<<nblk(e->N, 256), 256, 0, e->stream>>>(d_pos, e->d_perm, e->N, e->d_spos); LAUNCHED(e);
+    gather_pos_kernel<<<nblk(e->N, 256), 256, 0, e->stream>>>(d_pos, e->d_perm, e->N, e->d_spos, (float4*)e->d_px); LAUNCHED(e);
     return PSE_OK;
 }
 
@@ -512,12 +545,12 @@ static inline unsigned int persistent_grid(const pse_engine* e, size_t work_bloc
     return (unsigned int)(work_blocks < cap ? (work_blocks ? work_blocks : 1) : cap);
 }
 
-static int run_spmv_plain(pse_engine* e, const float4* x, float4* y) {
+static int run_spmv_plain(pse_engine* e, float4* y) {
     ProfScope ps(e, PH_SPMV);
     constexpr int TPP = 8;
     LanczosArgs la = {};
     spmv_kernel<TPP, SPMV_PLAIN><<<persistent_grid(e, nblk((size_t)e->N * TPP, 256), 8), 256, 0, e->stream>>>(
-        e->d_spos, x, y, e->N, e->d_nn, e->d_head, e->d_nl, e->d_table, e->rp, e->box, la);
+        e->d_px, y, e->N, e->d_nn, e->d_head, e->d_nl, e->d_table, e->rp, e->box, la);
     LAUNCHED(e);
     return PSE_OK;
 }
@@ -593,11 +626,11 @@ static void lanczos_iteration(pse_engine* e, int j) {
     {
     ProfScope ps(e, PH_LANCZOS_SPMV);
     spmv_kernel<TPP, SPMV_LANCZOS><<<persistent_grid(e, nblk((size_t)N * TPP, 256), 8), 256, 0, e->stream>>>(
-        e->d_spos, e->d_u, e->d_y, N, e->d_nn, e->d_head, e->d_nl, e->d_table, e->rp, e->box, la);
+        e->d_px, e->d_y, N, e->d_nn, e->d_head, e->d_nl, e->d_table, e->rp, e->box, la);
     LAUNCHED(e);
     }
     ProfScope ps(e, PH_LANCZOS_VEC);
-    lanczos_update_kernel<<<persistent_grid(e, nblk(N, 256), 8), 256, 0, e->stream>>>(e->d_y, Vj, e->d_u, N, e->d_alpha + j, e->d_beta + j + 1,
+    lanczos_update_kernel<<<persistent_grid(e, nblk(N, 256), 8), 256, 0, e->stream>>>(e->d_y, Vj, e->d_px, N, e->d_alpha + j, e->d_beta + j + 1,
                                                                e->d_partials, e->d_counter);
     LAUNCHED(e);
 }
@@ -620,8 +653,8 @@ static int run_lanczos(pse_engine* e, float4* U, int accumulate, uint32_t key, c
     cudaStream_t st = e->stream;
     {
     ProfScope ps(e, PH_LANCZOS_VEC);
-    psi_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_u, e->d_perm, N, d_u_particles, key); LAUNCHED(e);
-    dot_kernel<<<persistent_grid(e, nblk(N, 256), 8), 256, 0, st>>>(e->d_u, e->d_u, N, e->d_beta, e->d_partials, e->d_counter, true); LAUNCHED(e);
+    psi_kernel<<<nblk(N, 256), 256, 0, st>>>((float4*)e->d_px + 1, 2, e->d_perm, N, d_u_particles, key); LAUNCHED(e);
+    dot_px_kernel<<<persistent_grid(e, nblk(N, 256), 8), 256, 0, st>>>(e->d_px, N, e->d_beta, e->d_partials, e->d_counter, true); LAUNCHED(e);
     }
 
     float* alpha = e->h_ab;
@@ -677,8 +710,8 @@ static int run_lanczos(pse_engine* e, float4* U, int accumulate, uint32_t key, c
 extern "C" int pse_mreal(pse_engine* e, const float4* d_pos, const float4* d_F, float4* d_U) {
     if (!e || !d_pos || !d_F || !d_U) return PSE_EINVAL;
     CKRC(ensure_neighbors(e, d_pos));
-    gather4_kernel<<<nblk(e->N, 256), 256, 0, e->stream>>>(d_F, e->d_perm, e->N, e->d_sx); LAUNCHED(e);
-    CKRC(run_spmv_plain(e, e->d_sx, e->d_sy));
+    gather_vec_kernel<<<nblk(e->N, 256), 256, 0, e->stream>>>(d_F, e->d_perm, e->N, nullptr, (float4*)e->d_px); LAUNCHED(e);
+    CKRC(run_spmv_plain(e, e->d_sy));
     scatter_add_kernel<<<nblk(e->N, 256), 256, 0, e->stream>>>(e->d_sy, e->d_perm, e->N, d_U, 0); LAUNCHED(e);
     CK(cudaGetLastError());
     return PSE_OK;
@@ -703,11 +736,11 @@ extern "C" int pse_velocity(pse_engine* e, const float4* d_pos, const float4* d_
     const bool wnoise = (parts & 2u) && thermal, rnoise = (parts & 4u) && thermal;
     const uint32_t key = timestep + e->prm.seed_hashed;  // PSEv1/Brownian.cu:117,176
     CKRC(ensure_neighbors(e, d_pos));
-    if (det) { gather4_kernel<<<nblk(N, 256), 256, 0, st>>>(d_F, e->d_perm, N, e->d_sx); LAUNCHED(e); }
+    if (det) { gather_vec_kernel<<<nblk(N, 256), 256, 0, st>>>(d_F, e->d_perm, N, e->d_sx, (float4*)e->d_px); LAUNCHED(e); }
     int acc = 0;
     if (det || wnoise) { CKRC(run_wave(e, e->d_sx, d_U, 0, det, wnoise, key, d_u_grid)); acc = 1; }
     if (det) {
-        CKRC(run_spmv_plain(e, e->d_sx, e->d_sy));
+        CKRC(run_spmv_plain(e, e->d_sy));
         scatter_add_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_sy, e->d_perm, N, d_U, acc); LAUNCHED(e);
         acc = 1;
     }

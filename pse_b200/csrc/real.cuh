@@ -43,6 +43,13 @@ __device__ __forceinline__ void rpy_pair(const float3 r, const float r2, const f
     u.z += Imrr * Fj.z + c * r.z;
 }
 
+// Slot-ordered particle record of the real-space kernels: position and the vector being multiplied share
+// one 32-byte sector, so a neighbour gather costs one sector instead of two.
+struct __align__(32) PX {
+    float4 p;  // position (x, y, z, -)
+    float4 x;  // input vector of the SpMV: force, psi, or the unnormalised Lanczos vector u_j
+};
+
 enum { SPMV_PLAIN = 0, SPMV_LANCZOS = 1 };
 
 struct LanczosArgs {
@@ -62,7 +69,7 @@ struct LanczosArgs {
 // number of partial sums (and of arrivals on the finishing counter) is O(SMs), not O(N).
 template <int TPP, int MODE>
 __global__ void __launch_bounds__(256)
-spmv_kernel(const float4* __restrict__ spos, const float4* __restrict__ x, float4* __restrict__ y, uint32_t N,
+spmv_kernel(const PX* __restrict__ px, float4* __restrict__ y, uint32_t N,
             const uint32_t* __restrict__ nn, const uint32_t* __restrict__ head, const uint32_t* __restrict__ nl,
             const float4* __restrict__ table, RealParams rp, PseBox box, LanczosArgs la) {
     constexpr int ROWS = 256 / TPP;
@@ -79,31 +86,31 @@ spmv_kernel(const float4* __restrict__ spos, const float4* __restrict__ x, float
         float4 pi = make_float4(0.f, 0.f, 0.f, 0.f), xi = pi;
         const bool live = row < N;
         if (live) {
-            pi = __ldg(spos + row);
-            xi = __ldg(x + row);
+            pi = __ldg(&px[row].p);
+            xi = __ldg(&px[row].x);
             const uint32_t n = __ldg(nn + row);
             const uint32_t* __restrict__ list = nl + __ldg(head + row);
             uint32_t k = sub;
             // two neighbours per trip: both gathers are in flight before either is consumed
             for (; k + TPP < n; k += 2 * TPP) {
                 const uint32_t j0 = __ldg(list + k), j1 = __ldg(list + k + TPP);
-                const float4 p0 = __ldg(spos + j0), p1 = __ldg(spos + j1);
+                const float4 p0 = __ldg(&px[j0].p), p1 = __ldg(&px[j1].p);
                 const float3 r0 = box.min_image(make_float3(PSE_SUB(pi.x, p0.x), PSE_SUB(pi.y, p0.y), PSE_SUB(pi.z, p0.z)));
                 const float3 r1 = box.min_image(make_float3(PSE_SUB(pi.x, p1.x), PSE_SUB(pi.y, p1.y), PSE_SUB(pi.z, p1.z)));
                 const float d0 = r0.x * r0.x + r0.y * r0.y + r0.z * r0.z, d1 = r1.x * r1.x + r1.y * r1.y + r1.z * r1.z;
                 const bool in0 = d0 < rp.rcut_sq && d0 >= rp.dr_sq, in1 = d1 < rp.rcut_sq && d1 >= rp.dr_sq;
                 float4 x0, x1;
-                if (in0) x0 = __ldg(x + j0);
-                if (in1) x1 = __ldg(x + j1);
+                if (in0) x0 = __ldg(&px[j0].x);
+                if (in1) x1 = __ldg(&px[j1].x);
                 if (in0) rpy_pair(r0, d0, x0, table, rp, u);
                 if (in1) rpy_pair(r1, d1, x1, table, rp, u);
             }
             if (k < n) {
                 const uint32_t j0 = __ldg(list + k);
-                const float4 p0 = __ldg(spos + j0);
+                const float4 p0 = __ldg(&px[j0].p);
                 const float3 r0 = box.min_image(make_float3(PSE_SUB(pi.x, p0.x), PSE_SUB(pi.y, p0.y), PSE_SUB(pi.z, p0.z)));
                 const float d0 = r0.x * r0.x + r0.y * r0.y + r0.z * r0.z;
-                if (d0 < rp.rcut_sq && d0 >= rp.dr_sq) rpy_pair(r0, d0, __ldg(x + j0), table, rp, u);
+                if (d0 < rp.rcut_sq && d0 >= rp.dr_sq) rpy_pair(r0, d0, __ldg(&px[j0].x), table, rp, u);
             }
         }
         u.x = group_sum<TPP>(u.x);
@@ -135,7 +142,7 @@ spmv_kernel(const float4* __restrict__ spos, const float4* __restrict__ x, float
 // w = y - alpha_j v_j ;  beta_{j+1} = ||w|| ; u_{j+1} = w (left unnormalised; the next
 // spmv_kernel<LANCZOS> folds 1/beta_{j+1} in).   PSEv1/Brownian.cu:493-514
 __global__ void __launch_bounds__(256)
-lanczos_update_kernel(const float4* __restrict__ y, const float4* __restrict__ vj, float4* __restrict__ u_next, uint32_t N,
+lanczos_update_kernel(const float4* __restrict__ y, const float4* __restrict__ vj, PX* __restrict__ px, uint32_t N,
                       const float* __restrict__ alpha_j, float* __restrict__ beta_next, float* partials,
                       unsigned int* counter) {
     __shared__ float red[32];
@@ -144,22 +151,21 @@ lanczos_update_kernel(const float4* __restrict__ y, const float4* __restrict__ v
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
         const float4 yy = __ldg(y + i), v = __ldg(vj + i);
         float3 w = make_float3(yy.x - a * v.x, yy.y - a * v.y, yy.z - a * v.z);
-        u_next[i] = make_float4(w.x, w.y, w.z, 0.f);
+        px[i].x = make_float4(w.x, w.y, w.z, 0.f);
         part += w.x * w.x + w.y * w.y + w.z * w.z;
     }
     float tot = block_sum(part, red);
     grid_sum_finish(tot, partials, counter, beta_next, red, /*take_sqrt=*/true);
 }
 
-// dot(a, b) over xyz -> *out (deterministic); take_sqrt gives the norm when a == b
+// |px.x|^2 (or its square root) over xyz -> *out (deterministic)
 __global__ void __launch_bounds__(256)
-dot_kernel(const float4* __restrict__ a, const float4* __restrict__ b, uint32_t N, float* out, float* partials,
-           unsigned int* counter, bool take_sqrt) {
+dot_px_kernel(const PX* __restrict__ px, uint32_t N, float* out, float* partials, unsigned int* counter, bool take_sqrt) {
     __shared__ float red[32];
     float part = 0.f;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
-        const float4 p = __ldg(a + i), q = __ldg(b + i);
-        part += p.x * q.x + p.y * q.y + p.z * q.z;
+        const float4 p = __ldg(&px[i].x);
+        part += p.x * p.x + p.y * p.y + p.z * p.z;
     }
     float tot = block_sum(part, red);
     grid_sum_finish(tot, partials, counter, out, red, take_sqrt);

@@ -247,8 +247,8 @@ scale_kernel(float2* __restrict__ spec, WaveParams wp, PseBox box, int do_det, i
 }
 
 // particle noise psi (slot order) : 3 uniforms on (-sqrt3, sqrt3), PSEv1/Brownian.cu:99-130
-__global__ void psi_kernel(float4* __restrict__ psi, const uint32_t* __restrict__ perm, uint32_t N,
-                           const float* __restrict__ u_particles, uint32_t key) {
+__global__ void psi_kernel(float4* __restrict__ psi /* element s at psi[s * stride] */, int stride, const uint32_t* __restrict__ perm,
+                           uint32_t N, const float* __restrict__ u_particles, uint32_t key) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= N) return;
     const uint32_t id = perm[s];
@@ -262,5 +262,5 @@ __global__ void psi_kernel(float4* __restrict__ psi, const uint32_t* __restrict_
         const uint4 b = pse_philox(id, 0u, PSE_RNG_DOMAIN_PARTICLE, key);
         x = pse_uniform(b.x, -a, a); y = pse_uniform(b.y, -a, a); z = pse_uniform(b.z, -a, a);
     }
-    psi[s] = make_float4(x, y, z, 0.f);
+    psi[(size_t)s * stride] = make_float4(x, y, z, 0.f);
 }

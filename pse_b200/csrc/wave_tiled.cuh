@@ -79,16 +79,25 @@ __device__ __forceinline__ int tile_candidates(int t0, int e, int P, int N, int*
 // (PSEv1/Mobility.cu:222-241); the minimum image only undoes that wrap, so the displacement is taken
 // directly from the unwrapped node, and the Gaussian is split as w_xy(i,j) * w_z(k).  Differences are
 // float round-off (1e-7 relative), far inside the 1e-5 parity budget.
+// exp(x) for x <= 0 through ex2 with a compensated argument: t = x*log2(e) is rounded to float (|t| up to ~15,
+// ulp ~1e-6), so the rounding residual r is recovered with an fma and applied to first order.  Relative error
+// ~3e-7 instead of ~1e-6 for __expf, at 4 extra instructions.
+__device__ __forceinline__ float exp_neg(float x) {
+    const float L2E_HI = 1.4426950216293335f, L2E_LO = 1.9259629911e-8f;
+    const float t = x * L2E_HI;
+    const float r = fmaf(x, L2E_HI, -t) + x * L2E_LO;
+    return exp2f(t) * fmaf(r, 0.6931471805599453f, 1.0f);
+}
 __device__ __forceinline__ float weight_z(const PseBox& box, const WaveParams& wp, int iz_unwrapped, float pz) {
     const float rz = fmaf(wp.hz, (float)iz_unwrapped, -0.5f * box.Lz) - pz;
-    return __expf(-wp.expfac * rz * rz);
+    return exp_neg(-wp.expfac * rz * rz);
 }
 __device__ __forceinline__ float weight_xy(const PseBox& box, const WaveParams& wp, int ix_unwrapped, int iy_unwrapped, float px,
                                            float py, float pref) {
     const float gy = fmaf(wp.hy, (float)iy_unwrapped, -0.5f * box.Ly);
     const float rx = fmaf(box.xy, gy, fmaf(wp.hx, (float)ix_unwrapped, -0.5f * box.Lx)) - px;
     const float ry = gy - py;
-    return pref * __expf(-wp.expfac * fmaf(rx, rx, ry * ry));
+    return pref * exp_neg(-wp.expfac * fmaf(rx, rx, ry * ry));
 }
 // worg.w packs the wrap shifts of the three axes: unwrapped = wrapped + (shift - 1) * N, 2 bits per axis
 __device__ __forceinline__ int3 unwrapped_origin(const int4 o, const WaveParams& wp) {
@@ -285,8 +294,10 @@ static inline size_t spread_tile_smem(int P) {
 }
 
 // ---- interpolation: one block per origin cell --------------------------------------------------------
-// dynamic smem: g[3][H*H*HS] with H = TILE + P - 1, HS = H | 1 (odd stride) ; per-warp weights [NW][P*P + P]
-// 16 warps per block; each warp walks the cell's particles with the next particle's record prefetched.
+// dynamic smem: g[3][H*H*HS] with H = TILE + P - 1, HS = H | 1 (odd stride).
+// 16 warps per block; each warp walks the cell's particles with the next particle's record prefetched; the
+// Gaussian weight of a node is evaluated directly (ex2 + FMAs) instead of through staged factor tables, which
+// keeps the shared-memory pipe for the grid values only.
 #define INTERP_THREADS 512
 template <int P>
 __global__ void __launch_bounds__(INTERP_THREADS, 2)
@@ -297,7 +308,6 @@ interp_tile_kernel(const float4* __restrict__ wpos, const int4* __restrict__ wor
     constexpr int PP = P * P, PPP = PP * P, NR = (PPP + 31) / 32, NW = INTERP_THREADS / 32;
     constexpr int H = TILE + P - 1, HS = H | 1, GT = H * H * HS;
     float* g = smem;
-    float* wts = smem + 3 * GT;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t cell = blockIdx.x;
     const uint32_t cb = __ldg(wcell_start + cell), ce = __ldg(wcell_start + cell + 1);
@@ -311,32 +321,31 @@ interp_tile_kernel(const float4* __restrict__ wpos, const int4* __restrict__ wor
     int4 o_n = make_int4(0, 0, 0, 0);
     uint32_t id_n = 0;
     if (w < ce) { pp_n = __ldg(wpos + w); o_n = __ldg(worg + w); id_n = __ldg(perm + __ldg(wperm + w)); }
-    // stage the halo tile (periodic wrap per node): one (x,y) row of H nodes per thread pass
-    for (int row = tid; row < H * H; row += INTERP_THREADS) {
-        const int ly = row % H, lx = row / H;
+    // stage the halo tile (periodic wrap per node); z fastest across lanes -> coalesced row segments
+    for (int t = tid; t < H * H * H; t += INTERP_THREADS) {
+        const int lz = t % H, ly = (t / H) % H, lx = t / (H * H);
         int x = t0x + lx; if (x >= wp.Nx) x -= wp.Nx;
         int y = t0y + ly; if (y >= wp.Ny) y -= wp.Ny;
-        const size_t rowbase = ((size_t)x * wp.Ny + y) * wp.Nz;
-        const int node0 = (lx * H + ly) * HS;
-#pragma unroll 4
-        for (int lz = 0; lz < H; ++lz) {
-            int z = t0z + lz; if (z >= wp.Nz) z -= wp.Nz;
-            g[node0 + lz] = __ldg(grid + rowbase + z);
-            g[GT + node0 + lz] = __ldg(grid + G + rowbase + z);
-            g[2 * GT + node0 + lz] = __ldg(grid + 2 * G + rowbase + z);
-        }
+        int z = t0z + lz; if (z >= wp.Nz) z -= wp.Nz;
+        const size_t idx = ((size_t)x * wp.Ny + y) * wp.Nz + z;
+        const int node = (lx * H + ly) * HS + lz;
+        g[node] = __ldg(grid + idx);
+        g[GT + node] = __ldg(grid + G + idx);
+        g[2 * GT + node] = __ldg(grid + 2 * G + idx);
     }
-    // this lane's support nodes: constant over particles
-    int my_node[NR], my_w[NR];  // tile offset; (ij << 8 | k), -1 when beyond the support
+    // this lane's support nodes (i,j,k), constant over particles: tile offset and displacement offsets
+    int my_node[NR];
+    float my_dx[NR], my_dy[NR], my_dz[NR];  // node offset from the support origin, in length units (dx includes the shear)
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
         const int t = lane + 32 * r;
         const int i = t / PP, j = (t - i * PP) / P, k = t - i * PP - j * P;
-        my_node[r] = (i * H + j) * HS + k;
-        my_w[r] = t < PPP ? (((i * P + j) << 8) | k) : -1;
+        my_node[r] = t < PPP ? (i * H + j) * HS + k : -1;
+        my_dy[r] = wp.hy * (float)j;
+        my_dx[r] = fmaf(box.xy, my_dy[r], wp.hx * (float)i);
+        my_dz[r] = wp.hz * (float)k;
     }
     __syncthreads();
-    float* mywt = wts + wid * (PP + P);
     const float pref = wp.quadW * wp.prefac;
     while (w < ce) {
         const float4 pp = pp_n;
@@ -346,39 +355,34 @@ interp_tile_kernel(const float4* __restrict__ wpos, const int4* __restrict__ wor
         if (wn < ce) { pp_n = __ldg(wpos + wn); o_n = __ldg(worg + wn); id_n = __ldg(perm + __ldg(wperm + wn)); }
         float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
         if (accumulate && lane == 0) old = U[id];
+        // displacement of the support origin node from the particle (unwrapped node, see weight_xy)
         const int3 u = unwrapped_origin(o, wp);
-#pragma unroll
-        for (int r = lane; r < PP + P; r += 32) {
-            if (r < PP) {
-                const int i = r / P, j = r - i * P;
-                mywt[r] = weight_xy(box, wp, u.x + i, u.y + j, pp.x, pp.y, pref);
-            } else {
-                mywt[r] = weight_z(box, wp, u.z + (r - PP), pp.z);
-            }
-        }
-        __syncwarp();
+        const float gy0 = fmaf(wp.hy, (float)u.y, -0.5f * box.Ly);
+        const float rx0 = fmaf(box.xy, gy0, fmaf(wp.hx, (float)u.x, -0.5f * box.Lx)) - pp.x;
+        const float ry0 = gy0 - pp.y;
+        const float rz0 = fmaf(wp.hz, (float)u.z, -0.5f * box.Lz) - pp.z;
         const int base = ((o.x - t0x) * H + (o.y - t0y)) * HS + (o.z - t0z);
         float ax = 0.f, ay = 0.f, az = 0.f;
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
-            if (my_w[r] >= 0) {
-                const float wgt = mywt[my_w[r] >> 8] * mywt[PP + (my_w[r] & 255)];
+            if (my_node[r] >= 0) {
+                const float rx = rx0 + my_dx[r], ry = ry0 + my_dy[r], rz = rz0 + my_dz[r];
+                const float wgt = exp_neg(-wp.expfac * fmaf(rx, rx, fmaf(ry, ry, rz * rz)));
                 const int node = base + my_node[r];
-                ax += wgt * g[node];
-                ay += wgt * g[GT + node];
-                az += wgt * g[2 * GT + node];
+                ax = fmaf(wgt, g[node], ax);
+                ay = fmaf(wgt, g[GT + node], ay);
+                az = fmaf(wgt, g[2 * GT + node], az);
             }
         }
         ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az);
-        if (lane == 0) U[id] = make_float4(old.x + ax, old.y + ay, old.z + az, 0.f);
-        __syncwarp();
+        if (lane == 0) U[id] = make_float4(fmaf(pref, ax, old.x), fmaf(pref, ay, old.y), fmaf(pref, az, old.z), 0.f);
         w = wn;
     }
 }
 
 static inline size_t interp_tile_smem(int P) {
     const int H = TILE + P - 1, HS = H | 1;
-    return (3 * (size_t)H * H * HS + (INTERP_THREADS / 32) * (size_t)(P * P + P)) * sizeof(float);
+    return (3 * (size_t)H * H * HS) * sizeof(float);
 }
 
 // ---- dispatch on the (runtime) support size ------------------------------------------------------------
