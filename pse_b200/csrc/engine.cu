@@ -94,6 +94,7 @@ struct pse_engine {
     float4 *d_hpos, *d_hF;  // device staging for pse_step_host
     int3* d_himage;
     int num_sms;
+    bool spmv_smem_table;
     // profiling
     bool prof_on;
     std::vector<cudaEvent_t>* prof_pool;
@@ -104,6 +105,9 @@ struct pse_engine {
     // stats
     uint64_t launches, fft_execs, nlist_builds;
 };
+
+// bytes of the real-space table when staged in shared memory by the SpMV (float2 per knot)
+static inline size_t spmv_table_smem(const pse_engine* e) { return (size_t)(e->prm.ewald_n + 2) * sizeof(float2); }
 
 static int fail(pse_engine* e, int code, const char* fmt, ...) {
     va_list ap;
@@ -328,6 +332,13 @@ extern "C" int pse_create(const pse_config* cfg, void* stream, pse_engine** out)
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         e->num_sms = sms;
+        e->spmv_smem_table = spmv_table_smem(e) <= 64 * 1024;
+        const char* env = getenv("PSE_SPMV_SMEM_TABLE");
+        if (env) e->spmv_smem_table = env[0] != '0' && spmv_table_smem(e) <= 200 * 1024;
+        if (e->spmv_smem_table) {
+            cudaFuncSetAttribute(spmv_kernel<8, SPMV_PLAIN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spmv_table_smem(e));
+            cudaFuncSetAttribute(spmv_kernel<8, SPMV_LANCZOS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spmv_table_smem(e));
+        }
     }
     e->m_lanczos = 2;  // PSEv1/Stokes.cc:132
     e->prof_pool = new std::vector<cudaEvent_t>();
@@ -545,13 +556,26 @@ static inline unsigned int persistent_grid(const pse_engine* e, size_t work_bloc
     return (unsigned int)(work_blocks < cap ? (work_blocks ? work_blocks : 1) : cap);
 }
 
+template <int MODE>
+static void launch_spmv(pse_engine* e, float4* y, const LanczosArgs& la) {
+    constexpr int TPP = 8;
+    const unsigned int work = nblk((size_t)e->N * TPP, 256);
+    if (e->spmv_smem_table) {
+        const size_t sm = spmv_table_smem(e);
+        const int bps = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (sm + 1024)));
+        spmv_kernel<TPP, MODE, true><<<persistent_grid(e, work, bps), 256, sm, e->stream>>>(
+            e->d_px, y, e->N, e->d_nn, e->d_head, e->d_nl, e->d_table, e->rp, e->box, la);
+    } else {
+        spmv_kernel<TPP, MODE, false><<<persistent_grid(e, work, 8), 256, 0, e->stream>>>(
+            e->d_px, y, e->N, e->d_nn, e->d_head, e->d_nl, e->d_table, e->rp, e->box, la);
+    }
+    LAUNCHED(e);
+}
+
 static int run_spmv_plain(pse_engine* e, float4* y) {
     ProfScope ps(e, PH_SPMV);
-    constexpr int TPP = 8;
     LanczosArgs la = {};
-    spmv_kernel<TPP, SPMV_PLAIN><<<persistent_grid(e, nblk((size_t)e->N * TPP, 256), 8), 256, 0, e->stream>>>(
-        e->d_px, y, e->N, e->d_nn, e->d_head, e->d_nl, e->d_table, e->rp, e->box, la);
-    LAUNCHED(e);
+    launch_spmv<SPMV_PLAIN>(e, y, la);
     return PSE_OK;
 }
 
@@ -612,7 +636,6 @@ static int run_wave(pse_engine* e, const float4* sF, float4* U, int accumulate, 
 
 // one Lanczos iteration j (two kernels)
 static void lanczos_iteration(pse_engine* e, int j) {
-    constexpr int TPP = 8;
     const uint32_t N = e->N;
     float4* Vj = e->d_V + (size_t)j * N;
     LanczosArgs la;
@@ -625,9 +648,7 @@ static void lanczos_iteration(pse_engine* e, int j) {
     la.first = j == 0;
     {
     ProfScope ps(e, PH_LANCZOS_SPMV);
-    spmv_kernel<TPP, SPMV_LANCZOS><<<persistent_grid(e, nblk((size_t)N * TPP, 256), 8), 256, 0, e->stream>>>(
-        e->d_px, e->d_y, N, e->d_nn, e->d_head, e->d_nl, e->d_table, e->rp, e->box, la);
-    LAUNCHED(e);
+    launch_spmv<SPMV_LANCZOS>(e, e->d_y, la);
     }
     ProfScope ps(e, PH_LANCZOS_VEC);
     lanczos_update_kernel<<<persistent_grid(e, nblk(N, 256), 8), 256, 0, e->stream>>>(e->d_y, Vj, e->d_px, N, e->d_alpha + j, e->d_beta + j + 1,

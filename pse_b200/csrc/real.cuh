@@ -11,6 +11,7 @@
 #pragma once
 #include "box.cuh"
 #include "common.cuh"
+#include <type_traits>
 
 struct RealParams {
     float self;     // M_real self term (PSEv1/Stokes.cc:319)
@@ -27,12 +28,26 @@ struct RealParams {
 // precomputed reciprocals (table index (dist-dr)*ewald_n/(rcut-dr), fac = dist/dr - ind - 1, (r.F)/r^2).
 // The table is piecewise linear and continuous, so an index that lands one entry off at a knot gives the
 // same value to round-off; measured parity against the reference kernel stays at 1e-7.
-__device__ __forceinline__ void rpy_pair(const float3 r, const float r2, const float4 Fj, const float4* __restrict__ table,
+// TAB is either the reference-layout global table (float4: f_k, g_k, f_k+1, g_k+1) or its shared-memory copy
+// (float2 per knot: entry k and k+1 are read separately).
+struct TableGlobal {
+    const float4* t;
+    __device__ __forceinline__ float4 at(int k) const { return __ldg(t + k); }
+};
+struct TableShared {
+    const float2* t;
+    __device__ __forceinline__ float4 at(int k) const {
+        const float2 a = t[k], b = t[k + 1];
+        return make_float4(a.x, a.y, b.x, b.y);
+    }
+};
+template <class TAB>
+__device__ __forceinline__ void rpy_pair(const float3 r, const float r2, const float4 Fj, const TAB& table,
                                          const RealParams& rp, float3& u) {
     const float inv_dist = rsqrtf(r2);
     const float dist = r2 * inv_dist;
     const int r_ind = __float2int_rd((dist - rp.dr) * rp.tab_scale);
-    const float4 t = __ldg(table + r_ind);
+    const float4 t = table.at(r_ind);
     const float fac = dist * rp.inv_dr - (float)r_ind - 1.0f;
     const float Imrr = t.x + (t.z - t.x) * fac;
     const float rr = t.y + (t.w - t.y) * fac;
@@ -49,6 +64,13 @@ struct __align__(32) PX {
     float4 p;  // position (x, y, z, -)
     float4 x;  // input vector of the SpMV: force, psi, or the unnormalised Lanczos vector u_j
 };
+
+// one 256-bit load of a whole record (LDG.E.256 on sm_100a): half the L1 wavefronts of two 128-bit loads
+__device__ __forceinline__ void ld_px(const PX* ptr, float4& p, float4& x) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(p.x), "=f"(p.y), "=f"(p.z), "=f"(p.w), "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
+                 : "l"(ptr));
+}
 
 enum { SPMV_PLAIN = 0, SPMV_LANCZOS = 1 };
 
@@ -67,13 +89,27 @@ struct LanczosArgs {
 //          y = s (M x) - beta_j v_{j-1};  alpha_j = v_j . y     (PSEv1/Brownian.cu:481-490)
 // Persistent grid (a multiple of the SM count): each block walks row groups with a grid stride, so the
 // number of partial sums (and of arrivals on the finishing counter) is O(SMs), not O(N).
-template <int TPP, int MODE>
+// SMEM_TABLE: the real-space table is staged once per (persistent) block in shared memory as float2 knots; the
+// per-pair lookup is then two LDS.64 instead of a 16-byte global gather that touches up to 32 cache lines per
+// warp (the L1 wavefront limiter of the first version, profiles/r1_ncu_summary.md).
+template <int TPP, int MODE, bool SMEM_TABLE>
 __global__ void __launch_bounds__(256)
 spmv_kernel(const PX* __restrict__ px, float4* __restrict__ y, uint32_t N,
             const uint32_t* __restrict__ nn, const uint32_t* __restrict__ head, const uint32_t* __restrict__ nl,
-            const float4* __restrict__ table, RealParams rp, PseBox box, LanczosArgs la) {
+            const float4* __restrict__ gtable, RealParams rp, PseBox box, LanczosArgs la) {
     constexpr int ROWS = 256 / TPP;
     const int sub = threadIdx.x % TPP;
+    extern __shared__ __align__(16) float2 stab[];
+    if (SMEM_TABLE) {
+        for (int k = threadIdx.x; k <= rp.ewald_n; k += blockDim.x) {
+            const float4 t = __ldg(gtable + k);
+            stab[k] = make_float2(t.x, t.y);
+            if (k == rp.ewald_n) stab[k + 1] = make_float2(t.z, t.w);
+        }
+        __syncthreads();
+    }
+    typename std::conditional<SMEM_TABLE, TableShared, TableGlobal>::type table;
+    if constexpr (SMEM_TABLE) table.t = stab; else table.t = gtable;
     float part = 0.f;
     float beta = 0.f, s = 0.f;
     if (MODE == SPMV_LANCZOS) {
@@ -86,31 +122,30 @@ spmv_kernel(const PX* __restrict__ px, float4* __restrict__ y, uint32_t N,
         float4 pi = make_float4(0.f, 0.f, 0.f, 0.f), xi = pi;
         const bool live = row < N;
         if (live) {
-            pi = __ldg(&px[row].p);
-            xi = __ldg(&px[row].x);
+            ld_px(px + row, pi, xi);
             const uint32_t n = __ldg(nn + row);
             const uint32_t* __restrict__ list = nl + __ldg(head + row);
             uint32_t k = sub;
             // two neighbours per trip: both gathers are in flight before either is consumed
             for (; k + TPP < n; k += 2 * TPP) {
                 const uint32_t j0 = __ldg(list + k), j1 = __ldg(list + k + TPP);
-                const float4 p0 = __ldg(&px[j0].p), p1 = __ldg(&px[j1].p);
+                float4 p0, p1, x0, x1;
+                ld_px(px + j0, p0, x0);
+                ld_px(px + j1, p1, x1);
                 const float3 r0 = box.min_image(make_float3(PSE_SUB(pi.x, p0.x), PSE_SUB(pi.y, p0.y), PSE_SUB(pi.z, p0.z)));
                 const float3 r1 = box.min_image(make_float3(PSE_SUB(pi.x, p1.x), PSE_SUB(pi.y, p1.y), PSE_SUB(pi.z, p1.z)));
                 const float d0 = r0.x * r0.x + r0.y * r0.y + r0.z * r0.z, d1 = r1.x * r1.x + r1.y * r1.y + r1.z * r1.z;
                 const bool in0 = d0 < rp.rcut_sq && d0 >= rp.dr_sq, in1 = d1 < rp.rcut_sq && d1 >= rp.dr_sq;
-                float4 x0, x1;
-                if (in0) x0 = __ldg(&px[j0].x);
-                if (in1) x1 = __ldg(&px[j1].x);
                 if (in0) rpy_pair(r0, d0, x0, table, rp, u);
                 if (in1) rpy_pair(r1, d1, x1, table, rp, u);
             }
             if (k < n) {
                 const uint32_t j0 = __ldg(list + k);
-                const float4 p0 = __ldg(&px[j0].p);
+                float4 p0, x0;
+                ld_px(px + j0, p0, x0);
                 const float3 r0 = box.min_image(make_float3(PSE_SUB(pi.x, p0.x), PSE_SUB(pi.y, p0.y), PSE_SUB(pi.z, p0.z)));
                 const float d0 = r0.x * r0.x + r0.y * r0.y + r0.z * r0.z;
-                if (d0 < rp.rcut_sq && d0 >= rp.dr_sq) rpy_pair(r0, d0, __ldg(&px[j0].x), table, rp, u);
+                if (d0 < rp.rcut_sq && d0 >= rp.dr_sq) rpy_pair(r0, d0, x0, table, rp, u);
             }
         }
         u.x = group_sum<TPP>(u.x);

@@ -74,30 +74,29 @@ __device__ __forceinline__ int tile_candidates(int t0, int e, int P, int N, int*
     return n;
 }
 
-// Gaussian factors of one particle for support node (ox+i, oy+j, oz+k), o = UNWRAPPED support origin.
-// The reference evaluates prefac*expf(-expfac*|minImage(node - pos)|^2) with the node wrapped into the box
-// (PSEv1/Mobility.cu:222-241); the minimum image only undoes that wrap, so the displacement is taken
-// directly from the unwrapped node, and the Gaussian is split as w_xy(i,j) * w_z(k).  Differences are
-// float round-off (1e-7 relative), far inside the 1e-5 parity budget.
-// exp(x) for x <= 0 through ex2 with a compensated argument: t = x*log2(e) is rounded to float (|t| up to ~15,
-// ulp ~1e-6), so the rounding residual r is recovered with an fma and applied to first order.  Relative error
-// ~3e-7 instead of ~1e-6 for __expf, at 4 extra instructions.
-__device__ __forceinline__ float exp_neg(float x) {
-    const float L2E_HI = 1.4426950216293335f, L2E_LO = 1.9259629911e-8f;
-    const float t = x * L2E_HI;
-    const float r = fmaf(x, L2E_HI, -t) + x * L2E_LO;
-    return exp2f(t) * fmaf(r, 0.6931471805599453f, 1.0f);
+// Gaussian factors of one particle for the WRAPPED support node (ix, iy, iz), split as w_xy(i,j) * w_z(k).
+// The node position and the minimum-image displacement are formed operation by operation as the reference does
+// (PSEv1/Mobility.cu:222-238: h*index - L/2, shear, node - pos, BoxDim::minImage) because at L ~ 240 one ulp
+// of a coordinate is ~8e-6 and any re-association of these sums moves individual weights by ~1e-5 relative —
+// harmless for accuracy, but it would eat the whole 1e-5 parity budget.  Only exp(a+b) -> exp(a)*exp(b)
+// differs (1e-7).
+__device__ __forceinline__ float weight_z(const PseBox& box, const WaveParams& wp, int iz, float pz) {
+    const float gz = wp.hz * (float)iz - box.Lz * 0.5f;
+    float rz = gz - pz;
+    rz = PSE_SUB(rz, PSE_MUL(box.Lz, rintf(PSE_MUL(rz, box.Lzinv))));
+    return expf(-wp.expfac * (rz * rz));
 }
-__device__ __forceinline__ float weight_z(const PseBox& box, const WaveParams& wp, int iz_unwrapped, float pz) {
-    const float rz = fmaf(wp.hz, (float)iz_unwrapped, -0.5f * box.Lz) - pz;
-    return exp_neg(-wp.expfac * rz * rz);
-}
-__device__ __forceinline__ float weight_xy(const PseBox& box, const WaveParams& wp, int ix_unwrapped, int iy_unwrapped, float px,
-                                           float py, float pref) {
-    const float gy = fmaf(wp.hy, (float)iy_unwrapped, -0.5f * box.Ly);
-    const float rx = fmaf(box.xy, gy, fmaf(wp.hx, (float)ix_unwrapped, -0.5f * box.Lx)) - px;
-    const float ry = gy - py;
-    return pref * exp_neg(-wp.expfac * fmaf(rx, rx, ry * ry));
+__device__ __forceinline__ float weight_xy(const PseBox& box, const WaveParams& wp, int ix, int iy, float px, float py,
+                                           float pref) {
+    float gx = wp.hx * (float)ix - box.Lx * 0.5f;
+    const float gy = wp.hy * (float)iy - box.Ly * 0.5f;
+    gx = gx + box.xy * gy;
+    float rx = gx - px, ry = gy - py;
+    const float img = rintf(PSE_MUL(ry, box.Lyinv));
+    ry = PSE_SUB(ry, PSE_MUL(box.Ly, img));
+    rx = PSE_SUB(rx, PSE_MUL(PSE_MUL(box.Ly, box.xy), img));
+    rx = PSE_SUB(rx, PSE_MUL(box.Lx, rintf(PSE_MUL(rx, box.Lxinv))));
+    return pref * expf(-wp.expfac * (rx * rx + ry * ry));
 }
 // worg.w packs the wrap shifts of the three axes: unwrapped = wrapped + (shift - 1) * N, 2 bits per axis
 __device__ __forceinline__ int3 unwrapped_origin(const int4 o, const WaveParams& wp) {
@@ -218,10 +217,9 @@ spread_tile_kernel(const float4* __restrict__ wpos, const float4* __restrict__ w
                     m |= (uint32_t)((unsigned)(lz + i) < (unsigned)ez) << (2 * P + i);
                 }
                 const float4 pp = __ldg(wpos + w), F = __ldg(wF + w);
-                const int3 u = unwrapped_origin(o, wp);
-                a_pos[slot] = make_float4(pp.x, pp.y, pp.z, __int_as_float((u.x + 1024) | ((u.y + 1024) << 16)));
+                a_pos[slot] = make_float4(pp.x, pp.y, pp.z, __int_as_float(o.x | (o.y << 16)));
                 a_rec[slot] = make_float4(F.x, F.y, F.z, __int_as_float((lx * TILE + ly) * TILE_ZS + lz));
-                a_oz[slot] = u.z;
+                a_oz[slot] = o.z;
                 a_mask[slot] = m;
             }
             nact += total;
@@ -237,9 +235,9 @@ spread_tile_kernel(const float4* __restrict__ wpos, const float4* __restrict__ w
                 const int oxy = __float_as_int(pp.w);
                 if (r < PP) {
                     const int i = r / P, j = r - i * P;
-                    swxy[q * PP + r] = weight_xy(box, wp, (oxy & 0xffff) - 1024 + i, (oxy >> 16) - 1024 + j, pp.x, pp.y, wp.prefac);
+                    swxy[q * PP + r] = weight_xy(box, wp, wrap_node((oxy & 0xffff) + i, wp.Nx), wrap_node((oxy >> 16) + j, wp.Ny), pp.x, pp.y, wp.prefac);
                 } else {
-                    swz[q * P + (r - PP)] = weight_z(box, wp, a_oz[c0 + q] + (r - PP), pp.z);
+                    swz[q * P + (r - PP)] = weight_z(box, wp, wrap_node(a_oz[c0 + q] + (r - PP), wp.Nz), pp.z);
                 }
             }
             __syncthreads();
@@ -308,6 +306,7 @@ interp_tile_kernel(const float4* __restrict__ wpos, const int4* __restrict__ wor
     constexpr int PP = P * P, PPP = PP * P, NR = (PPP + 31) / 32, NW = INTERP_THREADS / 32;
     constexpr int H = TILE + P - 1, HS = H | 1, GT = H * H * HS;
     float* g = smem;
+    float* wts = smem + 3 * GT;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t cell = blockIdx.x;
     const uint32_t cb = __ldg(wcell_start + cell), ce = __ldg(wcell_start + cell + 1);
@@ -333,19 +332,17 @@ interp_tile_kernel(const float4* __restrict__ wpos, const int4* __restrict__ wor
         g[GT + node] = __ldg(grid + G + idx);
         g[2 * GT + node] = __ldg(grid + 2 * G + idx);
     }
-    // this lane's support nodes (i,j,k), constant over particles: tile offset and displacement offsets
-    int my_node[NR];
-    float my_dx[NR], my_dy[NR], my_dz[NR];  // node offset from the support origin, in length units (dx includes the shear)
+    // this lane's support nodes (i,j,k), constant over particles: tile offset and factor indices
+    int my_node[NR], my_w[NR];  // tile offset; (ij << 8 | k), -1 beyond the support
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
         const int t = lane + 32 * r;
         const int i = t / PP, j = (t - i * PP) / P, k = t - i * PP - j * P;
-        my_node[r] = t < PPP ? (i * H + j) * HS + k : -1;
-        my_dy[r] = wp.hy * (float)j;
-        my_dx[r] = fmaf(box.xy, my_dy[r], wp.hx * (float)i);
-        my_dz[r] = wp.hz * (float)k;
+        my_node[r] = (i * H + j) * HS + k;
+        my_w[r] = t < PPP ? (((i * P + j) << 8) | k) : -1;
     }
     __syncthreads();
+    float* mywt = wts + wid * (PP + P);
     const float pref = wp.quadW * wp.prefac;
     while (w < ce) {
         const float4 pp = pp_n;
@@ -355,19 +352,22 @@ interp_tile_kernel(const float4* __restrict__ wpos, const int4* __restrict__ wor
         if (wn < ce) { pp_n = __ldg(wpos + wn); o_n = __ldg(worg + wn); id_n = __ldg(perm + __ldg(wperm + wn)); }
         float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
         if (accumulate && lane == 0) old = U[id];
-        // displacement of the support origin node from the particle (unwrapped node, see weight_xy)
-        const int3 u = unwrapped_origin(o, wp);
-        const float gy0 = fmaf(wp.hy, (float)u.y, -0.5f * box.Ly);
-        const float rx0 = fmaf(box.xy, gy0, fmaf(wp.hx, (float)u.x, -0.5f * box.Lx)) - pp.x;
-        const float ry0 = gy0 - pp.y;
-        const float rz0 = fmaf(wp.hz, (float)u.z, -0.5f * box.Lz) - pp.z;
+#pragma unroll
+        for (int r = lane; r < PP + P; r += 32) {
+            if (r < PP) {
+                const int i = r / P, j = r - i * P;
+                mywt[r] = weight_xy(box, wp, wrap_node(o.x + i, wp.Nx), wrap_node(o.y + j, wp.Ny), pp.x, pp.y, pref);
+            } else {
+                mywt[r] = weight_z(box, wp, wrap_node(o.z + (r - PP), wp.Nz), pp.z);
+            }
+        }
+        __syncwarp();
         const int base = ((o.x - t0x) * H + (o.y - t0y)) * HS + (o.z - t0z);
         float ax = 0.f, ay = 0.f, az = 0.f;
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
-            if (my_node[r] >= 0) {
-                const float rx = rx0 + my_dx[r], ry = ry0 + my_dy[r], rz = rz0 + my_dz[r];
-                const float wgt = exp_neg(-wp.expfac * fmaf(rx, rx, fmaf(ry, ry, rz * rz)));
+            if (my_w[r] >= 0) {
+                const float wgt = mywt[my_w[r] >> 8] * mywt[PP + (my_w[r] & 255)];
                 const int node = base + my_node[r];
                 ax = fmaf(wgt, g[node], ax);
                 ay = fmaf(wgt, g[GT + node], ay);
@@ -375,14 +375,15 @@ interp_tile_kernel(const float4* __restrict__ wpos, const int4* __restrict__ wor
             }
         }
         ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az);
-        if (lane == 0) U[id] = make_float4(fmaf(pref, ax, old.x), fmaf(pref, ay, old.y), fmaf(pref, az, old.z), 0.f);
+        if (lane == 0) U[id] = make_float4(old.x + ax, old.y + ay, old.z + az, 0.f);
+        __syncwarp();
         w = wn;
     }
 }
 
 static inline size_t interp_tile_smem(int P) {
     const int H = TILE + P - 1, HS = H | 1;
-    return (3 * (size_t)H * H * HS) * sizeof(float);
+    return (3 * (size_t)H * H * HS + (INTERP_THREADS / 32) * (size_t)(P * P + P)) * sizeof(float);
 }
 
 // ---- dispatch on the (runtime) support size ------------------------------------------------------------
