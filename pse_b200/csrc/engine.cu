@@ -618,7 +618,7 @@ static int run_wave(pse_engine* e, const float4* sF, float4* U, int accumulate, 
     const float noise_fac = sqrtf((float)(2.0 * T / dt / e->wp.quadW));  // PSEv1/Brownian.cu:198
     {
         ProfScope ps(e, PH_SCALE);
-        scale_kernel<<<nblk(e->Gh, 256), 256, 0, st>>>(e->d_spec, e->wp, e->box, det ? 1 : 0, noise ? 1 : 0, noise_fac, d_u_grid, key); LAUNCHED(e);
+        scale_kernel<<<dim3(e->wp.Ny, e->wp.Nx), 128, 0, st>>>(e->d_spec, e->wp, e->box, det ? 1 : 0, noise ? 1 : 0, noise_fac, d_u_grid, key); LAUNCHED(e);
     }
     {
         ProfScope ps(e, PH_FFT_INV);

@@ -190,15 +190,16 @@ __device__ __forceinline__ float sinc_of(const KVec& kv) {
 // spectrum.  A node n with a Nyquist index and its mirror carry wave vectors that are NOT negatives of
 // each other (PSEv1/Helper.cu:308-311 maps index N/2 to -N/2 for both; under shear even |k| differs), so
 // the half-spectrum C2R path evaluates both wave vectors and averages.
-__global__ void __launch_bounds__(256)
+// Launch: grid (Ny, Nx), one block per (ii, jj) row of the half spectrum, threads stride over kz (coalesced,
+// no per-thread integer division).
+__global__ void __launch_bounds__(128)
 scale_kernel(float2* __restrict__ spec, WaveParams wp, PseBox box, int do_det, int do_noise, float noise_fac,
              const float* __restrict__ u_grid, uint32_t key) {
     const size_t nh = (size_t)wp.Nx * wp.Ny * wp.Nzh;
-    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= nh) return;
-    const int kk = (int)(tid % wp.Nzh);
-    const int jj = (int)((tid / wp.Nzh) % wp.Ny);
-    const int ii = (int)(tid / ((size_t)wp.Nzh * wp.Ny));
+    const int jj = blockIdx.x, ii = blockIdx.y;
+    const size_t rowbase = ((size_t)ii * wp.Ny + jj) * wp.Nzh;
+    for (int kk = threadIdx.x; kk < wp.Nzh; kk += blockDim.x) {
+    const size_t tid = rowbase + kk;
     float2 fX = make_float2(0.f, 0.f), fY = fX, fZ = fX;
     if (do_det) { fX = spec[tid]; fY = spec[nh + tid]; fZ = spec[2 * nh + tid]; }
     float2 oX = make_float2(0.f, 0.f), oY = oX, oZ = oX;
@@ -244,6 +245,7 @@ scale_kernel(float2* __restrict__ spec, WaveParams wp, PseBox box, int do_det, i
         }
     }
     spec[tid] = oX; spec[nh + tid] = oY; spec[2 * nh + tid] = oZ;
+    }
 }
 
 // particle noise psi (slot order) : 3 uniforms on (-sqrt3, sqrt3), PSEv1/Brownian.cu:99-130

@@ -19,8 +19,8 @@
 #include "wave.cuh"
 
 #define TILE 16
-#define TILE_ZS 20       // padded z stride of the accumulator tile (bank spread for the 6x6 (j,k) footprints)
-#define SPREAD_CHUNK 64  // particles whose weights are staged at once
+#define TILE_ZS 18       // padded z stride of the accumulator tile (bank spread for the 6x6 (j,k) footprints)
+#define SPREAD_CHUNK 32  // particles whose weights are staged at once
 #define TILED_MAX_P 10   // 3P validity bits must fit one 32-bit word
 
 struct TileGrid {
@@ -115,7 +115,7 @@ __device__ __forceinline__ int3 unwrapped_origin(const int4 o, const WaveParams&
 //   store    the finished tile is written once, coalesced.
 // dynamic smem: acc[3][TILE*TILE*TILE_ZS] | a_pos[CAP] f4 | a_rec[CAP] f4 | a_oz[CAP] | a_mask[CAP] |
 //               wxy[CHUNK][P*P] | wz[CHUNK][P]
-#define SPREAD_CAP 1024
+#define SPREAD_CAP 384   // staged particles per filter round; sized so that three blocks fit one SM
 #define SPREAD_MAX_SEG 64
 
 template <int P>
