@@ -169,14 +169,15 @@ int pse_step_host(pse_engine* e, float* h_pos4, int* h_image3, const float* h_F4
 /* ---- introspection ---------------------------------------------------------------------- */
 
 typedef struct {
-    uint64_t nnz;           /* stored neighbours */
+    uint64_t nnz;           /* stored neighbours (r < r_cut + r_buff at build time) */
+    uint64_t nnz_active;    /* neighbours inside r_cut at the current positions (rows the SpMV walks) */
     uint64_t kernel_launches; /* engine kernels launched since create (cuFFT launches not counted) */
     uint64_t fft_execs;
     uint64_t nlist_builds;
     int lanczos_m;          /* iterations used by the last Brownian evaluation */
     float lanczos_stepnorm; /* its final relative step norm */
 } pse_stats;
-int pse_get_stats(const pse_engine* e, pse_stats* out);
+int pse_get_stats(pse_engine* e, pse_stats* out); /* synchronises the stream */
 
 /* Optional per-phase device timing with CUDA events on the engine's stream (off by default; adds two
  * event records per phase).  pse_get_profile synchronises the stream, returns the number of phases and

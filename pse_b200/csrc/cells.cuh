@@ -241,6 +241,15 @@ __global__ void nlist_kernel(const float4* __restrict__ spos, uint32_t N, PseBox
     if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(max_nn, m);
 }
 
+// sum of nn -> *total (uint64), for statistics only
+__global__ void nnz_kernel(const uint32_t* __restrict__ nn, uint32_t N, unsigned long long* __restrict__ total) {
+    unsigned long long s = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) s += nn[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(total, s);
+}
+
 // ell[slot * cap + k] -> nl[head[slot] + k], 8 lanes per row
 __global__ void compact_rows_kernel(const uint32_t* __restrict__ ell, uint32_t cap, const uint32_t* __restrict__ nn,
                                     const uint32_t* __restrict__ head, uint32_t N, uint32_t* __restrict__ nl) {

@@ -29,10 +29,10 @@ int pse_tridiag_sqrt_e1(int m, const double* diag, const double* off, double* c,
 static char g_create_error[512] = "no error";
 
 // phases for the optional CUDA-event profile (pse_set_profiling / pse_get_profile)
-enum Phase { PH_BIN = 0, PH_NLIST, PH_REORDER, PH_WBIN, PH_SPREAD, PH_FFT_FWD, PH_SCALE, PH_FFT_INV, PH_INTERP, PH_SPMV,
+enum Phase { PH_BIN = 0, PH_NLIST, PH_REORDER, PH_WBIN, PH_SPREAD, PH_FFT_FWD, PH_SCALE, PH_FFT_INV, PH_INTERP, PH_PRUNE, PH_SPMV,
              PH_LANCZOS_SPMV, PH_LANCZOS_VEC, PH_COMBINE, PH_INTEGRATE, PH_COUNT };
 static const char* kPhaseNames[PH_COUNT] = {"bin", "nlist", "reorder", "wave_bin", "spread", "fft_r2c", "scale", "fft_c2r",
-                                            "interp", "spmv", "lanczos_spmv", "lanczos_vec", "combine", "integrate"};
+                                            "interp", "prune", "spmv", "lanczos_spmv", "lanczos_vec", "combine", "integrate"};
 struct ProfSpan { int phase; cudaEvent_t a, b; };
 
 struct pse_engine {
@@ -57,6 +57,9 @@ struct pse_engine {
     PX* d_px;  // packed (position, vector) records for the SpMV
     // neighbour list (slot numbering)
     uint32_t *d_nn, *d_head, *d_nl;
+    uint32_t *d_nn_act, *d_nl_act;  // per-step pruned list (pairs inside r_cut at the current positions)
+    size_t nl_act_cap;
+    bool prune, pruned_valid;
     size_t nl_cap;
     uint32_t nl_stride;            // row stride of the fixed-stride search output
     uint32_t* d_ell;
@@ -95,6 +98,7 @@ struct pse_engine {
     int3* d_himage;
     int num_sms;
     bool spmv_smem_table;
+    int spmv_tpp;  // lanes per row in the SpMV
     // profiling
     bool prof_on;
     std::vector<cudaEvent_t>* prof_pool;
@@ -177,6 +181,12 @@ extern "C" const char* pse_profile_phase_name(int i) { return (i >= 0 && i < PH_
 
 static inline unsigned int nblk(size_t n, int b) { return (unsigned int)((n + b - 1) / b); }
 
+// persistent launch: a whole number of waves of resident blocks
+static inline unsigned int persistent_grid(const pse_engine* e, size_t work_blocks, int blocks_per_sm) {
+    size_t cap = (size_t)e->num_sms * blocks_per_sm;
+    return (unsigned int)(work_blocks < cap ? (work_blocks ? work_blocks : 1) : cap);
+}
+
 // ---- exclusive scan driver -------------------------------------------------------------------
 static int exclusive_scan(pse_engine* e, const uint32_t* in, uint32_t* out, uint32_t n, uint32_t* tmp) {
     unsigned int nb = nblk(n, SCAN_BLOCK);
@@ -239,6 +249,10 @@ static int alloc_all(pse_engine* e) {
     CK(cudaMalloc(&e->d_px, sizeof(PX) * N));
     CK(cudaMalloc(&e->d_nn, sizeof(uint32_t) * (N + 1)));
     CK(cudaMalloc(&e->d_head, sizeof(uint32_t) * (N + 1)));
+    CK(cudaMalloc(&e->d_nn_act, sizeof(uint32_t) * (N + 1)));
+    e->d_nl_act = nullptr; e->nl_act_cap = 0;
+    e->prune = true;
+    { const char* env = getenv("PSE_PRUNE"); if (env) e->prune = env[0] != '0'; }
     e->d_nl = nullptr; e->nl_cap = 0; e->nl_stride = 0;
     CK(cudaMalloc(&e->d_nlinfo, 2 * sizeof(unsigned long long)));
     CK(cudaMallocHost(&e->h_nlinfo, 2 * sizeof(unsigned long long)));
@@ -335,10 +349,9 @@ extern "C" int pse_create(const pse_config* cfg, void* stream, pse_engine** out)
         e->spmv_smem_table = spmv_table_smem(e) <= 64 * 1024;
         const char* env = getenv("PSE_SPMV_SMEM_TABLE");
         if (env) e->spmv_smem_table = env[0] != '0' && spmv_table_smem(e) <= 200 * 1024;
-        if (e->spmv_smem_table) {
-            cudaFuncSetAttribute(spmv_kernel<8, SPMV_PLAIN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spmv_table_smem(e));
-            cudaFuncSetAttribute(spmv_kernel<8, SPMV_LANCZOS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)spmv_table_smem(e));
-        }
+        e->spmv_tpp = 8;
+        const char* tpp = getenv("PSE_SPMV_TPP");
+        if (tpp) e->spmv_tpp = atoi(tpp);
     }
     e->m_lanczos = 2;  // PSEv1/Stokes.cc:132
     e->prof_pool = new std::vector<cudaEvent_t>();
@@ -376,7 +389,7 @@ extern "C" void pse_destroy(pse_engine* e) {
                     e->d_spos, e->d_sx, e->d_sy, e->d_px, e->d_nn, e->d_head, e->d_nl, e->d_pos_build, e->d_flag, e->d_grid,
                     e->d_spec, e->d_V, e->d_u, e->d_y, e->d_alpha, e->d_beta, e->d_coef, e->d_partials, e->d_counter,
                     e->d_vel_work, e->d_hpos, e->d_hF, e->d_himage, e->d_org, e->d_worg, e->d_wcell_of, e->d_wcount,
-                    e->d_wstart, e->d_wperm, e->d_wpos, e->d_wF, e->d_wtmp, e->d_ell};
+                    e->d_wstart, e->d_wperm, e->d_wpos, e->d_wF, e->d_wtmp, e->d_ell, e->d_nn_act, e->d_nl_act};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (e->h_flag) cudaFreeHost(e->h_flag);
@@ -412,9 +425,17 @@ extern "C" int pse_set_lanczos_m(pse_engine* e, int m) {
     return PSE_OK;
 }
 extern "C" int pse_get_lanczos_m(const pse_engine* e) { return e ? e->m_lanczos : PSE_EINVAL; }
-extern "C" int pse_get_stats(const pse_engine* e, pse_stats* out) {
+extern "C" int pse_get_stats(pse_engine* e, pse_stats* out) {
     if (!e || !out) return PSE_EINVAL;
-    out->nnz = e->nnz; out->kernel_launches = e->launches; out->fft_execs = e->fft_execs;
+    out->nnz = e->nnz;
+    out->nnz_active = e->nnz;
+    if (e->prune && e->pruned_valid && e->nlist_valid) {
+        CK(cudaMemsetAsync(e->d_nlinfo, 0, sizeof(unsigned long long), e->stream));
+        nnz_kernel<<<e->num_sms, 256, 0, e->stream>>>(e->d_nn_act, e->N, e->d_nlinfo);
+        CK(cudaMemcpyAsync(e->h_nlinfo, e->d_nlinfo, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        out->nnz_active = e->h_nlinfo[0];
+    } out->kernel_launches = e->launches; out->fft_execs = e->fft_execs;
     out->nlist_builds = e->nlist_builds; out->lanczos_m = e->m_lanczos; out->lanczos_stepnorm = e->last_stepnorm;
     return PSE_OK;
 }
@@ -475,6 +496,12 @@ extern "C" int pse_build_neighbors(pse_engine* e, const float4* d_pos) {
         e->nl_cap = (size_t)(e->nnz * 1.2) + 1024;
         CK(cudaMalloc(&e->d_nl, sizeof(uint32_t) * e->nl_cap));
     }
+    if (e->prune && e->nl_cap > e->nl_act_cap) {
+        if (e->d_nl_act) cudaFree(e->d_nl_act);
+        e->d_nl_act = nullptr;
+        e->nl_act_cap = e->nl_cap;
+        CK(cudaMalloc(&e->d_nl_act, sizeof(uint32_t) * e->nl_act_cap));
+    }
     compact_rows_kernel<<<nblk((size_t)N * 8, 256), 256, 0, st>>>(e->d_ell, e->nl_stride, e->d_nn, e->d_head, N, e->d_nl); LAUNCHED(e);
     CK(cudaMemcpyAsync(e->d_pos_build, d_pos, sizeof(float4) * N, cudaMemcpyDeviceToDevice, st));
     delete ps;
@@ -511,9 +538,23 @@ static int ensure_neighbors(pse_engine* e, const float4* d_pos) {
         e->flag_pending = false;
         rebuild = stale_from_bits(e, *e->h_flag);
     }
-    if (rebuild) return pse_build_neighbors(e, d_pos);
-    ProfScope ps(e, PH_REORDER);
-    gather_pos_kernel<<<nblk(e->N, 256), 256, 0, e->stream>>>(d_pos, e->d_perm, e->N, e->d_spos, (float4*)e->d_px); LAUNCHED(e);
+    if (rebuild) {
+        CKRC(pse_build_neighbors(e, d_pos));
+    } else {
+        ProfScope ps(e, PH_REORDER);
+        gather_pos_kernel<<<nblk(e->N, 256), 256, 0, e->stream>>>(d_pos, e->d_perm, e->N, e->d_spos, (float4*)e->d_px); LAUNCHED(e);
+    }
+    e->pruned_valid = false;
+    return PSE_OK;
+}
+
+// neighbour rows the SpMV walks: the buffered list, or (default) its per-step pruning to r < r_cut
+static int ensure_pruned(pse_engine* e) {
+    if (!e->prune || e->pruned_valid) return PSE_OK;
+    ProfScope ps(e, PH_PRUNE);
+    prune_kernel<<<persistent_grid(e, nblk((size_t)e->N * 8, 256), 8), 256, 0, e->stream>>>(e->d_spos, e->N, e->d_nn, e->d_head, e->d_nl, e->rp,
+                                                                                         e->box, e->d_nn_act, e->d_nl_act); LAUNCHED(e);
+    e->pruned_valid = true;
     return PSE_OK;
 }
 
@@ -550,29 +591,33 @@ extern "C" int pse_grid_index(pse_engine* e, const float4* d_pos, int3* d_out) {
 }
 
 // ---- building blocks (slot order) -----------------------------------------------------------------
-// persistent launch: a whole number of waves of resident blocks
-static inline unsigned int persistent_grid(const pse_engine* e, size_t work_blocks, int blocks_per_sm) {
-    size_t cap = (size_t)e->num_sms * blocks_per_sm;
-    return (unsigned int)(work_blocks < cap ? (work_blocks ? work_blocks : 1) : cap);
-}
-
-template <int MODE>
-static void launch_spmv(pse_engine* e, float4* y, const LanczosArgs& la) {
-    constexpr int TPP = 8;
+template <int TPP, int MODE>
+static void launch_spmv_tpp(pse_engine* e, float4* y, const LanczosArgs& la) {
     const unsigned int work = nblk((size_t)e->N * TPP, 256);
     if (e->spmv_smem_table) {
         const size_t sm = spmv_table_smem(e);
         const int bps = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (sm + 1024)));
+        cudaFuncSetAttribute(spmv_kernel<TPP, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         spmv_kernel<TPP, MODE, true><<<persistent_grid(e, work, bps), 256, sm, e->stream>>>(
-            e->d_px, y, e->N, e->d_nn, e->d_head, e->d_nl, e->d_table, e->rp, e->box, la);
+            e->d_px, y, e->N, e->prune ? e->d_nn_act : e->d_nn, e->d_head, e->prune ? e->d_nl_act : e->d_nl, e->d_table, e->rp, e->box, la);
     } else {
         spmv_kernel<TPP, MODE, false><<<persistent_grid(e, work, 8), 256, 0, e->stream>>>(
-            e->d_px, y, e->N, e->d_nn, e->d_head, e->d_nl, e->d_table, e->rp, e->box, la);
+            e->d_px, y, e->N, e->prune ? e->d_nn_act : e->d_nn, e->d_head, e->prune ? e->d_nl_act : e->d_nl, e->d_table, e->rp, e->box, la);
     }
     LAUNCHED(e);
 }
+template <int MODE>
+static void launch_spmv(pse_engine* e, float4* y, const LanczosArgs& la) {
+    switch (e->spmv_tpp) {
+        case 4: launch_spmv_tpp<4, MODE>(e, y, la); break;
+        case 16: launch_spmv_tpp<16, MODE>(e, y, la); break;
+        case 32: launch_spmv_tpp<32, MODE>(e, y, la); break;
+        default: launch_spmv_tpp<8, MODE>(e, y, la); break;
+    }
+}
 
 static int run_spmv_plain(pse_engine* e, float4* y) {
+    CKRC(ensure_pruned(e));
     ProfScope ps(e, PH_SPMV);
     LanczosArgs la = {};
     launch_spmv<SPMV_PLAIN>(e, y, la);
@@ -670,6 +715,7 @@ static int solve_coeffs(pse_engine* e, int m, const float* alpha, const float* b
 
 // U[perm] (+)= sqrt(2T/dt) * M_real^{1/2} psi, psi drawn per particle id (PSEv1/Brownian.cu:357-765)
 static int run_lanczos(pse_engine* e, float4* U, int accumulate, uint32_t key, const float* d_u_particles, int* m_out) {
+    CKRC(ensure_pruned(e));
     const uint32_t N = e->N;
     cudaStream_t st = e->stream;
     {

@@ -72,6 +72,45 @@ __device__ __forceinline__ void ld_px(const PX* ptr, float4& p, float4& x) {
                  : "l"(ptr));
 }
 
+// Per-step pruning of the buffered neighbour list: keeps, in row order, the neighbours that are inside the
+// real-space cutoff at the CURRENT positions (dr^2 <= r^2 < rcut^2, the filter of PSEv1/Mobility.cu:652).  The
+// m+1 SpMVs of a step then gather only pairs that contribute (the SpMV is bound by the gathered records, so
+// its cost is proportional to the listed pairs).  8 lanes per row, ballot-ordered compaction, same row offsets.
+__global__ void __launch_bounds__(256)
+prune_kernel(const float4* __restrict__ spos, uint32_t N, const uint32_t* __restrict__ nn, const uint32_t* __restrict__ head,
+             const uint32_t* __restrict__ nl, RealParams rp, PseBox box, uint32_t* __restrict__ nn_act, uint32_t* __restrict__ nl_act) {
+    const int sub = threadIdx.x & 7;
+    const int grp = (threadIdx.x & 31) >> 3;  // group inside the warp
+    for (uint32_t row0 = blockIdx.x * 32; row0 < N; row0 += gridDim.x * 32) {
+        const uint32_t row = row0 + (threadIdx.x >> 3);
+        const bool live = row < N;
+        uint32_t n = 0, h = 0;
+        float4 pi = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live) { n = __ldg(nn + row); h = __ldg(head + row); pi = __ldg(spos + row); }
+        // all 32 lanes iterate together (ballot needs convergence): trip count = longest row in the warp
+        uint32_t nmax = n;
+#pragma unroll
+        for (int o = 8; o < 32; o <<= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
+        uint32_t kept = 0;
+        for (uint32_t k0 = 0; k0 < nmax; k0 += 8) {
+            const uint32_t k = k0 + sub;
+            bool in = false;
+            uint32_t j = 0;
+            if (k < n) {
+                j = __ldg(nl + h + k);
+                const float4 pj = __ldg(spos + j);
+                const float3 r = box.min_image(make_float3(PSE_SUB(pi.x, pj.x), PSE_SUB(pi.y, pj.y), PSE_SUB(pi.z, pj.z)));
+                const float d = r.x * r.x + r.y * r.y + r.z * r.z;
+                in = d < rp.rcut_sq && d >= rp.dr_sq;
+            }
+            const uint32_t ball = (__ballot_sync(0xffffffffu, in) >> (grp * 8)) & 0xffu;
+            if (in) nl_act[h + kept + __popc(ball & ((1u << sub) - 1u))] = j;
+            kept += __popc(ball);
+        }
+        if (live && sub == 0) nn_act[row] = kept;
+    }
+}
+
 enum { SPMV_PLAIN = 0, SPMV_LANCZOS = 1 };
 
 struct LanczosArgs {
