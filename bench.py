@@ -137,7 +137,8 @@ def main():
     L = util.box_length(N, phi)
     T, dt = 1.0, 1e-3
     cfg = E.make_config(N, L, xi=args.xi, error=args.error, T=T, dt=dt, seed=1 + rank, r_buff=args.r_buff)
-    eng = E.Engine(cfg)
+    stream = torch.cuda.Stream()          # the engine's launching stream; all events below are recorded on it
+    eng = E.Engine(cfg, stream=stream)
     p = eng.params
     pos_np = util.lattice_positions(N, L, seed=rank)
     F_np = util.random_forces(N, seed=100 + rank)
@@ -222,10 +223,10 @@ def main():
     s0 = eng.stats()
     sampler = ClockSampler(local); sampler.start()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
+    a.record(stream)
     for _ in range(K):
         m = eng.step(pos, img, F, step_no); step_no += 1
-    b.record()
+    b.record(stream)
     barrier()
     clocks = sampler.summary()
     ms = max_over_ranks(a.elapsed_time(b))
@@ -277,10 +278,10 @@ def main():
     # deterministic M.F time (second half of the BASELINE metric)
     barrier()
     eng.mobility(pos, F)
-    a.record()
+    a.record(stream)
     for _ in range(5):
         eng.mobility(pos, F)
-    b.record(); torch.cuda.synchronize()
+    b.record(stream); torch.cuda.synchronize()
     line["mf_us"] = a.elapsed_time(b) / 5 * 1e3
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:

@@ -173,6 +173,7 @@ typedef struct {
     uint64_t nnz_active;    /* neighbours inside r_cut at the current positions (rows the SpMV walks) */
     uint64_t kernel_launches; /* engine kernels launched since create (cuFFT launches not counted) */
     uint64_t fft_execs;
+    uint64_t graph_launches; /* replays of the captured step graph */
     uint64_t nlist_builds;
     int lanczos_m;          /* iterations used by the last Brownian evaluation */
     float lanczos_stepnorm; /* its final relative step norm */

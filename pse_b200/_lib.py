@@ -51,7 +51,7 @@ class pse_params(ctypes.Structure):
 
 class pse_stats(ctypes.Structure):
     _fields_ = [
-        ("nnz", ctypes.c_uint64), ("nnz_active", ctypes.c_uint64), ("kernel_launches", ctypes.c_uint64), ("fft_execs", ctypes.c_uint64),
+        ("nnz", ctypes.c_uint64), ("nnz_active", ctypes.c_uint64), ("kernel_launches", ctypes.c_uint64), ("fft_execs", ctypes.c_uint64), ("graph_launches", ctypes.c_uint64),
         ("nlist_builds", ctypes.c_uint64), ("lanczos_m", ctypes.c_int), ("lanczos_stepnorm", ctypes.c_float),
     ]
 

@@ -42,7 +42,7 @@ struct pse_engine {
     WaveParams wp;
     RealParams rp;
     CellGrid cg;
-    cudaStream_t stream;
+    cudaStream_t stream, own_stream;
     uint32_t N;
     size_t G, Gh;
     char err[512];
@@ -97,6 +97,13 @@ struct pse_engine {
     float4 *d_hpos, *d_hF;  // device staging for pse_step_host
     int3* d_himage;
     int num_sms;
+    // per-step device scalars + captured step graph
+    StepDev* d_stepdev;
+    StepDev* h_stepdev;  // pinned
+    bool use_graph;
+    cudaGraphExec_t graph_exec;
+    struct { const void *pos, *F, *U; int m_batch; float xy; uint32_t nl_gen; bool valid; } graph_key;
+    uint32_t nl_gen;  // bumped whenever list buffers are reallocated
     bool spmv_smem_table;
     int spmv_tpp;  // lanes per row in the SpMV
     // profiling
@@ -107,7 +114,7 @@ struct pse_engine {
     double prof_ms[PH_COUNT];
     uint64_t prof_calls[PH_COUNT];
     // stats
-    uint64_t launches, fft_execs, nlist_builds;
+    uint64_t launches, fft_execs, nlist_builds, graph_launches, graph_nodes;
 };
 
 // bytes of the real-space table when staged in shared memory by the SpMV (float2 per knot)
@@ -273,6 +280,10 @@ static int alloc_all(pse_engine* e) {
     CK(cudaMemset(e->d_counter, 0, sizeof(unsigned int)));
     CK(cudaMallocHost(&e->h_ab, sizeof(float) * (2 * LANCZOS_M_MAX + 4)));
     CK(cudaMalloc(&e->d_vel_work, sizeof(float4) * N));
+    CK(cudaMalloc(&e->d_stepdev, sizeof(StepDev)));
+    CK(cudaMallocHost(&e->h_stepdev, sizeof(StepDev)));
+    e->use_graph = true;
+    { const char* env = getenv("PSE_GRAPH"); if (env) e->use_graph = env[0] != '0'; }
     e->d_hpos = e->d_hF = nullptr; e->d_himage = nullptr;
     {
         const WaveParams& wp = e->wp;
@@ -327,16 +338,25 @@ extern "C" int pse_create(const pse_config* cfg, void* stream, pse_engine** out)
     strcpy(e->err, "no error");
     e->cfg = c; e->prm = prm; e->N = c.N;
     e->stream = (cudaStream_t)stream;
+    e->own_stream = nullptr;
+    if (!e->stream) {
+        // the legacy default stream cannot be captured into a CUDA graph: use an own (blocking) stream, which keeps
+        // the implicit ordering with work the caller issues on the default stream
+        if (cudaStreamCreate(&e->own_stream) != cudaSuccess) { delete eng; return fail(nullptr, PSE_ECUDA, "pse_create: cudaStreamCreate failed"); }
+        e->stream = e->own_stream;
+    }
     e->rlist = rlist;
     refresh_box(e, c.box);
     e->G = (size_t)prm.Nx * prm.Ny * prm.Nz;
     WaveParams& wp = e->wp;
     wp.Nx = prm.Nx; wp.Ny = prm.Ny; wp.Nz = prm.Nz; wp.Nzh = prm.Nz / 2 + 1; wp.P = prm.P;
+    wp.Nzp = wp.Nzh;
+    { const char* env = getenv("PSE_SPEC_PAD"); int pad = env ? atoi(env) : 16; if (pad > 1) wp.Nzp = ((wp.Nzh + pad - 1) / pad) * pad; }
     wp.hx = prm.hx; wp.hy = prm.hy; wp.hz = prm.hz;
     wp.prefac = prm.prefac; wp.expfac = prm.expfac; wp.quadW = prm.quadW;
     wp.xi = c.xi; wp.eta = prm.eta;
     wp.two_pi_k = (c.flags & PSE_FLAG_REF_PI) ? (float)(2.0 * 3.1416926536) : (float)(2.0 * 3.14159265358979323846);
-    e->Gh = (size_t)prm.Nx * prm.Ny * wp.Nzh;
+    e->Gh = (size_t)prm.Nx * prm.Ny * wp.Nzp;
     RealParams& rp = e->rp;
     rp.self = prm.self; rp.rcut = prm.rcut; rp.rcut_sq = prm.rcut * prm.rcut; rp.dr = prm.dr; rp.dr_sq = prm.dr * prm.dr;
     rp.ewald_n = prm.ewald_n;
@@ -369,8 +389,9 @@ extern "C" int pse_create(const pse_config* cfg, void* stream, pse_engine** out)
         return PSE_ECUDA;
     }
     int n[3] = {prm.Nx, prm.Ny, prm.Nz};
-    if (cufftPlanMany(&e->plan_f, 3, n, nullptr, 1, 0, nullptr, 1, 0, CUFFT_R2C, 3) != CUFFT_SUCCESS ||
-        cufftPlanMany(&e->plan_b, 3, n, nullptr, 1, 0, nullptr, 1, 0, CUFFT_C2R, 3) != CUFFT_SUCCESS) {
+    int rembed[3] = {prm.Nx, prm.Ny, prm.Nz}, cembed[3] = {prm.Nx, prm.Ny, wp.Nzp};  // spectrum rows padded to Nzp
+    if (cufftPlanMany(&e->plan_f, 3, n, rembed, 1, (int)e->G, cembed, 1, (int)e->Gh, CUFFT_R2C, 3) != CUFFT_SUCCESS ||
+        cufftPlanMany(&e->plan_b, 3, n, cembed, 1, (int)e->Gh, rembed, 1, (int)e->G, CUFFT_C2R, 3) != CUFFT_SUCCESS) {
         fail(nullptr, PSE_ECUDA, "pse_create: cufftPlanMany failed for %dx%dx%d", n[0], n[1], n[2]);
         pse_destroy(e);
         return PSE_ECUDA;
@@ -393,6 +414,10 @@ extern "C" void pse_destroy(pse_engine* e) {
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (e->h_flag) cudaFreeHost(e->h_flag);
+    if (e->h_stepdev) cudaFreeHost(e->h_stepdev);
+    if (e->d_stepdev) cudaFree(e->d_stepdev);
+    if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
     if (e->h_nlinfo) cudaFreeHost(e->h_nlinfo);
     if (e->d_nlinfo) cudaFree(e->d_nlinfo);
     if (e->h_ab) cudaFreeHost(e->h_ab);
@@ -435,7 +460,7 @@ extern "C" int pse_get_stats(pse_engine* e, pse_stats* out) {
         CK(cudaMemcpyAsync(e->h_nlinfo, e->d_nlinfo, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
         CK(cudaStreamSynchronize(e->stream));
         out->nnz_active = e->h_nlinfo[0];
-    } out->kernel_launches = e->launches; out->fft_execs = e->fft_execs;
+    } out->kernel_launches = e->launches; out->fft_execs = e->fft_execs; out->graph_launches = e->graph_launches;
     out->nlist_builds = e->nlist_builds; out->lanczos_m = e->m_lanczos; out->lanczos_stepnorm = e->last_stepnorm;
     return PSE_OK;
 }
@@ -495,12 +520,14 @@ extern "C" int pse_build_neighbors(pse_engine* e, const float4* d_pos) {
         e->d_nl = nullptr;
         e->nl_cap = (size_t)(e->nnz * 1.2) + 1024;
         CK(cudaMalloc(&e->d_nl, sizeof(uint32_t) * e->nl_cap));
+        e->nl_gen++;
     }
     if (e->prune && e->nl_cap > e->nl_act_cap) {
         if (e->d_nl_act) cudaFree(e->d_nl_act);
         e->d_nl_act = nullptr;
         e->nl_act_cap = e->nl_cap;
         CK(cudaMalloc(&e->d_nl_act, sizeof(uint32_t) * e->nl_act_cap));
+        e->nl_gen++;
     }
     compact_rows_kernel<<<nblk((size_t)N * 8, 256), 256, 0, st>>>(e->d_ell, e->nl_stride, e->d_nn, e->d_head, N, e->d_nl); LAUNCHED(e);
     CK(cudaMemcpyAsync(e->d_pos_build, d_pos, sizeof(float4) * N, cudaMemcpyDeviceToDevice, st));
@@ -641,8 +668,7 @@ static int run_wbin(pse_engine* e, const float4* sF) {
 }
 
 // wave-space pipeline on slot-ordered (spos, sF): result scattered into U (particle-id order)
-static int run_wave(pse_engine* e, const float4* sF, float4* U, int accumulate, bool det, bool noise, uint32_t key,
-                    const float* d_u_grid) {
+static int run_wave(pse_engine* e, const float4* sF, float4* U, int accumulate, bool det, bool noise, const float* d_u_grid) {
     cudaStream_t st = e->stream;
     const int P = e->wp.P;
     if (e->tiled) CKRC(run_wbin(e, det ? sF : nullptr));
@@ -659,11 +685,9 @@ static int run_wave(pse_engine* e, const float4* sF, float4* U, int accumulate, 
         ProfScope ps(e, PH_FFT_FWD);
         CKFFT(cufftExecR2C(e->plan_f, e->d_grid, (cufftComplex*)e->d_spec)); e->fft_execs++;
     }
-    const float T = e->cfg.T, dt = e->cfg.dt;
-    const float noise_fac = sqrtf((float)(2.0 * T / dt / e->wp.quadW));  // PSEv1/Brownian.cu:198
     {
         ProfScope ps(e, PH_SCALE);
-        scale_kernel<<<dim3(e->wp.Ny, e->wp.Nx), 128, 0, st>>>(e->d_spec, e->wp, e->box, det ? 1 : 0, noise ? 1 : 0, noise_fac, d_u_grid, key); LAUNCHED(e);
+        scale_kernel<<<dim3(e->wp.Ny, e->wp.Nx), 128, 0, st>>>(e->d_spec, e->wp, e->box, det ? 1 : 0, noise ? 1 : 0, e->d_stepdev, d_u_grid); LAUNCHED(e);
     }
     {
         ProfScope ps(e, PH_FFT_INV);
@@ -713,24 +737,36 @@ static int solve_coeffs(pse_engine* e, int m, const float* alpha, const float* b
     return PSE_OK;
 }
 
-// U[perm] (+)= sqrt(2T/dt) * M_real^{1/2} psi, psi drawn per particle id (PSEv1/Brownian.cu:357-765)
-static int run_lanczos(pse_engine* e, float4* U, int accumulate, uint32_t key, const float* d_u_particles, int* m_out) {
+// U[perm] (+)= sqrt(2T/dt) * M_real^{1/2} psi, psi drawn per particle id (PSEv1/Brownian.cu:357-765).
+// lanczos_batch: everything up to the first host decision — psi, |psi|, the first m_in - 1 iterations and the
+// read-back of alpha/beta.  No host synchronisation inside, so it can be part of the captured step graph.
+static int lanczos_batch_size(const pse_engine* e) {
+    int m = e->m_lanczos - 1;  // PSEv1/Brownian.cu:465-466
+    return m < 1 ? 1 : m;
+}
+static int lanczos_batch(pse_engine* e, const float* d_u_particles, int m) {
     CKRC(ensure_pruned(e));
     const uint32_t N = e->N;
     cudaStream_t st = e->stream;
     {
     ProfScope ps(e, PH_LANCZOS_VEC);
-    psi_kernel<<<nblk(N, 256), 256, 0, st>>>((float4*)e->d_px + 1, 2, e->d_perm, N, d_u_particles, key); LAUNCHED(e);
+    psi_kernel<<<nblk(N, 256), 256, 0, st>>>((float4*)e->d_px + 1, 2, e->d_perm, N, d_u_particles, e->d_stepdev); LAUNCHED(e);
     dot_px_kernel<<<persistent_grid(e, nblk(N, 256), 8), 256, 0, st>>>(e->d_px, N, e->d_beta, e->d_partials, e->d_counter, true); LAUNCHED(e);
     }
-
     float* alpha = e->h_ab;
     float* beta = e->h_ab + LANCZOS_M_MAX + 1;
-    int m = e->m_lanczos - 1;  // PSEv1/Brownian.cu:465-466
-    if (m < 1) m = 1;
     for (int j = 0; j < m; ++j) lanczos_iteration(e, j);
     CK(cudaMemcpyAsync(alpha, e->d_alpha, sizeof(float) * m, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(beta, e->d_beta, sizeof(float) * (m + 1), cudaMemcpyDeviceToHost, st));
+    return PSE_OK;
+}
+
+// host side: tridiagonal solves, adaptive iterations until the step norm drops below `error`, final combination
+static int lanczos_finish(pse_engine* e, float4* U, int accumulate, int m, int* m_out) {
+    const uint32_t N = e->N;
+    cudaStream_t st = e->stream;
+    float* alpha = e->h_ab;
+    float* beta = e->h_ab + LANCZOS_M_MAX + 1;
     CK(cudaStreamSynchronize(st));
     for (int j = 0; j < m; ++j)
         if (beta[j + 1] < 1e-8f) { m = j > 0 ? j : 1; break; }  // breakdown, PSEv1/Brownian.cu:507-510
@@ -788,32 +824,82 @@ extern "C" int pse_mwave(pse_engine* e, const float4* d_pos, const float4* d_F, 
     if (!e || !d_pos || !d_F || !d_U) return PSE_EINVAL;
     CKRC(ensure_neighbors(e, d_pos));
     gather4_kernel<<<nblk(e->N, 256), 256, 0, e->stream>>>(d_F, e->d_perm, e->N, e->d_sx); LAUNCHED(e);
-    CKRC(run_wave(e, e->d_sx, d_U, 0, true, false, 0u, nullptr));
+    CKRC(run_wave(e, e->d_sx, d_U, 0, true, false, nullptr));
     CK(cudaGetLastError());
+    return PSE_OK;
+}
+
+// per-step scalars -> device (ordered on the stream before the kernels that read them)
+static int upload_stepdev(pse_engine* e, uint32_t timestep) {
+    e->h_stepdev->key = timestep + e->prm.seed_hashed;  // PSEv1/Brownian.cu:117,176
+    e->h_stepdev->noise_fac = sqrtf((float)(2.0 * e->cfg.T / e->cfg.dt / e->wp.quadW));  // PSEv1/Brownian.cu:198
+    CK(cudaMemcpyAsync(e->d_stepdev, e->h_stepdev, sizeof(StepDev), cudaMemcpyHostToDevice, e->stream));
+    return PSE_OK;
+}
+
+// the fixed-topology part of a full velocity evaluation (everything between the neighbour-list decision and the
+// first Lanczos host solve): slot gathers, wave-space pipeline, pruning, deterministic SpMV, Lanczos batch
+static int velocity_fixed_part(pse_engine* e, const float4* d_F, float4* d_U, bool det, bool wnoise, bool rnoise,
+                               const float* d_u_particles, const float* d_u_grid, int m_batch) {
+    const uint32_t N = e->N;
+    cudaStream_t st = e->stream;
+    if (det) { gather_vec_kernel<<<nblk(N, 256), 256, 0, st>>>(d_F, e->d_perm, N, e->d_sx, (float4*)e->d_px); LAUNCHED(e); }
+    int acc = 0;
+    if (det || wnoise) { CKRC(run_wave(e, e->d_sx, d_U, 0, det, wnoise, d_u_grid)); acc = 1; }
+    if (det) {
+        CKRC(run_spmv_plain(e, e->d_sy));
+        scatter_add_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_sy, e->d_perm, N, d_U, acc); LAUNCHED(e);
+        acc = 1;
+    }
+    if (rnoise) CKRC(lanczos_batch(e, d_u_particles, m_batch));
+    if (!acc && !rnoise) CK(cudaMemsetAsync(d_U, 0, sizeof(float4) * N, st));
     return PSE_OK;
 }
 
 extern "C" int pse_velocity(pse_engine* e, const float4* d_pos, const float4* d_F, float4* d_U, uint32_t timestep,
                             const float* d_u_particles, const float* d_u_grid, uint32_t parts, int* m_out) {
     if (!e || !d_pos || !d_F || !d_U) return PSE_EINVAL;
-    const uint32_t N = e->N;
     cudaStream_t st = e->stream;
     const bool det = parts & 1u;
     const bool thermal = e->cfg.T > 0.f;  // PSEv1/Brownian.cu:855,885
     const bool wnoise = (parts & 2u) && thermal, rnoise = (parts & 4u) && thermal;
-    const uint32_t key = timestep + e->prm.seed_hashed;  // PSEv1/Brownian.cu:117,176
-    CKRC(ensure_neighbors(e, d_pos));
-    if (det) { gather_vec_kernel<<<nblk(N, 256), 256, 0, st>>>(d_F, e->d_perm, N, e->d_sx, (float4*)e->d_px); LAUNCHED(e); }
-    int acc = 0;
-    if (det || wnoise) { CKRC(run_wave(e, e->d_sx, d_U, 0, det, wnoise, key, d_u_grid)); acc = 1; }
-    if (det) {
-        CKRC(run_spmv_plain(e, e->d_sy));
-        scatter_add_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_sy, e->d_perm, N, d_U, acc); LAUNCHED(e);
-        acc = 1;
-    }
+    CKRC(ensure_neighbors(e, d_pos));  // host decision (list still valid?) happens before the fixed part
+    CKRC(upload_stepdev(e, timestep));
+    const int m_batch = lanczos_batch_size(e);
     if (m_out) *m_out = e->m_lanczos;
-    if (rnoise) { CKRC(run_lanczos(e, d_U, acc, key, d_u_particles, m_out)); acc = 1; }
-    if (!acc) CK(cudaMemsetAsync(d_U, 0, sizeof(float4) * N, st));
+
+    // Step loop as a captured CUDA graph (the reference issues ~60 launches + 15 blocking copies per step,
+    // PSEv1/Stokes.cu:298-355, Brownian.cu:440-739).  The graph is keyed on everything frozen at capture time.
+    const bool graphable = e->use_graph && !e->prof_on && det && wnoise && rnoise && !d_u_particles && !d_u_grid;
+    if (graphable) {
+        auto& k = e->graph_key;
+        const bool hit = k.valid && k.pos == d_pos && k.F == d_F && k.U == d_U && k.m_batch == m_batch && k.xy == e->box.xy &&
+                         k.nl_gen == e->nl_gen;
+        if (!hit) {
+            if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+            k.valid = false;
+            e->pruned_valid = false;
+            cudaGraph_t graph = nullptr;
+            const uint64_t l0 = e->launches;
+            CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            int rc = velocity_fixed_part(e, d_F, d_U, det, wnoise, rnoise, nullptr, nullptr, m_batch);
+            cudaError_t ce = cudaStreamEndCapture(st, &graph);
+            if (rc != PSE_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (ce != cudaSuccess) return fail(e, PSE_ECUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+            ce = cudaGraphInstantiate(&e->graph_exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) return fail(e, PSE_ECUDA, "graph instantiate failed: %s", cudaGetErrorString(ce));
+            e->graph_nodes = e->launches - l0;
+            k.pos = d_pos; k.F = d_F; k.U = d_U; k.m_batch = m_batch; k.xy = e->box.xy; k.nl_gen = e->nl_gen; k.valid = true;
+        }
+        else e->launches += e->graph_nodes;  // kernels replayed by the graph
+        CK(cudaGraphLaunch(e->graph_exec, st));
+        e->graph_launches++;
+        e->pruned_valid = true;
+    } else {
+        CKRC(velocity_fixed_part(e, d_F, d_U, det, wnoise, rnoise, d_u_particles, d_u_grid, m_batch));
+    }
+    if (rnoise) CKRC(lanczos_finish(e, d_U, (det || wnoise) ? 1 : 0, m_batch, m_out));
     CK(cudaGetLastError());
     return PSE_OK;
 }

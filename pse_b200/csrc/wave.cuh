@@ -14,6 +14,7 @@
 
 struct WaveParams {
     int Nx, Ny, Nz, Nzh;  // Nzh = Nz/2 + 1
+    int Nzp;              // padded row length of the half spectrum in memory (>= Nzh)
     int P;
     float hx, hy, hz;
     float prefac, expfac, quadW;
@@ -125,6 +126,13 @@ interp_warp_kernel(const float4* __restrict__ pos, uint32_t N, PseBox box, WaveP
 }
 
 // ---- k-space scaling + random modes, half spectrum ---------------------------------------------
+// Per-step scalars kept in device memory so that one captured CUDA graph of the step can be replayed with a new
+// time step / temperature (kernel parameters are frozen at capture time).
+struct StepDev {
+    uint32_t key;     // timestep + hashed seed (RNG stream key)
+    float noise_fac;  // sqrt(2 T / dt / quadW)
+};
+
 struct KVec { float kx, ky, kz, w; };  // w = B(k)/G without the sinc^2 factor, as gridk.w
 
 // wave vector and scaling of full-grid node (i,j,k): PSEv1/Helper.cu:300-329
@@ -193,11 +201,13 @@ __device__ __forceinline__ float sinc_of(const KVec& kv) {
 // Launch: grid (Ny, Nx), one block per (ii, jj) row of the half spectrum, threads stride over kz (coalesced,
 // no per-thread integer division).
 __global__ void __launch_bounds__(128)
-scale_kernel(float2* __restrict__ spec, WaveParams wp, PseBox box, int do_det, int do_noise, float noise_fac,
-             const float* __restrict__ u_grid, uint32_t key) {
-    const size_t nh = (size_t)wp.Nx * wp.Ny * wp.Nzh;
+scale_kernel(float2* __restrict__ spec, WaveParams wp, PseBox box, int do_det, int do_noise, const StepDev* __restrict__ sd,
+             const float* __restrict__ u_grid) {
+    const uint32_t key = sd->key;
+    const float noise_fac = sd->noise_fac;
+    const size_t nh = (size_t)wp.Nx * wp.Ny * wp.Nzp;
     const int jj = blockIdx.x, ii = blockIdx.y;
-    const size_t rowbase = ((size_t)ii * wp.Ny + jj) * wp.Nzh;
+    const size_t rowbase = ((size_t)ii * wp.Ny + jj) * wp.Nzp;
     for (int kk = threadIdx.x; kk < wp.Nzh; kk += blockDim.x) {
     const size_t tid = rowbase + kk;
     float2 fX = make_float2(0.f, 0.f), fY = fX, fZ = fX;
@@ -250,7 +260,8 @@ scale_kernel(float2* __restrict__ spec, WaveParams wp, PseBox box, int do_det, i
 
 // particle noise psi (slot order) : 3 uniforms on (-sqrt3, sqrt3), PSEv1/Brownian.cu:99-130
 __global__ void psi_kernel(float4* __restrict__ psi /* element s at psi[s * stride] */, int stride, const uint32_t* __restrict__ perm,
-                           uint32_t N, const float* __restrict__ u_particles, uint32_t key) {
+                           uint32_t N, const float* __restrict__ u_particles, const StepDev* __restrict__ sd) {
+    const uint32_t key = sd->key;
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= N) return;
     const uint32_t id = perm[s];

@@ -316,6 +316,31 @@ def test_tiled_wave_path_is_bitwise_reproducible_and_matches_scatter_path(cuda):
     close(a, s2.eng.mwave(s2.pos, s2.F), 1e-5)  # tiled path uses ex2-based exponentials
 
 
+@pytest.mark.parametrize("xy", [0.0, 0.25, 0.5, -0.5])
+def test_config4_sheared_suspension_parity(cuda, xy):
+    """BASELINE.json config 4: N = 100k, phi = 0.3 steady-shear suspension, deformed box with tilt swept over the
+    wrapped-strain range of the variant ([-0.5, 0.5]): integer outputs exact, M.F vs the reference."""
+    s = System(100000, util.box_length(100000, 0.3), xy=xy, seed=21, lattice=True)
+    assert s.p.Nx == 108
+    gi = s.eng.grid_index(s.pos).cpu().numpy()
+    assert np.array_equal(gi, s.orc.grid_index(s.pos_np))
+    nn, head, nl = s.nl_np()
+    onn, ohead, onl = s.orc.neighbors(s.pos_np, s.p.rcut + 0.4, brute=False)
+    assert np.array_equal(nn, onn) and np.array_equal(nl, onl)
+    if s.ref is None:
+        pytest.skip("reference library not built")
+    close(s.eng.mobility(s.pos, s.F), s.ref.mobility(s.pos, s.F))
+    # one sheared step: affine advection v.x += rate * y (PSEv1/Stokes.cu:168)
+    import torch
+    pe, pr = s.pos.clone(), s.pos.clone()
+    ie = torch.zeros((s.N, 3), dtype=torch.int32, device="cuda"); ir = ie.clone()
+    vel = torch.zeros_like(s.F); vel[:, 3] = 1.0
+    s.eng.set_temperature(0.0)
+    s.ref.step(pr, vel, torch.zeros((s.N, 3), device="cuda"), ir, s.F, 0.0, s.dt, 0, shear_rate=1.0)
+    s.eng.step(pe, ie, s.F, 0, shear_rate=1.0)
+    assert torch.equal(ie, ir) and float((pe - pr).abs().max()) < 1e-5
+
+
 # ---------------------------------------------------------------- properties at the headline size
 @pytest.fixture(scope="module")
 def big(cuda):

@@ -100,10 +100,10 @@ def test_replica_logic_world_size_2_gloo(tmp_path):
         dist.all_gather_object(gathered, seeds)
         assert len(set(gathered[0]) | set(gathered[1])) == 6 or gathered[0] != gathered[1]
         dist.barrier(); dist.destroy_process_group()
-        print("ok", rank)
+        open(os.path.join({str(tmp_path)!r}, f"ok_{{rank}}"), "w").write("ok")
     """))
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                           "--master-port", "29533", str(script)], capture_output=True, text=True, env=env, timeout=240)
     assert out.returncode == 0, out.stderr[-2000:]
-    assert "ok 0" in out.stdout and "ok 1" in out.stdout
+    assert (tmp_path / "ok_0").exists() and (tmp_path / "ok_1").exists()
