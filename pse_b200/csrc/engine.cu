@@ -23,6 +23,7 @@
 #include "wave_tiled.cuh"
 
 int pse_tridiag_sqrt_e1(int m, const double* diag, const double* off, double* c, double* lambda_min_out);
+int pse_fit_rpy_poly(double xi, double rcut, float* out, int max_intervals, double* max_err_out);
 
 #define LANCZOS_M_MAX 100  // PSEv1/Brownian.cu:397
 
@@ -105,6 +106,10 @@ struct pse_engine {
     struct { const void *pos, *F, *U; int m_batch; float xy; uint32_t nl_gen; bool valid; } graph_key;
     uint32_t nl_gen;  // bumped whenever list buffers are reallocated
     bool spmv_smem_table;
+    int spmv_table_mode;  // TABLE_GLOBAL / TABLE_SHARED / TABLE_POLY
+    float4* d_poly;       // polynomial blocks, 3 float4 per interval
+    int npoly;
+    double poly_max_err;
     int spmv_tpp;  // lanes per row in the SpMV
     // profiling
     bool prof_on;
@@ -369,6 +374,12 @@ extern "C" int pse_create(const pse_config* cfg, void* stream, pse_engine** out)
         e->spmv_smem_table = spmv_table_smem(e) <= 64 * 1024;
         const char* env = getenv("PSE_SPMV_SMEM_TABLE");
         if (env) e->spmv_smem_table = env[0] != '0' && spmv_table_smem(e) <= 200 * 1024;
+        e->spmv_table_mode = e->spmv_smem_table ? TABLE_SHARED : TABLE_GLOBAL;
+        const char* tm = getenv("PSE_SPMV_TABLE");  // "poly" | "shared" | "global"
+        // measured on B200 (profiles/r1_summary.md): shared knots 272 us, polynomial blocks 283 us, global table 295 us per
+        // SpMV at N = 1M -> the lookup is not the limiter (the gathered 32-byte records are); knots stay the default
+        if (tm && tm[0] == 'p') e->spmv_table_mode = TABLE_POLY;
+        else if (tm && tm[0] == 'g') e->spmv_table_mode = TABLE_GLOBAL;
         e->spmv_tpp = 8;
         const char* tpp = getenv("PSE_SPMV_TPP");
         if (tpp) e->spmv_tpp = atoi(tpp);
@@ -387,6 +398,24 @@ extern "C" int pse_create(const pse_config* cfg, void* stream, pse_engine** out)
         fail(nullptr, PSE_ECUDA, "pse_create: table upload failed");
         pse_destroy(e);
         return PSE_ECUDA;
+    }
+    {
+        std::vector<float> pc(16 * 256);
+        e->npoly = pse_fit_rpy_poly(c.xi, prm.rcut, pc.data(), 256, &e->poly_max_err);
+        if (e->npoly <= 0 || e->poly_max_err > 1e-7) {
+            if (e->spmv_table_mode == TABLE_POLY) e->spmv_table_mode = e->spmv_smem_table ? TABLE_SHARED : TABLE_GLOBAL;
+            e->npoly = 0;
+        } else {
+            std::vector<float> blk(4 * PSE_POLY_STRIDE * (size_t)e->npoly, 0.f);
+            for (int k = 0; k < e->npoly; ++k)
+                for (int q = 0; q < 16; ++q) blk[4 * PSE_POLY_STRIDE * k + q] = pc[16 * k + q];
+            if (cudaMalloc(&e->d_poly, blk.size() * sizeof(float)) != cudaSuccess ||
+                cudaMemcpy(e->d_poly, blk.data(), blk.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+                fail(nullptr, PSE_ECUDA, "pse_create: polynomial table upload failed");
+                pse_destroy(e);
+                return PSE_ECUDA;
+            }
+        }
     }
     int n[3] = {prm.Nx, prm.Ny, prm.Nz};
     int rembed[3] = {prm.Nx, prm.Ny, prm.Nz}, cembed[3] = {prm.Nx, prm.Ny, wp.Nzp};  // spectrum rows padded to Nzp
@@ -410,7 +439,7 @@ extern "C" void pse_destroy(pse_engine* e) {
                     e->d_spos, e->d_sx, e->d_sy, e->d_px, e->d_nn, e->d_head, e->d_nl, e->d_pos_build, e->d_flag, e->d_grid,
                     e->d_spec, e->d_V, e->d_u, e->d_y, e->d_alpha, e->d_beta, e->d_coef, e->d_partials, e->d_counter,
                     e->d_vel_work, e->d_hpos, e->d_hF, e->d_himage, e->d_org, e->d_worg, e->d_wcell_of, e->d_wcount,
-                    e->d_wstart, e->d_wperm, e->d_wpos, e->d_wF, e->d_wtmp, e->d_ell, e->d_nn_act, e->d_nl_act};
+                    e->d_wstart, e->d_wperm, e->d_wpos, e->d_wF, e->d_wtmp, e->d_ell, e->d_nn_act, e->d_nl_act, e->d_poly};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (e->h_flag) cudaFreeHost(e->h_flag);
@@ -621,15 +650,21 @@ extern "C" int pse_grid_index(pse_engine* e, const float4* d_pos, int3* d_out) {
 template <int TPP, int MODE>
 static void launch_spmv_tpp(pse_engine* e, float4* y, const LanczosArgs& la) {
     const unsigned int work = nblk((size_t)e->N * TPP, 256);
-    if (e->spmv_smem_table) {
+    const uint32_t* nn = e->prune ? e->d_nn_act : e->d_nn;
+    const uint32_t* nl = e->prune ? e->d_nl_act : e->d_nl;
+    if (e->spmv_table_mode == TABLE_POLY) {
+        const size_t sm = (size_t)e->npoly * PSE_POLY_STRIDE * sizeof(float4);
+        spmv_kernel<TPP, MODE, TABLE_POLY><<<persistent_grid(e, work, 8), 256, sm, e->stream>>>(
+            e->d_px, y, e->N, nn, e->d_head, nl, e->d_poly, e->npoly, e->rp, e->box, la);
+    } else if (e->spmv_table_mode == TABLE_SHARED) {
         const size_t sm = spmv_table_smem(e);
         const int bps = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (sm + 1024)));
-        cudaFuncSetAttribute(spmv_kernel<TPP, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        spmv_kernel<TPP, MODE, true><<<persistent_grid(e, work, bps), 256, sm, e->stream>>>(
-            e->d_px, y, e->N, e->prune ? e->d_nn_act : e->d_nn, e->d_head, e->prune ? e->d_nl_act : e->d_nl, e->d_table, e->rp, e->box, la);
+        cudaFuncSetAttribute(spmv_kernel<TPP, MODE, TABLE_SHARED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        spmv_kernel<TPP, MODE, TABLE_SHARED><<<persistent_grid(e, work, bps), 256, sm, e->stream>>>(
+            e->d_px, y, e->N, nn, e->d_head, nl, e->d_table, 0, e->rp, e->box, la);
     } else {
-        spmv_kernel<TPP, MODE, false><<<persistent_grid(e, work, 8), 256, 0, e->stream>>>(
-            e->d_px, y, e->N, e->prune ? e->d_nn_act : e->d_nn, e->d_head, e->prune ? e->d_nl_act : e->d_nl, e->d_table, e->rp, e->box, la);
+        spmv_kernel<TPP, MODE, TABLE_GLOBAL><<<persistent_grid(e, work, 8), 256, 0, e->stream>>>(
+            e->d_px, y, e->N, nn, e->d_head, nl, e->d_table, 0, e->rp, e->box, la);
     }
     LAUNCHED(e);
 }

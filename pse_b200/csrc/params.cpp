@@ -145,3 +145,52 @@ extern "C" int pse_ewald_table(const pse_config* c, float* out) {
     }
     return PSE_OK;
 }
+
+// Piecewise degree-7 polynomial fit of f(r), g(r) on intervals [k W, (k+1) W), W = 0.5 (PSE_POLY_W in real.cuh),
+// exact closed forms sampled at 8 Chebyshev nodes per interval, monomial coefficients in t = 2 (r - kW)/W - 1.
+// out: 16 floats per interval (f0..f7, g0..g7); returns the number of intervals covering [0, rcut].
+// max_err_out (optional): largest |poly - exact| over a fine scan, for the self-check at create time.
+int pse_fit_rpy_poly(double xi, double rcut, float* out, int max_intervals, double* max_err_out) {
+    const double W = 0.5;
+    const int nI = (int)ceil(rcut / W) + 1;
+    if (nI > max_intervals) return -nI;
+    const int n = 8;
+    double maxerr = 0.0;
+    for (int k = 0; k < nI; ++k) {
+        double tn[n], A[n][n + 2];
+        for (int q = 0; q < n; ++q) {
+            tn[q] = cos(3.14159265358979323846 * (2 * q + 1) / (2.0 * n));
+            double r = (k + 0.5 * (tn[q] + 1.0)) * W;
+            if (r < 1e-3) r = 1e-3;
+            double f, g;
+            pse_rpy_real_fg(r, xi, 1.0, &f, &g);
+            double p = 1.0;
+            for (int c = 0; c < n; ++c) { A[q][c] = p; p *= tn[q]; }
+            A[q][n] = f; A[q][n + 1] = g;
+        }
+        for (int c = 0; c < n; ++c) {  // Gauss-Jordan with partial pivoting, two right-hand sides
+            int piv = c;
+            for (int q = c + 1; q < n; ++q) if (fabs(A[q][c]) > fabs(A[piv][c])) piv = q;
+            for (int j = 0; j < n + 2; ++j) std::swap(A[c][j], A[piv][j]);
+            for (int q = 0; q < n; ++q) {
+                if (q == c) continue;
+                double m = A[q][c] / A[c][c];
+                for (int j = c; j < n + 2; ++j) A[q][j] -= m * A[c][j];
+            }
+        }
+        float* o = out + 16 * k;
+        for (int c = 0; c < n; ++c) { o[c] = (float)(A[c][n] / A[c][c]); o[8 + c] = (float)(A[c][n + 1] / A[c][c]); }
+        for (int sI = 0; sI < 64; ++sI) {  // error scan (float Horner, as on the device)
+            double r = (k + (sI + 0.5) / 64.0) * W;
+            if (r < 2e-3 || r > rcut) continue;
+            float t = (float)(2.0 * (r / W - k) - 1.0);
+            float pf = o[7], pg = o[15];
+            for (int c = 6; c >= 0; --c) { pf = pf * t + o[c]; pg = pg * t + o[8 + c]; }
+            double f, g;
+            pse_rpy_real_fg(r, xi, 1.0, &f, &g);
+            maxerr = std::max(maxerr, std::max(fabs(pf - f), fabs(pg - g)));
+        }
+    }
+    if (max_err_out) *max_err_out = maxerr;
+    return nI;
+}

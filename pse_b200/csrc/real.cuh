@@ -32,13 +32,42 @@ struct RealParams {
 // (float2 per knot: entry k and k+1 are read separately).
 struct TableGlobal {
     const float4* t;
-    __device__ __forceinline__ float4 at(int k) const { return __ldg(t + k); }
+    __device__ __forceinline__ void fg(float dist, const RealParams& rp, float& Imrr, float& rr) const {
+        const int r_ind = __float2int_rd((dist - rp.dr) * rp.tab_scale);
+        const float4 e = __ldg(t + r_ind);
+        const float fac = dist * rp.inv_dr - (float)r_ind - 1.0f;
+        Imrr = e.x + (e.z - e.x) * fac;
+        rr = e.y + (e.w - e.y) * fac;
+    }
 };
 struct TableShared {
     const float2* t;
-    __device__ __forceinline__ float4 at(int k) const {
-        const float2 a = t[k], b = t[k + 1];
-        return make_float4(a.x, a.y, b.x, b.y);
+    __device__ __forceinline__ void fg(float dist, const RealParams& rp, float& Imrr, float& rr) const {
+        const int r_ind = __float2int_rd((dist - rp.dr) * rp.tab_scale);
+        const float2 a = t[r_ind], b = t[r_ind + 1];
+        const float fac = dist * rp.inv_dr - (float)r_ind - 1.0f;
+        Imrr = a.x + (b.x - a.x) * fac;
+        rr = a.y + (b.y - a.y) * fac;
+    }
+};
+// Piecewise degree-7 polynomials of the exact f(r), g(r) on intervals of width PSE_POLY_W (the RPY kink at
+// r = 2a is an interval boundary), fitted in double at Chebyshev nodes when the engine is created.  They agree
+// with the closed forms to ~1e-8 and therefore with the reference's linearly interpolated table to its own
+// interpolation error (~1e-7 relative), while the coefficient blocks (a few hundred bytes in all) are read with
+// four conflict-free LDS.128 (block stride 20 words: eight consecutive intervals land in disjoint banks) instead of
+// random 16-byte knots out of a 42-84 KB table.
+#define PSE_POLY_W 0.5f
+#define PSE_POLY_STRIDE 5  // float4 per interval: f0..f3 | f4..f7 | g0..g3 | g4..g7 | pad
+struct TablePoly {
+    const float4* c;
+    __device__ __forceinline__ void fg(float dist, const RealParams&, float& Imrr, float& rr) const {
+        const float s = dist * (1.0f / PSE_POLY_W);
+        const int iv = __float2int_rd(s);
+        const float t = 2.0f * (s - (float)iv) - 1.0f;
+        const float4* b = c + PSE_POLY_STRIDE * iv;
+        const float4 f0 = b[0], f1 = b[1], g0 = b[2], g1 = b[3];
+        Imrr = fmaf(fmaf(fmaf(fmaf(fmaf(fmaf(fmaf(f1.w, t, f1.z), t, f1.y), t, f1.x), t, f0.w), t, f0.z), t, f0.y), t, f0.x);
+        rr = fmaf(fmaf(fmaf(fmaf(fmaf(fmaf(fmaf(g1.w, t, g1.z), t, g1.y), t, g1.x), t, g0.w), t, g0.z), t, g0.y), t, g0.x);
     }
 };
 template <class TAB>
@@ -46,11 +75,8 @@ __device__ __forceinline__ void rpy_pair(const float3 r, const float r2, const f
                                          const RealParams& rp, float3& u) {
     const float inv_dist = rsqrtf(r2);
     const float dist = r2 * inv_dist;
-    const int r_ind = __float2int_rd((dist - rp.dr) * rp.tab_scale);
-    const float4 t = table.at(r_ind);
-    const float fac = dist * rp.inv_dr - (float)r_ind - 1.0f;
-    const float Imrr = t.x + (t.z - t.x) * fac;
-    const float rr = t.y + (t.w - t.y) * fac;
+    float Imrr, rr;
+    table.fg(dist, rp, Imrr, rr);
     const float rdotf = (r.x * Fj.x + r.y * Fj.y + r.z * Fj.z) * (inv_dist * inv_dist);
     const float c = (rr - Imrr) * rdotf;
     u.x += Imrr * Fj.x + c * r.x;
@@ -131,24 +157,32 @@ struct LanczosArgs {
 // SMEM_TABLE: the real-space table is staged once per (persistent) block in shared memory as float2 knots; the
 // per-pair lookup is then two LDS.64 instead of a 16-byte global gather that touches up to 32 cache lines per
 // warp (the L1 wavefront limiter of the first version, profiles/r1_ncu_summary.md).
-template <int TPP, int MODE, bool SMEM_TABLE>
+enum { TABLE_GLOBAL = 0, TABLE_SHARED = 1, TABLE_POLY = 2 };
+template <int TPP, int MODE, int TABLE>
 __global__ void __launch_bounds__(256)
 spmv_kernel(const PX* __restrict__ px, float4* __restrict__ y, uint32_t N,
             const uint32_t* __restrict__ nn, const uint32_t* __restrict__ head, const uint32_t* __restrict__ nl,
-            const float4* __restrict__ gtable, RealParams rp, PseBox box, LanczosArgs la) {
+            const float4* __restrict__ gtable /* knots, or polynomial blocks for TABLE_POLY */, int npoly, RealParams rp,
+            PseBox box, LanczosArgs la) {
     constexpr int ROWS = 256 / TPP;
     const int sub = threadIdx.x % TPP;
     extern __shared__ __align__(16) float2 stab[];
-    if (SMEM_TABLE) {
+    if (TABLE == TABLE_SHARED) {
         for (int k = threadIdx.x; k <= rp.ewald_n; k += blockDim.x) {
             const float4 t = __ldg(gtable + k);
             stab[k] = make_float2(t.x, t.y);
             if (k == rp.ewald_n) stab[k + 1] = make_float2(t.z, t.w);
         }
         __syncthreads();
+    } else if (TABLE == TABLE_POLY) {
+        float4* sp = reinterpret_cast<float4*>(stab);
+        for (int k = threadIdx.x; k < PSE_POLY_STRIDE * npoly; k += blockDim.x) sp[k] = __ldg(gtable + k);
+        __syncthreads();
     }
-    typename std::conditional<SMEM_TABLE, TableShared, TableGlobal>::type table;
-    if constexpr (SMEM_TABLE) table.t = stab; else table.t = gtable;
+    typename std::conditional<TABLE == TABLE_SHARED, TableShared, typename std::conditional<TABLE == TABLE_POLY, TablePoly, TableGlobal>::type>::type table;
+    if constexpr (TABLE == TABLE_SHARED) table.t = stab;
+    else if constexpr (TABLE == TABLE_POLY) table.c = reinterpret_cast<const float4*>(stab);
+    else table.t = gtable;
     float part = 0.f;
     float beta = 0.f, s = 0.f;
     if (MODE == SPMV_LANCZOS) {
