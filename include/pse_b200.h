@@ -187,6 +187,29 @@ int pse_set_profiling(pse_engine* e, int on);
 int pse_get_profile(pse_engine* e, double* ms_out, uint64_t* calls_out, int n);
 const char* pse_profile_phase_name(int i);
 
+/* ---- multi-GPU: slab-decomposed deterministic mobility (one engine per rank, replicated particle data) ------------
+ * New work (the reference is single-GPU: "only one GPU is supported", PSEv1/Stokes.cc:104).  The engine exposes
+ * the local phases; the caller issues the collectives between them on the buffers it owns:
+ *   pse_shard_fwd     -> all-to-all (a2a_send_floats / a2a_recv_floats per peer, in floats)
+ *   pse_shard_kspace  -> all-to-all back (roles of the two size arrays swapped)
+ *   pse_shard_inv     -> send halo_floats to rank-1, receive from rank+1 (periodic)
+ *   pse_shard_finish  -> all-reduce(SUM) of the N x float4 partial velocities
+ * pse_b200/sharded.py does this with torch.distributed (NCCL). */
+typedef struct {
+    int rank, world;
+    int x0, x1;          /* own x planes of the grid */
+    int y0, y1;          /* own y rows in the transposed (k-space) layout */
+    uint32_t row0, row1; /* own rows (slots) of the real-space SpMV */
+    uint64_t a2a_send_floats[16], a2a_recv_floats[16];
+    uint64_t halo_floats;
+} pse_shard_info;
+int pse_shard_plan(const pse_config* cfg, int rank, int world, pse_shard_info* out); /* host only: the decomposition */
+int pse_shard_setup(pse_engine* e, int rank, int world, pse_shard_info* out);
+int pse_shard_fwd(pse_engine* e, const float4* d_pos, const float4* d_F, float* d_send);
+int pse_shard_kspace(pse_engine* e, const float* d_recv, float* d_send);
+int pse_shard_inv(pse_engine* e, const float* d_recv, float* d_halo_send);
+int pse_shard_finish(pse_engine* e, const float* d_halo_recv, float4* d_U);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,6 +56,14 @@ class pse_stats(ctypes.Structure):
     ]
 
 
+class pse_shard_info(ctypes.Structure):
+    _fields_ = [
+        ("rank", ctypes.c_int), ("world", ctypes.c_int), ("x0", ctypes.c_int), ("x1", ctypes.c_int),
+        ("y0", ctypes.c_int), ("y1", ctypes.c_int), ("row0", ctypes.c_uint32), ("row1", ctypes.c_uint32),
+        ("a2a_send_floats", ctypes.c_uint64 * 16), ("a2a_recv_floats", ctypes.c_uint64 * 16), ("halo_floats", ctypes.c_uint64),
+    ]
+
+
 # every symbol include/pse_b200.h declares: name -> (restype, argtypes)
 _vp, _u32, _f, _i, _d = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_float, ctypes.c_int, ctypes.c_double
 _cfgp, _prmp = ctypes.POINTER(pse_config), ctypes.POINTER(pse_params)
@@ -87,6 +95,12 @@ SYMBOLS = {
     "pse_step": (_i, [_vp, _vp, _vp, _vp, _vp, _u32, _f, ctypes.POINTER(_i)]),
     "pse_step_host": (_i, [_vp, _vp, _vp, _vp, _vp, _u32, _f, ctypes.POINTER(_i)]),
     "pse_get_stats": (_i, [_vp, ctypes.POINTER(pse_stats)]),
+    "pse_shard_plan": (_i, [_cfgp, _i, _i, ctypes.POINTER(pse_shard_info)]),
+    "pse_shard_setup": (_i, [_vp, _i, _i, ctypes.POINTER(pse_shard_info)]),
+    "pse_shard_fwd": (_i, [_vp, _vp, _vp, _vp]),
+    "pse_shard_kspace": (_i, [_vp, _vp, _vp]),
+    "pse_shard_inv": (_i, [_vp, _vp, _vp]),
+    "pse_shard_finish": (_i, [_vp, _vp, _vp]),
     "pse_set_profiling": (_i, [_vp, _i]),
     "pse_get_profile": (_i, [_vp, ctypes.POINTER(_d), ctypes.POINTER(ctypes.c_uint64), _i]),
     "pse_profile_phase_name": (ctypes.c_char_p, [_i]),

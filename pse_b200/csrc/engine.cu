@@ -35,6 +35,8 @@ enum Phase { PH_BIN = 0, PH_NLIST, PH_REORDER, PH_WBIN, PH_SPREAD, PH_FFT_FWD, P
 static const char* kPhaseNames[PH_COUNT] = {"bin", "nlist", "reorder", "wave_bin", "spread", "fft_r2c", "scale", "fft_c2r",
                                             "interp", "prune", "spmv", "lanczos_spmv", "lanczos_vec", "combine", "integrate"};
 struct ProfSpan { int phase; cudaEvent_t a, b; };
+struct ShardState;
+static void shard_free(ShardState* s);
 
 struct pse_engine {
     pse_config cfg;
@@ -98,6 +100,7 @@ struct pse_engine {
     float4 *d_hpos, *d_hF;  // device staging for pse_step_host
     int3* d_himage;
     int num_sms;
+    struct ShardState* shard;  // multi-GPU slab decomposition of the deterministic mobility (pse_shard_*)
     // per-step device scalars + captured step graph
     StepDev* d_stepdev;
     StepDev* h_stepdev;  // pinned
@@ -356,7 +359,7 @@ extern "C" int pse_create(const pse_config* cfg, void* stream, pse_engine** out)
     WaveParams& wp = e->wp;
     wp.Nx = prm.Nx; wp.Ny = prm.Ny; wp.Nz = prm.Nz; wp.Nzh = prm.Nz / 2 + 1; wp.P = prm.P;
     wp.Nzp = wp.Nzh;
-    { const char* env = getenv("PSE_SPEC_PAD"); int pad = env ? atoi(env) : 16; if (pad > 1) wp.Nzp = ((wp.Nzh + pad - 1) / pad) * pad; }
+    { const char* env = getenv("PSE_SPEC_PAD"); int pad = env ? atoi(env) : 1; if (pad > 1) wp.Nzp = ((wp.Nzh + pad - 1) / pad) * pad; }
     wp.hx = prm.hx; wp.hy = prm.hy; wp.hz = prm.hz;
     wp.prefac = prm.prefac; wp.expfac = prm.expfac; wp.quadW = prm.quadW;
     wp.xi = c.xi; wp.eta = prm.eta;
@@ -446,6 +449,7 @@ extern "C" void pse_destroy(pse_engine* e) {
     if (e->h_stepdev) cudaFreeHost(e->h_stepdev);
     if (e->d_stepdev) cudaFree(e->d_stepdev);
     if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+    if (e->shard) shard_free(e->shard);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     if (e->h_nlinfo) cudaFreeHost(e->h_nlinfo);
     if (e->d_nlinfo) cudaFree(e->d_nlinfo);
@@ -1003,4 +1007,256 @@ extern "C" int pse_test_tridiag_sqrt_e1(int m, const double* diag, const double*
 extern "C" void pse_test_philox4x32(const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
     uint4 r = pse_philox4x32(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
     out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+// ===================================================================================================
+// Multi-GPU: slab decomposition of the deterministic mobility U = M F (first stage).
+// One engine per rank; particle data are replicated (every rank is handed the same positions / forces),
+// the WORK is sharded:
+//   wave space   x-slabs of node tiles: tile-owned spreading of the own slab (no halo add: the gather form
+//                reads whatever particles reach the tile), 2-D (y,z) R2C per own x plane, all-to-all transpose
+//                to y-slabs, 1-D FFT along x, scaling, inverse 1-D, all-to-all back, 2-D C2R, P-1 halo planes
+//                from the next rank, interpolation of the particles whose support origin lies in the own slab;
+//   real space   contiguous slot ranges (x-slabs, since slots are in x-major cell order): pruning + SpMV of the
+//                own rows.
+// Each rank accumulates its contributions into a zero-initialised U (particle-id order); one all-reduce(SUM)
+// completes M F everywhere.  The collectives themselves (2 all-to-all, 1 neighbour exchange, 1 all-reduce) are
+// issued by the host layer with torch.distributed/NCCL on the buffers exposed here (pse_b200/sharded.py).
+// ===================================================================================================
+#define SHARD_MAX_WORLD 16
+struct ShardBounds { int xs[SHARD_MAX_WORLD + 1], ys[SHARD_MAX_WORLD + 1]; int world; };
+struct ShardState {
+    int rank, world;
+    ShardBounds b;
+    int tx0, tx1, x0, x1, y0, y1;
+    uint32_t row0, row1;
+    cufftHandle p2f, p2b, p1;
+    bool have2d, have1d;
+    float2 *d_sloc, *d_tr;
+};
+static void shard_free(ShardState* s) {
+    if (!s) return;
+    if (s->have2d) { cufftDestroy(s->p2f); cufftDestroy(s->p2b); }
+    if (s->have1d) cufftDestroy(s->p1);
+    if (s->d_sloc) cudaFree(s->d_sloc);
+    if (s->d_tr) cudaFree(s->d_tr);
+    delete s;
+}
+
+// slab layout  s[c][xl][y][kz]  <->  per-destination blocks  [q][c][xl][y - ys[q]][kz]
+__global__ void shard_slab_blocks_kernel(float2* __restrict__ slab, float2* __restrict__ blocks, ShardBounds b, int nxl, int Ny, int Nzp,
+                                         int to_blocks) {
+    const size_t n = (size_t)3 * nxl * Ny * Nzp;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+        const int kz = (int)(t % Nzp);
+        const int y = (int)((t / Nzp) % Ny);
+        const int xl = (int)((t / ((size_t)Nzp * Ny)) % nxl);
+        const int c = (int)(t / ((size_t)Nzp * Ny * nxl));
+        int q = 0;
+        while (y >= b.ys[q + 1]) ++q;
+        const int nyl = b.ys[q + 1] - b.ys[q];
+        const size_t off = (size_t)3 * nxl * Nzp * b.ys[q] + (((size_t)c * nxl + xl) * nyl + (y - b.ys[q])) * Nzp + kz;
+        if (to_blocks) blocks[off] = slab[t]; else slab[t] = blocks[off];
+    }
+}
+// transposed layout  t[c][x][yl][kz]  <->  per-source blocks  [r][c][x - xs[r]][yl][kz]
+__global__ void shard_trans_blocks_kernel(float2* __restrict__ tr, float2* __restrict__ blocks, ShardBounds b, int Nx, int nyl, int Nzp,
+                                          int to_blocks) {
+    const size_t n = (size_t)3 * Nx * nyl * Nzp;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+        const int kz = (int)(t % Nzp);
+        const int yl = (int)((t / Nzp) % nyl);
+        const int x = (int)((t / ((size_t)Nzp * nyl)) % Nx);
+        const int c = (int)(t / ((size_t)Nzp * nyl * Nx));
+        int r = 0;
+        while (x >= b.xs[r + 1]) ++r;
+        const int nxr = b.xs[r + 1] - b.xs[r];
+        const size_t off = (size_t)3 * nyl * Nzp * b.xs[r] + (((size_t)c * nxr + (x - b.xs[r])) * nyl + yl) * Nzp + kz;
+        if (to_blocks) blocks[off] = tr[t]; else tr[t] = blocks[off];
+    }
+}
+// g[c][x0 + i][y][z], i < nplanes  <->  contiguous halo buffer [c][i][y][z]   (x wrapped)
+__global__ void shard_halo_kernel(float* __restrict__ grid, float* __restrict__ halo, size_t G, int Nx, size_t plane, int xfirst, int nplanes,
+                                  int to_halo) {
+    const size_t n = (size_t)3 * nplanes * plane;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+        const size_t in_plane = t % plane;
+        const int i = (int)((t / plane) % nplanes);
+        const int c = (int)(t / (plane * nplanes));
+        const int x = (xfirst + i) % Nx;
+        const size_t gi = (size_t)c * G + (size_t)x * plane + in_plane;
+        if (to_halo) halo[t] = grid[gi]; else grid[gi] = halo[t];
+    }
+}
+
+// slab bounds of every rank: x planes in whole tiles, y rows and SpMV rows in even shares
+static int shard_bounds(int Nx, int Ny, int ntx, uint32_t N, int world, ShardBounds* b, int* tb, uint32_t* rows) {
+    if (world < 1 || world > SHARD_MAX_WORLD || world > ntx) return PSE_EINVAL;
+    b->world = world;
+    for (int r = 0; r <= world; ++r) {
+        tb[r] = (int)(((long long)ntx * r) / world);
+        b->xs[r] = std::min(tb[r] * TILE, Nx);
+        b->ys[r] = (int)(((long long)Ny * r) / world);
+        rows[r] = (uint32_t)(((unsigned long long)N * r) / world);
+    }
+    b->xs[world] = Nx;
+    return PSE_OK;
+}
+static void shard_fill_info(const ShardBounds& b, const int* tb, const uint32_t* rows, int rank, int Ny, int Nz, int Nzp, int P,
+                            pse_shard_info* out) {
+    memset(out, 0, sizeof(*out));
+    const int world = b.world;
+    out->rank = rank; out->world = world;
+    out->x0 = b.xs[rank]; out->x1 = b.xs[rank + 1]; out->y0 = b.ys[rank]; out->y1 = b.ys[rank + 1];
+    out->row0 = rows[rank]; out->row1 = rows[rank + 1];
+    const int nxl = out->x1 - out->x0, nyl = out->y1 - out->y0;
+    for (int q = 0; q < world; ++q) {
+        out->a2a_send_floats[q] = (uint64_t)2 * 3 * nxl * (b.ys[q + 1] - b.ys[q]) * Nzp;
+        out->a2a_recv_floats[q] = (uint64_t)2 * 3 * (b.xs[q + 1] - b.xs[q]) * nyl * Nzp;
+    }
+    out->halo_floats = (uint64_t)3 * (P - 1) * Ny * Nz;
+    (void)tb;
+}
+
+// host-only: the decomposition a given configuration gets (no GPU needed; used by the CPU tests)
+extern "C" int pse_shard_plan(const pse_config* cfg, int rank, int world, pse_shard_info* out) {
+    if (!cfg || !out || rank < 0 || rank >= world) return PSE_EINVAL;
+    pse_params p;
+    int rc = pse_derive_params(cfg, &p);
+    if (rc != PSE_OK) return rc;
+    ShardBounds b; int tb[SHARD_MAX_WORLD + 1]; uint32_t rows[SHARD_MAX_WORLD + 1];
+    rc = shard_bounds(p.Nx, p.Ny, (p.Nx + TILE - 1) / TILE, cfg->N, world, &b, tb, rows);
+    if (rc != PSE_OK) return rc;
+    shard_fill_info(b, tb, rows, rank, p.Ny, p.Nz, p.Nz / 2 + 1, p.P, out);
+    return PSE_OK;
+}
+
+extern "C" int pse_shard_setup(pse_engine* e, int rank, int world, pse_shard_info* out) {
+    if (!e || !out || world < 1 || world > SHARD_MAX_WORLD || rank < 0 || rank >= world) return PSE_EINVAL;
+    if (!e->tiled) return fail(e, PSE_EINVAL, "pse_shard_setup: needs the tile-owned wave path (P <= 10, grid >= TILE + P)");
+    const WaveParams& wp = e->wp;
+    if (world > e->tg.ntx) return fail(e, PSE_EINVAL, "pse_shard_setup: %d ranks but only %d x-tiles of %d nodes", world, e->tg.ntx, TILE);
+    if (e->shard) { shard_free(e->shard); e->shard = nullptr; }
+    ShardState* s = new ShardState();
+    memset(s, 0, sizeof(*s));
+    s->rank = rank; s->world = world;
+    int tb[SHARD_MAX_WORLD + 1]; uint32_t rows[SHARD_MAX_WORLD + 1];
+    if (shard_bounds(wp.Nx, wp.Ny, e->tg.ntx, e->N, world, &s->b, tb, rows) != PSE_OK) { delete s; return PSE_EINVAL; }
+    s->tx0 = tb[rank]; s->tx1 = tb[rank + 1];
+    s->x0 = s->b.xs[rank]; s->x1 = s->b.xs[rank + 1];
+    s->y0 = s->b.ys[rank]; s->y1 = s->b.ys[rank + 1];
+    s->row0 = rows[rank]; s->row1 = rows[rank + 1];
+    const int nxl = s->x1 - s->x0, nyl = s->y1 - s->y0;
+    if (nxl < wp.P - 1) { delete s; return fail(e, PSE_EINVAL, "pse_shard_setup: slab thinner than the halo"); }
+    e->shard = s;
+    CK(cudaMalloc(&s->d_sloc, sizeof(float2) * 3 * (size_t)nxl * wp.Ny * wp.Nzp));
+    CK(cudaMalloc(&s->d_tr, sizeof(float2) * 3 * (size_t)wp.Nx * std::max(nyl, 1) * wp.Nzp));
+    int n2[2] = {wp.Ny, wp.Nz}, re[2] = {wp.Ny, wp.Nz}, ce[2] = {wp.Ny, wp.Nzp};
+    CKFFT(cufftPlanMany(&s->p2f, 2, n2, re, 1, wp.Ny * wp.Nz, ce, 1, wp.Ny * wp.Nzp, CUFFT_R2C, nxl));
+    CKFFT(cufftPlanMany(&s->p2b, 2, n2, ce, 1, wp.Ny * wp.Nzp, re, 1, wp.Ny * wp.Nz, CUFFT_C2R, nxl));
+    s->have2d = true;
+    cufftSetStream(s->p2f, e->stream); cufftSetStream(s->p2b, e->stream);
+    if (nyl > 0) {
+        int n1[1] = {wp.Nx}, em[1] = {wp.Nx};
+        CKFFT(cufftPlanMany(&s->p1, 1, n1, em, nyl * wp.Nzp, 1, em, nyl * wp.Nzp, 1, CUFFT_C2C, nyl * wp.Nzp));
+        s->have1d = true;
+        cufftSetStream(s->p1, e->stream);
+    }
+    shard_fill_info(s->b, tb, rows, rank, wp.Ny, wp.Nz, wp.Nzp, wp.P, out);
+    return PSE_OK;
+}
+
+// phase 1: bin, spread the own slab, 2-D R2C of the own planes, pack for the forward transpose
+extern "C" int pse_shard_fwd(pse_engine* e, const float4* d_pos, const float4* d_F, float* d_send) {
+    if (!e || !e->shard || !d_pos || !d_F || !d_send) return PSE_EINVAL;
+    ShardState* s = e->shard;
+    const WaveParams& wp = e->wp;
+    cudaStream_t st = e->stream;
+    CKRC(ensure_neighbors(e, d_pos));
+    gather_vec_kernel<<<nblk(e->N, 256), 256, 0, st>>>(d_F, e->d_perm, e->N, e->d_sx, (float4*)e->d_px); LAUNCHED(e);
+    CKRC(run_wbin(e, e->d_sx));
+    TileGrid tg = e->tg;
+    tg.tile0 = s->tx0 * tg.nty * tg.ntz;
+    const int ntiles = (s->tx1 - s->tx0) * tg.nty * tg.ntz;
+    launch_spread_tile(wp.P, st, e->d_wpos, e->d_wF, e->d_worg, e->d_wstart, e->box, e->wp, tg, e->d_grid, ntiles); LAUNCHED(e);
+    const int nxl = s->x1 - s->x0;
+    const size_t plane = (size_t)wp.Ny * wp.Nz;
+    for (int c = 0; c < 3; ++c)
+        CKFFT(cufftExecR2C(s->p2f, e->d_grid + c * e->G + s->x0 * plane, (cufftComplex*)(s->d_sloc + (size_t)c * nxl * wp.Ny * wp.Nzp)));
+    e->fft_execs++;
+    shard_slab_blocks_kernel<<<e->num_sms * 8, 256, 0, st>>>(s->d_sloc, (float2*)d_send, s->b, nxl, wp.Ny, wp.Nzp, 1); LAUNCHED(e);
+    CK(cudaGetLastError());
+    return PSE_OK;
+}
+
+// phase 2: unpack to y-slabs, FFT along x, Green's-function scaling, inverse along x, pack for the way back
+extern "C" int pse_shard_kspace(pse_engine* e, const float* d_recv, float* d_send) {
+    if (!e || !e->shard || !d_recv || !d_send) return PSE_EINVAL;
+    ShardState* s = e->shard;
+    const WaveParams& wp = e->wp;
+    cudaStream_t st = e->stream;
+    const int nyl = s->y1 - s->y0;
+    if (nyl > 0) {
+        shard_trans_blocks_kernel<<<e->num_sms * 8, 256, 0, st>>>(s->d_tr, (float2*)d_recv, s->b, wp.Nx, nyl, wp.Nzp, 0); LAUNCHED(e);
+        const size_t comp = (size_t)wp.Nx * nyl * wp.Nzp;
+        for (int c = 0; c < 3; ++c) CKFFT(cufftExecC2C(s->p1, (cufftComplex*)(s->d_tr + c * comp), (cufftComplex*)(s->d_tr + c * comp), CUFFT_FORWARD));
+        CKRC(upload_stepdev(e, 0));
+        scale_kernel<<<dim3(nyl, wp.Nx), 128, 0, st>>>(s->d_tr, e->wp, e->box, 1, 0, e->d_stepdev, nullptr, s->y0, nyl); LAUNCHED(e);
+        for (int c = 0; c < 3; ++c) CKFFT(cufftExecC2C(s->p1, (cufftComplex*)(s->d_tr + c * comp), (cufftComplex*)(s->d_tr + c * comp), CUFFT_INVERSE));
+        e->fft_execs += 2;
+        shard_trans_blocks_kernel<<<e->num_sms * 8, 256, 0, st>>>(s->d_tr, (float2*)d_send, s->b, wp.Nx, nyl, wp.Nzp, 1); LAUNCHED(e);
+    }
+    CK(cudaGetLastError());
+    return PSE_OK;
+}
+
+// phase 3: unpack to the own x-slab, 2-D C2R, export the first P-1 planes for the previous rank
+extern "C" int pse_shard_inv(pse_engine* e, const float* d_recv, float* d_halo_send) {
+    if (!e || !e->shard || !d_recv || !d_halo_send) return PSE_EINVAL;
+    ShardState* s = e->shard;
+    const WaveParams& wp = e->wp;
+    cudaStream_t st = e->stream;
+    const int nxl = s->x1 - s->x0;
+    const size_t plane = (size_t)wp.Ny * wp.Nz;
+    shard_slab_blocks_kernel<<<e->num_sms * 8, 256, 0, st>>>(s->d_sloc, (float2*)d_recv, s->b, nxl, wp.Ny, wp.Nzp, 0); LAUNCHED(e);
+    for (int c = 0; c < 3; ++c)
+        CKFFT(cufftExecC2R(s->p2b, (cufftComplex*)(s->d_sloc + (size_t)c * nxl * wp.Ny * wp.Nzp), e->d_grid + c * e->G + s->x0 * plane));
+    e->fft_execs++;
+    shard_halo_kernel<<<e->num_sms * 4, 256, 0, st>>>(e->d_grid, d_halo_send, e->G, wp.Nx, plane, s->x0, wp.P - 1, 1); LAUNCHED(e);
+    CK(cudaGetLastError());
+    return PSE_OK;
+}
+
+// phase 4: import the halo planes of the next rank, interpolate the own particles, real-space SpMV of the own rows.
+// d_U (particle-id order) receives this rank's partial result; sum over ranks = M F.
+extern "C" int pse_shard_finish(pse_engine* e, const float* d_halo_recv, float4* d_U) {
+    if (!e || !e->shard || !d_halo_recv || !d_U) return PSE_EINVAL;
+    ShardState* s = e->shard;
+    const WaveParams& wp = e->wp;
+    cudaStream_t st = e->stream;
+    const size_t plane = (size_t)wp.Ny * wp.Nz;
+    shard_halo_kernel<<<e->num_sms * 4, 256, 0, st>>>(e->d_grid, const_cast<float*>(d_halo_recv), e->G, wp.Nx, plane, s->x1 % wp.Nx, wp.P - 1, 0); LAUNCHED(e);
+    CK(cudaMemsetAsync(d_U, 0, sizeof(float4) * e->N, st));
+    TileGrid tg = e->tg;
+    tg.tile0 = s->tx0 * tg.nty * tg.ntz;
+    const int ntiles = (s->tx1 - s->tx0) * tg.nty * tg.ntz;
+    launch_interp_tile(wp.P, st, e->d_wpos, e->d_worg, e->d_wstart, e->d_wperm, e->d_perm, e->box, e->wp, tg, e->d_grid, d_U, 0, ntiles); LAUNCHED(e);
+    // real space, own rows only
+    const uint32_t nrows = s->row1 - s->row0;
+    if (nrows) {
+        const uint32_t* nn = e->d_nn; const uint32_t* nl = e->d_nl;
+        if (e->prune) {
+            prune_kernel<<<persistent_grid(e, nblk((size_t)nrows * 8, 256), 8), 256, 0, st>>>(e->d_spos, s->row1, e->d_nn, e->d_head, e->d_nl, e->rp,
+                                                                                         e->box, e->d_nn_act, e->d_nl_act, s->row0); LAUNCHED(e);
+            nn = e->d_nn_act; nl = e->d_nl_act;
+            e->pruned_valid = false;  // only a row range is pruned
+        }
+        LanczosArgs la = {};
+        const unsigned int work = nblk((size_t)nrows * 8, 256);
+        spmv_kernel<8, SPMV_PLAIN, TABLE_GLOBAL><<<persistent_grid(e, work, 8), 256, 0, st>>>(e->d_px, e->d_sy, s->row1, nn, e->d_head, nl, e->d_table, 0,
+                                                                                       e->rp, e->box, la, s->row0); LAUNCHED(e);
+        scatter_add_kernel<<<nblk(nrows, 256), 256, 0, st>>>(e->d_sy, e->d_perm, s->row1, d_U, 1, s->row0); LAUNCHED(e);
+    }
+    CK(cudaGetLastError());
+    return PSE_OK;
 }

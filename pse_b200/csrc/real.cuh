@@ -104,10 +104,11 @@ __device__ __forceinline__ void ld_px(const PX* ptr, float4& p, float4& x) {
 // its cost is proportional to the listed pairs).  8 lanes per row, ballot-ordered compaction, same row offsets.
 __global__ void __launch_bounds__(256)
 prune_kernel(const float4* __restrict__ spos, uint32_t N, const uint32_t* __restrict__ nn, const uint32_t* __restrict__ head,
-             const uint32_t* __restrict__ nl, RealParams rp, PseBox box, uint32_t* __restrict__ nn_act, uint32_t* __restrict__ nl_act) {
+             const uint32_t* __restrict__ nl, RealParams rp, PseBox box, uint32_t* __restrict__ nn_act, uint32_t* __restrict__ nl_act,
+             uint32_t row_begin = 0) {
     const int sub = threadIdx.x & 7;
     const int grp = (threadIdx.x & 31) >> 3;  // group inside the warp
-    for (uint32_t row0 = blockIdx.x * 32; row0 < N; row0 += gridDim.x * 32) {
+    for (uint32_t row0 = row_begin + blockIdx.x * 32; row0 < N; row0 += gridDim.x * 32) {
         const uint32_t row = row0 + (threadIdx.x >> 3);
         const bool live = row < N;
         uint32_t n = 0, h = 0;
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(256)
 spmv_kernel(const PX* __restrict__ px, float4* __restrict__ y, uint32_t N,
             const uint32_t* __restrict__ nn, const uint32_t* __restrict__ head, const uint32_t* __restrict__ nl,
             const float4* __restrict__ gtable /* knots, or polynomial blocks for TABLE_POLY */, int npoly, RealParams rp,
-            PseBox box, LanczosArgs la) {
+            PseBox box, LanczosArgs la, uint32_t row_begin = 0) {
     constexpr int ROWS = 256 / TPP;
     const int sub = threadIdx.x % TPP;
     extern __shared__ __align__(16) float2 stab[];
@@ -189,7 +190,7 @@ spmv_kernel(const PX* __restrict__ px, float4* __restrict__ y, uint32_t N,
         beta = __ldcg(la.beta_j);
         s = beta > 1e-8f ? 1.0f / beta : 0.f;  // breakdown guard, PSEv1/Brownian.cu:507-510
     }
-    for (uint32_t row0 = blockIdx.x * ROWS; row0 < N; row0 += gridDim.x * ROWS) {
+    for (uint32_t row0 = row_begin + blockIdx.x * ROWS; row0 < N; row0 += gridDim.x * ROWS) {  // rows [row_begin, N)
         const uint32_t row = row0 + threadIdx.x / TPP;
         float3 u = make_float3(0.f, 0.f, 0.f);
         float4 pi = make_float4(0.f, 0.f, 0.f, 0.f), xi = pi;
@@ -302,8 +303,8 @@ basis_combine_kernel(const float4* __restrict__ V, const float* __restrict__ c, 
 
 // U[perm[slot]] (+)= y[slot]
 __global__ void scatter_add_kernel(const float4* __restrict__ y, const uint32_t* __restrict__ perm, uint32_t N,
-                                   float4* __restrict__ U, int accumulate) {
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+                                   float4* __restrict__ U, int accumulate, uint32_t row_begin = 0) {
+    const uint32_t s = row_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= N) return;
     const float4 v = __ldg(y + s);
     const uint32_t p = perm[s];

@@ -202,12 +202,14 @@ __device__ __forceinline__ float sinc_of(const KVec& kv) {
 // no per-thread integer division).
 __global__ void __launch_bounds__(128)
 scale_kernel(float2* __restrict__ spec, WaveParams wp, PseBox box, int do_det, int do_noise, const StepDev* __restrict__ sd,
-             const float* __restrict__ u_grid) {
+             const float* __restrict__ u_grid, int y0 = 0, int ny_local = -1) {
+    // sharded layout: this rank holds y rows [y0, y0 + ny_local) of every x plane, spec[c][x][y_local][kz]
+    if (ny_local < 0) ny_local = wp.Ny;
     const uint32_t key = sd->key;
     const float noise_fac = sd->noise_fac;
-    const size_t nh = (size_t)wp.Nx * wp.Ny * wp.Nzp;
-    const int jj = blockIdx.x, ii = blockIdx.y;
-    const size_t rowbase = ((size_t)ii * wp.Ny + jj) * wp.Nzp;
+    const size_t nh = (size_t)wp.Nx * ny_local * wp.Nzp;
+    const int jj = blockIdx.x + y0, ii = blockIdx.y;
+    const size_t rowbase = ((size_t)ii * ny_local + blockIdx.x) * wp.Nzp;
     for (int kk = threadIdx.x; kk < wp.Nzh; kk += blockDim.x) {
     const size_t tid = rowbase + kk;
     float2 fX = make_float2(0.f, 0.f), fY = fX, fZ = fX;

@@ -25,6 +25,7 @@
 
 struct TileGrid {
     int ntx, nty, ntz, ntile;
+    int tile0;  // first tile handled by a launch (0 unless the grid is sharded into x-slabs of tiles)
 };
 
 // ---- binning by support-origin tile --------------------------------------------------------------
@@ -140,7 +141,8 @@ spread_tile_kernel(const float4* __restrict__ wpos, const float4* __restrict__ w
     __shared__ int s_nact;
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int bz = blockIdx.x % tg.ntz, by = (blockIdx.x / tg.ntz) % tg.nty, bx = blockIdx.x / (tg.ntz * tg.nty);
+    const int tile = blockIdx.x + tg.tile0;
+    const int bz = tile % tg.ntz, by = (tile / tg.ntz) % tg.nty, bx = tile / (tg.ntz * tg.nty);
     const int t0x = bx * TILE, t0y = by * TILE, t0z = bz * TILE;
     const int ex = min(TILE, wp.Nx - t0x), ey = min(TILE, wp.Ny - t0y), ez = min(TILE, wp.Nz - t0z);
 
@@ -308,7 +310,7 @@ interp_tile_kernel(const float4* __restrict__ wpos, const int4* __restrict__ wor
     float* g = smem;
     float* wts = smem + 3 * GT;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const uint32_t cell = blockIdx.x;
+    const uint32_t cell = blockIdx.x + tg.tile0;
     const uint32_t cb = __ldg(wcell_start + cell), ce = __ldg(wcell_start + cell + 1);
     if (cb == ce) return;
     const int bz = cell % tg.ntz, by = (cell / tg.ntz) % tg.nty, bx = cell / (tg.ntz * tg.nty);
@@ -406,18 +408,22 @@ static cudaError_t tiled_set_attributes(int P) {
 }
 
 static void launch_spread_tile(int P, cudaStream_t st, const float4* wpos, const float4* wF, const int4* worg, const uint32_t* wstart,
-                               const PseBox& box, const WaveParams& wp, const TileGrid& tg, float* grid) {
+                               const PseBox& box, const WaveParams& wp, const TileGrid& tg, float* grid, int ntiles = -1) {
+    if (ntiles < 0) ntiles = tg.ntile;
+    if (ntiles == 0) return;
     switch (P) {
-#define X(p) case p: spread_tile_kernel<p><<<tg.ntile, 256, spread_tile_smem(p), st>>>(wpos, wF, worg, wstart, box, wp, tg, grid); break;
+#define X(p) case p: spread_tile_kernel<p><<<ntiles, 256, spread_tile_smem(p), st>>>(wpos, wF, worg, wstart, box, wp, tg, grid); break;
         PSE_FOR_EACH_P(X)
 #undef X
     }
 }
 static void launch_interp_tile(int P, cudaStream_t st, const float4* wpos, const int4* worg, const uint32_t* wstart, const uint32_t* wperm,
                                const uint32_t* perm, const PseBox& box, const WaveParams& wp, const TileGrid& tg, const float* grid,
-                               float4* U, int accumulate) {
+                               float4* U, int accumulate, int ntiles = -1) {
+    if (ntiles < 0) ntiles = tg.ntile;
+    if (ntiles == 0) return;
     switch (P) {
-#define X(p) case p: interp_tile_kernel<p><<<tg.ntile, INTERP_THREADS, interp_tile_smem(p), st>>>(wpos, worg, wstart, wperm, perm, box, wp, tg, grid, U, accumulate); break;
+#define X(p) case p: interp_tile_kernel<p><<<ntiles, INTERP_THREADS, interp_tile_smem(p), st>>>(wpos, worg, wstart, wperm, perm, box, wp, tg, grid, U, accumulate); break;
         PSE_FOR_EACH_P(X)
 #undef X
     }

@@ -107,3 +107,56 @@ def test_replica_logic_world_size_2_gloo(tmp_path):
                           "--master-port", "29533", str(script)], capture_output=True, text=True, env=env, timeout=240)
     assert out.returncode == 0, out.stderr[-2000:]
     assert (tmp_path / "ok_0").exists() and (tmp_path / "ok_1").exists()
+
+
+def test_shard_plan_all_to_all_is_consistent_world_3_gloo(tmp_path):
+    """Slab decomposition of the multi-GPU mobility (pse_b200/sharded.py): the per-peer split sizes every rank derives
+    must agree pairwise, cover the grid, and drive a real (gloo, CPU) all_to_all_single there and back; halo ring."""
+    script = tmp_path / "w.py"
+    script.write_text(textwrap.dedent(f"""
+        import os, sys
+        sys.path.insert(0, {ROOT!r})
+        import torch, torch.distributed as dist
+        from pse_b200 import engine as E, sharded as S
+        from tests import util
+        dist.init_process_group("gloo")
+        rank, world = dist.get_rank(), dist.get_world_size()
+        cfg = E.make_config(100000, util.box_length(100000, 0.2))       # 125^3 grid: 8 x-tiles, uneven slabs
+        info = S.plan(cfg, rank, world)
+        send, recv = S.split_sizes(info)
+        allinfo = [None] * world
+        dist.all_gather_object(allinfo, (info.x0, info.x1, info.y0, info.y1, info.row0, info.row1, send, recv))
+        assert allinfo[0][0] == 0 and allinfo[-1][1] == 125 and allinfo[0][2] == 0 and allinfo[-1][3] == 125
+        assert allinfo[0][4] == 0 and allinfo[-1][5] == 100000
+        for r in range(world - 1):
+            assert allinfo[r][1] == allinfo[r + 1][0] and allinfo[r][3] == allinfo[r + 1][2] and allinfo[r][5] == allinfo[r + 1][4]
+            assert allinfo[r][0] % 16 == 0                              # slabs are whole tiles
+        for r in range(world):
+            for q in range(world):
+                assert allinfo[r][6][q] == allinfo[q][7][r]            # what r sends to q is what q expects from r
+        a = torch.cat([torch.full((n,), float(rank * 100 + q)) for q, n in enumerate(send)])
+        b = torch.empty(sum(recv))
+        dist.all_to_all_single(b, a, recv, send)
+        off = 0
+        for r, n in enumerate(recv):
+            assert bool((b[off:off + n] == r * 100 + rank).all()); off += n
+        back = torch.empty(sum(send))
+        dist.all_to_all_single(back, b, send, recv)                     # the way back swaps the roles
+        assert torch.equal(back, a)
+        dst, src = S.halo_peers(rank, world)
+        peers = [None] * world
+        dist.all_gather_object(peers, (dst, src))
+        assert all(peers[peers[r][0]][1] == r for r in range(world))    # my destination expects me as its source
+        try:
+            S.plan(E.make_config(1000, 34.7), rank, 8)                  # 36^3 grid has 3 x-tiles: 8 ranks refused
+            raise SystemExit("expected an error")
+        except E.PSEError:
+            pass
+        dist.barrier(); dist.destroy_process_group()
+        open(os.path.join({str(tmp_path)!r}, f"ok_{{rank}}"), "w").write("ok")
+    """))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29534")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=3", "--master-addr", "127.0.0.1",
+                          "--master-port", "29534", str(script)], capture_output=True, text=True, env=env, timeout=240)
+    assert out.returncode == 0, out.stderr[-3000:]
+    assert all((tmp_path / f"ok_{r}").exists() for r in range(3))
