@@ -283,6 +283,26 @@ def main():
         eng.mobility(pos, F)
     b.record(stream); torch.cuda.synchronize()
     line["mf_us"] = a.elapsed_time(b) / 5 * 1e3
+    # multi-GPU: the deterministic M.F additionally runs slab-decomposed over all ranks (one suspension, strong scaling)
+    if world > 1:
+        try:
+            from pse_b200 import sharded as S
+            cfg_s = E.make_config(N, L, xi=args.xi, error=args.error, T=T, dt=dt, seed=1, r_buff=args.r_buff)
+            pos_s = torch.from_numpy(util.lattice_positions(N, L, seed=0)).cuda(); F_s = torch.from_numpy(util.random_forces(N, seed=100)).cuda()
+            del eng
+            torch.cuda.empty_cache()
+            sm = S.ShardedMobility(cfg_s)
+            sm.mobility(pos_s, F_s); sm.mobility(pos_s, F_s)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(5):
+                sm.mobility(pos_s, F_s)
+            torch.cuda.synchronize()
+            line["mf_us_sharded"] = max_over_ranks(time.perf_counter() - t0) / 5 * 1e6
+            line["config"]["mf_sharded"] = f"one suspension over {world} ranks: x-slab spreading/FFT with 2 all-to-all transposes, halo exchange, row-sharded SpMV, all-reduce"
+        except Exception as ex:
+            line["mf_us_sharded"] = None
+            line["config"]["mf_sharded"] = f"unavailable: {ex}"
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             line["cpu_baseline"] = cpu_baseline(args)

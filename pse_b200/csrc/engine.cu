@@ -1033,12 +1033,15 @@ struct ShardState {
     cufftHandle p2f, p2b, p1;
     bool have2d, have1d;
     float2 *d_sloc, *d_tr;
+    float* d_stage;       // own real planes, component stride padded so every cuFFT base is aligned
+    size_t stage_stride;
 };
 static void shard_free(ShardState* s) {
     if (!s) return;
     if (s->have2d) { cufftDestroy(s->p2f); cufftDestroy(s->p2b); }
     if (s->have1d) cufftDestroy(s->p1);
     if (s->d_sloc) cudaFree(s->d_sloc);
+    if (s->d_stage) cudaFree(s->d_stage);
     if (s->d_tr) cudaFree(s->d_tr);
     delete s;
 }
@@ -1150,6 +1153,9 @@ extern "C" int pse_shard_setup(pse_engine* e, int rank, int world, pse_shard_inf
     if (nxl < wp.P - 1) { delete s; return fail(e, PSE_EINVAL, "pse_shard_setup: slab thinner than the halo"); }
     e->shard = s;
     CK(cudaMalloc(&s->d_sloc, sizeof(float2) * 3 * (size_t)nxl * wp.Ny * wp.Nzp));
+    // cuFFT wants the real side of an R2C/C2R 8-byte aligned; the own planes of an odd grid are not, so they are staged
+    s->stage_stride = (((size_t)nxl * wp.Ny * wp.Nz + 3) / 4) * 4;
+    CK(cudaMalloc(&s->d_stage, sizeof(float) * 3 * s->stage_stride));
     CK(cudaMalloc(&s->d_tr, sizeof(float2) * 3 * (size_t)wp.Nx * std::max(nyl, 1) * wp.Nzp));
     int n2[2] = {wp.Ny, wp.Nz}, re[2] = {wp.Ny, wp.Nz}, ce[2] = {wp.Ny, wp.Nzp};
     CKFFT(cufftPlanMany(&s->p2f, 2, n2, re, 1, wp.Ny * wp.Nz, ce, 1, wp.Ny * wp.Nzp, CUFFT_R2C, nxl));
@@ -1181,8 +1187,11 @@ extern "C" int pse_shard_fwd(pse_engine* e, const float4* d_pos, const float4* d
     launch_spread_tile(wp.P, st, e->d_wpos, e->d_wF, e->d_worg, e->d_wstart, e->box, e->wp, tg, e->d_grid, ntiles); LAUNCHED(e);
     const int nxl = s->x1 - s->x0;
     const size_t plane = (size_t)wp.Ny * wp.Nz;
-    for (int c = 0; c < 3; ++c)
-        CKFFT(cufftExecR2C(s->p2f, e->d_grid + c * e->G + s->x0 * plane, (cufftComplex*)(s->d_sloc + (size_t)c * nxl * wp.Ny * wp.Nzp)));
+    for (int c = 0; c < 3; ++c) {
+        CK(cudaMemcpyAsync(s->d_stage + c * s->stage_stride, e->d_grid + c * e->G + s->x0 * plane, sizeof(float) * nxl * plane,
+                           cudaMemcpyDeviceToDevice, st));
+        CKFFT(cufftExecR2C(s->p2f, s->d_stage + c * s->stage_stride, (cufftComplex*)(s->d_sloc + (size_t)c * nxl * wp.Ny * wp.Nzp)));
+    }
     e->fft_execs++;
     shard_slab_blocks_kernel<<<e->num_sms * 8, 256, 0, st>>>(s->d_sloc, (float2*)d_send, s->b, nxl, wp.Ny, wp.Nzp, 1); LAUNCHED(e);
     CK(cudaGetLastError());
@@ -1219,8 +1228,11 @@ extern "C" int pse_shard_inv(pse_engine* e, const float* d_recv, float* d_halo_s
     const int nxl = s->x1 - s->x0;
     const size_t plane = (size_t)wp.Ny * wp.Nz;
     shard_slab_blocks_kernel<<<e->num_sms * 8, 256, 0, st>>>(s->d_sloc, (float2*)d_recv, s->b, nxl, wp.Ny, wp.Nzp, 0); LAUNCHED(e);
-    for (int c = 0; c < 3; ++c)
-        CKFFT(cufftExecC2R(s->p2b, (cufftComplex*)(s->d_sloc + (size_t)c * nxl * wp.Ny * wp.Nzp), e->d_grid + c * e->G + s->x0 * plane));
+    for (int c = 0; c < 3; ++c) {
+        CKFFT(cufftExecC2R(s->p2b, (cufftComplex*)(s->d_sloc + (size_t)c * nxl * wp.Ny * wp.Nzp), s->d_stage + c * s->stage_stride));
+        CK(cudaMemcpyAsync(e->d_grid + c * e->G + s->x0 * plane, s->d_stage + c * s->stage_stride, sizeof(float) * nxl * plane,
+                           cudaMemcpyDeviceToDevice, st));
+    }
     e->fft_execs++;
     shard_halo_kernel<<<e->num_sms * 4, 256, 0, st>>>(e->d_grid, d_halo_send, e->G, wp.Nx, plane, s->x0, wp.P - 1, 1); LAUNCHED(e);
     CK(cudaGetLastError());
