@@ -23,7 +23,7 @@
 #include "wave_tiled.cuh"
 
 int pse_tridiag_sqrt_e1(int m, const double* diag, const double* off, double* c, double* lambda_min_out);
-int pse_fit_rpy_poly(double xi, double rcut, float* out, int max_intervals, double* max_err_out);
+int pse_fit_rpy_cheb(double xi, double rcut, float* out, double* max_err_out);
 
 #define LANCZOS_M_MAX 100  // PSEv1/Brownian.cu:397
 
@@ -46,6 +46,12 @@ struct pse_engine {
     RealParams rp;
     CellGrid cg;
     cudaStream_t stream, own_stream;
+    cudaStream_t stream2;         // second stream: the real-space branch of a step runs beside the wave-space branch
+    cudaEvent_t ev_fork, ev_join;
+    cudaStream_t stream_h2d;      // pse_step_host: forces and images are uploaded beside the position-only head of the step
+    cudaEvent_t ev_F, ev_img;
+    bool wait_F, wait_img;        // uploads in flight that the next consumer on `stream` has to wait for
+    bool overlap;
     uint32_t N;
     size_t G, Gh;
     char err[512];
@@ -88,6 +94,7 @@ struct pse_engine {
     int4 *d_org, *d_worg;
     uint32_t *d_wcell_of, *d_wcount, *d_wstart, *d_wperm, *d_wtmp;
     float4 *d_wpos, *d_wF;
+    float* d_wwt;  // Gaussian factor rows, W order: [N][P*P + P]
     // Lanczos
     float4 *d_V, *d_u, *d_y;
     float *d_alpha, *d_beta, *d_coef, *d_partials;
@@ -110,10 +117,10 @@ struct pse_engine {
     uint32_t nl_gen;  // bumped whenever list buffers are reallocated
     bool spmv_smem_table;
     int spmv_table_mode;  // TABLE_GLOBAL / TABLE_SHARED / TABLE_POLY
-    float4* d_poly;       // polynomial blocks, 3 float4 per interval
-    int npoly;
-    double poly_max_err;
+    ChebCoef cheb;        // constant-bank polynomial form of f, g for r >= 2a
+    double cheb_max_err;
     int spmv_tpp;  // lanes per row in the SpMV
+    int spmv_map, spmv_stream_idx, spmv_bps;  // SM-local row mapping, no-L1-allocate index loads, blocks per SM (0 = auto)
     // profiling
     bool prof_on;
     std::vector<cudaEvent_t>* prof_pool;
@@ -312,6 +319,7 @@ static int alloc_all(pse_engine* e) {
             CK(cudaMalloc(&e->d_wtmp, sizeof(uint32_t) * N));
             CK(cudaMalloc(&e->d_wpos, sizeof(float4) * N));
             CK(cudaMalloc(&e->d_wF, sizeof(float4) * N));
+            CK(cudaMalloc(&e->d_wwt, sizeof(float) * (size_t)N * (wp.P * wp.P + wp.P)));
             CK(tiled_set_attributes(wp.P));
         }
     }
@@ -347,11 +355,19 @@ extern "C" int pse_create(const pse_config* cfg, void* stream, pse_engine** out)
     e->cfg = c; e->prm = prm; e->N = c.N;
     e->stream = (cudaStream_t)stream;
     e->own_stream = nullptr;
+    e->stream2 = nullptr; e->ev_fork = e->ev_join = nullptr;
+    { const char* v = getenv("PSE_OVERLAP"); e->overlap = v ? atoi(v) != 0 : true; }
     if (!e->stream) {
         // the legacy default stream cannot be captured into a CUDA graph: use an own (blocking) stream, which keeps
         // the implicit ordering with work the caller issues on the default stream
         if (cudaStreamCreate(&e->own_stream) != cudaSuccess) { delete eng; return fail(nullptr, PSE_ECUDA, "pse_create: cudaStreamCreate failed"); }
         e->stream = e->own_stream;
+    }
+    if (e->overlap && (cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+                       cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+                       cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess)) {
+        pse_destroy(e);
+        return fail(nullptr, PSE_ECUDA, "pse_create: second stream / events");
     }
     e->rlist = rlist;
     refresh_box(e, c.box);
@@ -378,12 +394,16 @@ extern "C" int pse_create(const pse_config* cfg, void* stream, pse_engine** out)
         const char* env = getenv("PSE_SPMV_SMEM_TABLE");
         if (env) e->spmv_smem_table = env[0] != '0' && spmv_table_smem(e) <= 200 * 1024;
         e->spmv_table_mode = e->spmv_smem_table ? TABLE_SHARED : TABLE_GLOBAL;
-        const char* tm = getenv("PSE_SPMV_TABLE");  // "poly" | "shared" | "global"
-        // measured on B200 (profiles/r1_summary.md): shared knots 272 us, polynomial blocks 283 us, global table 295 us per
-        // SpMV at N = 1M -> the lookup is not the limiter (the gathered 32-byte records are); knots stay the default
-        if (tm && tm[0] == 'p') e->spmv_table_mode = TABLE_POLY;
-        else if (tm && tm[0] == 'g') e->spmv_table_mode = TABLE_GLOBAL;
+        // measured on B200, per SpMV at N = 1M (profiles/r1_summary.md): the kernel is bound by the L1/shared data pipe, a
+        // third of whose wavefronts were table knots.  "poly" (default) evaluates f, g from constant-bank polynomials instead;
+        // "shared" / "global" keep the reference's linearly interpolated table.
+        const char* tm = getenv("PSE_SPMV_TABLE");
+        if (!tm || tm[0] == 'p') e->spmv_table_mode = TABLE_POLY;
+        else if (tm[0] == 'g') e->spmv_table_mode = TABLE_GLOBAL;
         e->spmv_tpp = 8;
+        { const char* v = getenv("PSE_SPMV_MAP"); e->spmv_map = v ? atoi(v) : 0; }
+        { const char* v = getenv("PSE_SPMV_STREAM"); e->spmv_stream_idx = v ? atoi(v) : 0; }
+        { const char* v = getenv("PSE_SPMV_BPS"); e->spmv_bps = v ? atoi(v) : 0; }
         const char* tpp = getenv("PSE_SPMV_TPP");
         if (tpp) e->spmv_tpp = atoi(tpp);
     }
@@ -403,21 +423,13 @@ extern "C" int pse_create(const pse_config* cfg, void* stream, pse_engine** out)
         return PSE_ECUDA;
     }
     {
-        std::vector<float> pc(16 * 256);
-        e->npoly = pse_fit_rpy_poly(c.xi, prm.rcut, pc.data(), 256, &e->poly_max_err);
-        if (e->npoly <= 0 || e->poly_max_err > 1e-7) {
+        float pc[3 + 2 * (PSE_CHEB_DEG + 1)];
+        const int frc = pse_fit_rpy_cheb(c.xi, prm.rcut, pc, &e->cheb_max_err);
+        if (frc != PSE_OK || !(e->cheb_max_err < 3e-6)) {  // keep the table when the fit is not at rounding level
             if (e->spmv_table_mode == TABLE_POLY) e->spmv_table_mode = e->spmv_smem_table ? TABLE_SHARED : TABLE_GLOBAL;
-            e->npoly = 0;
         } else {
-            std::vector<float> blk(4 * PSE_POLY_STRIDE * (size_t)e->npoly, 0.f);
-            for (int k = 0; k < e->npoly; ++k)
-                for (int q = 0; q < 16; ++q) blk[4 * PSE_POLY_STRIDE * k + q] = pc[16 * k + q];
-            if (cudaMalloc(&e->d_poly, blk.size() * sizeof(float)) != cudaSuccess ||
-                cudaMemcpy(e->d_poly, blk.data(), blk.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
-                fail(nullptr, PSE_ECUDA, "pse_create: polynomial table upload failed");
-                pse_destroy(e);
-                return PSE_ECUDA;
-            }
+            e->cheb.A = pc[0]; e->cheb.B = pc[1]; e->cheb.ne = pc[2];
+            for (int k = 0; k <= PSE_CHEB_DEG; ++k) { e->cheb.cf[k] = pc[3 + k]; e->cheb.cg[k] = pc[3 + PSE_CHEB_DEG + 1 + k]; }
         }
     }
     int n[3] = {prm.Nx, prm.Ny, prm.Nz};
@@ -442,7 +454,7 @@ extern "C" void pse_destroy(pse_engine* e) {
                     e->d_spos, e->d_sx, e->d_sy, e->d_px, e->d_nn, e->d_head, e->d_nl, e->d_pos_build, e->d_flag, e->d_grid,
                     e->d_spec, e->d_V, e->d_u, e->d_y, e->d_alpha, e->d_beta, e->d_coef, e->d_partials, e->d_counter,
                     e->d_vel_work, e->d_hpos, e->d_hF, e->d_himage, e->d_org, e->d_worg, e->d_wcell_of, e->d_wcount,
-                    e->d_wstart, e->d_wperm, e->d_wpos, e->d_wF, e->d_wtmp, e->d_ell, e->d_nn_act, e->d_nl_act, e->d_poly};
+                    e->d_wstart, e->d_wperm, e->d_wpos, e->d_wF, e->d_wwt, e->d_wtmp, e->d_ell, e->d_nn_act, e->d_nl_act};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (e->h_flag) cudaFreeHost(e->h_flag);
@@ -451,6 +463,12 @@ extern "C" void pse_destroy(pse_engine* e) {
     if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
     if (e->shard) shard_free(e->shard);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    if (e->stream2) cudaStreamDestroy(e->stream2);
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    if (e->ev_join) cudaEventDestroy(e->ev_join);
+    if (e->stream_h2d) cudaStreamDestroy(e->stream_h2d);
+    if (e->ev_F) cudaEventDestroy(e->ev_F);
+    if (e->ev_img) cudaEventDestroy(e->ev_img);
     if (e->h_nlinfo) cudaFreeHost(e->h_nlinfo);
     if (e->d_nlinfo) cudaFree(e->d_nlinfo);
     if (e->h_ab) cudaFreeHost(e->h_ab);
@@ -657,18 +675,18 @@ static void launch_spmv_tpp(pse_engine* e, float4* y, const LanczosArgs& la) {
     const uint32_t* nn = e->prune ? e->d_nn_act : e->d_nn;
     const uint32_t* nl = e->prune ? e->d_nl_act : e->d_nl;
     if (e->spmv_table_mode == TABLE_POLY) {
-        const size_t sm = (size_t)e->npoly * PSE_POLY_STRIDE * sizeof(float4);
-        spmv_kernel<TPP, MODE, TABLE_POLY><<<persistent_grid(e, work, 8), 256, sm, e->stream>>>(
-            e->d_px, y, e->N, nn, e->d_head, nl, e->d_poly, e->npoly, e->rp, e->box, la);
+        spmv_kernel<TPP, MODE, TABLE_POLY><<<persistent_grid(e, work, e->spmv_bps > 0 ? e->spmv_bps : 8), 256, 0, e->stream>>>(
+            e->d_px, y, e->N, nn, e->d_head, nl, e->d_table, e->cheb, e->rp, e->box, la, 0, e->spmv_map ? e->num_sms : 0, e->spmv_stream_idx);
     } else if (e->spmv_table_mode == TABLE_SHARED) {
         const size_t sm = spmv_table_smem(e);
-        const int bps = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (sm + 1024)));
+        int bps = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (sm + 1024)));
+        if (e->spmv_bps > 0) bps = std::min(bps, e->spmv_bps);
         cudaFuncSetAttribute(spmv_kernel<TPP, MODE, TABLE_SHARED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         spmv_kernel<TPP, MODE, TABLE_SHARED><<<persistent_grid(e, work, bps), 256, sm, e->stream>>>(
-            e->d_px, y, e->N, nn, e->d_head, nl, e->d_table, 0, e->rp, e->box, la);
+            e->d_px, y, e->N, nn, e->d_head, nl, e->d_table, e->cheb, e->rp, e->box, la, 0, e->spmv_map ? e->num_sms : 0, e->spmv_stream_idx);
     } else {
-        spmv_kernel<TPP, MODE, TABLE_GLOBAL><<<persistent_grid(e, work, 8), 256, 0, e->stream>>>(
-            e->d_px, y, e->N, nn, e->d_head, nl, e->d_table, 0, e->rp, e->box, la);
+        spmv_kernel<TPP, MODE, TABLE_GLOBAL><<<persistent_grid(e, work, e->spmv_bps > 0 ? e->spmv_bps : 8), 256, 0, e->stream>>>(
+            e->d_px, y, e->N, nn, e->d_head, nl, e->d_table, e->cheb, e->rp, e->box, la, 0, e->spmv_map ? e->num_sms : 0, e->spmv_stream_idx);
     }
     LAUNCHED(e);
 }
@@ -703,6 +721,7 @@ static int run_wbin(pse_engine* e, const float4* sF) {
     cell_fill_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_wcell_of, N, e->d_wstart, e->d_wcount, e->d_wtmp); LAUNCHED(e);
     cell_sort_block_kernel<<<nt, 128, 0, st>>>(e->d_wstart, e->d_wtmp, e->d_wperm); LAUNCHED(e);
     wgather_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_spos, sF, e->d_org, e->d_wperm, N, e->d_wpos, e->d_wF, e->d_worg); LAUNCHED(e);
+    launch_wweights(e->wp.P, st, e->d_wpos, e->d_worg, N, e->box, e->wp, e->d_wwt); LAUNCHED(e);
     return PSE_OK;
 }
 
@@ -715,7 +734,7 @@ static int run_wave(pse_engine* e, const float4* sF, float4* U, int accumulate, 
         {
         ProfScope ps(e, PH_SPREAD);
         if (e->tiled) {
-            launch_spread_tile(P, st, e->d_wpos, e->d_wF, e->d_worg, e->d_wstart, e->box, e->wp, e->tg, e->d_grid); LAUNCHED(e);
+            launch_spread_tile(P, st, e->d_wF, e->d_worg, e->d_wwt, e->d_wstart, e->wp, e->tg, e->d_grid); LAUNCHED(e);
         } else {
             CK(cudaMemsetAsync(e->d_grid, 0, sizeof(float) * 3 * e->G, st));
             spread_scatter_kernel<<<nblk((size_t)e->N * 32, 256), 256, 0, st>>>(e->d_spos, sF, e->N, e->box, e->wp, e->d_grid); LAUNCHED(e);
@@ -734,7 +753,7 @@ static int run_wave(pse_engine* e, const float4* sF, float4* U, int accumulate, 
     }
     ProfScope ps(e, PH_INTERP);
     if (e->tiled) {
-        launch_interp_tile(P, st, e->d_wpos, e->d_worg, e->d_wstart, e->d_wperm, e->d_perm, e->box, e->wp, e->tg, e->d_grid, U, accumulate);
+        launch_interp_tile(P, st, e->d_worg, e->d_wwt, e->d_wstart, e->d_wperm, e->d_perm, e->wp, e->tg, e->d_grid, U, accumulate);
         LAUNCHED(e);
     } else {
         interp_warp_kernel<<<nblk((size_t)e->N * 32, 256), 256, 0, st>>>(e->d_spos, e->N, e->box, e->wp, e->d_grid, e->d_perm, U, accumulate); LAUNCHED(e);
@@ -883,14 +902,32 @@ static int velocity_fixed_part(pse_engine* e, const float4* d_F, float4* d_U, bo
     const uint32_t N = e->N;
     cudaStream_t st = e->stream;
     if (det) { gather_vec_kernel<<<nblk(N, 256), 256, 0, st>>>(d_F, e->d_perm, N, e->d_sx, (float4*)e->d_px); LAUNCHED(e); }
+    // The real-space branch (prune, M_real F, Lanczos) and the wave-space branch (bin, spread, FFTs, interpolate) touch
+    // disjoint buffers until their results meet in d_U, and they stress different units (L1 gathers vs shared memory /
+    // HBM), so they are issued on two streams and joined before the accumulation.  Profiling keeps them serial so
+    // that the per-phase times stay meaningful.
+    const bool wave = det || wnoise, real = det || rnoise;
+    const bool fork = e->overlap && !e->prof_on && wave && real && e->stream2;
+    int rc = PSE_OK;
+    if (fork) {
+        CK(cudaEventRecord(e->ev_fork, st));
+        CK(cudaStreamWaitEvent(e->stream2, e->ev_fork, 0));
+        e->stream = e->stream2;
+    }
+    if (det) rc = run_spmv_plain(e, e->d_sy);
+    if (rc == PSE_OK && rnoise) rc = lanczos_batch(e, d_u_particles, m_batch);
+    if (fork) {
+        e->stream = st;
+        if (rc == PSE_OK) CK(cudaEventRecord(e->ev_join, e->stream2));
+    }
+    if (rc != PSE_OK) return rc;
     int acc = 0;
-    if (det || wnoise) { CKRC(run_wave(e, e->d_sx, d_U, 0, det, wnoise, d_u_grid)); acc = 1; }
+    if (wave) { CKRC(run_wave(e, e->d_sx, d_U, 0, det, wnoise, d_u_grid)); acc = 1; }
+    if (fork) CK(cudaStreamWaitEvent(st, e->ev_join, 0));
     if (det) {
-        CKRC(run_spmv_plain(e, e->d_sy));
         scatter_add_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_sy, e->d_perm, N, d_U, acc); LAUNCHED(e);
         acc = 1;
     }
-    if (rnoise) CKRC(lanczos_batch(e, d_u_particles, m_batch));
     if (!acc && !rnoise) CK(cudaMemsetAsync(d_U, 0, sizeof(float4) * N, st));
     return PSE_OK;
 }
@@ -903,6 +940,7 @@ extern "C" int pse_velocity(pse_engine* e, const float4* d_pos, const float4* d_
     const bool thermal = e->cfg.T > 0.f;  // PSEv1/Brownian.cu:855,885
     const bool wnoise = (parts & 2u) && thermal, rnoise = (parts & 4u) && thermal;
     CKRC(ensure_neighbors(e, d_pos));  // host decision (list still valid?) happens before the fixed part
+    if (e->wait_F) { e->wait_F = false; CK(cudaStreamWaitEvent(st, e->ev_F, 0)); }
     CKRC(upload_stepdev(e, timestep));
     const int m_batch = lanczos_batch_size(e);
     if (m_out) *m_out = e->m_lanczos;
@@ -968,6 +1006,7 @@ extern "C" int pse_step(pse_engine* e, float4* d_pos, int3* d_image, const float
     if (!e || !d_pos || !d_F) return PSE_EINVAL;
     float4* vel = d_vel ? d_vel : e->d_vel_work;
     CKRC(pse_velocity(e, d_pos, d_F, vel, timestep, nullptr, nullptr, 7u, m_out));
+    if (e->wait_img) { e->wait_img = false; CK(cudaStreamWaitEvent(e->stream, e->ev_img, 0)); }
     {
         ProfScope ps(e, PH_INTEGRATE);
         integrate_kernel<<<nblk(e->N, 256), 256, 0, e->stream>>>(d_pos, d_image, vel, e->N, e->box, e->cfg.dt, shear_rate); LAUNCHED(e);
@@ -986,10 +1025,21 @@ extern "C" int pse_step_host(pse_engine* e, float* h_pos4, int* h_image3, const 
         CK(cudaMalloc(&e->d_hF, sizeof(float4) * N));
         CK(cudaMalloc(&e->d_himage, sizeof(int3) * N));
     }
+    if (!e->stream_h2d) {
+        CK(cudaStreamCreateWithFlags(&e->stream_h2d, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&e->ev_F, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&e->ev_img, cudaEventDisableTiming));
+    }
+    // positions first, on the compute stream; forces and images follow on the copy stream while the neighbour-list check
+    // (and rebuild) runs, and are waited for where they are first read (pse_velocity / integrate_kernel).  The previous
+    // call ended with a stream synchronisation, so nothing is still reading the staging buffers.
     CK(cudaMemcpyAsync(e->d_hpos, h_pos4, sizeof(float4) * N, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(e->d_hF, h_F4, sizeof(float4) * N, cudaMemcpyHostToDevice, st));
-    if (h_image3) CK(cudaMemcpyAsync(e->d_himage, h_image3, sizeof(int3) * N, cudaMemcpyHostToDevice, st));
-    else CK(cudaMemsetAsync(e->d_himage, 0, sizeof(int3) * N, st));
+    CK(cudaMemcpyAsync(e->d_hF, h_F4, sizeof(float4) * N, cudaMemcpyHostToDevice, e->stream_h2d));
+    CK(cudaEventRecord(e->ev_F, e->stream_h2d));
+    if (h_image3) CK(cudaMemcpyAsync(e->d_himage, h_image3, sizeof(int3) * N, cudaMemcpyHostToDevice, e->stream_h2d));
+    else CK(cudaMemsetAsync(e->d_himage, 0, sizeof(int3) * N, e->stream_h2d));
+    CK(cudaEventRecord(e->ev_img, e->stream_h2d));
+    e->wait_F = e->wait_img = true;
     CKRC(pse_step(e, e->d_hpos, e->d_himage, e->d_hF, h_vel4 ? e->d_vel_work : nullptr, timestep, shear_rate, m_out));
     CK(cudaMemcpyAsync(h_pos4, e->d_hpos, sizeof(float4) * N, cudaMemcpyDeviceToHost, st));
     if (h_image3) CK(cudaMemcpyAsync(h_image3, e->d_himage, sizeof(int3) * N, cudaMemcpyDeviceToHost, st));
@@ -1184,7 +1234,7 @@ extern "C" int pse_shard_fwd(pse_engine* e, const float4* d_pos, const float4* d
     TileGrid tg = e->tg;
     tg.tile0 = s->tx0 * tg.nty * tg.ntz;
     const int ntiles = (s->tx1 - s->tx0) * tg.nty * tg.ntz;
-    launch_spread_tile(wp.P, st, e->d_wpos, e->d_wF, e->d_worg, e->d_wstart, e->box, e->wp, tg, e->d_grid, ntiles); LAUNCHED(e);
+    launch_spread_tile(wp.P, st, e->d_wF, e->d_worg, e->d_wwt, e->d_wstart, e->wp, tg, e->d_grid, ntiles); LAUNCHED(e);
     const int nxl = s->x1 - s->x0;
     const size_t plane = (size_t)wp.Ny * wp.Nz;
     for (int c = 0; c < 3; ++c) {
@@ -1252,7 +1302,7 @@ extern "C" int pse_shard_finish(pse_engine* e, const float* d_halo_recv, float4*
     TileGrid tg = e->tg;
     tg.tile0 = s->tx0 * tg.nty * tg.ntz;
     const int ntiles = (s->tx1 - s->tx0) * tg.nty * tg.ntz;
-    launch_interp_tile(wp.P, st, e->d_wpos, e->d_worg, e->d_wstart, e->d_wperm, e->d_perm, e->box, e->wp, tg, e->d_grid, d_U, 0, ntiles); LAUNCHED(e);
+    launch_interp_tile(wp.P, st, e->d_worg, e->d_wwt, e->d_wstart, e->d_wperm, e->d_perm, e->wp, tg, e->d_grid, d_U, 0, ntiles); LAUNCHED(e);
     // real space, own rows only
     const uint32_t nrows = s->row1 - s->row0;
     if (nrows) {
@@ -1265,7 +1315,7 @@ extern "C" int pse_shard_finish(pse_engine* e, const float* d_halo_recv, float4*
         }
         LanczosArgs la = {};
         const unsigned int work = nblk((size_t)nrows * 8, 256);
-        spmv_kernel<8, SPMV_PLAIN, TABLE_GLOBAL><<<persistent_grid(e, work, 8), 256, 0, st>>>(e->d_px, e->d_sy, s->row1, nn, e->d_head, nl, e->d_table, 0,
+        spmv_kernel<8, SPMV_PLAIN, TABLE_GLOBAL><<<persistent_grid(e, work, 8), 256, 0, st>>>(e->d_px, e->d_sy, s->row1, nn, e->d_head, nl, e->d_table, e->cheb,
                                                                                        e->rp, e->box, la, s->row0); LAUNCHED(e);
         scatter_add_kernel<<<nblk(nrows, 256), 256, 0, st>>>(e->d_sy, e->d_perm, s->row1, d_U, 1, s->row0); LAUNCHED(e);
     }

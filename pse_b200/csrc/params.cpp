@@ -9,6 +9,8 @@
 #include <algorithm>
 #include <vector>
 
+#define PSE_CHEB_DEG 10  // keep in step with real.cuh
+
 static const double kPiRef = 3.1415926536;  // the literal the reference uses everywhere
 
 static int round_up_235(int n) {
@@ -146,51 +148,56 @@ extern "C" int pse_ewald_table(const pse_config* c, float* out) {
     return PSE_OK;
 }
 
-// Piecewise degree-7 polynomial fit of f(r), g(r) on intervals [k W, (k+1) W), W = 0.5 (PSE_POLY_W in real.cuh),
-// exact closed forms sampled at 8 Chebyshev nodes per interval, monomial coefficients in t = 2 (r - kW)/W - 1.
-// out: 16 floats per interval (f0..f7, g0..g7); returns the number of intervals covering [0, rcut].
-// max_err_out (optional): largest |poly - exact| over a fine scan, for the self-check at create time.
-int pse_fit_rpy_poly(double xi, double rcut, float* out, int max_intervals, double* max_err_out) {
-    const double W = 0.5;
-    const int nI = (int)ceil(rcut / W) + 1;
-    if (nI > max_intervals) return -nI;
-    const int n = 8;
-    double maxerr = 0.0;
-    for (int k = 0; k < nI; ++k) {
-        double tn[n], A[n][n + 2];
+// Single-interval polynomial form of the real-space functions for non-overlapping pairs (2a <= r <= rcut):
+//     f(r) = exp(-xi^2 (r - 2a)^2) * Pf(t),   g(r) = exp(-xi^2 (r - 2a)^2) * Pg(t),   t = A / r + B  in [-1, 1].
+// Dividing out the leading Gaussian and expanding in 1/r makes degree PSE_CHEB_DEG polynomials accurate to the
+// rounding level of fp32 (a polynomial in r needs degree ~16 for the same).  Exact closed forms are sampled at the
+// Chebyshev nodes of the 1/r interval; the monomial coefficients come from the Vandermonde system in double.
+// out: A, B, -xi^2 log2(e), Pf[0..deg], Pg[0..deg]  (3 + 2 (deg + 1) floats).
+// max_err_out: largest |fit - exact| / max|exact| over a scan evaluated in float exactly as the device does.
+int pse_fit_rpy_cheb(double xi, double rcut, float* out, double* max_err_out) {
+    const int n = PSE_CHEB_DEG + 1;
+    const double lo = 2.0, pi = 3.14159265358979323846;
+    if (!(rcut > lo + 1e-3)) return PSE_EINVAL;
+    const double s_lo = 1.0 / rcut, s_hi = 1.0 / lo;
+    const double A = 2.0 / (s_hi - s_lo), B = -(s_hi + s_lo) / (s_hi - s_lo);
+    double M[PSE_CHEB_DEG + 1][PSE_CHEB_DEG + 3];
+    for (int q = 0; q < n; ++q) {
+        const double t = cos(pi * (2 * q + 1) / (2.0 * n));
+        const double r = 1.0 / (0.5 * (s_hi + s_lo) + 0.5 * (s_hi - s_lo) * t);
+        double f, g;
+        pse_rpy_real_fg(r, xi, 1.0, &f, &g);
+        const double e = exp(xi * xi * (r - lo) * (r - lo));
+        double pw = 1.0;
+        for (int c = 0; c < n; ++c) { M[q][c] = pw; pw *= t; }
+        M[q][n] = f * e; M[q][n + 1] = g * e;
+    }
+    for (int c = 0; c < n; ++c) {  // Gauss-Jordan with partial pivoting, two right-hand sides
+        int piv = c;
+        for (int q = c + 1; q < n; ++q) if (fabs(M[q][c]) > fabs(M[piv][c])) piv = q;
+        for (int j = 0; j < n + 2; ++j) std::swap(M[c][j], M[piv][j]);
         for (int q = 0; q < n; ++q) {
-            tn[q] = cos(3.14159265358979323846 * (2 * q + 1) / (2.0 * n));
-            double r = (k + 0.5 * (tn[q] + 1.0)) * W;
-            if (r < 1e-3) r = 1e-3;
-            double f, g;
-            pse_rpy_real_fg(r, xi, 1.0, &f, &g);
-            double p = 1.0;
-            for (int c = 0; c < n; ++c) { A[q][c] = p; p *= tn[q]; }
-            A[q][n] = f; A[q][n + 1] = g;
-        }
-        for (int c = 0; c < n; ++c) {  // Gauss-Jordan with partial pivoting, two right-hand sides
-            int piv = c;
-            for (int q = c + 1; q < n; ++q) if (fabs(A[q][c]) > fabs(A[piv][c])) piv = q;
-            for (int j = 0; j < n + 2; ++j) std::swap(A[c][j], A[piv][j]);
-            for (int q = 0; q < n; ++q) {
-                if (q == c) continue;
-                double m = A[q][c] / A[c][c];
-                for (int j = c; j < n + 2; ++j) A[q][j] -= m * A[c][j];
-            }
-        }
-        float* o = out + 16 * k;
-        for (int c = 0; c < n; ++c) { o[c] = (float)(A[c][n] / A[c][c]); o[8 + c] = (float)(A[c][n + 1] / A[c][c]); }
-        for (int sI = 0; sI < 64; ++sI) {  // error scan (float Horner, as on the device)
-            double r = (k + (sI + 0.5) / 64.0) * W;
-            if (r < 2e-3 || r > rcut) continue;
-            float t = (float)(2.0 * (r / W - k) - 1.0);
-            float pf = o[7], pg = o[15];
-            for (int c = 6; c >= 0; --c) { pf = pf * t + o[c]; pg = pg * t + o[8 + c]; }
-            double f, g;
-            pse_rpy_real_fg(r, xi, 1.0, &f, &g);
-            maxerr = std::max(maxerr, std::max(fabs(pf - f), fabs(pg - g)));
+            if (q == c) continue;
+            const double m = M[q][c] / M[c][c];
+            for (int j = c; j < n + 2; ++j) M[q][j] -= m * M[c][j];
         }
     }
-    if (max_err_out) *max_err_out = maxerr;
-    return nI;
+    out[0] = (float)A; out[1] = (float)B; out[2] = (float)(-xi * xi * 1.4426950408889634);
+    float* cf = out + 3; float* cg = out + 3 + n;
+    for (int c = 0; c < n; ++c) { cf[c] = (float)(M[c][n] / M[c][c]); cg[c] = (float)(M[c][n + 1] / M[c][c]); }
+    double ef = 0, eg = 0, mf = 0, mg = 0;
+    const int S = 4000;
+    for (int k = 0; k <= S; ++k) {
+        const double r = lo + (rcut - lo) * k / S;
+        double f, g;
+        pse_rpy_real_fg(r, xi, 1.0, &f, &g);
+        const float rf = (float)r, inv = 1.0f / rf, t = out[0] * inv + out[1];
+        float pf = cf[n - 1], pg = cg[n - 1];
+        for (int c = n - 2; c >= 0; --c) { pf = pf * t + cf[c]; pg = pg * t + cg[c]; }
+        const float d = rf - 2.0f, e = exp2f(out[2] * d * d);
+        ef = std::max(ef, fabs((double)(pf * e) - f)); eg = std::max(eg, fabs((double)(pg * e) - g));
+        mf = std::max(mf, fabs(f)); mg = std::max(mg, fabs(g));
+    }
+    if (max_err_out) *max_err_out = std::max(ef / mf, eg / mg);
+    return PSE_OK;
 }

@@ -32,7 +32,7 @@ struct RealParams {
 // (float2 per knot: entry k and k+1 are read separately).
 struct TableGlobal {
     const float4* t;
-    __device__ __forceinline__ void fg(float dist, const RealParams& rp, float& Imrr, float& rr) const {
+    __device__ __forceinline__ void fg(float dist, float, const RealParams& rp, float& Imrr, float& rr) const {
         const int r_ind = __float2int_rd((dist - rp.dr) * rp.tab_scale);
         const float4 e = __ldg(t + r_ind);
         const float fac = dist * rp.inv_dr - (float)r_ind - 1.0f;
@@ -42,7 +42,7 @@ struct TableGlobal {
 };
 struct TableShared {
     const float2* t;
-    __device__ __forceinline__ void fg(float dist, const RealParams& rp, float& Imrr, float& rr) const {
+    __device__ __forceinline__ void fg(float dist, float, const RealParams& rp, float& Imrr, float& rr) const {
         const int r_ind = __float2int_rd((dist - rp.dr) * rp.tab_scale);
         const float2 a = t[r_ind], b = t[r_ind + 1];
         const float fac = dist * rp.inv_dr - (float)r_ind - 1.0f;
@@ -50,24 +50,38 @@ struct TableShared {
         rr = a.y + (b.y - a.y) * fac;
     }
 };
-// Piecewise degree-7 polynomials of the exact f(r), g(r) on intervals of width PSE_POLY_W (the RPY kink at
-// r = 2a is an interval boundary), fitted in double at Chebyshev nodes when the engine is created.  They agree
-// with the closed forms to ~1e-8 and therefore with the reference's linearly interpolated table to its own
-// interpolation error (~1e-7 relative), while the coefficient blocks (a few hundred bytes in all) are read with
-// four conflict-free LDS.128 (block stride 20 words: eight consecutive intervals land in disjoint banks) instead of
-// random 16-byte knots out of a 42-84 KB table.
-#define PSE_POLY_W 0.5f
-#define PSE_POLY_STRIDE 5  // float4 per interval: f0..f3 | f4..f7 | g0..g3 | g4..g7 | pad
-struct TablePoly {
-    const float4* c;
-    __device__ __forceinline__ void fg(float dist, const RealParams&, float& Imrr, float& rr) const {
-        const float s = dist * (1.0f / PSE_POLY_W);
-        const int iv = __float2int_rd(s);
-        const float t = 2.0f * (s - (float)iv) - 1.0f;
-        const float4* b = c + PSE_POLY_STRIDE * iv;
-        const float4 f0 = b[0], f1 = b[1], g0 = b[2], g1 = b[3];
-        Imrr = fmaf(fmaf(fmaf(fmaf(fmaf(fmaf(fmaf(f1.w, t, f1.z), t, f1.y), t, f1.x), t, f0.w), t, f0.z), t, f0.y), t, f0.x);
-        rr = fmaf(fmaf(fmaf(fmaf(fmaf(fmaf(fmaf(g1.w, t, g1.z), t, g1.y), t, g1.x), t, g0.w), t, g0.z), t, g0.y), t, g0.x);
+// Non-overlapping pairs (r >= 2a, every pair of a physical suspension) take no table at all:
+//     f = exp(-xi^2 (r-2a)^2) Pf(t), g = exp(-xi^2 (r-2a)^2) Pg(t), t = A/r + B, degree PSE_CHEB_DEG
+// (pse_fit_rpy_cheb in params.cpp; agreement with the closed forms ~1e-6 of max|f|, i.e. the same size as the
+// reference table's own linear-interpolation error).  The coefficients arrive as kernel parameters, so they are
+// constant-bank operands of the FMAs: the lookup leaves the L1/shared data pipe, which is what bounds this kernel
+// (profiles/r1_summary.md).  Overlapping pairs (r < 2a) fall back to the global table.
+#define PSE_CHEB_DEG 10
+struct ChebCoef {
+    float A, B, ne;  // t = A / r + B;  ne = -xi^2 log2(e)
+    float cf[PSE_CHEB_DEG + 1], cg[PSE_CHEB_DEG + 1];
+};
+struct TableCheb {
+    ChebCoef c;
+    const float4* t;
+    __device__ __forceinline__ void fg(float dist, float inv_dist, const RealParams& rp, float& Imrr, float& rr) const {
+        if (dist >= 2.0f) {
+            const float tt = fmaf(c.A, inv_dist, c.B);
+            float pf = c.cf[PSE_CHEB_DEG], pg = c.cg[PSE_CHEB_DEG];
+#pragma unroll
+            for (int k = PSE_CHEB_DEG - 1; k >= 0; --k) { pf = fmaf(pf, tt, c.cf[k]); pg = fmaf(pg, tt, c.cg[k]); }
+            const float d = dist - 2.0f;
+            float e;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(c.ne * d * d));
+            Imrr = pf * e;
+            rr = pg * e;
+        } else {
+            const int r_ind = __float2int_rd((dist - rp.dr) * rp.tab_scale);
+            const float4 e = __ldg(t + r_ind);
+            const float fac = dist * rp.inv_dr - (float)r_ind - 1.0f;
+            Imrr = e.x + (e.z - e.x) * fac;
+            rr = e.y + (e.w - e.y) * fac;
+        }
     }
 };
 template <class TAB>
@@ -76,7 +90,7 @@ __device__ __forceinline__ void rpy_pair(const float3 r, const float r2, const f
     const float inv_dist = rsqrtf(r2);
     const float dist = r2 * inv_dist;
     float Imrr, rr;
-    table.fg(dist, rp, Imrr, rr);
+    table.fg(dist, inv_dist, rp, Imrr, rr);
     const float rdotf = (r.x * Fj.x + r.y * Fj.y + r.z * Fj.z) * (inv_dist * inv_dist);
     const float c = (rr - Imrr) * rdotf;
     u.x += Imrr * Fj.x + c * r.x;
@@ -96,6 +110,14 @@ __device__ __forceinline__ void ld_px(const PX* ptr, float4& p, float4& x) {
     asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(p.x), "=f"(p.y), "=f"(p.z), "=f"(p.w), "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w)
                  : "l"(ptr));
+}
+
+// streaming 32-bit load that does not allocate in L1: the neighbour indices are read once per SpMV and must not evict
+// the gathered records
+__device__ __forceinline__ uint32_t ld_stream(const uint32_t* ptr) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(ptr));
+    return v;
 }
 
 // Per-step pruning of the buffered neighbour list: keeps, in row order, the neighbours that are inside the
@@ -163,8 +185,8 @@ template <int TPP, int MODE, int TABLE>
 __global__ void __launch_bounds__(256)
 spmv_kernel(const PX* __restrict__ px, float4* __restrict__ y, uint32_t N,
             const uint32_t* __restrict__ nn, const uint32_t* __restrict__ head, const uint32_t* __restrict__ nl,
-            const float4* __restrict__ gtable /* knots, or polynomial blocks for TABLE_POLY */, int npoly, RealParams rp,
-            PseBox box, LanczosArgs la, uint32_t row_begin = 0) {
+            const float4* __restrict__ gtable, ChebCoef cheb, RealParams rp,
+            PseBox box, LanczosArgs la, uint32_t row_begin = 0, int nsm = 0, int stream_idx = 0) {
     constexpr int ROWS = 256 / TPP;
     const int sub = threadIdx.x % TPP;
     extern __shared__ __align__(16) float2 stab[];
@@ -175,14 +197,10 @@ spmv_kernel(const PX* __restrict__ px, float4* __restrict__ y, uint32_t N,
             if (k == rp.ewald_n) stab[k + 1] = make_float2(t.z, t.w);
         }
         __syncthreads();
-    } else if (TABLE == TABLE_POLY) {
-        float4* sp = reinterpret_cast<float4*>(stab);
-        for (int k = threadIdx.x; k < PSE_POLY_STRIDE * npoly; k += blockDim.x) sp[k] = __ldg(gtable + k);
-        __syncthreads();
     }
-    typename std::conditional<TABLE == TABLE_SHARED, TableShared, typename std::conditional<TABLE == TABLE_POLY, TablePoly, TableGlobal>::type>::type table;
+    typename std::conditional<TABLE == TABLE_SHARED, TableShared, typename std::conditional<TABLE == TABLE_POLY, TableCheb, TableGlobal>::type>::type table;
     if constexpr (TABLE == TABLE_SHARED) table.t = stab;
-    else if constexpr (TABLE == TABLE_POLY) table.c = reinterpret_cast<const float4*>(stab);
+    else if constexpr (TABLE == TABLE_POLY) { table.c = cheb; table.t = gtable; }
     else table.t = gtable;
     float part = 0.f;
     float beta = 0.f, s = 0.f;
@@ -190,7 +208,19 @@ spmv_kernel(const PX* __restrict__ px, float4* __restrict__ y, uint32_t N,
         beta = __ldcg(la.beta_j);
         s = beta > 1e-8f ? 1.0f / beta : 0.f;  // breakdown guard, PSEv1/Brownian.cu:507-510
     }
-    for (uint32_t row0 = row_begin + blockIdx.x * ROWS; row0 < N; row0 += gridDim.x * ROWS) {  // rows [row_begin, N)
+    // Row groups of ROWS rows.  The blocks that share an SM (block b lands on SM b % nsm when the grid is a whole number of
+    // waves) interleave over ONE contiguous range of cell-ordered rows, so the records they gather overlap in L1; without
+    // that knowledge (nsm == 0) the groups are dealt out with a grid stride.  Only locality depends on the placement.
+    const uint32_t ngroups = (N - row_begin + ROWS - 1) / ROWS;
+    uint32_t g_begin = blockIdx.x, g_end = ngroups, g_step = gridDim.x;
+    if (nsm > 0 && gridDim.x % nsm == 0) {
+        const uint32_t sm = blockIdx.x % nsm;
+        g_step = gridDim.x / nsm;
+        g_begin = (uint32_t)(((uint64_t)ngroups * sm) / nsm) + blockIdx.x / nsm;
+        g_end = (uint32_t)(((uint64_t)ngroups * (sm + 1)) / nsm);
+    }
+    for (uint32_t g = g_begin; g < g_end; g += g_step) {  // rows [row_begin, N)
+        const uint32_t row0 = row_begin + g * ROWS;
         const uint32_t row = row0 + threadIdx.x / TPP;
         float3 u = make_float3(0.f, 0.f, 0.f);
         float4 pi = make_float4(0.f, 0.f, 0.f, 0.f), xi = pi;
@@ -202,7 +232,7 @@ spmv_kernel(const PX* __restrict__ px, float4* __restrict__ y, uint32_t N,
             uint32_t k = sub;
             // two neighbours per trip: both gathers are in flight before either is consumed
             for (; k + TPP < n; k += 2 * TPP) {
-                const uint32_t j0 = __ldg(list + k), j1 = __ldg(list + k + TPP);
+                const uint32_t j0 = stream_idx ? ld_stream(list + k) : __ldg(list + k), j1 = stream_idx ? ld_stream(list + k + TPP) : __ldg(list + k + TPP);
                 float4 p0, p1, x0, x1;
                 ld_px(px + j0, p0, x0);
                 ld_px(px + j1, p1, x1);
@@ -214,7 +244,7 @@ spmv_kernel(const PX* __restrict__ px, float4* __restrict__ y, uint32_t N,
                 if (in1) rpy_pair(r1, d1, x1, table, rp, u);
             }
             if (k < n) {
-                const uint32_t j0 = __ldg(list + k);
+                const uint32_t j0 = stream_idx ? ld_stream(list + k) : __ldg(list + k);
                 float4 p0, x0;
                 ld_px(px + j0, p0, x0);
                 const float3 r0 = box.min_image(make_float3(PSE_SUB(pi.x, p0.x), PSE_SUB(pi.y, p0.y), PSE_SUB(pi.z, p0.z)));

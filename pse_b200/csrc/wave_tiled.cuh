@@ -104,41 +104,102 @@ __device__ __forceinline__ int3 unwrapped_origin(const int4 o, const WaveParams&
     return make_int3(o.x + ((o.w & 3) - 1) * wp.Nx, o.y + (((o.w >> 2) & 3) - 1) * wp.Ny, o.z + (((o.w >> 4) & 3) - 1) * wp.Nz);
 }
 
+// ---- Gaussian factors of every particle, once per call ---------------------------------------------------
+// wwt[w][0 .. P*P) = w_xy(i, j) (prefac included), wwt[w][P*P .. P*P + P) = w_z(k), W order.  A particle is visited by
+// (1 + (P-1)/TILE)^3 ~ 2.3 tiles when spreading and once when interpolating; evaluating the reference-exact factors
+// (~100 instructions each with the minimum-image arithmetic and expf) in every visit was a third of the spreading
+// kernel's instructions (profiles/r1_summary.md).  P (P + 1) is even, so rows are 8-byte aligned for cp.async.
+// A block computes the rows of WW_PB consecutive particles into shared memory - one task per (particle, i) row of w_xy
+// and one per particle for the w_z row, xy tasks first so that warps do not mix the two - and writes them out as one
+// contiguous, fully coalesced range (scattered 4-byte stores of single rows ran at a third of the speed).
+#define WW_PB 32
+template <int P>
+__global__ void __launch_bounds__(256)
+wweights_kernel(const float4* __restrict__ wpos, const int4* __restrict__ worg, uint32_t N, PseBox box, WaveParams wp,
+                float* __restrict__ wwt) {
+    constexpr int PP = P * P, WS = PP + P;
+    __shared__ __align__(16) float rows[WW_PB * WS];
+    const uint32_t w0 = blockIdx.x * WW_PB;
+    const int np = (int)min((uint32_t)WW_PB, N - w0);
+    for (int t = threadIdx.x; t < WW_PB * (P + 1); t += blockDim.x) {
+        if (t < WW_PB * P) {
+            const int q = t / P, i = t - q * P;
+            if (q < np) {
+                const float4 pp = __ldg(wpos + w0 + q);
+                const int4 o = __ldg(worg + w0 + q);
+                const int ix = wrap_node(o.x + i, wp.Nx);
+#pragma unroll
+                for (int j = 0; j < P; ++j) rows[q * WS + i * P + j] = weight_xy(box, wp, ix, wrap_node(o.y + j, wp.Ny), pp.x, pp.y, wp.prefac);
+            }
+        } else {
+            const int q = t - WW_PB * P;
+            if (q < np) {
+                const float pz = __ldg(&wpos[w0 + q].z);
+                const int oz = __ldg(&worg[w0 + q].z);
+#pragma unroll
+                for (int k = 0; k < P; ++k) rows[q * WS + PP + k] = weight_z(box, wp, wrap_node(oz + k, wp.Nz), pz);
+            }
+        }
+    }
+    __syncthreads();
+    float2* dst = reinterpret_cast<float2*>(wwt + (size_t)w0 * WS);  // WS is even and w0 * WS * 4 is a multiple of 8
+    const float2* src = reinterpret_cast<const float2*>(rows);
+    for (int t = threadIdx.x; t < np * (WS / 2); t += blockDim.x) dst[t] = src[t];
+}
+
 // ---- spreading: one block per node tile -------------------------------------------------------------
-// Structure of one block (256 threads):
+// Structure of one block (P^3 threads rounded up to warps, at most 256):
 //   filter   all threads scan the particles of the candidate origin cells (<= 4x4x4, normally 2x2x2), keep the
 //            ones whose support reaches the tile and stage them, order preserved, in shared memory
-//            (position, force, wrapped origin, per-axis validity bits, tile offset) - one global latency;
-//   weights  per chunk of SPREAD_CHUNK staged particles: P^2 + P Gaussian factors each;
+//            (force, tile offset, per-axis validity bits, W index) - one global latency;
+//   factors  per chunk of SPREAD_CHUNK staged particles the precomputed rows of wwt are copied in with cp.async,
+//            double buffered: the copy of chunk c+1 is in flight while chunk c is scattered;
 //   scatter  one particle at a time, one thread per support node: acc[node] += w F (plain shared-memory
-//            adds; the per-particle barrier orders particles, so the sum is deterministic).  The next
-//            particle's record and weights are fetched before the barrier (software pipeline).
+//            adds; the per-particle barrier orders particles, so the sum is deterministic).  Two register sets
+//            alternate so that the next particle's record and factors are fetched before the barrier.
 //   store    the finished tile is written once, coalesced.
-// dynamic smem: acc[3][TILE*TILE*TILE_ZS] | a_pos[CAP] f4 | a_rec[CAP] f4 | a_oz[CAP] | a_mask[CAP] |
-//               wxy[CHUNK][P*P] | wz[CHUNK][P]
+// dynamic smem: acc[3][TILE*TILE*TILE_ZS] | a_rec[CAP] f4 | a_mask[CAP] | a_w[CAP] | wbuf[2][CHUNK][P*P+P]
 #define SPREAD_CAP 384   // staged particles per filter round; sized so that three blocks fit one SM
 #define SPREAD_MAX_SEG 64
 
+template <int P> struct SpreadCfg {
+    static constexpr int PPP = P * P * P;
+    static constexpr int NT = PPP >= 256 ? 256 : ((PPP + 31) / 32) * 32;  // threads per block
+    static constexpr int NPASS = (PPP + NT - 1) / NT;                     // support nodes per thread
+    static constexpr int WS = P * P + P;
+};
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+// acc[addr + OFF] += w * f on a 32-bit shared-window address (keeps the generic->shared conversion out of the loop)
+template <int OFF> __device__ __forceinline__ void smem_fma(uint32_t addr, float w, float f) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF));
+    v = fmaf(w, f, v);
+    asm volatile("st.shared.f32 [%0+%1], %2;" ::"r"(addr), "n"(OFF), "f"(v));
+}
+
 template <int P>
-__global__ void __launch_bounds__(256)
-spread_tile_kernel(const float4* __restrict__ wpos, const float4* __restrict__ wF, const int4* __restrict__ worg,
-                   const uint32_t* __restrict__ wcell_start, PseBox box, WaveParams wp, TileGrid tg, float* __restrict__ grid) {
+__global__ void __launch_bounds__(SpreadCfg<P>::NT)
+spread_tile_kernel(const float4* __restrict__ wF, const int4* __restrict__ worg, const float* __restrict__ wwt,
+                   const uint32_t* __restrict__ wcell_start, WaveParams wp, TileGrid tg, float* __restrict__ grid) {
     extern __shared__ __align__(16) float smem[];
     constexpr int PP = P * P, PPP = PP * P;
+    constexpr int NT = SpreadCfg<P>::NT, NW = NT / 32, npass = SpreadCfg<P>::NPASS, WS = SpreadCfg<P>::WS;
     constexpr int ACC = TILE * TILE * TILE_ZS;
     float* acc = smem;
-    float4* a_pos = reinterpret_cast<float4*>(acc + 3 * ACC);
-    float4* a_rec = a_pos + SPREAD_CAP;
-    int* a_oz = reinterpret_cast<int*>(a_rec + SPREAD_CAP);
-    uint32_t* a_mask = reinterpret_cast<uint32_t*>(a_oz + SPREAD_CAP);
-    float* swxy = reinterpret_cast<float*>(a_mask + SPREAD_CAP);
-    float* swz = swxy + SPREAD_CHUNK * PP;
+    float4* a_rec = reinterpret_cast<float4*>(acc + 3 * ACC);
+    uint32_t* a_mask = reinterpret_cast<uint32_t*>(a_rec + SPREAD_CAP);
+    uint32_t* a_w = a_mask + SPREAD_CAP;
+    float* wbuf = reinterpret_cast<float*>(a_w + SPREAD_CAP);  // [2][SPREAD_CHUNK][WS]
     __shared__ int s_cand[3][4];
     __shared__ int s_ncand[3];
     __shared__ uint32_t s_seg_b[SPREAD_MAX_SEG], s_seg_off[SPREAD_MAX_SEG + 1];
     __shared__ int s_nseg;
-    __shared__ int s_warp_cnt[8];
-    __shared__ int s_nact;
+    __shared__ int s_warp_cnt[2][NW];
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int tile = blockIdx.x + tg.tile0;
@@ -146,7 +207,7 @@ spread_tile_kernel(const float4* __restrict__ wpos, const float4* __restrict__ w
     const int t0x = bx * TILE, t0y = by * TILE, t0z = bz * TILE;
     const int ex = min(TILE, wp.Nx - t0x), ey = min(TILE, wp.Ny - t0y), ez = min(TILE, wp.Nz - t0z);
 
-    for (int i = tid; i < 3 * ACC; i += blockDim.x) acc[i] = 0.f;
+    for (int i = tid; i < 3 * ACC; i += NT) acc[i] = 0.f;
     if (tid < 3) {
         const int t0 = tid == 0 ? t0x : tid == 1 ? t0y : t0z, e = tid == 0 ? ex : tid == 1 ? ey : ez;
         const int N = tid == 0 ? wp.Nx : tid == 1 ? wp.Ny : wp.Nz;
@@ -166,17 +227,17 @@ spread_tile_kernel(const float4* __restrict__ wpos, const float4* __restrict__ w
         s_seg_off[n] = off;
         s_nseg = n;
     }
-    // this thread's support node(s) (i,j,k): constant over particles.  P^3 <= 1000 needs <= 4 passes of 256.
-    constexpr int npass = (PPP + 255) / 256;
-    int my_off[npass], my_ij[npass], my_k[npass];
+    // this thread's support node(s) (i,j,k): constant over particles
+    uint32_t my_acc[npass];  // shared-window byte address of acc[my node]
+    int my_ij[npass], my_k[npass];
     uint32_t my_bits[npass];
 #pragma unroll
     for (int r = 0; r < npass; ++r) {
-        const int t = tid + r * 256;
+        const int t = tid + r * NT;
         const int i = t / PP, j = (t - i * PP) / P, k = t - i * PP - j * P;
-        my_off[r] = (i * TILE + j) * TILE_ZS + k;
+        my_acc[r] = (uint32_t)__cvta_generic_to_shared(acc + (i * TILE + j) * TILE_ZS + k);
         my_ij[r] = i * P + j;
-        my_k[r] = k;
+        my_k[r] = PP + k;
         my_bits[r] = t < PPP ? ((1u << i) | (1u << (P + j)) | (1u << (2 * P + k))) : 0xffffffffu;  // never matches
     }
     __syncthreads();
@@ -184,91 +245,111 @@ spread_tile_kernel(const float4* __restrict__ wpos, const float4* __restrict__ w
     const uint32_t ncandidates = s_seg_off[nseg];
 
     uint32_t next = 0;  // next candidate (flat index) to examine
+    int trip = 0;
     while (next < ncandidates) {
         // ---- filter: ordered compaction of up to SPREAD_CAP reaching particles
         int nact = 0;
-        while (next < ncandidates && nact <= SPREAD_CAP - 256) {
+        while (next < ncandidates && nact <= SPREAD_CAP - NT) {
             const uint32_t t = next + tid;
             bool act = false;
             int lx = 0, ly = 0, lz = 0;
-            int4 o = make_int4(0, 0, 0, 0);
             uint32_t w = 0;
             if (t < ncandidates) {
                 int sgi = 0;
                 while (sgi + 1 < nseg && t >= s_seg_off[sgi + 1]) ++sgi;
                 w = s_seg_b[sgi] + (t - s_seg_off[sgi]);
-                o = __ldg(worg + w);
+                const int4 o = __ldg(worg + w);
                 lx = o.x - t0x; if (lx >= ex) lx -= wp.Nx;
                 ly = o.y - t0y; if (ly >= ey) ly -= wp.Ny;
                 lz = o.z - t0z; if (lz >= ez) lz -= wp.Nz;
                 act = lx > -P && ly > -P && lz > -P;
             }
             const uint32_t ball = __ballot_sync(0xffffffffu, act);
-            if (lane == 0) s_warp_cnt[wid] = __popc(ball);
+            int* cnt = s_warp_cnt[trip & 1];  // the counters alternate: one barrier per filter trip
+            if (lane == 0) cnt[wid] = __popc(ball);
             __syncthreads();
-            int before = nact;
-            for (int q = 0; q < wid; ++q) before += s_warp_cnt[q];
-            int total = 0;
-            for (int q = 0; q < 8; ++q) total += s_warp_cnt[q];
+            int before = nact, total = 0;
+#pragma unroll
+            for (int q = 0; q < NW; ++q) { const int v = cnt[q]; total += v; if (q < wid) before += v; }
             if (act) {
                 const int slot = before + __popc(ball & ((1u << lane) - 1u));
                 uint32_t m = 0;
+#pragma unroll
                 for (int i = 0; i < P; ++i) {
                     m |= (uint32_t)((unsigned)(lx + i) < (unsigned)ex) << i;
                     m |= (uint32_t)((unsigned)(ly + i) < (unsigned)ey) << (P + i);
                     m |= (uint32_t)((unsigned)(lz + i) < (unsigned)ez) << (2 * P + i);
                 }
-                const float4 pp = __ldg(wpos + w), F = __ldg(wF + w);
-                a_pos[slot] = make_float4(pp.x, pp.y, pp.z, __int_as_float(o.x | (o.y << 16)));
-                a_rec[slot] = make_float4(F.x, F.y, F.z, __int_as_float((lx * TILE + ly) * TILE_ZS + lz));
-                a_oz[slot] = o.z;
+                const float4 F = __ldg(wF + w);
+                a_rec[slot] = make_float4(F.x, F.y, F.z, __int_as_float(4 * ((lx * TILE + ly) * TILE_ZS + lz)));  // byte offset of the origin node
                 a_mask[slot] = m;
+                a_w[slot] = w;
             }
             nact += total;
-            next += 256;
-            __syncthreads();
+            next += NT;
+            ++trip;
         }
+        __syncthreads();
         // ---- chunks of staged particles
-        for (int c0 = 0; c0 < nact; c0 += SPREAD_CHUNK) {
+        auto fetch_chunk = [&](int c0, int buf) {  // rows of wwt -> wbuf[buf], 8 bytes per copy
             const int nch = min(SPREAD_CHUNK, nact - c0);
-            for (int t = tid; t < nch * (PP + P); t += blockDim.x) {
-                const int q = t / (PP + P), r = t - q * (PP + P);
-                const float4 pp = a_pos[c0 + q];
-                const int oxy = __float_as_int(pp.w);
-                if (r < PP) {
-                    const int i = r / P, j = r - i * P;
-                    swxy[q * PP + r] = weight_xy(box, wp, wrap_node((oxy & 0xffff) + i, wp.Nx), wrap_node((oxy >> 16) + j, wp.Ny), pp.x, pp.y, wp.prefac);
-                } else {
-                    swz[q * P + (r - PP)] = weight_z(box, wp, wrap_node(a_oz[c0 + q] + (r - PP), wp.Nz), pp.z);
-                }
+            float* dst = wbuf + buf * (SPREAD_CHUNK * WS);
+            for (int t = tid; t < nch * (WS / 2); t += NT) {
+                const int q = t / (WS / 2), r = t - q * (WS / 2);
+                cp_async8(dst + q * WS + 2 * r, wwt + (size_t)a_w[c0 + q] * WS + 2 * r);
             }
+            cp_async_commit();
+        };
+        if (nact > 0) fetch_chunk(0, 0);
+        int buf = 0;
+        for (int c0 = 0; c0 < nact; c0 += SPREAD_CHUNK, buf ^= 1) {
+            const int nch = min(SPREAD_CHUNK, nact - c0);
+            if (c0 + SPREAD_CHUNK < nact) { fetch_chunk(c0 + SPREAD_CHUNK, buf ^ 1); cp_async_wait<1>(); }
+            else cp_async_wait<0>();
             __syncthreads();
-            float4 rec_n = a_rec[c0];
-            uint32_t m_n = a_mask[c0];
-            float w_n[npass];
+            const float* wq = wbuf + buf * (SPREAD_CHUNK * WS);
+            const float4* recs = a_rec + c0;
+            const uint32_t* masks = a_mask + c0;
+            // two register sets (A: even particles, B: odd), each loaded one barrier ahead of its use
+            float4 recA = recs[0], recB;
+            uint32_t mA = masks[0], mB = 0;
+            float wA[npass], wB[npass];
 #pragma unroll
-            for (int r = 0; r < npass; ++r) w_n[r] = swxy[my_ij[r]] * swz[my_k[r]];
-            for (int q = 0; q < nch; ++q) {
-                const float4 rec = rec_n;
-                const uint32_t m = m_n;
-                float w[npass];
-#pragma unroll
-                for (int r = 0; r < npass; ++r) w[r] = w_n[r];
+            for (int r = 0; r < npass; ++r) { wA[r] = wq[my_ij[r]] * wq[my_k[r]]; wB[r] = 0.f; }
+            for (int q = 0; q < nch; q += 2) {
                 if (q + 1 < nch) {
-                    rec_n = a_rec[c0 + q + 1];
-                    m_n = a_mask[c0 + q + 1];
+                    recB = recs[q + 1]; mB = masks[q + 1];
 #pragma unroll
-                    for (int r = 0; r < npass; ++r) w_n[r] = swxy[(q + 1) * PP + my_ij[r]] * swz[(q + 1) * P + my_k[r]];
+                    for (int r = 0; r < npass; ++r) wB[r] = wq[(q + 1) * WS + my_ij[r]] * wq[(q + 1) * WS + my_k[r]];
                 }
-                const int base = __float_as_int(rec.w);
+                {
+                    const int base = __float_as_int(recA.w);
 #pragma unroll
-                for (int r = 0; r < npass; ++r) {
-                    if ((m & my_bits[r]) == my_bits[r]) {
-                        const int node = base + my_off[r];
-                        acc[node] += w[r] * rec.x;
-                        acc[ACC + node] += w[r] * rec.y;
-                        acc[2 * ACC + node] += w[r] * rec.z;
-                    }
+                    for (int r = 0; r < npass; ++r)
+                        if ((mA & my_bits[r]) == my_bits[r]) {
+                            const uint32_t a = my_acc[r] + base;
+                            smem_fma<0>(a, wA[r], recA.x);
+                            smem_fma<4 * ACC>(a, wA[r], recA.y);
+                            smem_fma<8 * ACC>(a, wA[r], recA.z);
+                        }
+                }
+                __syncthreads();
+                if (q + 1 >= nch) break;
+                if (q + 2 < nch) {
+                    recA = recs[q + 2]; mA = masks[q + 2];
+#pragma unroll
+                    for (int r = 0; r < npass; ++r) wA[r] = wq[(q + 2) * WS + my_ij[r]] * wq[(q + 2) * WS + my_k[r]];
+                }
+                {
+                    const int base = __float_as_int(recB.w);
+#pragma unroll
+                    for (int r = 0; r < npass; ++r)
+                        if ((mB & my_bits[r]) == my_bits[r]) {
+                            const uint32_t a = my_acc[r] + base;
+                            smem_fma<0>(a, wB[r], recB.x);
+                            smem_fma<4 * ACC>(a, wB[r], recB.y);
+                            smem_fma<8 * ACC>(a, wB[r], recB.z);
+                        }
                 }
                 __syncthreads();
             }
@@ -276,7 +357,7 @@ spread_tile_kernel(const float4* __restrict__ wpos, const float4* __restrict__ w
     }
     // ---- write the tile once
     const size_t G = (size_t)wp.Nx * wp.Ny * wp.Nz;
-    for (int t = tid; t < ex * ey * TILE; t += blockDim.x) {
+    for (int t = tid; t < ex * ey * TILE; t += NT) {
         const int lz = t % TILE, ly = (t / TILE) % ey, lx = t / (TILE * ey);
         if (lz < ez) {
             const int node = (lx * TILE + ly) * TILE_ZS + lz;
@@ -289,23 +370,23 @@ spread_tile_kernel(const float4* __restrict__ wpos, const float4* __restrict__ w
 }
 
 static inline size_t spread_tile_smem(int P) {
-    return (3 * (size_t)TILE * TILE * TILE_ZS) * sizeof(float) + SPREAD_CAP * (2 * sizeof(float4) + 2 * sizeof(int)) +
-           (size_t)SPREAD_CHUNK * (P * P + P) * sizeof(float);
+    return (3 * (size_t)TILE * TILE * TILE_ZS) * sizeof(float) + SPREAD_CAP * (sizeof(float4) + 2 * sizeof(uint32_t)) +
+           2 * (size_t)SPREAD_CHUNK * (P * P + P) * sizeof(float);
 }
 
 // ---- interpolation: one block per origin cell --------------------------------------------------------
 // dynamic smem: g[3][H*H*HS] with H = TILE + P - 1, HS = H | 1 (odd stride).
-// 16 warps per block; each warp walks the cell's particles with the next particle's record prefetched; the
-// Gaussian weight of a node is evaluated directly (ex2 + FMAs) instead of through staged factor tables, which
-// keeps the shared-memory pipe for the grid values only.
+// 16 warps per block; each warp walks the cell's particles with the next particle's origin and factor row
+// (wwt, computed once per call by wweights_kernel) prefetched into registers.
 #define INTERP_THREADS 512
 template <int P>
 __global__ void __launch_bounds__(INTERP_THREADS, 2)
-interp_tile_kernel(const float4* __restrict__ wpos, const int4* __restrict__ worg, const uint32_t* __restrict__ wcell_start,
-                   const uint32_t* __restrict__ wperm, const uint32_t* __restrict__ perm, PseBox box, WaveParams wp,
+interp_tile_kernel(const int4* __restrict__ worg, const float* __restrict__ wwt, const uint32_t* __restrict__ wcell_start,
+                   const uint32_t* __restrict__ wperm, const uint32_t* __restrict__ perm, WaveParams wp,
                    TileGrid tg, const float* __restrict__ grid, float4* __restrict__ U, int accumulate) {
     extern __shared__ __align__(16) float smem[];
-    constexpr int PP = P * P, PPP = PP * P, NR = (PPP + 31) / 32, NW = INTERP_THREADS / 32;
+    constexpr int PP = P * P, PPP = PP * P, NR = (PPP + 31) / 32, NW = INTERP_THREADS / 32, WS = PP + P;
+    constexpr int NWR = (WS + 31) / 32;  // factor words per lane
     constexpr int H = TILE + P - 1, HS = H | 1, GT = H * H * HS;
     float* g = smem;
     float* wts = smem + 3 * GT;
@@ -318,10 +399,16 @@ interp_tile_kernel(const float4* __restrict__ wpos, const int4* __restrict__ wor
     const size_t G = (size_t)wp.Nx * wp.Ny * wp.Nz;
     // first particle of this warp: issue its loads before staging the tile
     uint32_t w = cb + wid;
-    float4 pp_n = make_float4(0.f, 0.f, 0.f, 0.f);
     int4 o_n = make_int4(0, 0, 0, 0);
     uint32_t id_n = 0;
-    if (w < ce) { pp_n = __ldg(wpos + w); o_n = __ldg(worg + w); id_n = __ldg(perm + __ldg(wperm + w)); }
+    float wt_n[NWR];
+    auto fetch = [&](uint32_t ww) {  // origin, output slot and the precomputed factor row of particle ww
+        o_n = __ldg(worg + ww);
+        id_n = __ldg(perm + __ldg(wperm + ww));
+#pragma unroll
+        for (int r = 0; r < NWR; ++r) wt_n[r] = lane + 32 * r < WS ? __ldg(wwt + (size_t)ww * WS + lane + 32 * r) : 0.f;
+    };
+    if (w < ce) fetch(w);
     // stage the halo tile (periodic wrap per node); z fastest across lanes -> coalesced row segments
     for (int t = tid; t < H * H * H; t += INTERP_THREADS) {
         const int lz = t % H, ly = (t / H) % H, lx = t / (H * H);
@@ -344,25 +431,17 @@ interp_tile_kernel(const float4* __restrict__ wpos, const int4* __restrict__ wor
         my_w[r] = t < PPP ? (((i * P + j) << 8) | k) : -1;
     }
     __syncthreads();
-    float* mywt = wts + wid * (PP + P);
-    const float pref = wp.quadW * wp.prefac;
+    float* mywt = wts + wid * WS;
     while (w < ce) {
-        const float4 pp = pp_n;
         const int4 o = o_n;
         const uint32_t id = id_n;
+#pragma unroll
+        for (int r = 0; r < NWR; ++r)
+            if (lane + 32 * r < WS) mywt[lane + 32 * r] = wt_n[r];
         const uint32_t wn = w + NW;
-        if (wn < ce) { pp_n = __ldg(wpos + wn); o_n = __ldg(worg + wn); id_n = __ldg(perm + __ldg(wperm + wn)); }
+        if (wn < ce) fetch(wn);
         float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
         if (accumulate && lane == 0) old = U[id];
-#pragma unroll
-        for (int r = lane; r < PP + P; r += 32) {
-            if (r < PP) {
-                const int i = r / P, j = r - i * P;
-                mywt[r] = weight_xy(box, wp, wrap_node(o.x + i, wp.Nx), wrap_node(o.y + j, wp.Ny), pp.x, pp.y, pref);
-            } else {
-                mywt[r] = weight_z(box, wp, wrap_node(o.z + (r - PP), wp.Nz), pp.z);
-            }
-        }
         __syncwarp();
         const int base = ((o.x - t0x) * H + (o.y - t0y)) * HS + (o.z - t0z);
         float ax = 0.f, ay = 0.f, az = 0.f;
@@ -377,7 +456,7 @@ interp_tile_kernel(const float4* __restrict__ wpos, const int4* __restrict__ wor
             }
         }
         ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az);
-        if (lane == 0) U[id] = make_float4(old.x + ax, old.y + ay, old.z + az, 0.f);
+        if (lane == 0) U[id] = make_float4(old.x + wp.quadW * ax, old.y + wp.quadW * ay, old.z + wp.quadW * az, 0.f);  // quadrature weight h^3
         __syncwarp();
         w = wn;
     }
@@ -407,23 +486,32 @@ static cudaError_t tiled_set_attributes(int P) {
     return err;
 }
 
-static void launch_spread_tile(int P, cudaStream_t st, const float4* wpos, const float4* wF, const int4* worg, const uint32_t* wstart,
-                               const PseBox& box, const WaveParams& wp, const TileGrid& tg, float* grid, int ntiles = -1) {
-    if (ntiles < 0) ntiles = tg.ntile;
-    if (ntiles == 0) return;
+static void launch_wweights(int P, cudaStream_t st, const float4* wpos, const int4* worg, uint32_t N, const PseBox& box,
+                            const WaveParams& wp, float* wwt) {
+    const unsigned int nb = (N + WW_PB - 1) / WW_PB;
     switch (P) {
-#define X(p) case p: spread_tile_kernel<p><<<ntiles, 256, spread_tile_smem(p), st>>>(wpos, wF, worg, wstart, box, wp, tg, grid); break;
+#define X(p) case p: wweights_kernel<p><<<nb, 256, 0, st>>>(wpos, worg, N, box, wp, wwt); break;
         PSE_FOR_EACH_P(X)
 #undef X
     }
 }
-static void launch_interp_tile(int P, cudaStream_t st, const float4* wpos, const int4* worg, const uint32_t* wstart, const uint32_t* wperm,
-                               const uint32_t* perm, const PseBox& box, const WaveParams& wp, const TileGrid& tg, const float* grid,
+static void launch_spread_tile(int P, cudaStream_t st, const float4* wF, const int4* worg, const float* wwt, const uint32_t* wstart,
+                               const WaveParams& wp, const TileGrid& tg, float* grid, int ntiles = -1) {
+    if (ntiles < 0) ntiles = tg.ntile;
+    if (ntiles == 0) return;
+    switch (P) {
+#define X(p) case p: spread_tile_kernel<p><<<ntiles, SpreadCfg<p>::NT, spread_tile_smem(p), st>>>(wF, worg, wwt, wstart, wp, tg, grid); break;
+        PSE_FOR_EACH_P(X)
+#undef X
+    }
+}
+static void launch_interp_tile(int P, cudaStream_t st, const int4* worg, const float* wwt, const uint32_t* wstart, const uint32_t* wperm,
+                               const uint32_t* perm, const WaveParams& wp, const TileGrid& tg, const float* grid,
                                float4* U, int accumulate, int ntiles = -1) {
     if (ntiles < 0) ntiles = tg.ntile;
     if (ntiles == 0) return;
     switch (P) {
-#define X(p) case p: interp_tile_kernel<p><<<ntiles, INTERP_THREADS, interp_tile_smem(p), st>>>(wpos, worg, wstart, wperm, perm, box, wp, tg, grid, U, accumulate); break;
+#define X(p) case p: interp_tile_kernel<p><<<ntiles, INTERP_THREADS, interp_tile_smem(p), st>>>(worg, wwt, wstart, wperm, perm, wp, tg, grid, U, accumulate); break;
         PSE_FOR_EACH_P(X)
 #undef X
     }

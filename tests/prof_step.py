@@ -17,13 +17,17 @@ img = torch.zeros((N, 3), dtype=torch.int32, device="cuda")
 eng.lanczos_m = 5
 m = eng.step(pos, img, F, 0)
 torch.cuda.synchronize()
-eng.set_profiling(True)
+noprof = bool(os.environ.get("PSE_NOPROF"))
+if not noprof: eng.set_profiling(True)
 import time
 t0 = time.time()
 for t in range(1, steps + 1):
     m = eng.step(pos, img, F, t)
 torch.cuda.synchronize()
 wall = (time.time() - t0) / steps * 1e3
+if noprof:
+    print(f"N={N} steps={steps} m={m} wall/step={wall:.3f} ms (no profiling)  {eng.stats()}")
+    sys.exit(0)
 prof = eng.profile()
 tot = sum(v[0] for v in prof.values())
 print(f"N={N} steps={steps} m={m} wall/step={wall:.3f} ms  sum(phases)/step={tot/steps:.3f} ms  {eng.stats()}")
