@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpse_b200.so")
+LIB_PATH = os.environ.get("PSE_B200_LIB") or os.path.join(_HERE, "libpse_b200.so")  # override: tuning variants of the same ABI
 
 PSE_OK = 0
 PSE_EINVAL, PSE_ENODEVICE, PSE_ECUDA, PSE_EGRID, PSE_ENOMEM, PSE_EEIGEN, PSE_ECAPACITY = -1, -2, -3, -4, -5, -6, -7

@@ -120,7 +120,7 @@ struct pse_engine {
     ChebCoef cheb;        // constant-bank polynomial form of f, g for r >= 2a
     double cheb_max_err;
     int spmv_tpp;  // lanes per row in the SpMV
-    int spmv_map, spmv_stream_idx, spmv_bps;  // SM-local row mapping, no-L1-allocate index loads, blocks per SM (0 = auto)
+    int spmv_bps;  // blocks per SM of the persistent SpMV grid (0 = auto)
     // profiling
     bool prof_on;
     std::vector<cudaEvent_t>* prof_pool;
@@ -400,9 +400,7 @@ extern "C" int pse_create(const pse_config* cfg, void* stream, pse_engine** out)
         const char* tm = getenv("PSE_SPMV_TABLE");
         if (!tm || tm[0] == 'p') e->spmv_table_mode = TABLE_POLY;
         else if (tm[0] == 'g') e->spmv_table_mode = TABLE_GLOBAL;
-        e->spmv_tpp = 8;
-        { const char* v = getenv("PSE_SPMV_MAP"); e->spmv_map = v ? atoi(v) : 0; }
-        { const char* v = getenv("PSE_SPMV_STREAM"); e->spmv_stream_idx = v ? atoi(v) : 0; }
+        e->spmv_tpp = 4;  // measured: 4 lanes x 12 entries in flight 202 us, 8 x 6: 236 us, 16 x 3: 330 us per SpMV at N = 1M
         { const char* v = getenv("PSE_SPMV_BPS"); e->spmv_bps = v ? atoi(v) : 0; }
         const char* tpp = getenv("PSE_SPMV_TPP");
         if (tpp) e->spmv_tpp = atoi(tpp);
@@ -676,27 +674,26 @@ static void launch_spmv_tpp(pse_engine* e, float4* y, const LanczosArgs& la) {
     const uint32_t* nl = e->prune ? e->d_nl_act : e->d_nl;
     if (e->spmv_table_mode == TABLE_POLY) {
         spmv_kernel<TPP, MODE, TABLE_POLY><<<persistent_grid(e, work, e->spmv_bps > 0 ? e->spmv_bps : 8), 256, 0, e->stream>>>(
-            e->d_px, y, e->N, nn, e->d_head, nl, e->d_table, e->cheb, e->rp, e->box, la, 0, e->spmv_map ? e->num_sms : 0, e->spmv_stream_idx);
+            e->d_px, y, e->N, nn, e->d_head, nl, e->d_table, e->cheb, e->rp, e->box, la);
     } else if (e->spmv_table_mode == TABLE_SHARED) {
         const size_t sm = spmv_table_smem(e);
         int bps = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (sm + 1024)));
         if (e->spmv_bps > 0) bps = std::min(bps, e->spmv_bps);
         cudaFuncSetAttribute(spmv_kernel<TPP, MODE, TABLE_SHARED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         spmv_kernel<TPP, MODE, TABLE_SHARED><<<persistent_grid(e, work, bps), 256, sm, e->stream>>>(
-            e->d_px, y, e->N, nn, e->d_head, nl, e->d_table, e->cheb, e->rp, e->box, la, 0, e->spmv_map ? e->num_sms : 0, e->spmv_stream_idx);
+            e->d_px, y, e->N, nn, e->d_head, nl, e->d_table, e->cheb, e->rp, e->box, la);
     } else {
         spmv_kernel<TPP, MODE, TABLE_GLOBAL><<<persistent_grid(e, work, e->spmv_bps > 0 ? e->spmv_bps : 8), 256, 0, e->stream>>>(
-            e->d_px, y, e->N, nn, e->d_head, nl, e->d_table, e->cheb, e->rp, e->box, la, 0, e->spmv_map ? e->num_sms : 0, e->spmv_stream_idx);
+            e->d_px, y, e->N, nn, e->d_head, nl, e->d_table, e->cheb, e->rp, e->box, la);
     }
     LAUNCHED(e);
 }
 template <int MODE>
 static void launch_spmv(pse_engine* e, float4* y, const LanczosArgs& la) {
     switch (e->spmv_tpp) {
-        case 4: launch_spmv_tpp<4, MODE>(e, y, la); break;
+        case 8: launch_spmv_tpp<8, MODE>(e, y, la); break;
         case 16: launch_spmv_tpp<16, MODE>(e, y, la); break;
-        case 32: launch_spmv_tpp<32, MODE>(e, y, la); break;
-        default: launch_spmv_tpp<8, MODE>(e, y, la); break;
+        default: launch_spmv_tpp<4, MODE>(e, y, la); break;
     }
 }
 

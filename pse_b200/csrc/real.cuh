@@ -112,14 +112,6 @@ __device__ __forceinline__ void ld_px(const PX* ptr, float4& p, float4& x) {
                  : "l"(ptr));
 }
 
-// streaming 32-bit load that does not allocate in L1: the neighbour indices are read once per SpMV and must not evict
-// the gathered records
-__device__ __forceinline__ uint32_t ld_stream(const uint32_t* ptr) {
-    uint32_t v;
-    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(ptr));
-    return v;
-}
-
 // Per-step pruning of the buffered neighbour list: keeps, in row order, the neighbours that are inside the
 // real-space cutoff at the CURRENT positions (dr^2 <= r^2 < rcut^2, the filter of PSEv1/Mobility.cu:652).  The
 // m+1 SpMVs of a step then gather only pairs that contribute (the SpMV is bound by the gathered records, so
@@ -181,12 +173,19 @@ struct LanczosArgs {
 // per-pair lookup is then two LDS.64 instead of a 16-byte global gather that touches up to 32 cache lines per
 // warp (the L1 wavefront limiter of the first version, profiles/r1_ncu_summary.md).
 enum { TABLE_GLOBAL = 0, TABLE_SHARED = 1, TABLE_POLY = 2 };
+#ifndef SPMV_ROW_PASS
+#define SPMV_ROW_PASS 48
+#endif
+#ifndef SPMV_AHEAD
+#define SPMV_AHEAD 1
+#endif
+// SPMV_ROW_PASS: neighbour entries of a row covered by one pass (SPMV_ROW_PASS / TPP index registers per lane)
 template <int TPP, int MODE, int TABLE>
 __global__ void __launch_bounds__(256)
 spmv_kernel(const PX* __restrict__ px, float4* __restrict__ y, uint32_t N,
             const uint32_t* __restrict__ nn, const uint32_t* __restrict__ head, const uint32_t* __restrict__ nl,
             const float4* __restrict__ gtable, ChebCoef cheb, RealParams rp,
-            PseBox box, LanczosArgs la, uint32_t row_begin = 0, int nsm = 0, int stream_idx = 0) {
+            PseBox box, LanczosArgs la, uint32_t row_begin = 0) {
     constexpr int ROWS = 256 / TPP;
     const int sub = threadIdx.x % TPP;
     extern __shared__ __align__(16) float2 stab[];
@@ -208,48 +207,64 @@ spmv_kernel(const PX* __restrict__ px, float4* __restrict__ y, uint32_t N,
         beta = __ldcg(la.beta_j);
         s = beta > 1e-8f ? 1.0f / beta : 0.f;  // breakdown guard, PSEv1/Brownian.cu:507-510
     }
-    // Row groups of ROWS rows.  The blocks that share an SM (block b lands on SM b % nsm when the grid is a whole number of
-    // waves) interleave over ONE contiguous range of cell-ordered rows, so the records they gather overlap in L1; without
-    // that knowledge (nsm == 0) the groups are dealt out with a grid stride.  Only locality depends on the placement.
-    const uint32_t ngroups = (N - row_begin + ROWS - 1) / ROWS;
-    uint32_t g_begin = blockIdx.x, g_end = ngroups, g_step = gridDim.x;
-    if (nsm > 0 && gridDim.x % nsm == 0) {
-        const uint32_t sm = blockIdx.x % nsm;
-        g_step = gridDim.x / nsm;
-        g_begin = (uint32_t)(((uint64_t)ngroups * sm) / nsm) + blockIdx.x / nsm;
-        g_end = (uint32_t)(((uint64_t)ngroups * (sm + 1)) / nsm);
+    // row header (neighbour count, list offset) of the NEXT row group is fetched while the current one is processed
+    uint32_t n_next = 0, head_next = 0;
+    {
+        const uint32_t r = row_begin + blockIdx.x * ROWS + threadIdx.x / TPP;
+        if (r < N) { n_next = __ldg(nn + r); head_next = __ldg(head + r); }
     }
-    for (uint32_t g = g_begin; g < g_end; g += g_step) {  // rows [row_begin, N)
-        const uint32_t row0 = row_begin + g * ROWS;
+    for (uint32_t row0 = row_begin + blockIdx.x * ROWS; row0 < N; row0 += gridDim.x * ROWS) {  // rows [row_begin, N)
         const uint32_t row = row0 + threadIdx.x / TPP;
         float3 u = make_float3(0.f, 0.f, 0.f);
         float4 pi = make_float4(0.f, 0.f, 0.f, 0.f), xi = pi;
+        float4 vp = pi;
         const bool live = row < N;
+        const uint32_t n = n_next;
+        const uint32_t* __restrict__ list = nl + head_next;
+        {
+            const uint32_t r = row + gridDim.x * ROWS;
+            if (r < N) { n_next = __ldg(nn + r); head_next = __ldg(head + r); }
+        }
         if (live) {
             ld_px(px + row, pi, xi);
-            const uint32_t n = __ldg(nn + row);
-            const uint32_t* __restrict__ list = nl + __ldg(head + row);
-            uint32_t k = sub;
-            // two neighbours per trip: both gathers are in flight before either is consumed
-            for (; k + TPP < n; k += 2 * TPP) {
-                const uint32_t j0 = stream_idx ? ld_stream(list + k) : __ldg(list + k), j1 = stream_idx ? ld_stream(list + k + TPP) : __ldg(list + k + TPP);
-                float4 p0, p1, x0, x1;
-                ld_px(px + j0, p0, x0);
-                ld_px(px + j1, p1, x1);
-                const float3 r0 = box.min_image(make_float3(PSE_SUB(pi.x, p0.x), PSE_SUB(pi.y, p0.y), PSE_SUB(pi.z, p0.z)));
-                const float3 r1 = box.min_image(make_float3(PSE_SUB(pi.x, p1.x), PSE_SUB(pi.y, p1.y), PSE_SUB(pi.z, p1.z)));
-                const float d0 = r0.x * r0.x + r0.y * r0.y + r0.z * r0.z, d1 = r1.x * r1.x + r1.y * r1.y + r1.z * r1.z;
-                const bool in0 = d0 < rp.rcut_sq && d0 >= rp.dr_sq, in1 = d1 < rp.rcut_sq && d1 >= rp.dr_sq;
-                if (in0) rpy_pair(r0, d0, x0, table, rp, u);
-                if (in1) rpy_pair(r1, d1, x1, table, rp, u);
-            }
-            if (k < n) {
-                const uint32_t j0 = stream_idx ? ld_stream(list + k) : __ldg(list + k);
-                float4 p0, x0;
-                ld_px(px + j0, p0, x0);
-                const float3 r0 = box.min_image(make_float3(PSE_SUB(pi.x, p0.x), PSE_SUB(pi.y, p0.y), PSE_SUB(pi.z, p0.z)));
-                const float d0 = r0.x * r0.x + r0.y * r0.y + r0.z * r0.z;
-                if (d0 < rp.rcut_sq && d0 >= rp.dr_sq) rpy_pair(r0, d0, x0, table, rp, u);
+            if (MODE == SPMV_LANCZOS && !la.first && sub == 0) vp = __ldg(la.v_prev + row);
+            // The chain index -> record -> arithmetic is two dependent L2 latencies; with ~5 entries per lane the loop is
+            // too short to hide them by occupancy alone (42% of the stall samples, profiles/r1_summary.md).  So a lane
+            // loads all of its (up to SPMV_ROW_PASS / TPP) indices of the row at once, and the gathers run one pair ahead of the
+            // arithmetic.  Lane `sub` still owns entries sub, sub + TPP, ... in that order: sums are unchanged.
+            constexpr int SLOTS = TPP >= 32 ? 2 : SPMV_ROW_PASS / TPP;
+            for (uint32_t base = 0; base < n; base += SLOTS * TPP) {
+                uint32_t idx[SLOTS];
+#pragma unroll
+                for (int t = 0; t < SLOTS; ++t) {
+                    const uint32_t k = base + sub + t * TPP;
+                    idx[t] = k < n ? __ldg(list + k) : 0xffffffffu;
+                }
+                constexpr int AHEAD = SPMV_AHEAD, RING = AHEAD + 1;  // pairs of gathers in flight ahead of the arithmetic
+                float4 p[RING][2], x[RING][2];
+#pragma unroll
+                for (int h = 0; h < AHEAD; ++h)
+#pragma unroll
+                    for (int q = 0; q < 2; ++q)
+                        if (2 * h + q < SLOTS && idx[2 * h + q] != 0xffffffffu) ld_px(px + idx[2 * h + q], p[h % RING][q], x[h % RING][q]);
+#pragma unroll
+                for (int t = 0; t < SLOTS; t += 2) {
+                    const int cur = (t / 2) % RING, nxt = (t / 2 + AHEAD) % RING;
+                    if (t + 2 * AHEAD < SLOTS) {
+#pragma unroll
+                        for (int q = 0; q < 2; ++q)
+                            if (idx[t + 2 * AHEAD + q] != 0xffffffffu) ld_px(px + idx[t + 2 * AHEAD + q], p[nxt][q], x[nxt][q]);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        if (idx[t + q] != 0xffffffffu) {
+                            const float4 pj = p[cur][q];
+                            const float3 r = box.min_image(make_float3(PSE_SUB(pi.x, pj.x), PSE_SUB(pi.y, pj.y), PSE_SUB(pi.z, pj.z)));
+                            const float d = r.x * r.x + r.y * r.y + r.z * r.z;
+                            if (d < rp.rcut_sq && d >= rp.dr_sq) rpy_pair(r, d, x[cur][q], table, rp, u);
+                        }
+                    }
+                }
             }
         }
         u.x = group_sum<TPP>(u.x);
@@ -261,10 +276,7 @@ spmv_kernel(const PX* __restrict__ px, float4* __restrict__ y, uint32_t N,
             } else {
                 const float3 v = make_float3(s * xi.x, s * xi.y, s * xi.z);
                 float3 mv = make_float3(s * (u.x + rp.self * xi.x), s * (u.y + rp.self * xi.y), s * (u.z + rp.self * xi.z));
-                if (!la.first) {
-                    const float4 vp = __ldg(la.v_prev + row);
-                    mv.x -= beta * vp.x; mv.y -= beta * vp.y; mv.z -= beta * vp.z;
-                }
+                if (!la.first) { mv.x -= beta * vp.x; mv.y -= beta * vp.y; mv.z -= beta * vp.z; }
                 la.v_out[row] = make_float4(v.x, v.y, v.z, 0.f);
                 y[row] = make_float4(mv.x, mv.y, mv.z, 0.f);
                 part += v.x * mv.x + v.y * mv.y + v.z * mv.z;
