@@ -667,23 +667,23 @@ extern "C" int pse_grid_index(pse_engine* e, const float4* d_pos, int3* d_out) {
 }
 
 // ---- building blocks (slot order) -----------------------------------------------------------------
-template <int TPP, int MODE>
+template <int TPP, int MODE, bool PRUNED>
 static void launch_spmv_tpp(pse_engine* e, float4* y, const LanczosArgs& la) {
     const unsigned int work = nblk((size_t)e->N * TPP, 256);
-    const uint32_t* nn = e->prune ? e->d_nn_act : e->d_nn;
-    const uint32_t* nl = e->prune ? e->d_nl_act : e->d_nl;
+    const uint32_t* nn = PRUNED ? e->d_nn_act : e->d_nn;
+    const uint32_t* nl = PRUNED ? e->d_nl_act : e->d_nl;
     if (e->spmv_table_mode == TABLE_POLY) {
-        spmv_kernel<TPP, MODE, TABLE_POLY><<<persistent_grid(e, work, e->spmv_bps > 0 ? e->spmv_bps : 8), 256, 0, e->stream>>>(
+        spmv_kernel<TPP, MODE, TABLE_POLY, PRUNED><<<persistent_grid(e, work, e->spmv_bps > 0 ? e->spmv_bps : 8), 256, 0, e->stream>>>(
             e->d_px, y, e->N, nn, e->d_head, nl, e->d_table, e->cheb, e->rp, e->box, la);
     } else if (e->spmv_table_mode == TABLE_SHARED) {
         const size_t sm = spmv_table_smem(e);
         int bps = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (sm + 1024)));
         if (e->spmv_bps > 0) bps = std::min(bps, e->spmv_bps);
-        cudaFuncSetAttribute(spmv_kernel<TPP, MODE, TABLE_SHARED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        spmv_kernel<TPP, MODE, TABLE_SHARED><<<persistent_grid(e, work, bps), 256, sm, e->stream>>>(
+        cudaFuncSetAttribute(spmv_kernel<TPP, MODE, TABLE_SHARED, PRUNED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        spmv_kernel<TPP, MODE, TABLE_SHARED, PRUNED><<<persistent_grid(e, work, bps), 256, sm, e->stream>>>(
             e->d_px, y, e->N, nn, e->d_head, nl, e->d_table, e->cheb, e->rp, e->box, la);
     } else {
-        spmv_kernel<TPP, MODE, TABLE_GLOBAL><<<persistent_grid(e, work, e->spmv_bps > 0 ? e->spmv_bps : 8), 256, 0, e->stream>>>(
+        spmv_kernel<TPP, MODE, TABLE_GLOBAL, PRUNED><<<persistent_grid(e, work, e->spmv_bps > 0 ? e->spmv_bps : 8), 256, 0, e->stream>>>(
             e->d_px, y, e->N, nn, e->d_head, nl, e->d_table, e->cheb, e->rp, e->box, la);
     }
     LAUNCHED(e);
@@ -691,9 +691,8 @@ static void launch_spmv_tpp(pse_engine* e, float4* y, const LanczosArgs& la) {
 template <int MODE>
 static void launch_spmv(pse_engine* e, float4* y, const LanczosArgs& la) {
     switch (e->spmv_tpp) {
-        case 8: launch_spmv_tpp<8, MODE>(e, y, la); break;
-        case 16: launch_spmv_tpp<16, MODE>(e, y, la); break;
-        default: launch_spmv_tpp<4, MODE>(e, y, la); break;
+        case 8: e->prune ? launch_spmv_tpp<8, MODE, true>(e, y, la) : launch_spmv_tpp<8, MODE, false>(e, y, la); break;
+        default: e->prune ? launch_spmv_tpp<4, MODE, true>(e, y, la) : launch_spmv_tpp<4, MODE, false>(e, y, la); break;
     }
 }
 
@@ -1311,9 +1310,14 @@ extern "C" int pse_shard_finish(pse_engine* e, const float* d_halo_recv, float4*
             e->pruned_valid = false;  // only a row range is pruned
         }
         LanczosArgs la = {};
-        const unsigned int work = nblk((size_t)nrows * 8, 256);
-        spmv_kernel<8, SPMV_PLAIN, TABLE_GLOBAL><<<persistent_grid(e, work, 8), 256, 0, st>>>(e->d_px, e->d_sy, s->row1, nn, e->d_head, nl, e->d_table, e->cheb,
-                                                                                       e->rp, e->box, la, s->row0); LAUNCHED(e);
+        const unsigned int work = nblk((size_t)nrows * 4, 256);
+        if (e->prune)
+            spmv_kernel<4, SPMV_PLAIN, TABLE_GLOBAL, true><<<persistent_grid(e, work, 8), 256, 0, st>>>(e->d_px, e->d_sy, s->row1, nn, e->d_head, nl, e->d_table,
+                                                                                                  e->cheb, e->rp, e->box, la, s->row0);
+        else
+            spmv_kernel<4, SPMV_PLAIN, TABLE_GLOBAL, false><<<persistent_grid(e, work, 8), 256, 0, st>>>(e->d_px, e->d_sy, s->row1, nn, e->d_head, nl, e->d_table,
+                                                                                                   e->cheb, e->rp, e->box, la, s->row0);
+        LAUNCHED(e);
         scatter_add_kernel<<<nblk(nrows, 256), 256, 0, st>>>(e->d_sy, e->d_perm, s->row1, d_U, 1, s->row0); LAUNCHED(e);
     }
     CK(cudaGetLastError());

@@ -9,7 +9,7 @@
 #include <algorithm>
 #include <vector>
 
-#define PSE_CHEB_DEG 10  // keep in step with real.cuh
+#define PSE_CHEB_DEG 8  // keep in step with real.cuh
 
 static const double kPiRef = 3.1415926536;  // the literal the reference uses everywhere
 

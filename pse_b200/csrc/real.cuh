@@ -56,7 +56,7 @@ struct TableShared {
 // reference table's own linear-interpolation error).  The coefficients arrive as kernel parameters, so they are
 // constant-bank operands of the FMAs: the lookup leaves the L1/shared data pipe, which is what bounds this kernel
 // (profiles/r1_summary.md).  Overlapping pairs (r < 2a) fall back to the global table.
-#define PSE_CHEB_DEG 10
+#define PSE_CHEB_DEG 8
 struct ChebCoef {
     float A, B, ne;  // t = A / r + B;  ne = -xi^2 log2(e)
     float cf[PSE_CHEB_DEG + 1], cg[PSE_CHEB_DEG + 1];
@@ -112,6 +112,10 @@ __device__ __forceinline__ void ld_px(const PX* ptr, float4& p, float4& x) {
                  : "l"(ptr));
 }
 
+// Pruned lists carry, in the top bit of each entry, whether the minimum image of the pair differs from the plain
+// difference of the two positions; the SpMV then skips the image arithmetic for all other pairs (BoxDim::minImage
+// returns its argument unchanged, bit for bit, when every image index rounds to zero).  Needs N < 2^31.
+#define PSE_WRAP_BIT 0x80000000u
 // Per-step pruning of the buffered neighbour list: keeps, in row order, the neighbours that are inside the
 // real-space cutoff at the CURRENT positions (dr^2 <= r^2 < rcut^2, the filter of PSEv1/Mobility.cu:652).  The
 // m+1 SpMVs of a step then gather only pairs that contribute (the SpMV is bound by the gathered records, so
@@ -133,16 +137,18 @@ prune_kernel(const float4* __restrict__ spos, uint32_t N, const uint32_t* __rest
 #pragma unroll
         for (int o = 8; o < 32; o <<= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
         uint32_t kept = 0;
-        for (uint32_t k0 = 0; k0 < nmax; k0 += 8) {
+        for (uint32_t k0 = 0; k0 < nmax; k0 += 8) {  // (loading a pass of indices ahead, as the SpMV does, was slower here)
             const uint32_t k = k0 + sub;
             bool in = false;
             uint32_t j = 0;
             if (k < n) {
                 j = __ldg(nl + h + k);
                 const float4 pj = __ldg(spos + j);
-                const float3 r = box.min_image(make_float3(PSE_SUB(pi.x, pj.x), PSE_SUB(pi.y, pj.y), PSE_SUB(pi.z, pj.z)));
+                const float3 dl = make_float3(PSE_SUB(pi.x, pj.x), PSE_SUB(pi.y, pj.y), PSE_SUB(pi.z, pj.z));
+                const float3 r = box.min_image(dl);
                 const float d = r.x * r.x + r.y * r.y + r.z * r.z;
                 in = d < rp.rcut_sq && d >= rp.dr_sq;
+                if (r.x != dl.x || r.y != dl.y || r.z != dl.z) j |= PSE_WRAP_BIT;  // the pair crosses a periodic boundary
             }
             const uint32_t ball = (__ballot_sync(0xffffffffu, in) >> (grp * 8)) & 0xffu;
             if (in) nl_act[h + kept + __popc(ball & ((1u << sub) - 1u))] = j;
@@ -180,8 +186,8 @@ enum { TABLE_GLOBAL = 0, TABLE_SHARED = 1, TABLE_POLY = 2 };
 #define SPMV_AHEAD 1
 #endif
 // SPMV_ROW_PASS: neighbour entries of a row covered by one pass (SPMV_ROW_PASS / TPP index registers per lane)
-template <int TPP, int MODE, int TABLE>
-__global__ void __launch_bounds__(256)
+template <int TPP, int MODE, int TABLE, bool PRUNED>
+__global__ void __launch_bounds__(256, 4)
 spmv_kernel(const PX* __restrict__ px, float4* __restrict__ y, uint32_t N,
             const uint32_t* __restrict__ nn, const uint32_t* __restrict__ head, const uint32_t* __restrict__ nl,
             const float4* __restrict__ gtable, ChebCoef cheb, RealParams rp,
@@ -246,22 +252,24 @@ spmv_kernel(const PX* __restrict__ px, float4* __restrict__ y, uint32_t N,
                 for (int h = 0; h < AHEAD; ++h)
 #pragma unroll
                     for (int q = 0; q < 2; ++q)
-                        if (2 * h + q < SLOTS && idx[2 * h + q] != 0xffffffffu) ld_px(px + idx[2 * h + q], p[h % RING][q], x[h % RING][q]);
+                        if (2 * h + q < SLOTS && idx[2 * h + q] != 0xffffffffu) ld_px(px + (PRUNED ? idx[2 * h + q] & ~PSE_WRAP_BIT : idx[2 * h + q]), p[h % RING][q], x[h % RING][q]);
 #pragma unroll
                 for (int t = 0; t < SLOTS; t += 2) {
                     const int cur = (t / 2) % RING, nxt = (t / 2 + AHEAD) % RING;
                     if (t + 2 * AHEAD < SLOTS) {
 #pragma unroll
                         for (int q = 0; q < 2; ++q)
-                            if (idx[t + 2 * AHEAD + q] != 0xffffffffu) ld_px(px + idx[t + 2 * AHEAD + q], p[nxt][q], x[nxt][q]);
+                            if (idx[t + 2 * AHEAD + q] != 0xffffffffu) ld_px(px + (PRUNED ? idx[t + 2 * AHEAD + q] & ~PSE_WRAP_BIT : idx[t + 2 * AHEAD + q]), p[nxt][q], x[nxt][q]);
                     }
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
                         if (idx[t + q] != 0xffffffffu) {
                             const float4 pj = p[cur][q];
-                            const float3 r = box.min_image(make_float3(PSE_SUB(pi.x, pj.x), PSE_SUB(pi.y, pj.y), PSE_SUB(pi.z, pj.z)));
+                            float3 r = make_float3(PSE_SUB(pi.x, pj.x), PSE_SUB(pi.y, pj.y), PSE_SUB(pi.z, pj.z));
+                            if (!PRUNED || (idx[t + q] & PSE_WRAP_BIT)) r = box.min_image(r);
                             const float d = r.x * r.x + r.y * r.y + r.z * r.z;
-                            if (d < rp.rcut_sq && d >= rp.dr_sq) rpy_pair(r, d, x[cur][q], table, rp, u);
+                            // a pruned list was filtered with this very arithmetic at these very positions
+                            if (PRUNED || (d < rp.rcut_sq && d >= rp.dr_sq)) rpy_pair(r, d, x[cur][q], table, rp, u);
                         }
                     }
                 }
