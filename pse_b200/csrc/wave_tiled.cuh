@@ -375,21 +375,48 @@ static inline size_t spread_tile_smem(int P) {
 }
 
 // ---- interpolation: one block per origin cell --------------------------------------------------------
-// dynamic smem: g[3][H*H*HS] with H = TILE + P - 1, HS = H | 1 (odd stride).
-// 16 warps per block; each warp walks the cell's particles with the next particle's origin and factor row
-// (wwt, computed once per call by wweights_kernel) prefetched into registers.
+// The block stages the (TILE+P-1)^3 halo tile of the three velocity grids in shared memory; each of its 16 warps
+// walks particles of the cell.  A lane owns one (i, j) COLUMN of the support and walks its P z-nodes:
+//   * tile strides (x: H*H + pad, y: H, z: 1) chosen so that the 32 columns of a pass fall into 32 different banks
+//     (one wavefront per load instead of two with a node-per-lane mapping; interp_pad() searches the pad);
+//   * w_xy of the column is the lane's own word of the prefetched factor row, w_z(k) comes by shuffle - no
+//     shared-memory scratch for factors;
+//   * columns beyond a multiple of 32 (4 of the 36 for P = 6) are handled one NODE per lane when they fit a warp.
+// dynamic smem: g[3][H * XS].
 #define INTERP_THREADS 512
+__host__ __device__ constexpr int interp_pad(int P) {
+    const int H = TILE + P - 1, PP = P * P;
+    int best_pad = 0, best_cost = 1 << 30;
+    for (int pad = 0; pad < 32; ++pad) {
+        const int XS = H * H + pad;
+        int cost = 0;
+        for (int c0 = 0; c0 < PP; c0 += 32) {
+            int cnt[32] = {};
+            int mx = 0;
+            for (int c = c0; c < PP && c < c0 + 32; ++c) {
+                const int i = c / P, j = c % P;
+                const int b = (i * XS + j * H) % 32;
+                if (++cnt[b] > mx) mx = cnt[b];
+            }
+            cost += mx;
+        }
+        if (cost < best_cost) { best_cost = cost; best_pad = pad; }
+    }
+    return best_pad;
+}
 template <int P>
 __global__ void __launch_bounds__(INTERP_THREADS, 2)
 interp_tile_kernel(const int4* __restrict__ worg, const float* __restrict__ wwt, const uint32_t* __restrict__ wcell_start,
                    const uint32_t* __restrict__ wperm, const uint32_t* __restrict__ perm, WaveParams wp,
                    TileGrid tg, const float* __restrict__ grid, float4* __restrict__ U, int accumulate) {
     extern __shared__ __align__(16) float smem[];
-    constexpr int PP = P * P, PPP = PP * P, NR = (PPP + 31) / 32, NW = INTERP_THREADS / 32, WS = PP + P;
+    constexpr int PP = P * P, NW = INTERP_THREADS / 32, WS = PP + P;
     constexpr int NWR = (WS + 31) / 32;  // factor words per lane
-    constexpr int H = TILE + P - 1, HS = H | 1, GT = H * H * HS;
+    constexpr int H = TILE + P - 1, XS = H * H + interp_pad(P), GT = H * XS;
+    constexpr int NFULL = PP / 32;             // passes in which every lane has a column
+    constexpr int LEFT = PP - 32 * NFULL;      // remaining columns
+    constexpr bool LEFT_NODES = LEFT > 0 && LEFT * P <= 32;  // ... handled one node per lane
     float* g = smem;
-    float* wts = smem + 3 * GT;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t cell = blockIdx.x + tg.tile0;
     const uint32_t cb = __ldg(wcell_start + cell), ce = __ldg(wcell_start + cell + 1);
@@ -416,55 +443,89 @@ interp_tile_kernel(const int4* __restrict__ worg, const float* __restrict__ wwt,
         int y = t0y + ly; if (y >= wp.Ny) y -= wp.Ny;
         int z = t0z + lz; if (z >= wp.Nz) z -= wp.Nz;
         const size_t idx = ((size_t)x * wp.Ny + y) * wp.Nz + z;
-        const int node = (lx * H + ly) * HS + lz;
+        const int node = lx * XS + ly * H + lz;
         g[node] = __ldg(grid + idx);
         g[GT + node] = __ldg(grid + G + idx);
         g[2 * GT + node] = __ldg(grid + 2 * G + idx);
     }
-    // this lane's support nodes (i,j,k), constant over particles: tile offset and factor indices
-    int my_node[NR], my_w[NR];  // tile offset; (ij << 8 | k), -1 beyond the support
+    // this lane's columns: tile offset of (i, j, 0) for each full pass, and of the left-over column / node
+    int col_off[NFULL > 0 ? NFULL : 1];
 #pragma unroll
-    for (int r = 0; r < NR; ++r) {
-        const int t = lane + 32 * r;
-        const int i = t / PP, j = (t - i * PP) / P, k = t - i * PP - j * P;
-        my_node[r] = (i * H + j) * HS + k;
-        my_w[r] = t < PPP ? (((i * P + j) << 8) | k) : -1;
+    for (int r = 0; r < NFULL; ++r) {
+        const int c = lane + 32 * r;
+        col_off[r] = (c / P) * XS + (c % P) * H;
+    }
+    int left_off = -1, left_col = 0, left_k = 0;
+    if (LEFT > 0) {
+        if (LEFT_NODES) {
+            if (lane < LEFT * P) { left_col = 32 * NFULL + lane / P; left_k = lane % P; }
+            else left_col = -1;
+        } else {
+            left_col = lane < LEFT ? 32 * NFULL + lane : -1;
+        }
+        if (left_col >= 0) left_off = (left_col / P) * XS + (left_col % P) * H + left_k;
     }
     __syncthreads();
-    float* mywt = wts + wid * WS;
     while (w < ce) {
         const int4 o = o_n;
         const uint32_t id = id_n;
+        float wt[NWR];
 #pragma unroll
-        for (int r = 0; r < NWR; ++r)
-            if (lane + 32 * r < WS) mywt[lane + 32 * r] = wt_n[r];
+        for (int r = 0; r < NWR; ++r) wt[r] = wt_n[r];
         const uint32_t wn = w + NW;
         if (wn < ce) fetch(wn);
         float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
         if (accumulate && lane == 0) old = U[id];
-        __syncwarp();
-        const int base = ((o.x - t0x) * H + (o.y - t0y)) * HS + (o.z - t0z);
+        float wz[P];
+#pragma unroll
+        for (int k = 0; k < P; ++k) wz[k] = __shfl_sync(0xffffffffu, wt[(PP + k) / 32], (PP + k) % 32);
+        const float* gb = g + (o.x - t0x) * XS + (o.y - t0y) * H + (o.z - t0z);
         float ax = 0.f, ay = 0.f, az = 0.f;
 #pragma unroll
-        for (int r = 0; r < NR; ++r) {
-            if (my_w[r] >= 0) {
-                const float wgt = mywt[my_w[r] >> 8] * mywt[PP + (my_w[r] & 255)];
-                const int node = base + my_node[r];
-                ax = fmaf(wgt, g[node], ax);
-                ay = fmaf(wgt, g[GT + node], ay);
-                az = fmaf(wgt, g[2 * GT + node], az);
+        for (int r = 0; r < NFULL; ++r) {
+            const float* gc = gb + col_off[r];
+#pragma unroll
+            for (int k = 0; k < P; ++k) {
+                const float wgt = wt[r] * wz[k];
+                ax = fmaf(wgt, gc[k], ax);
+                ay = fmaf(wgt, gc[GT + k], ay);
+                az = fmaf(wgt, gc[2 * GT + k], az);
+            }
+        }
+        if (LEFT > 0) {
+            // factor words of the left-over columns live in other lanes: fetch by shuffle (all lanes take part)
+            const int src = left_col >= 0 ? left_col : 0;
+            const float wxy = __shfl_sync(0xffffffffu, wt[NFULL], src % 32);
+            if (LEFT_NODES) {
+                float wzl = wz[0];
+#pragma unroll
+                for (int k = 1; k < P; ++k) wzl = left_k == k ? wz[k] : wzl;
+                if (left_off >= 0) {
+                    const float wgt = wxy * wzl;
+                    ax = fmaf(wgt, gb[left_off], ax);
+                    ay = fmaf(wgt, gb[GT + left_off], ay);
+                    az = fmaf(wgt, gb[2 * GT + left_off], az);
+                }
+            } else if (left_off >= 0) {
+                const float* gc = gb + left_off;
+#pragma unroll
+                for (int k = 0; k < P; ++k) {
+                    const float wgt = wxy * wz[k];
+                    ax = fmaf(wgt, gc[k], ax);
+                    ay = fmaf(wgt, gc[GT + k], ay);
+                    az = fmaf(wgt, gc[2 * GT + k], az);
+                }
             }
         }
         ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az);
         if (lane == 0) U[id] = make_float4(old.x + wp.quadW * ax, old.y + wp.quadW * ay, old.z + wp.quadW * az, 0.f);  // quadrature weight h^3
-        __syncwarp();
         w = wn;
     }
 }
 
 static inline size_t interp_tile_smem(int P) {
-    const int H = TILE + P - 1, HS = H | 1;
-    return (3 * (size_t)H * H * HS + (INTERP_THREADS / 32) * (size_t)(P * P + P)) * sizeof(float);
+    const int H = TILE + P - 1, XS = H * H + interp_pad(P);
+    return 3 * (size_t)H * XS * sizeof(float);
 }
 
 // ---- dispatch on the (runtime) support size ------------------------------------------------------------
