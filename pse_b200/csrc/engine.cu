@@ -21,6 +21,7 @@
 #include "rng.cuh"
 #include "wave.cuh"
 #include "wave_tiled.cuh"
+#include "fft.cuh"
 
 int pse_tridiag_sqrt_e1(int m, const double* diag, const double* off, double* c, double* lambda_min_out);
 int pse_fit_rpy_cheb(double xi, double rcut, float* out, double* max_err_out);
@@ -88,6 +89,10 @@ struct pse_engine {
     float2* d_spec;
     cufftHandle plan_f, plan_b;
     bool plans_ok;
+    // own shared-memory FFT passes (fft.cuh); cuFFT stays as the fallback (PSE_FFT=cufft) and for the sharded path
+    bool own_fft;
+    Fft1D fft_ax[3];  // x, y, z
+    void* d_fft_tables;
     // tile-owned spreading / interpolation ("W order", rebinned per call)
     bool tiled;
     TileGrid tg;
@@ -326,6 +331,74 @@ static int alloc_all(pse_engine* e) {
     return PSE_OK;
 }
 
+// ---- own FFT: radix schedule and tables of one axis ------------------------------------------------------
+static bool fft_factor(int N, Fft1D* f) {
+    f->N = N; f->npass = 0; f->radices = 0ull;
+    int n = N;
+    const int radices[4] = {4, 2, 3, 5};
+    for (int r : radices)
+        while (n % r == 0 && n > 1) {
+            if (f->npass == FFT_MAX_PASSES) return false;
+            f->radices |= (unsigned long long)r << (4 * f->npass++);
+            n /= r;
+        }
+    return n == 1 && N >= 2 && N <= FFT_MAX_N;
+}
+static int setup_own_fft(pse_engine* e) {
+    e->own_fft = true;
+    { const char* env = getenv("PSE_FFT"); if (env && env[0] == 'c') e->own_fft = false; }
+    const int dims[3] = {e->wp.Nx, e->wp.Ny, e->wp.Nz};
+    for (int a = 0; a < 3; ++a)
+        if (!fft_factor(dims[a], &e->fft_ax[a])) e->own_fft = false;
+    if (e->wp.Nx * e->wp.Ny * 3ll >= (1ll << 31)) e->own_fft = false;
+    if (!e->own_fft) return PSE_OK;
+    // one allocation: per axis tw[N] (float2) | pos_of[N] | freq_of[N] (uint16)
+    size_t bytes = 0, off_tw[3], off_pos[3], off_frq[3];
+    for (int a = 0; a < 3; ++a) {
+        off_tw[a] = bytes; bytes += sizeof(float2) * dims[a];
+        off_pos[a] = bytes; bytes += sizeof(uint16_t) * dims[a];
+        off_frq[a] = bytes; bytes += sizeof(uint16_t) * dims[a];
+        bytes = (bytes + 15) / 16 * 16;
+    }
+    std::vector<unsigned char> host(bytes, 0);
+    for (int a = 0; a < 3; ++a) {
+        const Fft1D& f = e->fft_ax[a];
+        const int N = dims[a];
+        float2* tw = reinterpret_cast<float2*>(host.data() + off_tw[a]);
+        uint16_t* pos = reinterpret_cast<uint16_t*>(host.data() + off_pos[a]);
+        uint16_t* frq = reinterpret_cast<uint16_t*>(host.data() + off_frq[a]);
+        for (int k = 0; k < N; ++k) {
+            const double ang = -2.0 * 3.14159265358979323846 * k / N;
+            tw[k] = make_float2((float)cos(ang), (float)sin(ang));
+            int kk = k, span = N, p = 0;  // k = k1 + r1 (k2 + r2 (...)): digit k_i selects sub-block k_i of length span / r_i
+            for (int i = 0; i < f.npass; ++i) {
+                const int r = (int)((f.radices >> (4 * i)) & 15ull);
+                span /= r;
+                p += (kk % r) * span;
+                kk /= r;
+            }
+            pos[k] = (uint16_t)p;
+            frq[p] = (uint16_t)k;
+        }
+    }
+    CK(cudaMalloc(&e->d_fft_tables, bytes));
+    CK(cudaMemcpy(e->d_fft_tables, host.data(), bytes, cudaMemcpyHostToDevice));
+    for (int a = 0; a < 3; ++a) {
+        unsigned char* base = static_cast<unsigned char*>(e->d_fft_tables);
+        e->fft_ax[a].tw = reinterpret_cast<const float2*>(base + off_tw[a]);
+        e->fft_ax[a].pos_of = reinterpret_cast<const uint16_t*>(base + off_pos[a]);
+        e->fft_ax[a].freq_of = reinterpret_cast<const uint16_t*>(base + off_frq[a]);
+    }
+    const size_t smz = fft_smem_bytes(dims[2], FFT_Z_COLS), smy = fft_smem_bytes(dims[1], FFT_Y_COLS), smx = fft_smem_bytes(dims[0], 3 * FFT_X_COLS);
+    if (std::max(smz, std::max(smy, smx)) > 200 * 1024) { e->own_fft = false; return PSE_OK; }
+    CK(cudaFuncSetAttribute(fft_z_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smz));
+    CK(cudaFuncSetAttribute(fft_z_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smz));
+    CK(cudaFuncSetAttribute(fft_y_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smy));
+    CK(cudaFuncSetAttribute(fft_y_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smy));
+    CK(cudaFuncSetAttribute(fft_x_scale_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smx));
+    return PSE_OK;
+}
+
 extern "C" int pse_create(const pse_config* cfg, void* stream, pse_engine** out) {
     pse_engine* e = nullptr;
     if (!cfg || !out) return fail(e, PSE_EINVAL, "pse_create: null argument");
@@ -375,7 +448,7 @@ extern "C" int pse_create(const pse_config* cfg, void* stream, pse_engine** out)
     WaveParams& wp = e->wp;
     wp.Nx = prm.Nx; wp.Ny = prm.Ny; wp.Nz = prm.Nz; wp.Nzh = prm.Nz / 2 + 1; wp.P = prm.P;
     wp.Nzp = wp.Nzh;
-    { const char* env = getenv("PSE_SPEC_PAD"); int pad = env ? atoi(env) : 1; if (pad > 1) wp.Nzp = ((wp.Nzh + pad - 1) / pad) * pad; }
+    { const char* env = getenv("PSE_SPEC_PAD"); int pad = env ? atoi(env) : 8; if (pad > 1) wp.Nzp = ((wp.Nzh + pad - 1) / pad) * pad; }  // 64-byte rows
     wp.hx = prm.hx; wp.hy = prm.hy; wp.hz = prm.hz;
     wp.prefac = prm.prefac; wp.expfac = prm.expfac; wp.quadW = prm.quadW;
     wp.xi = c.xi; wp.eta = prm.eta;
@@ -439,6 +512,10 @@ extern "C" int pse_create(const pse_config* cfg, void* stream, pse_engine** out)
         return PSE_ECUDA;
     }
     e->plans_ok = true;
+    {
+        const int frc = setup_own_fft(e);
+        if (frc != PSE_OK) { pse_destroy(e); return frc; }
+    }
     cufftSetStream(e->plan_f, e->stream);
     cufftSetStream(e->plan_b, e->stream);
     *out = e;
@@ -448,6 +525,7 @@ extern "C" int pse_create(const pse_config* cfg, void* stream, pse_engine** out)
 extern "C" void pse_destroy(pse_engine* e) {
     if (!e) return;
     if (e->plans_ok) { cufftDestroy(e->plan_f); cufftDestroy(e->plan_b); }
+    if (e->d_fft_tables) cudaFree(e->d_fft_tables);
     void* bufs[] = {e->d_table, e->d_cell_of, e->d_cell_count, e->d_cell_start, e->d_scan_tmp, e->d_perm, e->d_slot_of,
                     e->d_spos, e->d_sx, e->d_sy, e->d_px, e->d_nn, e->d_head, e->d_nl, e->d_pos_build, e->d_flag, e->d_grid,
                     e->d_spec, e->d_V, e->d_u, e->d_y, e->d_alpha, e->d_beta, e->d_coef, e->d_partials, e->d_counter,
@@ -737,13 +815,37 @@ static int run_wave(pse_engine* e, const float4* sF, float4* U, int accumulate, 
         }
         }
         ProfScope ps(e, PH_FFT_FWD);
-        CKFFT(cufftExecR2C(e->plan_f, e->d_grid, (cufftComplex*)e->d_spec)); e->fft_execs++;
+        if (e->own_fft) {
+            const WaveParams& wp = e->wp;
+            const uint32_t nrows = 3u * wp.Nx * wp.Ny;
+            fft_z_forward_kernel<<<nblk(nrows, 2 * FFT_Z_COLS), FFT_THREADS, fft_smem_bytes(wp.Nz, FFT_Z_COLS), st>>>(
+                e->d_grid, e->d_spec, e->fft_ax[2], nrows, wp.Nzp); LAUNCHED(e);
+            fft_y_kernel<false><<<dim3(nblk(wp.Nzh, FFT_Y_COLS), 3 * wp.Nx), FFT_THREADS, fft_smem_bytes(wp.Ny, FFT_Y_COLS), st>>>(
+                e->d_spec, e->fft_ax[1], wp.Nzh, wp.Nzp); LAUNCHED(e);
+        } else {
+            CKFFT(cufftExecR2C(e->plan_f, e->d_grid, (cufftComplex*)e->d_spec));
+        }
+        e->fft_execs++;
     }
-    {
-        ProfScope ps(e, PH_SCALE);
-        scale_kernel<<<dim3(e->wp.Ny, e->wp.Nx), 128, 0, st>>>(e->d_spec, e->wp, e->box, det ? 1 : 0, noise ? 1 : 0, e->d_stepdev, d_u_grid); LAUNCHED(e);
-    }
-    {
+    if (e->own_fft) {
+        const WaveParams& wp = e->wp;
+        {
+            ProfScope ps(e, PH_SCALE);  // x forward + scaling + x inverse
+            fft_x_scale_kernel<<<dim3(nblk(wp.Nzh, FFT_X_COLS), wp.Ny), FFT_THREADS, fft_smem_bytes(wp.Nx, 3 * FFT_X_COLS), st>>>(
+                e->d_spec, e->fft_ax[0], e->fft_ax[1].freq_of, e->wp, e->box, det ? 1 : 0, noise ? 1 : 0, e->d_stepdev, d_u_grid); LAUNCHED(e);
+        }
+        ProfScope ps(e, PH_FFT_INV);
+        const uint32_t nrows = 3u * wp.Nx * wp.Ny;
+        fft_y_kernel<true><<<dim3(nblk(wp.Nzh, FFT_Y_COLS), 3 * wp.Nx), FFT_THREADS, fft_smem_bytes(wp.Ny, FFT_Y_COLS), st>>>(
+            e->d_spec, e->fft_ax[1], wp.Nzh, wp.Nzp); LAUNCHED(e);
+        fft_z_inverse_kernel<<<nblk(nrows, 2 * FFT_Z_COLS), FFT_THREADS, fft_smem_bytes(wp.Nz, FFT_Z_COLS), st>>>(
+            e->d_spec, e->d_grid, e->fft_ax[2], nrows, wp.Nzp); LAUNCHED(e);
+        e->fft_execs++;
+    } else {
+        {
+            ProfScope ps(e, PH_SCALE);
+            scale_kernel<<<dim3(e->wp.Ny, e->wp.Nx), 128, 0, st>>>(e->d_spec, e->wp, e->box, det ? 1 : 0, noise ? 1 : 0, e->d_stepdev, d_u_grid); LAUNCHED(e);
+        }
         ProfScope ps(e, PH_FFT_INV);
         CKFFT(cufftExecC2R(e->plan_b, (cufftComplex*)e->d_spec, e->d_grid)); e->fft_execs++;
     }

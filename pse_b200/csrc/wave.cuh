@@ -200,6 +200,50 @@ __device__ __forceinline__ float sinc_of(const KVec& kv) {
 // the half-spectrum C2R path evaluates both wave vectors and averages.
 // Launch: grid (Ny, Nx), one block per (ii, jj) row of the half spectrum, threads stride over kz (coalesced,
 // no per-thread integer division).
+__device__ __forceinline__ void scale_node(int ii, int jj, int kk, const float2 fX, const float2 fY, const float2 fZ, int do_det,
+                                           int do_noise, uint32_t key, float noise_fac, const float* __restrict__ u_grid,
+                                           const WaveParams& wp, const PseBox& box, float2& oX, float2& oY, float2& oZ) {
+    oX = make_float2(0.f, 0.f); oY = oX; oZ = oX;
+    if (ii == 0 && jj == 0 && kk == 0) return;
+    const bool ii_nyq = (ii == wp.Nx / 2) && (wp.Nx / 2 == (wp.Nx + 1) / 2);
+    const bool jj_nyq = (jj == wp.Ny / 2) && (wp.Ny / 2 == (wp.Ny + 1) / 2);
+    const bool kk_nyq = (kk == wp.Nz / 2) && (wp.Nz / 2 == (wp.Nz + 1) / 2);
+    const int mi = ii == 0 ? 0 : wp.Nx - ii, mj = jj == 0 ? 0 : wp.Ny - jj, mk = kk == 0 ? 0 : wp.Nz - kk;
+    const uint32_t idx = ((uint32_t)ii * wp.Ny + jj) * wp.Nz + kk;  // full-grid node index (reference numbering)
+    const uint32_t midx = ((uint32_t)mi * wp.Ny + mj) * wp.Nz + mk;
+    const bool self_conj = idx == midx;
+    const bool two = (ii_nyq || jj_nyq || kk_nyq) && !self_conj;  // mirror wave vector differs from -k
+    const KVec kv = k_of_node(ii, jj, kk, wp, box);
+    const float sinc = sinc_of(kv);
+    KVec kvm = kv;
+    float sincm = sinc;
+    if (two) { kvm = k_of_node(mi, mj, mk, wp, box); sincm = sinc_of(kvm); }
+    const float half = two ? 0.5f : 1.0f;
+    if (do_det) {
+        project_add(kv, half * kv.w * sinc * sinc, fX, fY, fZ, oX, oY, oZ);
+        if (two) project_add(kvm, half * kvm.w * sincm * sincm, fX, fY, fZ, oX, oY, oZ);
+    }
+    if (do_noise) {
+        float re[3], im[3];
+        if (self_conj) {
+            node_draws(idx, u_grid, key, re, im);
+            const float sqrt2 = 1.4142135623730951f;
+            re[0] *= sqrt2; re[1] *= sqrt2; re[2] *= sqrt2;
+            im[0] = im[1] = im[2] = 0.f;
+        } else {
+            // the mirror node shares this node's conjugate pair; it lives in the half spectrum only on
+            // the kz = 0 and kz = Nyquist planes.  Owner of the pair = the node the reference rule
+            // processes; if the rule processes both, the smaller index owns it.
+            const bool me = ref_processed(ii, jj, kk, wp), other = ref_processed(mi, mj, mk, wp);
+            const bool own = me && (!other || idx < midx);
+            node_draws(own ? idx : midx, u_grid, key, re, im);
+            if (!own) { im[0] = -im[0]; im[1] = -im[1]; im[2] = -im[2]; }
+        }
+        const float2 dX = make_float2(re[0], im[0]), dY = make_float2(re[1], im[1]), dZ = make_float2(re[2], im[2]);
+        project_add(kv, half * noise_fac * sqrtf(kv.w) * sinc, dX, dY, dZ, oX, oY, oZ);
+        if (two) project_add(kvm, half * noise_fac * sqrtf(kvm.w) * sincm, dX, dY, dZ, oX, oY, oZ);
+    }
+}
 __global__ void __launch_bounds__(128)
 scale_kernel(float2* __restrict__ spec, WaveParams wp, PseBox box, int do_det, int do_noise, const StepDev* __restrict__ sd,
              const float* __restrict__ u_grid, int y0 = 0, int ny_local = -1) {
@@ -211,52 +255,12 @@ scale_kernel(float2* __restrict__ spec, WaveParams wp, PseBox box, int do_det, i
     const int jj = blockIdx.x + y0, ii = blockIdx.y;
     const size_t rowbase = ((size_t)ii * ny_local + blockIdx.x) * wp.Nzp;
     for (int kk = threadIdx.x; kk < wp.Nzh; kk += blockDim.x) {
-    const size_t tid = rowbase + kk;
-    float2 fX = make_float2(0.f, 0.f), fY = fX, fZ = fX;
-    if (do_det) { fX = spec[tid]; fY = spec[nh + tid]; fZ = spec[2 * nh + tid]; }
-    float2 oX = make_float2(0.f, 0.f), oY = oX, oZ = oX;
-    const bool origin = (ii == 0 && jj == 0 && kk == 0);
-    if (!origin) {
-        const bool ii_nyq = (ii == wp.Nx / 2) && (wp.Nx / 2 == (wp.Nx + 1) / 2);
-        const bool jj_nyq = (jj == wp.Ny / 2) && (wp.Ny / 2 == (wp.Ny + 1) / 2);
-        const bool kk_nyq = (kk == wp.Nz / 2) && (wp.Nz / 2 == (wp.Nz + 1) / 2);
-        const int mi = ii == 0 ? 0 : wp.Nx - ii, mj = jj == 0 ? 0 : wp.Ny - jj, mk = kk == 0 ? 0 : wp.Nz - kk;
-        const uint32_t idx = ((uint32_t)ii * wp.Ny + jj) * wp.Nz + kk;  // full-grid node index (reference numbering)
-        const uint32_t midx = ((uint32_t)mi * wp.Ny + mj) * wp.Nz + mk;
-        const bool self_conj = idx == midx;
-        const bool two = (ii_nyq || jj_nyq || kk_nyq) && !self_conj;  // mirror wave vector differs from -k
-        const KVec kv = k_of_node(ii, jj, kk, wp, box);
-        const float sinc = sinc_of(kv);
-        KVec kvm = kv;
-        float sincm = sinc;
-        if (two) { kvm = k_of_node(mi, mj, mk, wp, box); sincm = sinc_of(kvm); }
-        const float half = two ? 0.5f : 1.0f;
-        if (do_det) {
-            project_add(kv, half * kv.w * sinc * sinc, fX, fY, fZ, oX, oY, oZ);
-            if (two) project_add(kvm, half * kvm.w * sincm * sincm, fX, fY, fZ, oX, oY, oZ);
-        }
-        if (do_noise) {
-            float re[3], im[3];
-            if (self_conj) {
-                node_draws(idx, u_grid, key, re, im);
-                const float sqrt2 = 1.4142135623730951f;
-                re[0] *= sqrt2; re[1] *= sqrt2; re[2] *= sqrt2;
-                im[0] = im[1] = im[2] = 0.f;
-            } else {
-                // the mirror node shares this node's conjugate pair; it lives in the half spectrum only on
-                // the kz = 0 and kz = Nyquist planes.  Owner of the pair = the node the reference rule
-                // processes; if the rule processes both, the smaller index owns it.
-                const bool me = ref_processed(ii, jj, kk, wp), other = ref_processed(mi, mj, mk, wp);
-                const bool own = me && (!other || idx < midx);
-                node_draws(own ? idx : midx, u_grid, key, re, im);
-                if (!own) { im[0] = -im[0]; im[1] = -im[1]; im[2] = -im[2]; }
-            }
-            const float2 dX = make_float2(re[0], im[0]), dY = make_float2(re[1], im[1]), dZ = make_float2(re[2], im[2]);
-            project_add(kv, half * noise_fac * sqrtf(kv.w) * sinc, dX, dY, dZ, oX, oY, oZ);
-            if (two) project_add(kvm, half * noise_fac * sqrtf(kvm.w) * sincm, dX, dY, dZ, oX, oY, oZ);
-        }
-    }
-    spec[tid] = oX; spec[nh + tid] = oY; spec[2 * nh + tid] = oZ;
+        const size_t tid = rowbase + kk;
+        float2 fX = make_float2(0.f, 0.f), fY = fX, fZ = fX;
+        if (do_det) { fX = spec[tid]; fY = spec[nh + tid]; fZ = spec[2 * nh + tid]; }
+        float2 oX, oY, oZ;
+        scale_node(ii, jj, kk, fX, fY, fZ, do_det, do_noise, key, noise_fac, u_grid, wp, box, oX, oY, oZ);
+        spec[tid] = oX; spec[nh + tid] = oY; spec[2 * nh + tid] = oZ;
     }
 }
 

@@ -161,6 +161,7 @@ wweights_kernel(const float4* __restrict__ wpos, const int4* __restrict__ worg, 
 // dynamic smem: acc[3][TILE*TILE*TILE_ZS] | a_rec[CAP] f4 | a_mask[CAP] | a_w[CAP] | wbuf[2][CHUNK][P*P+P]
 #define SPREAD_CAP 384   // staged particles per filter round; sized so that three blocks fit one SM
 #define SPREAD_MAX_SEG 64
+#define SPREAD_NODE_BIAS 2048  // > (TILED_MAX_P - 1) * (TILE * TILE_ZS + TILE_ZS + 1)
 
 template <int P> struct SpreadCfg {
     static constexpr int PPP = P * P * P;
@@ -190,6 +191,8 @@ spread_tile_kernel(const float4* __restrict__ wF, const int4* __restrict__ worg,
     constexpr int PP = P * P, PPP = PP * P;
     constexpr int NT = SpreadCfg<P>::NT, NW = NT / 32, npass = SpreadCfg<P>::NPASS, WS = SpreadCfg<P>::WS;
     constexpr int ACC = TILE * TILE * TILE_ZS;
+    // P <= 6: validity bits (3P) and origin node (13 bits) share the record's 4th word - one broadcast load per particle
+    constexpr bool PACKED = 3 * P + 13 <= 32;
     float* acc = smem;
     float4* a_rec = reinterpret_cast<float4*>(acc + 3 * ACC);
     uint32_t* a_mask = reinterpret_cast<uint32_t*>(a_rec + SPREAD_CAP);
@@ -281,8 +284,9 @@ spread_tile_kernel(const float4* __restrict__ wF, const int4* __restrict__ worg,
                     m |= (uint32_t)((unsigned)(lz + i) < (unsigned)ez) << (2 * P + i);
                 }
                 const float4 F = __ldg(wF + w);
-                a_rec[slot] = make_float4(F.x, F.y, F.z, __int_as_float(4 * ((lx * TILE + ly) * TILE_ZS + lz)));  // byte offset of the origin node
-                a_mask[slot] = m;
+                const int onode = (lx * TILE + ly) * TILE_ZS + lz;  // tile index of the origin node (may be negative)
+                if (PACKED) a_rec[slot] = make_float4(F.x, F.y, F.z, __int_as_float((int)(m | ((uint32_t)(onode + SPREAD_NODE_BIAS) << (3 * P)))));
+                else { a_rec[slot] = make_float4(F.x, F.y, F.z, __int_as_float(4 * onode)); a_mask[slot] = m; }
                 a_w[slot] = w;
             }
             nact += total;
@@ -312,21 +316,23 @@ spread_tile_kernel(const float4* __restrict__ wF, const int4* __restrict__ worg,
             const uint32_t* masks = a_mask + c0;
             // two register sets (A: even particles, B: odd), each loaded one barrier ahead of its use
             float4 recA = recs[0], recB;
-            uint32_t mA = masks[0], mB = 0;
+            uint32_t mA = PACKED ? 0u : masks[0], mB = 0;
             float wA[npass], wB[npass];
 #pragma unroll
             for (int r = 0; r < npass; ++r) { wA[r] = wq[my_ij[r]] * wq[my_k[r]]; wB[r] = 0.f; }
             for (int q = 0; q < nch; q += 2) {
                 if (q + 1 < nch) {
-                    recB = recs[q + 1]; mB = masks[q + 1];
+                    recB = recs[q + 1]; if (!PACKED) mB = masks[q + 1];
 #pragma unroll
                     for (int r = 0; r < npass; ++r) wB[r] = wq[(q + 1) * WS + my_ij[r]] * wq[(q + 1) * WS + my_k[r]];
                 }
                 {
-                    const int base = __float_as_int(recA.w);
+                    const uint32_t pk = (uint32_t)__float_as_int(recA.w);
+                    const uint32_t mm = PACKED ? pk : mA;  // (bits above 3P never match my_bits)
+                    const int base = PACKED ? 4 * ((int)(pk >> (3 * P)) - SPREAD_NODE_BIAS) : (int)pk;
 #pragma unroll
                     for (int r = 0; r < npass; ++r)
-                        if ((mA & my_bits[r]) == my_bits[r]) {
+                        if ((mm & my_bits[r]) == my_bits[r]) {
                             const uint32_t a = my_acc[r] + base;
                             smem_fma<0>(a, wA[r], recA.x);
                             smem_fma<4 * ACC>(a, wA[r], recA.y);
@@ -336,15 +342,17 @@ spread_tile_kernel(const float4* __restrict__ wF, const int4* __restrict__ worg,
                 __syncthreads();
                 if (q + 1 >= nch) break;
                 if (q + 2 < nch) {
-                    recA = recs[q + 2]; mA = masks[q + 2];
+                    recA = recs[q + 2]; if (!PACKED) mA = masks[q + 2];
 #pragma unroll
                     for (int r = 0; r < npass; ++r) wA[r] = wq[(q + 2) * WS + my_ij[r]] * wq[(q + 2) * WS + my_k[r]];
                 }
                 {
-                    const int base = __float_as_int(recB.w);
+                    const uint32_t pk = (uint32_t)__float_as_int(recB.w);
+                    const uint32_t mm = PACKED ? pk : mB;  // (bits above 3P never match my_bits)
+                    const int base = PACKED ? 4 * ((int)(pk >> (3 * P)) - SPREAD_NODE_BIAS) : (int)pk;
 #pragma unroll
                     for (int r = 0; r < npass; ++r)
-                        if ((mB & my_bits[r]) == my_bits[r]) {
+                        if ((mm & my_bits[r]) == my_bits[r]) {
                             const uint32_t a = my_acc[r] + base;
                             smem_fma<0>(a, wB[r], recB.x);
                             smem_fma<4 * ACC>(a, wB[r], recB.y);

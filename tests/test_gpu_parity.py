@@ -384,3 +384,31 @@ def test_full_size_parity_with_reference_kernels(big):
         close(Ue, Ur)
     finally:
         big.ref.set_noise_tables(None, None)
+
+
+# ---------------------------------------------------------------- own FFT passes vs cuFFT
+@pytest.mark.parametrize("N,phi,xy,Lfac", [(1000, 0.1, 0.0, (1, 1, 1)), (3000, 0.05, 0.3, (1, 1, 1)), (4000, 0.1, -0.2, (1.0, 1.3, 0.8)),
+                                           (20000, 0.2, 0.0, (1, 1, 1))])
+def test_own_fft_matches_cufft(cuda, monkeypatch, N, phi, xy, Lfac):
+    """fft.cuh (shared-memory passes, scaling fused into the x pass) against the cuFFT R2C/C2R + scale_kernel pipeline:
+    deterministic wave part and the wave-space noise for identical uniforms; grids with different radix mixes."""
+    import torch
+    from pse_b200 import engine as E
+    L0 = util.box_length(N, phi)
+    L = tuple(L0 * f for f in Lfac)
+    cfg = E.make_config(N, L if Lfac != (1, 1, 1) else L0, xy=xy, T=1.0, dt=1e-3, seed=3)
+    pos_np = util.random_positions(N, L0, 2)
+    pos_np[:, 1] *= Lfac[1]; pos_np[:, 2] *= Lfac[2]
+    pos = torch.from_numpy(pos_np).cuda(); F = torch.from_numpy(util.random_forces(N, 4)).cuda()
+    out = {}
+    for mode in ("own", "cufft"):
+        monkeypatch.setenv("PSE_FFT", mode)
+        eng = E.Engine(cfg)
+        p = eng.params
+        g = torch.Generator(device="cuda"); g.manual_seed(11)
+        ug = torch.rand((p.Nx * p.Ny * p.Nz, 6), device="cuda", generator=g)
+        out[mode] = (eng.mwave(pos, F).clone(), eng.velocity(pos, F, timestep=5, u_grid=ug, parts=2)[0].clone(), (p.Nx, p.Ny, p.Nz))
+        eng.close()
+    print("grid", out["own"][2])
+    close(out["own"][0], out["cufft"][0], 2e-6)
+    close(out["own"][1], out["cufft"][1], 2e-6)
