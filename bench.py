@@ -56,6 +56,22 @@ class ClockSampler(threading.Thread):
         self.index, self.rows, self.stop_flag = index, [], False
 
     def run(self):
+        # NVML in-process when available (a spawned nvidia-smi takes driver locks and was seen to stall the reference
+        # arm's per-step cudaMalloc/cudaFree by up to a second); nvidia-smi otherwise
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            bits = [("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                    ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap)]
+            while not self.stop_flag:
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append([str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx)] + ["Active" if r & b else "Not Active" for _, b in bits])
+                time.sleep(0.1)
+            return
+        except Exception:
+            pass
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
@@ -196,6 +212,8 @@ def main():
                     h_pos.copy_(pos, non_blocking=True); h_img.copy_(img, non_blocking=True)
                 b.record(); torch.cuda.synchronize()
                 total += a.elapsed_time(b)
+                if os.environ.get("PSE_BENCH_VERBOSE"):
+                    print(f"[ref step {t}] {a.elapsed_time(b):.2f} ms  m={ref.m_lanczos}  free={torch.cuda.mem_get_info()[0] >> 20} MiB", file=sys.stderr)
             return total
         ref_steps(W, 0, False)
         sampler = ClockSampler(local); sampler.start()
@@ -249,8 +267,17 @@ def main():
     dom = "lanczos_spmv" if "lanczos_spmv" in phases else "spmv"
     b_spmv = 56.0 * N + 4.0 * nnz
     t_dom = phases[dom]["us_per_launch"] * 1e-6
-    roof = {"bound": "hbm", "kernel": "spmv_kernel<8,LANCZOS>", "achieved": b_spmv / t_dom / 1e9, "peak": peak, "unit": "GB/s",
-            "frac": b_spmv / t_dom / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+    # DRAM bytes of one launch of that kernel from the committed `ncu --set full` capture of the same workload (profiles/)
+    traffic = None
+    try:
+        caps = json.load(open(os.path.join(ROOT, "profiles", "r1_top_kernels.json")))
+        tr = [c["dram__bytes_read.sum"] + c["dram__bytes_write.sum"] for c in caps if c["kernel"].startswith("void spmv_kernel<4, 1,")]
+        if tr and abs(N - 1000000) < 1:
+            traffic = 1e6 * sum(tr) / len(tr)  # the capture reports Mbyte
+    except Exception:
+        traffic = None
+    roof = {"bound": "hbm", "kernel": "spmv_kernel<4,LANCZOS,POLY,PRUNED>", "achieved": b_spmv / t_dom / 1e9, "peak": peak, "unit": "GB/s",
+            "frac": b_spmv / t_dom / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": b_spmv, "us_per_launch": t_dom * 1e6, "share_of_step": phases[dom]["ms_per_step"] / (ms / K)}
     b_step = (120.0 * G + 64.0 * N) + (m + 1) * b_spmv + 64.0 * N * m + 16.0 * N * (m + 1) + 72.0 * N
     roof["step"] = {"algorithmic_bytes": b_step, "achieved": b_step / (ms / K * 1e-3) / 1e9, "frac": b_step / (ms / K * 1e-3) / 1e9 / peak,
