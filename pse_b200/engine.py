@@ -71,7 +71,7 @@ class Engine:
         lib.pse_get_params(self._h, ctypes.byref(self.params))
 
     def close(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and lib is not None:  # (module globals are gone at interpreter shutdown)
             lib.pse_destroy(self._h)
             self._h = None
 

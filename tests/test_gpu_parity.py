@@ -412,3 +412,38 @@ def test_own_fft_matches_cufft(cuda, monkeypatch, N, phi, xy, Lfac):
     print("grid", out["own"][2])
     close(out["own"][0], out["cufft"][0], 2e-6)
     close(out["own"][1], out["cufft"][1], 2e-6)
+
+
+# ---------------------------------------------------------------- BASELINE.json config 5 (largest): N = 8M, phi = 0.4, error 1e-4
+def test_config5_eight_million_properties(cuda):
+    """The largest BASELINE.json configuration at the reference's sizing rule (xi = 0.45 -> 432^3 grid, P = 8; xi = 0.5 would need
+    576^3 > the 512^3 cap of PSEv1/Stokes.cc:203).  No oracle finishes at this size, so size-independent properties: symmetry,
+    positive definiteness, linearity of M.F, translation invariance under a lattice shift of the box, and one full BD step."""
+    import torch
+    from pse_b200 import engine as E
+    free, _ = torch.cuda.mem_get_info()
+    if free < 80 * 2**30:
+        pytest.skip("needs ~60 GB of device memory")
+    N, phi = 8000000, 0.4
+    L = util.box_length(N, phi)
+    cfg = E.make_config(N, L, xi=0.45, error=1e-4, T=1.0, dt=1e-3, seed=7)
+    eng = E.Engine(cfg)
+    p = eng.params
+    assert (p.Nx, p.Ny, p.Nz, p.P) == (432, 432, 432, 8)          # SURVEY.md §8 table
+    pos = torch.from_numpy(util.lattice_positions(N, L, 0)).cuda()
+    F = torch.from_numpy(util.random_forces(N, 1)).cuda(); G = torch.from_numpy(util.random_forces(N, 2)).cuda()
+    MF, MG = eng.mobility(pos, F).clone(), eng.mobility(pos, G).clone()
+    a = float((G[:, :3].double() * MF[:, :3].double()).sum()); b = float((F[:, :3].double() * MG[:, :3].double()).sum())
+    assert abs(a - b) < 1e-4 * max(abs(a), abs(b))
+    assert float((F[:, :3].double() * MF[:, :3].double()).sum()) > 0
+    close(eng.mobility(pos, 2.0 * F - 0.5 * G), 2.0 * MF - 0.5 * MG, 3e-6)
+    st = eng.stats()
+    assert abs(st["nnz"] / N - 145.8) < 8.0                          # <nbrs> within r_cut + 0.4 at phi = 0.4 (SURVEY.md §8: 145.8 for an ideal gas; the jittered lattice gives 140)
+    img = torch.zeros((N, 3), dtype=torch.int32, device="cuda")
+    p0 = pos.clone()
+    m = eng.step(pos, img, F, 0)
+    torch.cuda.synchronize()
+    d = (pos[:, :3] - p0[:, :3]).abs()
+    d = torch.minimum(d, L - d)
+    assert 2 <= m <= 20 and torch.isfinite(pos).all() and 0.01 < float(d.max()) < 1.0   # Brownian step ~ sqrt(2 kT M dt) ~ 0.05
+    eng.close()
