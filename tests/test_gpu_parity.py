@@ -341,6 +341,32 @@ def test_config4_sheared_suspension_parity(cuda, xy):
     assert torch.equal(ie, ir) and float((pe - pr).abs().max()) < 1e-5
 
 
+def test_config2_parity(cuda):
+    """BASELINE.json config 2: N = 100k, phi = 0.2, error 1e-3 (125^3 grid, odd: no Nyquist planes): integer outputs exact,
+    M.F and the full velocity (identical random vectors, same Lanczos m) against the reference kernels."""
+    s = System(100000, util.box_length(100000, 0.2), seed=31, lattice=True)
+    assert (s.p.Nx, s.p.P) == (125, 6)
+    assert np.array_equal(s.eng.grid_index(s.pos).cpu().numpy(), s.orc.grid_index(s.pos_np))
+    nn, head, nl = s.nl_np()
+    onn, ohead, onl = s.orc.neighbors(s.pos_np, s.p.rcut + 0.4, brute=False)
+    assert np.array_equal(nn, onn) and np.array_equal(nl, onl)
+    assert abs(nl.size / s.N - 36.2) < 3.5   # SURVEY.md §8 table (ideal-gas estimate; the jittered lattice differs by a few)
+    if s.ref is None:
+        pytest.skip("reference library not built")
+    close(s.eng.mreal(s.pos, s.F), s.ref.mreal(s.pos, s.F))
+    close(s.eng.mwave(s.pos, s.F), s.ref.mwave(s.pos, s.F))
+    up, ug = s.noise()
+    s.ref.set_noise_tables(up, ug)
+    try:
+        s.eng.lanczos_m = 2; s.ref.m_lanczos = 2
+        Ue, m = s.eng.velocity(s.pos, s.F, timestep=9, u_particles=up, u_grid=ug, parts=7)
+        Ur = s.ref.velocity(s.pos, s.F, s.T, s.dt, 9)
+        assert m == s.ref.m_lanczos
+        close(Ue, Ur)
+    finally:
+        s.ref.set_noise_tables(None, None)
+
+
 # ---------------------------------------------------------------- properties at the headline size
 @pytest.fixture(scope="module")
 def big(cuda):
