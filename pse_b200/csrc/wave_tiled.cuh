@@ -210,7 +210,7 @@ spread_tile_kernel(const float4* __restrict__ wF, const int4* __restrict__ worg,
     const int t0x = bx * TILE, t0y = by * TILE, t0z = bz * TILE;
     const int ex = min(TILE, wp.Nx - t0x), ey = min(TILE, wp.Ny - t0y), ez = min(TILE, wp.Nz - t0z);
 
-    for (int i = tid; i < 3 * ACC; i += NT) acc[i] = 0.f;
+    for (int i = tid; i < 3 * ACC / 4; i += NT) reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tid < 3) {
         const int t0 = tid == 0 ? t0x : tid == 1 ? t0y : t0z, e = tid == 0 ? ex : tid == 1 ? ey : ez;
         const int N = tid == 0 ? wp.Nx : tid == 1 ? wp.Ny : wp.Nz;
@@ -363,16 +363,29 @@ spread_tile_kernel(const float4* __restrict__ wF, const int4* __restrict__ worg,
             }
         }
     }
-    // ---- write the tile once
+    // ---- write the tile once: a thread moves four consecutive z nodes of the three components (TILE_ZS is even, so the
+    // shared reads are 8-byte aligned; the global stores are 16-byte vectors when Nz allows it)
     const size_t G = (size_t)wp.Nx * wp.Ny * wp.Nz;
-    for (int t = tid; t < ex * ey * TILE; t += NT) {
-        const int lz = t % TILE, ly = (t / TILE) % ey, lx = t / (TILE * ey);
-        if (lz < ez) {
-            const int node = (lx * TILE + ly) * TILE_ZS + lz;
-            const size_t idx = ((size_t)(t0x + lx) * wp.Ny + (t0y + ly)) * wp.Nz + (t0z + lz);
-            grid[idx] = acc[node];
-            grid[G + idx] = acc[ACC + node];
-            grid[2 * G + idx] = acc[2 * ACC + node];
+    const bool vec = (ez == TILE) && ((wp.Nz & 3) == 0);
+    for (int t = tid; t < ex * ey * (TILE / 4); t += NT) {
+        const int q = t & 3, row = t >> 2;
+        int lx, ly;
+        if (ey == TILE) { ly = row & (TILE - 1); lx = row >> 4; }
+        else { lx = row / ey; ly = row - lx * ey; }
+        const int node = (lx * TILE + ly) * TILE_ZS + 4 * q;
+        const size_t idx = ((size_t)(t0x + lx) * wp.Ny + (t0y + ly)) * wp.Nz + (t0z + 4 * q);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float2 a = *reinterpret_cast<const float2*>(acc + c * ACC + node);
+            const float2 b = *reinterpret_cast<const float2*>(acc + c * ACC + node + 2);
+            if (vec) {
+                *reinterpret_cast<float4*>(grid + c * G + idx) = make_float4(a.x, a.y, b.x, b.y);
+            } else {
+                const float v[4] = {a.x, a.y, b.x, b.y};
+#pragma unroll
+                for (int z = 0; z < 4; ++z)
+                    if (4 * q + z < ez) grid[c * G + idx + z] = v[z];
+            }
         }
     }
 }
