@@ -97,7 +97,7 @@ struct pse_engine {
     bool tiled;
     TileGrid tg;
     int4 *d_org, *d_worg;
-    uint32_t *d_wcell_of, *d_wcount, *d_wstart, *d_wperm, *d_wtmp;
+    uint32_t *d_wcell_of, *d_wcount, *d_wstart, *d_wperm, *d_wtmp, *d_wid;
     float4 *d_wpos, *d_wF;
     float* d_wwt;  // Gaussian factor rows, W order: [N][P*P + P]
     // Lanczos
@@ -321,6 +321,7 @@ static int alloc_all(pse_engine* e) {
             CK(cudaMalloc(&e->d_wcount, sizeof(uint32_t) * (tg.ntile + 1)));
             CK(cudaMalloc(&e->d_wstart, sizeof(uint32_t) * (tg.ntile + 1)));
             CK(cudaMalloc(&e->d_wperm, sizeof(uint32_t) * N));
+            CK(cudaMalloc(&e->d_wid, sizeof(uint32_t) * N));
             CK(cudaMalloc(&e->d_wtmp, sizeof(uint32_t) * N));
             CK(cudaMalloc(&e->d_wpos, sizeof(float4) * N));
             CK(cudaMalloc(&e->d_wF, sizeof(float4) * N));
@@ -530,7 +531,7 @@ extern "C" void pse_destroy(pse_engine* e) {
                     e->d_spos, e->d_sx, e->d_sy, e->d_px, e->d_nn, e->d_head, e->d_nl, e->d_pos_build, e->d_flag, e->d_grid,
                     e->d_spec, e->d_V, e->d_u, e->d_y, e->d_alpha, e->d_beta, e->d_coef, e->d_partials, e->d_counter,
                     e->d_vel_work, e->d_hpos, e->d_hF, e->d_himage, e->d_org, e->d_worg, e->d_wcell_of, e->d_wcount,
-                    e->d_wstart, e->d_wperm, e->d_wpos, e->d_wF, e->d_wwt, e->d_wtmp, e->d_ell, e->d_nn_act, e->d_nl_act};
+                    e->d_wstart, e->d_wperm, e->d_wid, e->d_wpos, e->d_wF, e->d_wwt, e->d_wtmp, e->d_ell, e->d_nn_act, e->d_nl_act};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (e->h_flag) cudaFreeHost(e->h_flag);
@@ -794,7 +795,7 @@ static int run_wbin(pse_engine* e, const float4* sF) {
     // unordered fill into scratch (d_wcell_of is free again after the fill reads it), then rank sort per tile
     cell_fill_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_wcell_of, N, e->d_wstart, e->d_wcount, e->d_wtmp); LAUNCHED(e);
     cell_sort_block_kernel<<<nt, 128, 0, st>>>(e->d_wstart, e->d_wtmp, e->d_wperm); LAUNCHED(e);
-    wgather_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_spos, sF, e->d_org, e->d_wperm, N, e->d_wpos, e->d_wF, e->d_worg); LAUNCHED(e);
+    wgather_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_spos, sF, e->d_org, e->d_wperm, e->d_perm, N, e->d_wpos, e->d_wF, e->d_worg, e->d_wid); LAUNCHED(e);
     launch_wweights(e->wp.P, st, e->d_wpos, e->d_worg, N, e->box, e->wp, e->d_wwt); LAUNCHED(e);
     return PSE_OK;
 }
@@ -851,7 +852,7 @@ static int run_wave(pse_engine* e, const float4* sF, float4* U, int accumulate, 
     }
     ProfScope ps(e, PH_INTERP);
     if (e->tiled) {
-        launch_interp_tile(P, st, e->d_worg, e->d_wwt, e->d_wstart, e->d_wperm, e->d_perm, e->wp, e->tg, e->d_grid, U, accumulate);
+        launch_interp_tile(P, st, e->d_worg, e->d_wwt, e->d_wstart, e->d_wid, e->wp, e->tg, e->d_grid, U, accumulate);
         LAUNCHED(e);
     } else {
         interp_warp_kernel<<<nblk((size_t)e->N * 32, 256), 256, 0, st>>>(e->d_spos, e->N, e->box, e->wp, e->d_grid, e->d_perm, U, accumulate); LAUNCHED(e);
@@ -1400,7 +1401,7 @@ extern "C" int pse_shard_finish(pse_engine* e, const float* d_halo_recv, float4*
     TileGrid tg = e->tg;
     tg.tile0 = s->tx0 * tg.nty * tg.ntz;
     const int ntiles = (s->tx1 - s->tx0) * tg.nty * tg.ntz;
-    launch_interp_tile(wp.P, st, e->d_worg, e->d_wwt, e->d_wstart, e->d_wperm, e->d_perm, e->wp, tg, e->d_grid, d_U, 0, ntiles); LAUNCHED(e);
+    launch_interp_tile(wp.P, st, e->d_worg, e->d_wwt, e->d_wstart, e->d_wid, e->wp, tg, e->d_grid, d_U, 0, ntiles); LAUNCHED(e);
     // real space, own rows only
     const uint32_t nrows = s->row1 - s->row0;
     if (nrows) {

@@ -44,11 +44,13 @@ __global__ void wbin_kernel(const float4* __restrict__ spos, uint32_t N, PseBox 
 }
 
 __global__ void wgather_kernel(const float4* __restrict__ spos, const float4* __restrict__ sF, const int4* __restrict__ org,
-                               const uint32_t* __restrict__ wperm, uint32_t N, float4* __restrict__ wpos,
-                               float4* __restrict__ wF, int4* __restrict__ worg) {
+                               const uint32_t* __restrict__ wperm, const uint32_t* __restrict__ perm, uint32_t N,
+                               float4* __restrict__ wpos, float4* __restrict__ wF, int4* __restrict__ worg,
+                               uint32_t* __restrict__ wid) {
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= N) return;
     const uint32_t s = wperm[w];
+    wid[w] = __ldg(perm + s);  // particle id of W slot w: interpolation writes U[id] without chasing two permutations
     wpos[w] = __ldg(spos + s);
     if (sF) wF[w] = __ldg(sF + s);
     worg[w] = org[s];
@@ -428,7 +430,7 @@ __host__ __device__ constexpr int interp_pad(int P) {
 template <int P>
 __global__ void __launch_bounds__(INTERP_THREADS, 2)
 interp_tile_kernel(const int4* __restrict__ worg, const float* __restrict__ wwt, const uint32_t* __restrict__ wcell_start,
-                   const uint32_t* __restrict__ wperm, const uint32_t* __restrict__ perm, WaveParams wp,
+                   const uint32_t* __restrict__ wpid, WaveParams wp,
                    TileGrid tg, const float* __restrict__ grid, float4* __restrict__ U, int accumulate) {
     extern __shared__ __align__(16) float smem[];
     constexpr int PP = P * P, NW = INTERP_THREADS / 32, WS = PP + P;
@@ -452,22 +454,26 @@ interp_tile_kernel(const int4* __restrict__ worg, const float* __restrict__ wwt,
     float wt_n[NWR];
     auto fetch = [&](uint32_t ww) {  // origin, output slot and the precomputed factor row of particle ww
         o_n = __ldg(worg + ww);
-        id_n = __ldg(perm + __ldg(wperm + ww));
+        id_n = __ldg(wpid + ww);
 #pragma unroll
         for (int r = 0; r < NWR; ++r) wt_n[r] = lane + 32 * r < WS ? __ldg(wwt + (size_t)ww * WS + lane + 32 * r) : 0.f;
     };
     if (w < ce) fetch(w);
-    // stage the halo tile (periodic wrap per node); z fastest across lanes -> coalesced row segments
-    for (int t = tid; t < H * H * H; t += INTERP_THREADS) {
-        const int lz = t % H, ly = (t / H) % H, lx = t / (H * H);
+    // stage the halo tile (periodic wrap per node): a warp takes whole x planes of the tile, its lanes run over the H*H
+    // (y, z) nodes of the plane with z fastest -> coalesced row segments, one constant division per node
+    for (int lx = wid; lx < H; lx += NW) {
         int x = t0x + lx; if (x >= wp.Nx) x -= wp.Nx;
-        int y = t0y + ly; if (y >= wp.Ny) y -= wp.Ny;
-        int z = t0z + lz; if (z >= wp.Nz) z -= wp.Nz;
-        const size_t idx = ((size_t)x * wp.Ny + y) * wp.Nz + z;
-        const int node = lx * XS + ly * H + lz;
-        g[node] = __ldg(grid + idx);
-        g[GT + node] = __ldg(grid + G + idx);
-        g[2 * GT + node] = __ldg(grid + 2 * G + idx);
+        const float* gx = grid + (size_t)x * wp.Ny * wp.Nz;
+        float* sx = g + lx * XS;
+        for (int e = lane; e < H * H; e += 32) {
+            const int ly = e / H, lz = e - ly * H;
+            int y = t0y + ly; if (y >= wp.Ny) y -= wp.Ny;
+            int z = t0z + lz; if (z >= wp.Nz) z -= wp.Nz;
+            const float* src = gx + y * wp.Nz + z;
+            sx[e] = __ldg(src);  // (node = lx * XS + ly * H + lz = lx * XS + e)
+            sx[GT + e] = __ldg(src + G);
+            sx[2 * GT + e] = __ldg(src + 2 * G);
+        }
     }
     // this lane's columns: tile offset of (i, j, 0) for each full pass, and of the left-over column / node
     int col_off[NFULL > 0 ? NFULL : 1];
@@ -587,13 +593,13 @@ static void launch_spread_tile(int P, cudaStream_t st, const float4* wF, const i
 #undef X
     }
 }
-static void launch_interp_tile(int P, cudaStream_t st, const int4* worg, const float* wwt, const uint32_t* wstart, const uint32_t* wperm,
-                               const uint32_t* perm, const WaveParams& wp, const TileGrid& tg, const float* grid,
+static void launch_interp_tile(int P, cudaStream_t st, const int4* worg, const float* wwt, const uint32_t* wstart, const uint32_t* wid,
+                               const WaveParams& wp, const TileGrid& tg, const float* grid,
                                float4* U, int accumulate, int ntiles = -1) {
     if (ntiles < 0) ntiles = tg.ntile;
     if (ntiles == 0) return;
     switch (P) {
-#define X(p) case p: interp_tile_kernel<p><<<ntiles, INTERP_THREADS, interp_tile_smem(p), st>>>(worg, wwt, wstart, wperm, perm, wp, tg, grid, U, accumulate); break;
+#define X(p) case p: interp_tile_kernel<p><<<ntiles, INTERP_THREADS, interp_tile_smem(p), st>>>(worg, wwt, wstart, wid, wp, tg, grid, U, accumulate); break;
         PSE_FOR_EACH_P(X)
 #undef X
     }
