@@ -135,20 +135,20 @@ struct StepDev {
 
 struct KVec { float kx, ky, kz, w; };  // w = B(k)/G without the sinc^2 factor, as gridk.w
 
-// wave vector and scaling of full-grid node (i,j,k): PSEv1/Helper.cu:300-329
+// wave vector and scaling of full-grid node (i,j,k): PSEv1/Helper.cu:300-329.  The reference's chains of IEEE divisions
+// (x / Lx, k2 / 4 / xi^2, ... / k2 / G) are folded into reciprocal multiplications and one division; the values move
+// by an ulp, far below the 1e-5 parity budget, and the scaling pass loses ~100 instructions per node.
 __device__ __forceinline__ KVec k_of_node(int i, int j, int k, const WaveParams& wp, const PseBox& box) {
     KVec kv;
-    float fx = (float)((i < (wp.Nx + 1) / 2) ? i : i - wp.Nx);
-    float fy = ((float)((j < (wp.Ny + 1) / 2) ? j : j - wp.Ny) - box.xy * fx * box.Ly / box.Lx) / box.Ly;
-    fx = fx / box.Lx;
-    float fz = (float)((k < (wp.Nz + 1) / 2) ? k : k - wp.Nz) / box.Lz;
+    const float fx0 = (float)((i < (wp.Nx + 1) / 2) ? i : i - wp.Nx);
+    const float fy = ((float)((j < (wp.Ny + 1) / 2) ? j : j - wp.Ny) - box.xy * fx0 * box.Ly * box.Lxinv) * box.Lyinv;
+    const float fx = fx0 * box.Lxinv;
+    const float fz = (float)((k < (wp.Nz + 1) / 2) ? k : k - wp.Nz) * box.Lzinv;
     kv.kx = fx * wp.two_pi_k; kv.ky = fy * wp.two_pi_k; kv.kz = fz * wp.two_pi_k;
     const float k2 = kv.kx * kv.kx + kv.ky * kv.ky + kv.kz * kv.kz;
-    const float xisq = wp.xi * wp.xi;
+    const float q = k2 * (0.25f / (wp.xi * wp.xi));  // k^2 / (4 xi^2)
     const float G = (float)(wp.Nx * wp.Ny * wp.Nz);
-    kv.w = (i == 0 && j == 0 && k == 0)
-               ? 0.f
-               : 6.0f * 3.1415926536f * (1.0f + k2 / 4.0f / xisq) * expf(-(1.f - wp.eta) * k2 / 4.0f / xisq) / k2 / G;
+    kv.w = (i == 0 && j == 0 && k == 0) ? 0.f : 6.0f * 3.1415926536f * (1.0f + q) * expf(-(1.f - wp.eta) * q) / (k2 * G);
     return kv;
 }
 
@@ -174,18 +174,20 @@ __device__ __forceinline__ void node_draws(uint32_t idx, const float* __restrict
 }
 
 // scaled value of one node for wave vector kv:  out += scale * (f - k (k.f)/k^2)   (complex 3-vector)
-__device__ __forceinline__ void project_add(const KVec& kv, float scale, const float2 fX, const float2 fY, const float2 fZ,
+__device__ __forceinline__ void project_add(const KVec& kv, float inv_ksq, float scale, const float2 fX, const float2 fY, const float2 fZ,
                                             float2& oX, float2& oY, float2& oZ) {
-    const float ksq = kv.kx * kv.kx + kv.ky * kv.ky + kv.kz * kv.kz;
-    const float2 kdF = make_float2((kv.kx * fX.x + kv.ky * fY.x + kv.kz * fZ.x) / ksq,
-                                   (kv.kx * fX.y + kv.ky * fY.y + kv.kz * fZ.y) / ksq);
+    const float2 kdF = make_float2((kv.kx * fX.x + kv.ky * fY.x + kv.kz * fZ.x) * inv_ksq,
+                                   (kv.kx * fX.y + kv.ky * fY.y + kv.kz * fZ.y) * inv_ksq);
     oX.x += (fX.x - kv.kx * kdF.x) * scale; oX.y += (fX.y - kv.kx * kdF.y) * scale;
     oY.x += (fY.x - kv.ky * kdF.x) * scale; oY.y += (fY.y - kv.ky * kdF.y) * scale;
     oZ.x += (fZ.x - kv.kz * kdF.x) * scale; oZ.y += (fZ.y - kv.kz * kdF.y) * scale;
 }
-__device__ __forceinline__ float sinc_of(const KVec& kv) {
-    const float k = sqrtf(kv.kx * kv.kx + kv.ky * kv.ky + kv.kz * kv.kz);
-    return sinf(k) / k;
+// sin(|k|)/|k| and 1/|k|^2 of a wave vector
+__device__ __forceinline__ void sinc_and_inv_ksq(const KVec& kv, float& sinc, float& inv_ksq) {
+    const float ksq = kv.kx * kv.kx + kv.ky * kv.ky + kv.kz * kv.kz;
+    const float inv_k = rsqrtf(ksq);
+    inv_ksq = inv_k * inv_k;
+    sinc = sinf(ksq * inv_k) * inv_k;
 }
 
 // One thread per half-spectrum node.  deterministic: u = B (I - kk/k^2) f  (PSEv1/Mobility.cu:264-299);
@@ -214,14 +216,15 @@ __device__ __forceinline__ void scale_node(int ii, int jj, int kk, const float2 
     const bool self_conj = idx == midx;
     const bool two = (ii_nyq || jj_nyq || kk_nyq) && !self_conj;  // mirror wave vector differs from -k
     const KVec kv = k_of_node(ii, jj, kk, wp, box);
-    const float sinc = sinc_of(kv);
+    float sinc, iksq;
+    sinc_and_inv_ksq(kv, sinc, iksq);
     KVec kvm = kv;
-    float sincm = sinc;
-    if (two) { kvm = k_of_node(mi, mj, mk, wp, box); sincm = sinc_of(kvm); }
+    float sincm = sinc, iksqm = iksq;
+    if (two) { kvm = k_of_node(mi, mj, mk, wp, box); sinc_and_inv_ksq(kvm, sincm, iksqm); }
     const float half = two ? 0.5f : 1.0f;
     if (do_det) {
-        project_add(kv, half * kv.w * sinc * sinc, fX, fY, fZ, oX, oY, oZ);
-        if (two) project_add(kvm, half * kvm.w * sincm * sincm, fX, fY, fZ, oX, oY, oZ);
+        project_add(kv, iksq, half * kv.w * sinc * sinc, fX, fY, fZ, oX, oY, oZ);
+        if (two) project_add(kvm, iksqm, half * kvm.w * sincm * sincm, fX, fY, fZ, oX, oY, oZ);
     }
     if (do_noise) {
         float re[3], im[3];
@@ -240,8 +243,8 @@ __device__ __forceinline__ void scale_node(int ii, int jj, int kk, const float2 
             if (!own) { im[0] = -im[0]; im[1] = -im[1]; im[2] = -im[2]; }
         }
         const float2 dX = make_float2(re[0], im[0]), dY = make_float2(re[1], im[1]), dZ = make_float2(re[2], im[2]);
-        project_add(kv, half * noise_fac * sqrtf(kv.w) * sinc, dX, dY, dZ, oX, oY, oZ);
-        if (two) project_add(kvm, half * noise_fac * sqrtf(kvm.w) * sincm, dX, dY, dZ, oX, oY, oZ);
+        project_add(kv, iksq, half * noise_fac * sqrtf(kv.w) * sinc, dX, dY, dZ, oX, oY, oZ);
+        if (two) project_add(kvm, iksqm, half * noise_fac * sqrtf(kvm.w) * sincm, dX, dY, dZ, oX, oY, oZ);
     }
 }
 __global__ void __launch_bounds__(128)
