@@ -94,9 +94,9 @@ __device__ __forceinline__ void rpy_pair(const float3 r, const float r2, const f
     table.fg(dist, inv_dist, rp, Imrr, rr);
     const float rdotf = (r.x * Fj.x + r.y * Fj.y + r.z * Fj.z) * (inv_dist * inv_dist);
     const float c = (rr - Imrr) * rdotf;
-    u.x += Imrr * Fj.x + c * r.x;
-    u.y += Imrr * Fj.y + c * r.y;
-    u.z += Imrr * Fj.z + c * r.z;
+    u.x = fmaf(c, r.x, fmaf(Imrr, Fj.x, u.x));
+    u.y = fmaf(c, r.y, fmaf(Imrr, Fj.y, u.y));
+    u.z = fmaf(c, r.z, fmaf(Imrr, Fj.z, u.z));
 }
 
 // Slot-ordered particle record of the real-space kernels: position and the vector being multiplied share
