@@ -64,6 +64,14 @@ struct PseBox {
         return w;
     }
 
+    // Same value, cheaper on the common path: when every component is below 0.49 L all three image indices round to
+    // zero and min_image() returns its argument bit for bit (x is only dragged by a NON-zero y image), so the 13
+    // operations above are skipped.  Used where pairs are tested by the ten-million (list build, pruning).
+    PSE_HD float3 min_image_fast(float3 w) const {
+        if (fabsf(w.x) < 0.98f * hix && fabsf(w.y) < 0.98f * hiy && fabsf(w.z) < 0.98f * hiz) return w;
+        return min_image(w);
+    }
+
     // wrap a position back into the primary cell by at most one image per axis
     PSE_HD void wrap(float3& w, int3& img) const {
         float tilt_x = PSE_MUL(xy, w.y);

@@ -223,7 +223,7 @@ __global__ void nlist_kernel(const float4* __restrict__ spos, uint32_t N, PseBox
                     for (uint32_t j = b; j < e; ++j) {
                         if (j == i) continue;
                         float4 pj = __ldg(spos + j);
-                        float3 d = box.min_image(make_float3(PSE_SUB(pi.x, pj.x), PSE_SUB(pi.y, pj.y), PSE_SUB(pi.z, pj.z)));
+                        float3 d = box.min_image_fast(make_float3(PSE_SUB(pi.x, pj.x), PSE_SUB(pi.y, pj.y), PSE_SUB(pi.z, pj.z)));
                         float r2 = pse_norm2_rn(d);
                         if (r2 < rlist_sq) {
                             if (count < cap) row[count] = j;

@@ -146,7 +146,7 @@ prune_kernel(const float4* __restrict__ spos, uint32_t N, const uint32_t* __rest
                 j = __ldg(nl + h + k);
                 const float4 pj = __ldg(spos + j);
                 const float3 dl = make_float3(PSE_SUB(pi.x, pj.x), PSE_SUB(pi.y, pj.y), PSE_SUB(pi.z, pj.z));
-                const float3 r = box.min_image(dl);
+                const float3 r = box.min_image_fast(dl);
                 const float d = r.x * r.x + r.y * r.y + r.z * r.z;
                 in = d < rp.rcut_sq && d >= rp.dr_sq;
                 if (r.x != dl.x || r.y != dl.y || r.z != dl.z) j |= PSE_WRAP_BIT;  // the pair crosses a periodic boundary
@@ -267,7 +267,8 @@ spmv_kernel(const PX* __restrict__ px, float4* __restrict__ y, uint32_t N,
                         if (idx[t + q] != 0xffffffffu) {
                             const float4 pj = p[cur][q];
                             float3 r = make_float3(PSE_SUB(pi.x, pj.x), PSE_SUB(pi.y, pj.y), PSE_SUB(pi.z, pj.z));
-                            if (!PRUNED || (idx[t + q] & PSE_WRAP_BIT)) r = box.min_image(r);
+                            if (!PRUNED) r = box.min_image_fast(r);
+                            else if (idx[t + q] & PSE_WRAP_BIT) r = box.min_image(r);
                             const float d = r.x * r.x + r.y * r.y + r.z * r.z;
                             // a pruned list was filtered with this very arithmetic at these very positions
                             if (PRUNED || (d < rp.rcut_sq && d >= rp.dr_sq)) rpy_pair(r, d, x[cur][q], table, rp, u);
