@@ -161,6 +161,24 @@ int pse_velocity(pse_engine* e, const float4* d_pos, const float4* d_F, float4* 
 int pse_step(pse_engine* e, float4* d_pos, int3* d_image, const float4* d_F, float4* d_vel, uint32_t timestep,
              float shear_rate, int* m_lanczos_out);
 
+/* Short-range conservative pair forces on the engine's own neighbour list.  The reference
+ * integrates whatever HOOMD pair potentials left in net_force (PSEv1/Stokes.cc:447,457: `m_pdata->getNetForce()`); this
+ * entry point is the stand-in for those force computes (hoomd.md.pair.lj / dpd_conservative in HOOMD 2.3.3 terms), so that
+ * a suspension can be run without HOOMD.  d_F[i] = (Fx, Fy, Fz, half the pair energy of particle i) as HOOMD's net_force;
+ * accumulate != 0 adds to d_F.  r_cut must not exceed the real-space cutoff of the engine (the list is complete up to it).
+ *   PSE_PAIR_LJ        U = 4 eps [(sigma/r)^12 - (sigma/r)^6]                     r < r_cut   (HOOMD shift mode "none")
+ *   PSE_PAIR_WCA       the same, r_cut = 2^(1/6) sigma, shifted by +eps (purely repulsive)
+ *   PSE_PAIR_HARMONIC  U = A (r_cut - r) - A (r_cut^2 - r^2) / (2 r_cut), F = A (1 - r/r_cut) rhat, A = epsilon
+ *                      (HOOMD dpd_conservative) */
+typedef struct pse_pair_params {
+    int32_t kind;
+    float epsilon, sigma, r_cut;
+} pse_pair_params;
+#define PSE_PAIR_LJ 0
+#define PSE_PAIR_WCA 1
+#define PSE_PAIR_HARMONIC 2
+int pse_pair_force(pse_engine* e, const float4* d_pos, const pse_pair_params* prm, float4* d_F, int accumulate);
+
 /* The same step through HOST buffers (pinned or pageable): copies positions, images and forces
  * in, runs pse_step, copies positions and images out, synchronises. */
 int pse_step_host(pse_engine* e, float* h_pos4, int* h_image3, const float* h_F4, float* h_vel4, uint32_t timestep,

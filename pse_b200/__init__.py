@@ -7,4 +7,4 @@ minimal particle/box shim in `pse_b200.system`.  All numerics run in libpse_b200
 behind the C ABI of include/pse_b200.h; there is no CPU or PyTorch fallback.
 """
 from . import _lib  # noqa: F401  (fails loudly when the native library is missing)
-from . import engine, integrate, shear_function, system, variant  # noqa: F401
+from . import engine, integrate, pair, shear_function, system, variant  # noqa: F401

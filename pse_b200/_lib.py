@@ -67,6 +67,12 @@ class pse_shard_info(ctypes.Structure):
 # every symbol include/pse_b200.h declares: name -> (restype, argtypes)
 _vp, _u32, _f, _i, _d = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_float, ctypes.c_int, ctypes.c_double
 _cfgp, _prmp = ctypes.POINTER(pse_config), ctypes.POINTER(pse_params)
+class pse_pair_params(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("epsilon", ctypes.c_float), ("sigma", ctypes.c_float), ("r_cut", ctypes.c_float)]
+
+
+PSE_PAIR_LJ, PSE_PAIR_WCA, PSE_PAIR_HARMONIC = 0, 1, 2
+
 SYMBOLS = {
     "pse_derive_params": (_i, [_cfgp, _prmp]),
     "pse_ewald_table": (_i, [_cfgp, ctypes.POINTER(_f)]),
@@ -94,6 +100,7 @@ SYMBOLS = {
     "pse_velocity": (_i, [_vp, _vp, _vp, _vp, _u32, _vp, _vp, _u32, ctypes.POINTER(_i)]),
     "pse_step": (_i, [_vp, _vp, _vp, _vp, _vp, _u32, _f, ctypes.POINTER(_i)]),
     "pse_step_host": (_i, [_vp, _vp, _vp, _vp, _vp, _u32, _f, ctypes.POINTER(_i)]),
+    "pse_pair_force": (_i, [_vp, _vp, ctypes.POINTER(pse_pair_params), _vp, _i]),
     "pse_get_stats": (_i, [_vp, ctypes.POINTER(pse_stats)]),
     "pse_shard_plan": (_i, [_cfgp, _i, _i, ctypes.POINTER(pse_shard_info)]),
     "pse_shard_setup": (_i, [_vp, _i, _i, ctypes.POINTER(pse_shard_info)]),

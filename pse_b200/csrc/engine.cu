@@ -1084,6 +1084,23 @@ extern "C" int pse_mobility(pse_engine* e, const float4* d_pos, const float4* d_
     return pse_velocity(e, d_pos, d_F, d_U, 0u, nullptr, nullptr, 1u, nullptr);
 }
 
+extern "C" int pse_pair_force(pse_engine* e, const float4* d_pos, const pse_pair_params* prm, float4* d_F, int accumulate) {
+    if (!e || !d_pos || !prm || !d_F) return PSE_EINVAL;
+    PairParams pp;
+    pp.kind = prm->kind; pp.eps = prm->epsilon; pp.sigma = prm->sigma; pp.rcut = prm->r_cut; pp.shift = 0.f;
+    if (prm->kind == PSE_PAIR_WCA) { pp.rcut = 1.122462048309373f * prm->sigma; pp.shift = prm->epsilon; }
+    else if (prm->kind != PSE_PAIR_LJ && prm->kind != PSE_PAIR_HARMONIC) return fail(e, PSE_EINVAL, "pse_pair_force: unknown kind %d", prm->kind);
+    if (!(pp.rcut > 0.f) || pp.rcut > e->prm.rcut)
+        return fail(e, PSE_EINVAL, "pse_pair_force: r_cut %g outside (0, %g] (the neighbour list is complete up to the real-space cutoff)",
+                    pp.rcut, e->prm.rcut);
+    pp.rcut_sq = pp.rcut * pp.rcut;
+    CKRC(ensure_neighbors(e, d_pos));
+    pair_force_kernel<<<nblk((size_t)e->N * 8, 256), 256, 0, e->stream>>>(e->d_spos, e->N, e->d_nn, e->d_head, e->d_nl, e->d_perm, pp, e->box,
+                                                                      d_F, accumulate); LAUNCHED(e);
+    CK(cudaGetLastError());
+    return PSE_OK;
+}
+
 // Euler update + affine shear advection + periodic wrap: PSEv1/Stokes.cu:137-192
 __global__ void integrate_kernel(float4* __restrict__ pos, int3* __restrict__ image, const float4* __restrict__ vel, uint32_t N,
                                  PseBox box, float dt, float shear_rate) {

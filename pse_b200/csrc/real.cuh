@@ -364,3 +364,49 @@ __global__ void scatter_add_kernel(const float4* __restrict__ y, const uint32_t*
     o.x += v.x; o.y += v.y; o.z += v.z; o.w = 0.f;
     U[p] = o;
 }
+
+
+// ---- short-range pair forces on the same list (pse_pair_force; stand-in for the HOOMD pair potentials that fill
+// net_force before Stokes::integrateStepOne reads it, PSEv1/Stokes.cc:447,457) ---------------------------------
+struct PairParams {
+    int kind;  // PSE_PAIR_LJ / WCA / HARMONIC
+    float eps, sigma, rcut_sq, rcut, shift;
+};
+// 8 lanes per row of the buffered list; F[perm[slot]] (+)= (sum_j f(r) r_ij, 1/2 sum_j U(r))
+__global__ void __launch_bounds__(256)
+pair_force_kernel(const float4* __restrict__ spos, uint32_t N, const uint32_t* __restrict__ nn, const uint32_t* __restrict__ head,
+                  const uint32_t* __restrict__ nl, const uint32_t* __restrict__ perm, PairParams pp, PseBox box,
+                  float4* __restrict__ F, int accumulate) {
+    const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int sub = threadIdx.x & 7;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < N) {
+        const float4 pi = __ldg(spos + row);
+        const uint32_t n = __ldg(nn + row);
+        const uint32_t* __restrict__ list = nl + __ldg(head + row);
+        for (uint32_t k = sub; k < n; k += 8) {
+            const float4 pj = __ldg(spos + __ldg(list + k));
+            const float3 r = box.min_image_fast(make_float3(PSE_SUB(pi.x, pj.x), PSE_SUB(pi.y, pj.y), PSE_SUB(pi.z, pj.z)));
+            const float r2 = r.x * r.x + r.y * r.y + r.z * r.z;
+            if (r2 >= pp.rcut_sq || r2 <= 0.f) continue;
+            float f_over_r, u;
+            if (pp.kind == 2) {  // harmonic (dpd_conservative)
+                const float rr = sqrtf(r2);
+                f_over_r = pp.eps * (1.0f / rr - 1.0f / pp.rcut);
+                u = pp.eps * (pp.rcut - rr) - pp.eps * (pp.rcut_sq - r2) / (2.0f * pp.rcut);
+            } else {  // Lennard-Jones, optionally shifted (WCA)
+                const float s2 = pp.sigma * pp.sigma / r2, s6 = s2 * s2 * s2;
+                f_over_r = 24.0f * pp.eps * s6 * (2.0f * s6 - 1.0f) / r2;
+                u = 4.0f * pp.eps * s6 * (s6 - 1.0f) + pp.shift;
+            }
+            acc.x += f_over_r * r.x; acc.y += f_over_r * r.y; acc.z += f_over_r * r.z; acc.w += 0.5f * u;
+        }
+    }
+    acc.x = group_sum<8>(acc.x); acc.y = group_sum<8>(acc.y); acc.z = group_sum<8>(acc.z); acc.w = group_sum<8>(acc.w);
+    if (row < N && sub == 0) {
+        const uint32_t p = perm[row];
+        float4 o = accumulate ? F[p] : make_float4(0.f, 0.f, 0.f, 0.f);
+        o.x += acc.x; o.y += acc.y; o.z += acc.z; o.w += acc.w;
+        F[p] = o;
+    }
+}

@@ -158,6 +158,16 @@ class Engine:
     def mobility(self, pos, F):
         return self._op(lib.pse_mobility, pos, F)
 
+    def pair_force(self, pos, kind, epsilon=1.0, sigma=2.0, r_cut=0.0, out=None, accumulate=False):
+        """Pair forces (F.xyz, per-particle energy) on the engine's neighbour list: the stand-in for the HOOMD pair
+        potentials whose net_force the reference integrates (PSEv1/Stokes.cc:447,457)."""
+        import torch
+        _check4(pos, self.N, "pos")
+        F = out if out is not None else torch.zeros((self.N, 4), dtype=torch.float32, device=pos.device)
+        prm = _lib.pse_pair_params(int(kind), float(epsilon), float(sigma), float(r_cut))
+        self._ck(lib.pse_pair_force(self._h, _ptr(pos), ctypes.byref(prm), _ptr(F), 1 if accumulate else 0))
+        return F
+
     def velocity(self, pos, F, timestep=0, u_particles=None, u_grid=None, parts=7):
         import torch
         _check4(pos, self.N, "pos"); _check4(F, self.N, "F")

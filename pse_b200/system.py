@@ -41,6 +41,8 @@ class System:
         self.dt = None          # set by integrate.mode_standard
         self.integrator = None  # set by integrate.PSEv1
         self.updaters = []
+        self.forces = []        # pair-force providers (pse_b200.pair); their sum replaces net_force every step
+        self.constant_force = None  # set_forces(): an external force added to the providers' sum
 
     def all(self):
         return Group(self)
@@ -49,9 +51,45 @@ class System:
         return self.timestep
 
     def set_forces(self, F):
+        """External (constant) force per particle, [N,3] or [N,4]; kept across steps."""
         import torch
         F = torch.as_tensor(F, dtype=torch.float32, device=self.pos.device)
         self.net_force[:, : F.shape[1]] = F
+        if self.forces:
+            self.constant_force = self.net_force.clone()
+
+    def _compute_forces(self):
+        """HOOMD's ForceCompute pass: net_force = external force + sum of the enabled pair providers."""
+        active = [f for f in self.forces if f.enabled]
+        if not active:
+            return
+        eng = self.integrator.cpp_method
+        if self.constant_force is None:
+            self.net_force.zero_()
+        else:
+            self.net_force.copy_(self.constant_force)
+        for f in active:
+            f.compute(eng, self.pos, self.net_force, True)
+
+    # -- restart / trajectory (SURVEY.md §8f, rank 4): positions, images, step counter, box, Lanczos m; the RNG is stateless
+    def save(self, path):
+        import numpy as np
+        m = self.integrator.cpp_method.lanczos_m if self.integrator is not None and hasattr(self.integrator, "cpp_method") else 0
+        np.savez(path, pos=self.pos.cpu().numpy(), image=self.image.cpu().numpy(), timestep=self.timestep,
+                 box=np.array([self.box.Lx, self.box.Ly, self.box.Lz, self.box.xy]), lanczos_m=m,
+                 net_force=self.net_force.cpu().numpy())
+
+    @classmethod
+    def load(cls, path, device="cuda"):
+        import numpy as np, torch
+        d = np.load(path if str(path).endswith(".npz") else str(path) + ".npz")
+        b = d["box"]
+        s = cls(d["pos"], Box(float(b[0]), float(b[1]), float(b[2]), float(b[3])), device=device)
+        s.image = torch.from_numpy(d["image"]).to(device)
+        s.net_force = torch.from_numpy(d["net_force"]).to(device)
+        s.timestep = int(d["timestep"])
+        s.restart_lanczos_m = int(d["lanczos_m"])
+        return s
 
     def run(self, nsteps):
         """`hoomd.run(n)`: updaters (box tilt) then the integrator, once per step."""
@@ -60,6 +98,7 @@ class System:
         for _ in range(int(nsteps)):
             for u in self.updaters:
                 u(self.timestep)
+            self._compute_forces()
             self.integrator.integrate_step(self.timestep)
             self.timestep += 1
 

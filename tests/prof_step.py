@@ -10,7 +10,7 @@ phi = float(sys.argv[2]) if len(sys.argv) > 2 else 0.3
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 L = util.box_length(N, phi)
 xi = float(os.environ.get("PSE_XI", 0.5)); error = float(os.environ.get("PSE_ERROR", 1e-3))
-cfg = E.make_config(N, L, xi=xi, error=error, T=1.0, dt=1e-3, seed=1)
+cfg = E.make_config(N, L, xi=xi, error=error, T=1.0, dt=1e-3, seed=1, flags=int(os.environ.get("PSE_FLAGS", 0)))
 eng = E.Engine(cfg)
 pos = torch.from_numpy(util.lattice_positions(N, L, 0)).cuda()
 F = torch.from_numpy(util.random_forces(N, 1)).cuda()

@@ -6,6 +6,7 @@ import subprocess
 import sys
 import textwrap
 
+import numpy as np
 import pytest
 
 import pse_b200 as PSEv1
@@ -160,3 +161,29 @@ def test_shard_plan_all_to_all_is_consistent_world_3_gloo(tmp_path):
                           "--master-port", "29534", str(script)], capture_output=True, text=True, env=env, timeout=240)
     assert out.returncode == 0, out.stderr[-3000:]
     assert all((tmp_path / f"ok_{r}").exists() for r in range(3))
+
+
+def test_system_save_load_roundtrip_cpu(tmp_path):
+    """Restart file: positions, images, step counter, box, forces survive a save/load (no GPU needed)."""
+    from pse_b200 import system as S
+    rng = np.random.default_rng(3)
+    s = S.System(rng.uniform(-5, 5, (50, 3)).astype(np.float32), S.Box(10.0, 12.0, 14.0, xy=0.25), device="cpu")
+    s.timestep = 1234
+    s.image[:, 0] = 2
+    s.set_forces(rng.normal(size=(50, 3)).astype(np.float32))
+    s.save(tmp_path / "r")
+    t = S.System.load(tmp_path / "r", device="cpu")
+    assert t.timestep == 1234 and (t.box.Lx, t.box.Ly, t.box.Lz, t.box.xy) == (10.0, 12.0, 14.0, 0.25)
+    assert np.array_equal(t.pos.numpy(), s.pos.numpy()) and np.array_equal(t.image.numpy(), s.image.numpy())
+    assert np.array_equal(t.net_force.numpy(), s.net_force.numpy())
+
+
+def test_pair_provider_validation():
+    from pse_b200 import pair, system as S
+    s = S.set_current(S.System(np.zeros((4, 3), dtype=np.float32), S.Box(10.0), device="cpu"))
+    with pytest.raises(RuntimeError):
+        pair.lj(r_cut=0.0)
+    w = pair.wca()
+    assert s.forces == [w] and w.enabled
+    w.disable()
+    assert not w.enabled
