@@ -104,7 +104,7 @@ struct pse_engine {
     float4 *d_V, *d_u, *d_y;
     float *d_alpha, *d_beta, *d_coef, *d_partials;
     unsigned int* d_counter;
-    float* h_ab;  // pinned: alpha[m_max] | beta[m_max+1]
+    float* h_ab;  // pinned: alpha[m_max + 1] | beta[m_max + 3] | coefficients[m_max + 2]
     int m_lanczos;
     float last_stepnorm;
     // step scratch
@@ -298,7 +298,7 @@ static int alloc_all(pse_engine* e) {
     CK(cudaMalloc(&e->d_partials, sizeof(float) * (N / 8 + 1024)));
     CK(cudaMalloc(&e->d_counter, sizeof(unsigned int)));
     CK(cudaMemset(e->d_counter, 0, sizeof(unsigned int)));
-    CK(cudaMallocHost(&e->h_ab, sizeof(float) * (2 * LANCZOS_M_MAX + 4)));
+    CK(cudaMallocHost(&e->h_ab, sizeof(float) * (3 * LANCZOS_M_MAX + 8)));  // + the combination coefficients
     CK(cudaMalloc(&e->d_vel_work, sizeof(float4) * N));
     CK(cudaMalloc(&e->d_stepdev, sizeof(StepDev)));
     CK(cudaMallocHost(&e->h_stepdev, sizeof(StepDev)));
@@ -919,7 +919,7 @@ static int lanczos_batch(pse_engine* e, const float* d_u_particles, int m) {
 }
 
 // host side: tridiagonal solves, adaptive iterations until the step norm drops below `error`, final combination
-static int lanczos_finish(pse_engine* e, float4* U, int accumulate, int m, int* m_out) {
+static int lanczos_finish(pse_engine* e, float4* U, int accumulate, int m, int* m_out, const float4* ydet) {
     const uint32_t N = e->N;
     cudaStream_t st = e->stream;
     float* alpha = e->h_ab;
@@ -953,13 +953,12 @@ static int lanczos_finish(pse_engine* e, float4* U, int accumulate, int m, int* 
     }
     c = c_prev;
     m = (int)c.size();
-    float hc[LANCZOS_M_MAX + 2];
-    for (int i = 0; i < m; ++i) hc[i] = (float)c[i];
+    float* hc = e->h_ab + 2 * LANCZOS_M_MAX + 4;  // pinned: the copy needs no host synchronisation (the next write to it
+    for (int i = 0; i < m; ++i) hc[i] = (float)c[i];  // comes after the next step's alpha/beta read-back sync)
     CK(cudaMemcpyAsync(e->d_coef, hc, sizeof(float) * m, cudaMemcpyHostToDevice, st));
-    CK(cudaStreamSynchronize(st));  // hc lives on this stack frame
     const float thermal = sqrtf((float)(2.0 * e->cfg.T / e->cfg.dt));  // PSEv1/Brownian.cu:739
     ProfScope ps(e, PH_COMBINE);
-    basis_combine_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_V, e->d_coef, m, N, (size_t)N, e->d_beta, thermal, e->d_perm, U, accumulate); LAUNCHED(e);
+    basis_combine_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_V, e->d_coef, m, N, (size_t)N, e->d_beta, thermal, e->d_perm, U, accumulate, ydet); LAUNCHED(e);
     e->m_lanczos = m;
     e->last_stepnorm = (float)stepnorm;
     if (m_out) *m_out = m;
@@ -1023,7 +1022,7 @@ static int velocity_fixed_part(pse_engine* e, const float4* d_F, float4* d_U, bo
     int acc = 0;
     if (wave) { CKRC(run_wave(e, e->d_sx, d_U, 0, det, wnoise, d_u_grid)); acc = 1; }
     if (fork) CK(cudaStreamWaitEvent(st, e->ev_join, 0));
-    if (det) {
+    if (det && !rnoise) {  // (with the real-space Brownian term the combination kernel adds M_real F in the same pass)
         scatter_add_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_sy, e->d_perm, N, d_U, acc); LAUNCHED(e);
         acc = 1;
     }
@@ -1075,7 +1074,7 @@ extern "C" int pse_velocity(pse_engine* e, const float4* d_pos, const float4* d_
     } else {
         CKRC(velocity_fixed_part(e, d_F, d_U, det, wnoise, rnoise, d_u_particles, d_u_grid, m_batch));
     }
-    if (rnoise) CKRC(lanczos_finish(e, d_U, (det || wnoise) ? 1 : 0, m_batch, m_out));
+    if (rnoise) CKRC(lanczos_finish(e, d_U, (det || wnoise) ? 1 : 0, m_batch, m_out, det ? e->d_sy : nullptr));
     CK(cudaGetLastError());
     return PSE_OK;
 }

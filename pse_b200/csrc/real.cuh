@@ -337,7 +337,7 @@ dot_px_kernel(const PX* __restrict__ px, uint32_t N, float* out, float* partials
 __global__ void __launch_bounds__(256)
 basis_combine_kernel(const float4* __restrict__ V, const float* __restrict__ c, int m, uint32_t N, size_t stride,
                      const float* __restrict__ psinorm, float thermal, const uint32_t* __restrict__ perm,
-                     float4* __restrict__ U, int accumulate) {
+                     float4* __restrict__ U, int accumulate, const float4* __restrict__ ydet /* slot-ordered M_real F or null */) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= N) return;
     float3 acc = make_float3(0.f, 0.f, 0.f);
@@ -349,6 +349,7 @@ basis_combine_kernel(const float4* __restrict__ V, const float* __restrict__ c, 
     const float sc = __ldcg(psinorm) * thermal;
     const uint32_t p = perm[s];
     float4 o = accumulate ? U[p] : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ydet) { const float4 yd = __ldg(ydet + s); o.x += yd.x; o.y += yd.y; o.z += yd.z; }
     o.x += sc * acc.x; o.y += sc * acc.y; o.z += sc * acc.z; o.w = 0.f;
     U[p] = o;
 }
