@@ -126,6 +126,7 @@ struct pse_engine {
     double cheb_max_err;
     int spmv_tpp;  // lanes per row in the SpMV
     int spmv_bps;  // blocks per SM of the persistent SpMV grid (0 = auto)
+    bool spmv_dual;  // M_real F computed inside the first Lanczos product of a full step
     // profiling
     bool prof_on;
     std::vector<cudaEvent_t>* prof_pool;
@@ -476,6 +477,7 @@ extern "C" int pse_create(const pse_config* cfg, void* stream, pse_engine** out)
         else if (tm[0] == 'g') e->spmv_table_mode = TABLE_GLOBAL;
         e->spmv_tpp = 4;  // measured: 4 lanes x 12 entries in flight 202 us, 8 x 6: 236 us, 16 x 3: 330 us per SpMV at N = 1M
         { const char* v = getenv("PSE_SPMV_BPS"); e->spmv_bps = v ? atoi(v) : 0; }
+        { const char* v = getenv("PSE_SPMV_DUAL"); e->spmv_dual = v ? atoi(v) != 0 : true; }
         const char* tpp = getenv("PSE_SPMV_TPP");
         if (tpp) e->spmv_tpp = atoi(tpp);
     }
@@ -767,6 +769,20 @@ static void launch_spmv_tpp(pse_engine* e, float4* y, const LanczosArgs& la) {
     }
     LAUNCHED(e);
 }
+// first Lanczos product of a full step with M_real F riding along (poly / global table modes, pruned lists)
+static bool launch_spmv_dual(pse_engine* e, float4* y, const LanczosArgs& la, const float4* x2, float4* y2) {
+    if (!e->prune || !e->spmv_dual || e->spmv_tpp != 4 || e->spmv_table_mode == TABLE_SHARED) return false;
+    const unsigned int work = nblk((size_t)e->N * 4, 256);
+    const unsigned int grid = persistent_grid(e, work, e->spmv_bps > 0 ? e->spmv_bps : 8);
+    if (e->spmv_table_mode == TABLE_POLY)
+        spmv_kernel<4, SPMV_LANCZOS, TABLE_POLY, true, true><<<grid, 256, 0, e->stream>>>(e->d_px, y, e->N, e->d_nn_act, e->d_head, e->d_nl_act, e->d_table,
+                                                                                     e->cheb, e->rp, e->box, la, 0, x2, y2);
+    else
+        spmv_kernel<4, SPMV_LANCZOS, TABLE_GLOBAL, true, true><<<grid, 256, 0, e->stream>>>(e->d_px, y, e->N, e->d_nn_act, e->d_head, e->d_nl_act, e->d_table,
+                                                                                       e->cheb, e->rp, e->box, la, 0, x2, y2);
+    LAUNCHED(e);
+    return true;
+}
 template <int MODE>
 static void launch_spmv(pse_engine* e, float4* y, const LanczosArgs& la) {
     switch (e->spmv_tpp) {
@@ -775,6 +791,9 @@ static void launch_spmv(pse_engine* e, float4* y, const LanczosArgs& la) {
     }
 }
 
+static bool spmv_dual_available(const pse_engine* e) {
+    return e->prune && e->spmv_dual && e->spmv_tpp == 4 && e->spmv_table_mode != TABLE_SHARED;
+}
 static int run_spmv_plain(pse_engine* e, float4* y) {
     CKRC(ensure_pruned(e));
     ProfScope ps(e, PH_SPMV);
@@ -861,7 +880,7 @@ static int run_wave(pse_engine* e, const float4* sF, float4* U, int accumulate, 
 }
 
 // one Lanczos iteration j (two kernels)
-static void lanczos_iteration(pse_engine* e, int j) {
+static void lanczos_iteration(pse_engine* e, int j, bool dual = false) {
     const uint32_t N = e->N;
     float4* Vj = e->d_V + (size_t)j * N;
     LanczosArgs la;
@@ -874,7 +893,7 @@ static void lanczos_iteration(pse_engine* e, int j) {
     la.first = j == 0;
     {
     ProfScope ps(e, PH_LANCZOS_SPMV);
-    launch_spmv<SPMV_LANCZOS>(e, e->d_y, la);
+    if (!(dual && launch_spmv_dual(e, e->d_y, la, e->d_sx, e->d_sy))) launch_spmv<SPMV_LANCZOS>(e, e->d_y, la);
     }
     ProfScope ps(e, PH_LANCZOS_VEC);
     lanczos_update_kernel<<<persistent_grid(e, nblk(N, 256), 8), 256, 0, e->stream>>>(e->d_y, Vj, e->d_px, N, e->d_alpha + j, e->d_beta + j + 1,
@@ -901,7 +920,7 @@ static int lanczos_batch_size(const pse_engine* e) {
     int m = e->m_lanczos - 1;  // PSEv1/Brownian.cu:465-466
     return m < 1 ? 1 : m;
 }
-static int lanczos_batch(pse_engine* e, const float* d_u_particles, int m) {
+static int lanczos_batch(pse_engine* e, const float* d_u_particles, int m, bool dual = false) {
     CKRC(ensure_pruned(e));
     const uint32_t N = e->N;
     cudaStream_t st = e->stream;
@@ -912,7 +931,7 @@ static int lanczos_batch(pse_engine* e, const float* d_u_particles, int m) {
     }
     float* alpha = e->h_ab;
     float* beta = e->h_ab + LANCZOS_M_MAX + 1;
-    for (int j = 0; j < m; ++j) lanczos_iteration(e, j);
+    for (int j = 0; j < m; ++j) lanczos_iteration(e, j, dual && j == 0);
     CK(cudaMemcpyAsync(alpha, e->d_alpha, sizeof(float) * m, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(beta, e->d_beta, sizeof(float) * (m + 1), cudaMemcpyDeviceToHost, st));
     return PSE_OK;
@@ -1012,8 +1031,10 @@ static int velocity_fixed_part(pse_engine* e, const float4* d_F, float4* d_U, bo
         CK(cudaStreamWaitEvent(e->stream2, e->ev_fork, 0));
         e->stream = e->stream2;
     }
-    if (det) rc = run_spmv_plain(e, e->d_sy);
-    if (rc == PSE_OK && rnoise) rc = lanczos_batch(e, d_u_particles, m_batch);
+    // full step: M_real F is computed inside the first Lanczos product (dual right-hand side) when that path is available
+    const bool dual = det && rnoise && m_batch >= 1 && spmv_dual_available(e);
+    if (det && !dual) rc = run_spmv_plain(e, e->d_sy);
+    if (rc == PSE_OK && rnoise) rc = lanczos_batch(e, d_u_particles, m_batch, dual);
     if (fork) {
         e->stream = st;
         if (rc == PSE_OK) CK(cudaEventRecord(e->ev_join, e->stream2));

@@ -99,6 +99,21 @@ __device__ __forceinline__ void rpy_pair(const float3 r, const float r2, const f
     u.z = fmaf(c, r.z, fmaf(Imrr, Fj.z, u.z));
 }
 
+// the same pair applied to two vectors at once (M_real F rides along with the first Lanczos product)
+template <class TAB>
+__device__ __forceinline__ void rpy_pair2(const float3 r, const float r2, const float4 Fa, const float4 Fb, const TAB& table,
+                                          const RealParams& rp, float3& ua, float3& ub) {
+    float inv_dist;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv_dist) : "f"(r2));
+    const float dist = r2 * inv_dist;
+    float Imrr, rr;
+    table.fg(dist, inv_dist, rp, Imrr, rr);
+    const float i2 = inv_dist * inv_dist, dg = rr - Imrr;
+    const float ca = dg * ((r.x * Fa.x + r.y * Fa.y + r.z * Fa.z) * i2), cb = dg * ((r.x * Fb.x + r.y * Fb.y + r.z * Fb.z) * i2);
+    ua.x = fmaf(ca, r.x, fmaf(Imrr, Fa.x, ua.x)); ua.y = fmaf(ca, r.y, fmaf(Imrr, Fa.y, ua.y)); ua.z = fmaf(ca, r.z, fmaf(Imrr, Fa.z, ua.z));
+    ub.x = fmaf(cb, r.x, fmaf(Imrr, Fb.x, ub.x)); ub.y = fmaf(cb, r.y, fmaf(Imrr, Fb.y, ub.y)); ub.z = fmaf(cb, r.z, fmaf(Imrr, Fb.z, ub.z));
+}
+
 // Slot-ordered particle record of the real-space kernels: position and the vector being multiplied share
 // one 32-byte sector, so a neighbour gather costs one sector instead of two.
 struct __align__(32) PX {
@@ -187,12 +202,15 @@ enum { TABLE_GLOBAL = 0, TABLE_SHARED = 1, TABLE_POLY = 2 };
 #define SPMV_AHEAD 1
 #endif
 // SPMV_ROW_PASS: neighbour entries of a row covered by one pass (SPMV_ROW_PASS / TPP index registers per lane)
-template <int TPP, int MODE, int TABLE, bool PRUNED>
-__global__ void __launch_bounds__(256, 4)
+// DUAL (first Lanczos iteration of a full step): a second vector x2 (the slot-ordered forces) is multiplied in the same
+// pass, y2 = M x2 - the pair geometry and f, g are shared, so the separate deterministic SpMV of the step disappears.
+template <int TPP, int MODE, int TABLE, bool PRUNED, bool DUAL = false>
+__global__ void __launch_bounds__(256, DUAL ? 3 : 4)
 spmv_kernel(const PX* __restrict__ px, float4* __restrict__ y, uint32_t N,
             const uint32_t* __restrict__ nn, const uint32_t* __restrict__ head, const uint32_t* __restrict__ nl,
             const float4* __restrict__ gtable, ChebCoef cheb, RealParams rp,
-            PseBox box, LanczosArgs la, uint32_t row_begin = 0) {
+            PseBox box, LanczosArgs la, uint32_t row_begin = 0, const float4* __restrict__ x2 = nullptr,
+            float4* __restrict__ y2 = nullptr) {
     constexpr int ROWS = 256 / TPP;
     const int sub = threadIdx.x % TPP;
     extern __shared__ __align__(16) float2 stab[];
@@ -222,7 +240,7 @@ spmv_kernel(const PX* __restrict__ px, float4* __restrict__ y, uint32_t N,
     }
     for (uint32_t row0 = row_begin + blockIdx.x * ROWS; row0 < N; row0 += gridDim.x * ROWS) {  // rows [row_begin, N)
         const uint32_t row = row0 + threadIdx.x / TPP;
-        float3 u = make_float3(0.f, 0.f, 0.f);
+        float3 u = make_float3(0.f, 0.f, 0.f), u2 = u;
         float4 pi = make_float4(0.f, 0.f, 0.f, 0.f), xi = pi;
         float4 vp = pi;
         const bool live = row < N;
@@ -248,19 +266,27 @@ spmv_kernel(const PX* __restrict__ px, float4* __restrict__ y, uint32_t N,
                     idx[t] = k < n ? __ldg(list + k) : 0xffffffffu;
                 }
                 constexpr int AHEAD = SPMV_AHEAD, RING = AHEAD + 1;  // pairs of gathers in flight ahead of the arithmetic
-                float4 p[RING][2], x[RING][2];
+                float4 p[RING][2], x[RING][2], xb[RING][2];
 #pragma unroll
                 for (int h = 0; h < AHEAD; ++h)
 #pragma unroll
                     for (int q = 0; q < 2; ++q)
-                        if (2 * h + q < SLOTS && idx[2 * h + q] != 0xffffffffu) ld_px(px + (PRUNED ? idx[2 * h + q] & ~PSE_WRAP_BIT : idx[2 * h + q]), p[h % RING][q], x[h % RING][q]);
+                        if (2 * h + q < SLOTS && idx[2 * h + q] != 0xffffffffu) {
+                            const uint32_t jj = PRUNED ? idx[2 * h + q] & ~PSE_WRAP_BIT : idx[2 * h + q];
+                            ld_px(px + jj, p[h % RING][q], x[h % RING][q]);
+                            if (DUAL) xb[h % RING][q] = __ldg(x2 + jj);
+                        }
 #pragma unroll
                 for (int t = 0; t < SLOTS; t += 2) {
                     const int cur = (t / 2) % RING, nxt = (t / 2 + AHEAD) % RING;
                     if (t + 2 * AHEAD < SLOTS) {
 #pragma unroll
                         for (int q = 0; q < 2; ++q)
-                            if (idx[t + 2 * AHEAD + q] != 0xffffffffu) ld_px(px + (PRUNED ? idx[t + 2 * AHEAD + q] & ~PSE_WRAP_BIT : idx[t + 2 * AHEAD + q]), p[nxt][q], x[nxt][q]);
+                            if (idx[t + 2 * AHEAD + q] != 0xffffffffu) {
+                                const uint32_t jj = PRUNED ? idx[t + 2 * AHEAD + q] & ~PSE_WRAP_BIT : idx[t + 2 * AHEAD + q];
+                                ld_px(px + jj, p[nxt][q], x[nxt][q]);
+                                if (DUAL) xb[nxt][q] = __ldg(x2 + jj);
+                            }
                     }
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
@@ -271,7 +297,10 @@ spmv_kernel(const PX* __restrict__ px, float4* __restrict__ y, uint32_t N,
                             else if (idx[t + q] & PSE_WRAP_BIT) r = box.min_image(r);
                             const float d = r.x * r.x + r.y * r.y + r.z * r.z;
                             // a pruned list was filtered with this very arithmetic at these very positions
-                            if (PRUNED || (d < rp.rcut_sq && d >= rp.dr_sq)) rpy_pair(r, d, x[cur][q], table, rp, u);
+                            if (PRUNED || (d < rp.rcut_sq && d >= rp.dr_sq)) {
+                                if (DUAL) rpy_pair2(r, d, x[cur][q], xb[cur][q], table, rp, u, u2);
+                                else rpy_pair(r, d, x[cur][q], table, rp, u);
+                            }
                         }
                     }
                 }
@@ -280,6 +309,13 @@ spmv_kernel(const PX* __restrict__ px, float4* __restrict__ y, uint32_t N,
         u.x = group_sum<TPP>(u.x);
         u.y = group_sum<TPP>(u.y);
         u.z = group_sum<TPP>(u.z);
+        if (DUAL) {
+            u2.x = group_sum<TPP>(u2.x); u2.y = group_sum<TPP>(u2.y); u2.z = group_sum<TPP>(u2.z);
+            if (live && sub == 0) {
+                const float4 fi = __ldg(x2 + row);
+                y2[row] = make_float4(u2.x + rp.self * fi.x, u2.y + rp.self * fi.y, u2.z + rp.self * fi.z, 0.f);
+            }
+        }
         if (live && sub == 0) {
             if (MODE == SPMV_PLAIN) {
                 y[row] = make_float4(u.x + rp.self * xi.x, u.y + rp.self * xi.y, u.z + rp.self * xi.z, 0.f);
