@@ -391,7 +391,7 @@ static int setup_own_fft(pse_engine* e) {
         e->fft_ax[a].pos_of = reinterpret_cast<const uint16_t*>(base + off_pos[a]);
         e->fft_ax[a].freq_of = reinterpret_cast<const uint16_t*>(base + off_frq[a]);
     }
-    const size_t smz = fft_smem_bytes(dims[2], FFT_Z_COLS), smy = fft_smem_bytes(dims[1], FFT_Y_COLS), smx = fft_smem_bytes(dims[0], 3 * FFT_X_COLS);
+    const size_t smz = fft_smem_bytes(dims[2], FFT_Z_COLS + 1), smy = fft_smem_bytes(dims[1], FFT_Y_CP), smx = fft_smem_bytes(dims[0], FFT_X_CP);
     if (std::max(smz, std::max(smy, smx)) > 200 * 1024) { e->own_fft = false; return PSE_OK; }
     CK(cudaFuncSetAttribute(fft_z_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smz));
     CK(cudaFuncSetAttribute(fft_z_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smz));
@@ -838,9 +838,9 @@ static int run_wave(pse_engine* e, const float4* sF, float4* U, int accumulate, 
         if (e->own_fft) {
             const WaveParams& wp = e->wp;
             const uint32_t nrows = 3u * wp.Nx * wp.Ny;
-            fft_z_forward_kernel<<<nblk(nrows, 2 * FFT_Z_COLS), FFT_THREADS, fft_smem_bytes(wp.Nz, FFT_Z_COLS), st>>>(
+            fft_z_forward_kernel<<<nblk(nrows, 2 * FFT_Z_COLS), FFT_THREADS, fft_smem_bytes(wp.Nz, FFT_Z_COLS + 1), st>>>(
                 e->d_grid, e->d_spec, e->fft_ax[2], nrows, wp.Nzp); LAUNCHED(e);
-            fft_y_kernel<false><<<dim3(nblk(wp.Nzh, FFT_Y_COLS), 3 * wp.Nx), FFT_THREADS, fft_smem_bytes(wp.Ny, FFT_Y_COLS), st>>>(
+            fft_y_kernel<false><<<dim3(nblk(wp.Nzh, FFT_Y_COLS), 3 * wp.Nx), FFT_THREADS, fft_smem_bytes(wp.Ny, FFT_Y_CP), st>>>(
                 e->d_spec, e->fft_ax[1], wp.Nzh, wp.Nzp); LAUNCHED(e);
         } else {
             CKFFT(cufftExecR2C(e->plan_f, e->d_grid, (cufftComplex*)e->d_spec));
@@ -851,14 +851,14 @@ static int run_wave(pse_engine* e, const float4* sF, float4* U, int accumulate, 
         const WaveParams& wp = e->wp;
         {
             ProfScope ps(e, PH_SCALE);  // x forward + scaling + x inverse
-            fft_x_scale_kernel<<<dim3(nblk(wp.Nzh, FFT_X_COLS), wp.Ny), FFT_THREADS, fft_smem_bytes(wp.Nx, 3 * FFT_X_COLS), st>>>(
+            fft_x_scale_kernel<<<dim3(nblk(wp.Nzh, FFT_X_COLS), wp.Ny), FFT_THREADS, fft_smem_bytes(wp.Nx, FFT_X_CP), st>>>(
                 e->d_spec, e->fft_ax[0], e->fft_ax[1].freq_of, e->wp, e->box, det ? 1 : 0, noise ? 1 : 0, e->d_stepdev, d_u_grid); LAUNCHED(e);
         }
         ProfScope ps(e, PH_FFT_INV);
         const uint32_t nrows = 3u * wp.Nx * wp.Ny;
-        fft_y_kernel<true><<<dim3(nblk(wp.Nzh, FFT_Y_COLS), 3 * wp.Nx), FFT_THREADS, fft_smem_bytes(wp.Ny, FFT_Y_COLS), st>>>(
+        fft_y_kernel<true><<<dim3(nblk(wp.Nzh, FFT_Y_COLS), 3 * wp.Nx), FFT_THREADS, fft_smem_bytes(wp.Ny, FFT_Y_CP), st>>>(
             e->d_spec, e->fft_ax[1], wp.Nzh, wp.Nzp); LAUNCHED(e);
-        fft_z_inverse_kernel<<<nblk(nrows, 2 * FFT_Z_COLS), FFT_THREADS, fft_smem_bytes(wp.Nz, FFT_Z_COLS), st>>>(
+        fft_z_inverse_kernel<<<nblk(nrows, 2 * FFT_Z_COLS), FFT_THREADS, fft_smem_bytes(wp.Nz, FFT_Z_COLS + 1), st>>>(
             e->d_spec, e->d_grid, e->fft_ax[2], nrows, wp.Nzp); LAUNCHED(e);
         e->fft_execs++;
     } else {

@@ -65,41 +65,48 @@ __device__ __forceinline__ void dft_small(float2 (&a)[R]) {
 }
 
 // one radix-R pass over interleaved columns (all threads of the block take part; caller syncs).
-// CG = column group (compile-time, >= ncol): thread t works on column t % CG of butterfly t / CG.
-template <int R, bool INV, int CG>
+// CG = column groups per butterfly (compile-time): thread t works on butterfly t / CG and on the VEC columns
+// (t % CG) + CG * u, u < VEC, which share the butterfly's index arithmetic and twiddles (a third of the instructions of a
+// one-column butterfly).  CG * VEC >= ncol.
+template <int R, bool INV, int CG, int VEC>
 __device__ __forceinline__ void fft_pass(float2* s, int CP, int ncol, int N, int n /* sub-transform length */, const float2* stw) {
     const int m = n / R, tws = N / n;
     const float inv_m = 1.0f / (float)m;
     constexpr int GROUPS = FFT_THREADS / CG;  // threads beyond GROUPS * CG idle when CG does not divide the block
-    const int col = threadIdx.x % CG;
-    if (col >= ncol || threadIdx.x >= GROUPS * CG) return;
-#pragma unroll 2
+    const int col0 = threadIdx.x % CG;
+    if (col0 >= ncol || threadIdx.x >= GROUPS * CG) return;
     for (int bf = threadIdx.x / CG; bf < N / R; bf += GROUPS) {
         const int b = (int)(((float)bf + 0.5f) * inv_m), j = bf - b * m;  // exact for these sizes (bf < 1024)
-        float2* base = s + (b * n + j) * CP + col;
-        float2 a[R];
-#pragma unroll
-        for (int q = 0; q < R; ++q) a[q] = base[q * m * CP];
+        float2* base = s + (b * n + j) * CP + col0;
+        const int stride = m * CP;
         // twiddles w_n^{j p}, p = 1 .. R-1, from one table entry
         float2 w[R];
         w[1] = stw[j * tws];
 #pragma unroll
         for (int p = 2; p < R; ++p) w[p] = cmul(w[p - 1], w[1]);
-        if (INV) {  // adjoint of the forward pass: conjugate twiddles first, then the conjugate butterfly
 #pragma unroll
-            for (int p = 1; p < R; ++p) a[p] = cmulc(a[p], w[p]);
-            dft_small<R, true>(a);
-        } else {
-            dft_small<R, false>(a);
+        for (int u = 0; u < VEC; ++u) {
+            if (col0 + CG * u >= ncol) break;
+            float2* bu = base + CG * u;
+            float2 a[R];
 #pragma unroll
-            for (int p = 1; p < R; ++p) a[p] = cmul(a[p], w[p]);
+            for (int q = 0; q < R; ++q) a[q] = bu[q * stride];
+            if (INV) {  // adjoint of the forward pass: conjugate twiddles first, then the conjugate butterfly
+#pragma unroll
+                for (int p = 1; p < R; ++p) a[p] = cmulc(a[p], w[p]);
+                dft_small<R, true>(a);
+            } else {
+                dft_small<R, false>(a);
+#pragma unroll
+                for (int p = 1; p < R; ++p) a[p] = cmul(a[p], w[p]);
+            }
+#pragma unroll
+            for (int q = 0; q < R; ++q) bu[q * stride] = a[q];
         }
-#pragma unroll
-        for (int q = 0; q < R; ++q) base[q * m * CP] = a[q];
     }
 }
 
-template <bool INV, int CG>
+template <bool INV, int CG, int VEC>
 __device__ __forceinline__ void fft_columns(float2* s, int CP, int ncol, const Fft1D& f, const float2* stw) {
     const int N = f.N, npass = f.npass;
     const unsigned long long radices = f.radices;
@@ -107,10 +114,10 @@ __device__ __forceinline__ void fft_columns(float2* s, int CP, int ncol, const F
         int n = N;
         for (int i = 0; i < npass; ++i) {
             const int r = (int)((radices >> (4 * i)) & 15ull);
-            if (r == 4) fft_pass<4, false, CG>(s, CP, ncol, N, n, stw);
-            else if (r == 2) fft_pass<2, false, CG>(s, CP, ncol, N, n, stw);
-            else if (r == 3) fft_pass<3, false, CG>(s, CP, ncol, N, n, stw);
-            else fft_pass<5, false, CG>(s, CP, ncol, N, n, stw);
+            if (r == 4) fft_pass<4, false, CG, VEC>(s, CP, ncol, N, n, stw);
+            else if (r == 2) fft_pass<2, false, CG, VEC>(s, CP, ncol, N, n, stw);
+            else if (r == 3) fft_pass<3, false, CG, VEC>(s, CP, ncol, N, n, stw);
+            else fft_pass<5, false, CG, VEC>(s, CP, ncol, N, n, stw);
             n /= r;
             __syncthreads();
         }
@@ -119,10 +126,10 @@ __device__ __forceinline__ void fft_columns(float2* s, int CP, int ncol, const F
         for (int i = npass - 1; i >= 0; --i) {
             const int r = (int)((radices >> (4 * i)) & 15ull);
             n *= r;
-            if (r == 4) fft_pass<4, true, CG>(s, CP, ncol, N, n, stw);
-            else if (r == 2) fft_pass<2, true, CG>(s, CP, ncol, N, n, stw);
-            else if (r == 3) fft_pass<3, true, CG>(s, CP, ncol, N, n, stw);
-            else fft_pass<5, true, CG>(s, CP, ncol, N, n, stw);
+            if (r == 4) fft_pass<4, true, CG, VEC>(s, CP, ncol, N, n, stw);
+            else if (r == 2) fft_pass<2, true, CG, VEC>(s, CP, ncol, N, n, stw);
+            else if (r == 3) fft_pass<3, true, CG, VEC>(s, CP, ncol, N, n, stw);
+            else fft_pass<5, true, CG, VEC>(s, CP, ncol, N, n, stw);
             __syncthreads();
         }
     }
@@ -154,7 +161,7 @@ fft_z_forward_kernel(const float* __restrict__ grid, float2* __restrict__ spec, 
         for (int z = lane; z < N; z += 32) dst[2 * z * CP] = row < nrows ? __ldg(src + z) : 0.f;
     }
     __syncthreads();
-    fft_columns<false, FFT_Z_COLS>(s, CP, FFT_Z_COLS, f, stw);
+    fft_columns<false, FFT_Z_COLS, 1>(s, CP, FFT_Z_COLS, f, stw);
     // X_a[k] = (Z[k] + conj Z[N-k]) / 2,  X_b[k] = (Z[k] - conj Z[N-k]) / (2i)
     for (int c = wid; c < FFT_Z_COLS; c += FFT_THREADS / 32) {
         const uint32_t ra = row0 + 2 * c, rb = ra + 1;
@@ -190,7 +197,7 @@ fft_z_inverse_kernel(const float2* __restrict__ spec, float* __restrict__ grid, 
         if (!selfc) s[__ldg(f.pos_of + N - k) * CP + c] = make_float2(xa.x + xby, xb.x - xay);
     }
     __syncthreads();
-    fft_columns<true, FFT_Z_COLS>(s, CP, FFT_Z_COLS, f, stw);
+    fft_columns<true, FFT_Z_COLS, 1>(s, CP, FFT_Z_COLS, f, stw);
     for (int r = wid; r < 2 * FFT_Z_COLS; r += FFT_THREADS / 32) {
         const uint32_t row = row0 + r;
         if (row >= nrows) continue;
@@ -202,11 +209,12 @@ fft_z_inverse_kernel(const float2* __restrict__ spec, float* __restrict__ grid, 
 
 // ---- y: in place on spec[plane][y][kz], plane = c * Nx + x -----------------------------------------------
 #define FFT_Y_COLS 16
+#define FFT_Y_CP 17
 template <bool INV>
 __global__ void __launch_bounds__(FFT_THREADS)
 fft_y_kernel(float2* __restrict__ spec, Fft1D f, int Nzh, int Nzp) {
     extern __shared__ __align__(16) float2 fsm[];
-    constexpr int CP = FFT_Y_COLS + 1;
+    constexpr int CP = FFT_Y_CP;
     const int N = f.N;
     float2* s = fsm;
     float2* stw = s + (size_t)N * CP;
@@ -217,7 +225,7 @@ fft_y_kernel(float2* __restrict__ spec, Fft1D f, int Nzh, int Nzp) {
     if (c < ncol)
         for (int y = threadIdx.x / FFT_Y_COLS; y < N; y += FFT_THREADS / FFT_Y_COLS) s[y * CP + c] = base[(size_t)y * Nzp + c];
     __syncthreads();
-    fft_columns<INV, FFT_Y_COLS>(s, CP, ncol, f, stw);
+    fft_columns<INV, FFT_Y_COLS, 1>(s, CP, ncol, f, stw);
     if (c < ncol)
         for (int y = threadIdx.x / FFT_Y_COLS; y < N; y += FFT_THREADS / FFT_Y_COLS) base[(size_t)y * Nzp + c] = s[y * CP + c];
 }
@@ -226,11 +234,12 @@ fft_y_kernel(float2* __restrict__ spec, Fft1D f, int Nzh, int Nzp) {
 // A block owns the 3 components of FFT_X_COLS consecutive kz at one stored y position: 3 * FFT_X_COLS columns of
 // length Nx.  The y index it sits at is freq_of_y[blockIdx.y] (the y pass left digit-reversed order).
 #define FFT_X_COLS 8
+#define FFT_X_CP 24
 __global__ void __launch_bounds__(FFT_THREADS)
 fft_x_scale_kernel(float2* __restrict__ spec, Fft1D fx, const uint16_t* __restrict__ freq_of_y, WaveParams wp, PseBox box,
                    int do_det, int do_noise, const StepDev* __restrict__ sd, const float* __restrict__ u_grid) {
     extern __shared__ __align__(16) float2 fsm[];
-    constexpr int NC = 3 * FFT_X_COLS, CP = NC + 1;
+    constexpr int NC = 3 * FFT_X_COLS, CP = FFT_X_CP;  // row stride = 8 (mod 16) float2 for the 2 x 8 half-warp patch
     const int N = fx.N;
     float2* s = fsm;
     float2* stw = s + (size_t)N * CP;
@@ -248,7 +257,7 @@ fft_x_scale_kernel(float2* __restrict__ spec, Fft1D fx, const uint16_t* __restri
             for (int x = threadIdx.x / NC; x < N; x += XG)
                 s[x * CP + col] = kcol < ncol ? base[cc * comp + (size_t)x * plane + kcol] : make_float2(0.f, 0.f);
         __syncthreads();
-        fft_columns<false, NC>(s, CP, NC, fx, stw);
+        fft_columns<false, 8, 3>(s, CP, NC, fx, stw);
     }
     {
         const uint32_t key = sd->key;
@@ -267,9 +276,9 @@ fft_x_scale_kernel(float2* __restrict__ spec, Fft1D fx, const uint16_t* __restri
         }
     }
     __syncthreads();
-    fft_columns<true, NC>(s, CP, NC, fx, stw);
+    fft_columns<true, 8, 3>(s, CP, NC, fx, stw);
     if (colthread && kcol < ncol)
         for (int x = threadIdx.x / NC; x < N; x += XG) base[cc * comp + (size_t)x * plane + kcol] = s[x * CP + col];
 }
 
-static inline size_t fft_smem_bytes(int N, int cols) { return ((size_t)N * (cols + 1) + N) * sizeof(float2); }
+static inline size_t fft_smem_bytes(int N, int cp) { return ((size_t)N * cp + N) * sizeof(float2); }  // cp = padded row length
