@@ -142,7 +142,9 @@ __device__ __forceinline__ void load_twiddles(float2* stw, const Fft1D& f) {
 // ---- z: real rows <-> half spectra, two rows per complex transform ---------------------------------------
 // rows = 3 * Nx * Ny contiguous real rows of Nz (component stride = Nx*Ny*Nz, i.e. simply consecutive rows);
 // spec rows of Nzp complex, frequencies kz = 0 .. Nz/2 in natural order.
+#ifndef FFT_Z_COLS
 #define FFT_Z_COLS 16
+#endif
 __global__ void __launch_bounds__(FFT_THREADS)
 fft_z_forward_kernel(const float* __restrict__ grid, float2* __restrict__ spec, Fft1D f, uint32_t nrows, int Nzp) {
     extern __shared__ __align__(16) float2 fsm[];
@@ -208,8 +210,12 @@ fft_z_inverse_kernel(const float2* __restrict__ spec, float* __restrict__ grid, 
 }
 
 // ---- y: in place on spec[plane][y][kz], plane = c * Nx + x -----------------------------------------------
+#ifndef FFT_Y_COLS
 #define FFT_Y_COLS 16
+#endif
+#ifndef FFT_Y_CP
 #define FFT_Y_CP 17
+#endif
 template <bool INV>
 __global__ void __launch_bounds__(FFT_THREADS)
 fft_y_kernel(float2* __restrict__ spec, Fft1D f, int Nzh, int Nzp) {

@@ -20,7 +20,9 @@
 
 #define TILE 16
 #define TILE_ZS 18       // padded z stride of the accumulator tile (bank spread for the 6x6 (j,k) footprints)
+#ifndef SPREAD_CHUNK
 #define SPREAD_CHUNK 32  // particles whose weights are staged at once
+#endif
 #define TILED_MAX_P 10   // 3P validity bits must fit one 32-bit word
 
 struct TileGrid {
@@ -161,7 +163,9 @@ wweights_kernel(const float4* __restrict__ wpos, const int4* __restrict__ worg, 
 //            alternate so that the next particle's record and factors are fetched before the barrier.
 //   store    the finished tile is written once, coalesced.
 // dynamic smem: acc[3][TILE*TILE*TILE_ZS] | a_rec[CAP] f4 | a_mask[CAP] | a_w[CAP] | wbuf[2][CHUNK][P*P+P]
+#ifndef SPREAD_CAP
 #define SPREAD_CAP 384   // staged particles per filter round; sized so that three blocks fit one SM
+#endif
 #define SPREAD_MAX_SEG 64
 #define SPREAD_NODE_BIAS 2048  // > (TILED_MAX_P - 1) * (TILE * TILE_ZS + TILE_ZS + 1)
 
@@ -406,7 +410,9 @@ static inline size_t spread_tile_smem(int P) {
 //     shared-memory scratch for factors;
 //   * columns beyond a multiple of 32 (4 of the 36 for P = 6) are handled one NODE per lane when they fit a warp.
 // dynamic smem: g[3][H * XS].
+#ifndef INTERP_THREADS
 #define INTERP_THREADS 512
+#endif
 __host__ __device__ constexpr int interp_pad(int P) {
     const int H = TILE + P - 1, PP = P * P;
     int best_pad = 0, best_cost = 1 << 30;
