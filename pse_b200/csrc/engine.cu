@@ -803,7 +803,7 @@ static int run_spmv_plain(pse_engine* e, float4* y) {
 }
 
 // bin the (slot-ordered) particles by the tile of their support origin and gather the W-order records
-static int run_wbin(pse_engine* e, const float4* sF) {
+static int run_wbin(pse_engine* e, const float4* sF, int wt_tile_lo = -1, int wt_tile_hi = -1 /* factor rows only for tiles [lo, hi) */) {
     ProfScope ps(e, PH_WBIN);
     cudaStream_t st = e->stream;
     const uint32_t N = e->N, nt = e->tg.ntile;
@@ -815,7 +815,20 @@ static int run_wbin(pse_engine* e, const float4* sF) {
     cell_fill_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_wcell_of, N, e->d_wstart, e->d_wcount, e->d_wtmp); LAUNCHED(e);
     cell_sort_block_kernel<<<nt, 128, 0, st>>>(e->d_wstart, e->d_wtmp, e->d_wperm); LAUNCHED(e);
     wgather_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_spos, sF, e->d_org, e->d_wperm, e->d_perm, N, e->d_wpos, e->d_wF, e->d_worg, e->d_wid); LAUNCHED(e);
-    launch_wweights(e->wp.P, st, e->d_wpos, e->d_worg, N, e->box, e->wp, e->d_wwt); LAUNCHED(e);
+    if (wt_tile_lo < 0) {
+        launch_wweights(e->wp.P, st, e->d_wpos, e->d_worg, N, e->box, e->wp, e->d_wwt); LAUNCHED(e);
+    } else {
+        // sharded call: W order is tile-sorted (x tile slowest), so the particles of a range of x-tile rows are one
+        // contiguous W range; its two ends come back through the pinned flag words
+        CK(cudaMemcpyAsync(e->h_nlinfo, e->d_wstart + wt_tile_lo, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(reinterpret_cast<uint32_t*>(e->h_nlinfo) + 1, e->d_wstart + wt_tile_hi, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const uint32_t w0 = reinterpret_cast<uint32_t*>(e->h_nlinfo)[0], w1 = reinterpret_cast<uint32_t*>(e->h_nlinfo)[1];
+        if (w1 > w0) {
+            const size_t WS = (size_t)e->wp.P * e->wp.P + e->wp.P;
+            launch_wweights(e->wp.P, st, e->d_wpos + w0, e->d_worg + w0, w1 - w0, e->box, e->wp, e->d_wwt + (size_t)w0 * WS); LAUNCHED(e);
+        }
+    }
     return PSE_OK;
 }
 
@@ -1366,17 +1379,43 @@ extern "C" int pse_shard_fwd(pse_engine* e, const float4* d_pos, const float4* d
     cudaStream_t st = e->stream;
     CKRC(ensure_neighbors(e, d_pos));
     gather_vec_kernel<<<nblk(e->N, 256), 256, 0, st>>>(d_F, e->d_perm, e->N, e->d_sx, (float4*)e->d_px); LAUNCHED(e);
-    CKRC(run_wbin(e, e->d_sx));
     TileGrid tg = e->tg;
+    {
+        // Gaussian factor rows only for the particles this rank spreads or interpolates: origin tiles [tx0 - 1, tx1) in x
+        // (the previous tile row reaches into the slab); a wrap of the previous row (tx0 = 0) falls back to all rows
+        const int per_row = tg.nty * tg.ntz;
+        if (s->tx0 >= 1) CKRC(run_wbin(e, e->d_sx, (s->tx0 - 1) * per_row, s->tx1 * per_row));
+        else if (s->world > 1 && s->tx1 < tg.ntx - 1) {
+            CKRC(run_wbin(e, e->d_sx, 0, s->tx1 * per_row));
+            // + the last tile row of the grid
+            CK(cudaMemcpyAsync(e->h_nlinfo, e->d_wstart + (tg.ntx - 1) * per_row, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            const uint32_t w0 = reinterpret_cast<uint32_t*>(e->h_nlinfo)[0];
+            if (e->N > w0) {
+                const size_t WS = (size_t)wp.P * wp.P + wp.P;
+                launch_wweights(wp.P, st, e->d_wpos + w0, e->d_worg + w0, e->N - w0, e->box, e->wp, e->d_wwt + (size_t)w0 * WS); LAUNCHED(e);
+            }
+        } else CKRC(run_wbin(e, e->d_sx));
+    }
     tg.tile0 = s->tx0 * tg.nty * tg.ntz;
     const int ntiles = (s->tx1 - s->tx0) * tg.nty * tg.ntz;
     launch_spread_tile(wp.P, st, e->d_wF, e->d_worg, e->d_wwt, e->d_wstart, e->wp, tg, e->d_grid, ntiles); LAUNCHED(e);
     const int nxl = s->x1 - s->x0;
     const size_t plane = (size_t)wp.Ny * wp.Nz;
-    for (int c = 0; c < 3; ++c) {
-        CK(cudaMemcpyAsync(s->d_stage + c * s->stage_stride, e->d_grid + c * e->G + s->x0 * plane, sizeof(float) * nxl * plane,
-                           cudaMemcpyDeviceToDevice, st));
-        CKFFT(cufftExecR2C(s->p2f, s->d_stage + c * s->stage_stride, (cufftComplex*)(s->d_sloc + (size_t)c * nxl * wp.Ny * wp.Nzp)));
+    if (e->own_fft) {  // z and y passes of the own planes (fft.cuh); the y index leaves in digit-reversed order
+        const uint32_t nrows = (uint32_t)nxl * wp.Ny;
+        for (int c = 0; c < 3; ++c) {
+            fft_z_forward_kernel<<<nblk(nrows, 2 * FFT_Z_COLS), FFT_THREADS, fft_smem_bytes(wp.Nz, FFT_Z_COLS + 1), st>>>(
+                e->d_grid + c * e->G + s->x0 * plane, s->d_sloc + (size_t)c * nxl * wp.Ny * wp.Nzp, e->fft_ax[2], nrows, wp.Nzp); LAUNCHED(e);
+        }
+        fft_y_kernel<false><<<dim3(nblk(wp.Nzh, FFT_Y_COLS), 3 * nxl), FFT_THREADS, fft_smem_bytes(wp.Ny, FFT_Y_CP), st>>>(
+            s->d_sloc, e->fft_ax[1], wp.Nzh, wp.Nzp); LAUNCHED(e);
+    } else {
+        for (int c = 0; c < 3; ++c) {
+            CK(cudaMemcpyAsync(s->d_stage + c * s->stage_stride, e->d_grid + c * e->G + s->x0 * plane, sizeof(float) * nxl * plane,
+                               cudaMemcpyDeviceToDevice, st));
+            CKFFT(cufftExecR2C(s->p2f, s->d_stage + c * s->stage_stride, (cufftComplex*)(s->d_sloc + (size_t)c * nxl * wp.Ny * wp.Nzp)));
+        }
     }
     e->fft_execs++;
     shard_slab_blocks_kernel<<<e->num_sms * 8, 256, 0, st>>>(s->d_sloc, (float2*)d_send, s->b, nxl, wp.Ny, wp.Nzp, 1); LAUNCHED(e);
@@ -1394,10 +1433,15 @@ extern "C" int pse_shard_kspace(pse_engine* e, const float* d_recv, float* d_sen
     if (nyl > 0) {
         shard_trans_blocks_kernel<<<e->num_sms * 8, 256, 0, st>>>(s->d_tr, (float2*)d_recv, s->b, wp.Nx, nyl, wp.Nzp, 0); LAUNCHED(e);
         const size_t comp = (size_t)wp.Nx * nyl * wp.Nzp;
-        for (int c = 0; c < 3; ++c) CKFFT(cufftExecC2C(s->p1, (cufftComplex*)(s->d_tr + c * comp), (cufftComplex*)(s->d_tr + c * comp), CUFFT_FORWARD));
         CKRC(upload_stepdev(e, 0));
-        scale_kernel<<<dim3(nyl, wp.Nx), 128, 0, st>>>(s->d_tr, e->wp, e->box, 1, 0, e->d_stepdev, nullptr, s->y0, nyl); LAUNCHED(e);
-        for (int c = 0; c < 3; ++c) CKFFT(cufftExecC2C(s->p1, (cufftComplex*)(s->d_tr + c * comp), (cufftComplex*)(s->d_tr + c * comp), CUFFT_INVERSE));
+        if (e->own_fft) {  // x forward + scaling + x inverse of the own stored-y rows in one kernel
+            fft_x_scale_kernel<<<dim3(nblk(wp.Nzh, FFT_X_COLS), nyl), FFT_THREADS, fft_smem_bytes(wp.Nx, FFT_X_CP), st>>>(
+                s->d_tr, e->fft_ax[0], e->fft_ax[1].freq_of, e->wp, e->box, 1, 0, e->d_stepdev, nullptr, s->y0, nyl); LAUNCHED(e);
+        } else {
+            for (int c = 0; c < 3; ++c) CKFFT(cufftExecC2C(s->p1, (cufftComplex*)(s->d_tr + c * comp), (cufftComplex*)(s->d_tr + c * comp), CUFFT_FORWARD));
+            scale_kernel<<<dim3(nyl, wp.Nx), 128, 0, st>>>(s->d_tr, e->wp, e->box, 1, 0, e->d_stepdev, nullptr, s->y0, nyl); LAUNCHED(e);
+            for (int c = 0; c < 3; ++c) CKFFT(cufftExecC2C(s->p1, (cufftComplex*)(s->d_tr + c * comp), (cufftComplex*)(s->d_tr + c * comp), CUFFT_INVERSE));
+        }
         e->fft_execs += 2;
         shard_trans_blocks_kernel<<<e->num_sms * 8, 256, 0, st>>>(s->d_tr, (float2*)d_send, s->b, wp.Nx, nyl, wp.Nzp, 1); LAUNCHED(e);
     }
@@ -1414,10 +1458,20 @@ extern "C" int pse_shard_inv(pse_engine* e, const float* d_recv, float* d_halo_s
     const int nxl = s->x1 - s->x0;
     const size_t plane = (size_t)wp.Ny * wp.Nz;
     shard_slab_blocks_kernel<<<e->num_sms * 8, 256, 0, st>>>(s->d_sloc, (float2*)d_recv, s->b, nxl, wp.Ny, wp.Nzp, 0); LAUNCHED(e);
-    for (int c = 0; c < 3; ++c) {
-        CKFFT(cufftExecC2R(s->p2b, (cufftComplex*)(s->d_sloc + (size_t)c * nxl * wp.Ny * wp.Nzp), s->d_stage + c * s->stage_stride));
-        CK(cudaMemcpyAsync(e->d_grid + c * e->G + s->x0 * plane, s->d_stage + c * s->stage_stride, sizeof(float) * nxl * plane,
-                           cudaMemcpyDeviceToDevice, st));
+    if (e->own_fft) {
+        const uint32_t nrows = (uint32_t)nxl * wp.Ny;
+        fft_y_kernel<true><<<dim3(nblk(wp.Nzh, FFT_Y_COLS), 3 * nxl), FFT_THREADS, fft_smem_bytes(wp.Ny, FFT_Y_CP), st>>>(
+            s->d_sloc, e->fft_ax[1], wp.Nzh, wp.Nzp); LAUNCHED(e);
+        for (int c = 0; c < 3; ++c) {
+            fft_z_inverse_kernel<<<nblk(nrows, 2 * FFT_Z_COLS), FFT_THREADS, fft_smem_bytes(wp.Nz, FFT_Z_COLS + 1), st>>>(
+                s->d_sloc + (size_t)c * nxl * wp.Ny * wp.Nzp, e->d_grid + c * e->G + s->x0 * plane, e->fft_ax[2], nrows, wp.Nzp); LAUNCHED(e);
+        }
+    } else {
+        for (int c = 0; c < 3; ++c) {
+            CKFFT(cufftExecC2R(s->p2b, (cufftComplex*)(s->d_sloc + (size_t)c * nxl * wp.Ny * wp.Nzp), s->d_stage + c * s->stage_stride));
+            CK(cudaMemcpyAsync(e->d_grid + c * e->G + s->x0 * plane, s->d_stage + c * s->stage_stride, sizeof(float) * nxl * plane,
+                               cudaMemcpyDeviceToDevice, st));
+        }
     }
     e->fft_execs++;
     shard_halo_kernel<<<e->num_sms * 4, 256, 0, st>>>(e->d_grid, d_halo_send, e->G, wp.Nx, plane, s->x0, wp.P - 1, 1); LAUNCHED(e);

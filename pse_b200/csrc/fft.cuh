@@ -243,7 +243,8 @@ fft_y_kernel(float2* __restrict__ spec, Fft1D f, int Nzh, int Nzp) {
 #define FFT_X_CP 24
 __global__ void __launch_bounds__(FFT_THREADS)
 fft_x_scale_kernel(float2* __restrict__ spec, Fft1D fx, const uint16_t* __restrict__ freq_of_y, WaveParams wp, PseBox box,
-                   int do_det, int do_noise, const StepDev* __restrict__ sd, const float* __restrict__ u_grid) {
+                   int do_det, int do_noise, const StepDev* __restrict__ sd, const float* __restrict__ u_grid,
+                   int y0 = 0, int ny_local = -1 /* sharded layout: this rank holds stored y positions [y0, y0 + ny_local) */) {
     extern __shared__ __align__(16) float2 fsm[];
     constexpr int NC = 3 * FFT_X_COLS, CP = FFT_X_CP;  // row stride = 8 (mod 16) float2 for the 2 x 8 half-warp patch
     const int N = fx.N;
@@ -251,9 +252,10 @@ fft_x_scale_kernel(float2* __restrict__ spec, Fft1D fx, const uint16_t* __restri
     float2* stw = s + (size_t)N * CP;
     load_twiddles(stw, fx);
     const int k0 = blockIdx.x * FFT_X_COLS, ncol = min(FFT_X_COLS, wp.Nzh - k0);
-    const int ypos = blockIdx.y;
-    const size_t plane = (size_t)wp.Ny * wp.Nzp, comp = (size_t)N * plane;
-    float2* base = spec + (size_t)ypos * wp.Nzp + k0;
+    if (ny_local < 0) ny_local = wp.Ny;
+    const int ypos = y0 + blockIdx.y;  // stored (digit-reversed) y position; blockIdx.y is the local row
+    const size_t plane = (size_t)ny_local * wp.Nzp, comp = (size_t)N * plane;
+    float2* base = spec + (size_t)blockIdx.y * wp.Nzp + k0;
     // column index = c * FFT_X_COLS + kzcol
     constexpr int XG = FFT_THREADS / NC;  // 10 rows of 24 columns per sweep (16 threads idle)
     const int col = threadIdx.x % NC, cc = col / FFT_X_COLS, kcol = col % FFT_X_COLS;

@@ -12,9 +12,14 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ok = True
-for N, phi, xy in ((int(sys.argv[1]) if len(sys.argv) > 1 else 200000, float(sys.argv[2]) if len(sys.argv) > 2 else 0.3, 0.0), (60000, 0.2, 0.3)):
+xi = float(sys.argv[3]) if len(sys.argv) > 3 else 0.5
+error = float(sys.argv[4]) if len(sys.argv) > 4 else 1e-3
+cases = [(int(sys.argv[1]) if len(sys.argv) > 1 else 200000, float(sys.argv[2]) if len(sys.argv) > 2 else 0.3, 0.0)]
+if len(sys.argv) <= 3:
+    cases.append((60000, 0.2, 0.3))
+for N, phi, xy in cases:
     L = util.box_length(N, phi)
-    cfg = E.make_config(N, L, xy=xy, T=1.0, dt=1e-3, seed=1)
+    cfg = E.make_config(N, L, xy=xy, T=1.0, dt=1e-3, seed=1, xi=xi, error=error)
     pos = torch.from_numpy(util.lattice_positions(N, L, 0)).cuda(); F = torch.from_numpy(util.random_forces(N, 1)).cuda()
     sm = S.ShardedMobility(cfg)
     U = sm.mobility(pos, F)
@@ -33,7 +38,7 @@ for N, phi, xy in ((int(sys.argv[1]) if len(sys.argv) > 1 else 200000, float(sys
         return (time.perf_counter() - t0) / n * 1e6
     t_sh = timeit(lambda: sm.mobility(pos, F)); t_1 = timeit(lambda: single.mobility(pos, F))
     if rank == 0:
-        print(f"N={N} grid={single.params.Nx} xy={xy} world={world}: sharded vs single rel L2 {l2:.2e} max {mx:.2e} identical_on_all_ranks={same} "
+        print(f"N={N} grid={single.params.Nx} P={single.params.P} xy={xy} world={world}: sharded vs single rel L2 {l2:.2e} max {mx:.2e} identical_on_all_ranks={same} "
               f"| M.F sharded {t_sh:.0f} us, single GPU {t_1:.0f} us", flush=True)
     ok &= l2 < 2e-6 and mx < 5e-6 and same
     del sm, single
