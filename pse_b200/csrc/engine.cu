@@ -1208,6 +1208,28 @@ extern "C" void pse_test_philox4x32(const uint32_t* ctr, const uint32_t* key, ui
     out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
 }
 
+// test hook: the constant-bank polynomial form of f(r), g(r) (coefficients + float-evaluated max error vs the closed forms)
+extern "C" int pse_test_fit_rpy_cheb(double xi, double rcut, float* out /* 3 + 2 (PSE_CHEB_DEG + 1) */, double* max_err) {
+    return pse_fit_rpy_cheb(xi, rcut, out, max_err);
+}
+
+// test hook: radix schedule and digit-reversal table of the in-place FFT of length N (host logic of fft.cuh / setup_own_fft)
+extern "C" int pse_test_fft_plan(int N, int* radix_out /* FFT_MAX_PASSES */, int* npass_out, uint16_t* pos_of /* N */) {
+    Fft1D f;
+    if (!fft_factor(N, &f)) return PSE_EINVAL;
+    *npass_out = f.npass;
+    for (int i = 0; i < f.npass; ++i) radix_out[i] = (int)((f.radices >> (4 * i)) & 15ull);
+    for (int k = 0; k < N; ++k) {
+        int kk = k, span = N, p = 0;
+        for (int i = 0; i < f.npass; ++i) {
+            const int r = radix_out[i];
+            span /= r; p += (kk % r) * span; kk /= r;
+        }
+        pos_of[k] = (uint16_t)p;
+    }
+    return PSE_OK;
+}
+
 // ===================================================================================================
 // Multi-GPU: slab decomposition of the deterministic mobility U = M F (first stage).
 // One engine per rank; particle data are replicated (every rank is handed the same positions / forces),

@@ -308,3 +308,61 @@ def test_oracle_integrate_wraps_and_shears():
     # particle 0: x advanced by (20 + 2*1)*1e-3 past hi + xy*y -> wrapped by -L; z wrapped by +L
     assert img[0].tolist() == [0, 0, -1] or img[0].tolist() == [1, 0, -1]
     assert img[1].tolist()[1] == 1 and pos[1, 1] < -9.9 and abs(pos[1, 0] - (2.0 * 9.995 * 1e-3 - 20 * 0.25)) < 1e-4
+
+
+@pytest.mark.parametrize("xi,error", [(0.5, 1e-3), (0.5, 1e-4), (0.8, 1e-3), (0.45, 1e-4), (0.3, 1e-3)])
+def test_constant_bank_polynomials_match_closed_forms(xi, error):
+    """f(r), g(r) = exp(-xi^2 (r-2)^2) P8(A/r + B) used by the SpMV for r >= 2a (real.cuh TableCheb): the host fit reports its own
+    float-evaluated error; here it is re-evaluated independently against the oracle's closed forms (oracle/pse_oracle.c:97)."""
+    rcut = math.sqrt(-math.log(error)) / xi
+    orc = O.Oracle(100, 40.0, xi=xi, error=error)
+    out = (ctypes.c_float * 21)(); err = ctypes.c_double()
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    lib.pse_test_fit_rpy_cheb.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)]
+    assert lib.pse_test_fit_rpy_cheb(xi, rcut, out, ctypes.byref(err)) == 0
+    c = np.array(out[:], dtype=np.float64)
+    A, B, ne, cf, cg = c[0], c[1], c[2], c[3:12], c[12:21]
+    r = np.linspace(2.0, rcut, 1501)
+    t = A / r + B
+    assert t.min() > -1.0001 and t.max() < 1.0001
+    e = np.exp2(ne * (r - 2.0) ** 2)
+    f = np.polynomial.polynomial.polyval(t, cf) * e
+    g = np.polynomial.polynomial.polyval(t, cg) * e
+    fo, go = np.array([orc.real_fg(x, xi) for x in r]).T
+    ef, eg = np.abs(f - fo).max() / np.abs(fo).max(), np.abs(g - go).max() / np.abs(go).max()
+    assert ef < 3e-6 and eg < 3e-6, (ef, eg)   # same bound as the engine applies before trusting the fit
+    assert err.value < 3e-6   # the engine keeps the reference table when this check fails
+
+
+@pytest.mark.parametrize("N", [36, 45, 64, 72, 108, 125, 135, 240, 432, 576])
+def test_inplace_fft_schedule_reproduces_numpy(N):
+    """Host logic of fft.cuh: a numpy transcription of the in-place decimation-in-frequency passes (radices from the engine's
+    planner) leaves X[k] at pos_of[k]; the adjoint passes (conjugate twiddles first) undo it up to the factor N."""
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    radix = (ctypes.c_int * 12)(); npass = ctypes.c_int(); pos = (ctypes.c_uint16 * N)()
+    assert lib.pse_test_fft_plan(N, radix, ctypes.byref(npass), pos) == 0
+    rad = list(radix[: npass.value]); pos = np.array(pos[:])
+    assert int(np.prod(rad)) == N and sorted(pos.tolist()) == list(range(N))
+    rng = np.random.default_rng(N)
+    x = rng.normal(size=N) + 1j * rng.normal(size=N)
+    w = np.exp(-2j * np.pi * np.arange(N) / N)
+    a = x.copy(); n = N
+    for r in rad:                                   # forward: butterfly, then twiddle w_n^{j p}
+        m = n // r
+        for b in range(N // n):
+            for j in range(m):
+                idx = b * n + j + m * np.arange(r)
+                y = np.array([sum(a[idx[q]] * np.exp(-2j * np.pi * p * q / r) for q in range(r)) for p in range(r)])
+                a[idx] = y * w[(j * np.arange(r) * (N // n)) % N]
+        n = m
+    X = np.fft.fft(x)
+    assert np.allclose(a[pos], X, rtol=1e-10, atol=1e-10)
+    n = 1
+    for r in reversed(rad):                         # adjoint: conjugate twiddle, then conjugate butterfly
+        n *= r; m = n // r
+        for b in range(N // n):
+            for j in range(m):
+                idx = b * n + j + m * np.arange(r)
+                y = a[idx] * np.conj(w[(j * np.arange(r) * (N // n)) % N])
+                a[idx] = np.array([sum(y[p] * np.exp(2j * np.pi * p * q / r) for p in range(r)) for q in range(r)])
+    assert np.allclose(a, N * x, rtol=1e-10, atol=1e-9)
