@@ -158,18 +158,6 @@ __global__ void gather_vec_kernel(const float4* __restrict__ F, const uint32_t* 
         px[2 * (size_t)s + 1] = v;
     }
 }
-// two payloads at once (positions and forces)
-__global__ void gather4x2_kernel(const float4* __restrict__ a, const float4* __restrict__ b,
-                                 const uint32_t* __restrict__ perm, uint32_t N, float4* __restrict__ oa,
-                                 float4* __restrict__ ob) {
-    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < N) {
-        uint32_t p = perm[s];
-        oa[s] = __ldg(a + p);
-        ob[s] = __ldg(b + p);
-    }
-}
-
 // ---- neighbour search ---------------------------------------------------------------------
 // Sorted enumeration of a periodic cell range: cells {lo, lo+1, ..., lo+len-1} mod nc, visited
 // in ascending cell number so that rows come out ascending in slot number.
