@@ -84,6 +84,7 @@ __global__ void cell_fill_kernel(const uint32_t* __restrict__ cell_of, uint32_t 
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     uint32_t c = cell_of[i];
+    if (c == 0xffffffffu) return;  // not binned (sharded wave binning leaves out particles of other slabs)
     uint32_t k = atomicAdd(cell_fill + c, 1u);
     perm[cell_start[c] + k] = i;
 }

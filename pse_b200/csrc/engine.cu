@@ -803,31 +803,32 @@ static int run_spmv_plain(pse_engine* e, float4* y) {
 }
 
 // bin the (slot-ordered) particles by the tile of their support origin and gather the W-order records
-static int run_wbin(pse_engine* e, const float4* sF, int wt_tile_lo = -1, int wt_tile_hi = -1 /* factor rows only for tiles [lo, hi) */) {
+// Bin the (slot-ordered) particles by the tile of their support origin and gather the W-order records and factor rows.
+// Sharded calls pass the x-tile rows they need ([row_lo, row_hi) plus row_wrap, the row before row 0): everything else -
+// binning, sorting, gathering, factor rows - then only sees that slab's particles.
+static int run_wbin(pse_engine* e, const float4* sF, int row_lo = -1, int row_hi = -1, int row_wrap = -1) {
     ProfScope ps(e, PH_WBIN);
     cudaStream_t st = e->stream;
     const uint32_t N = e->N, nt = e->tg.ntile;
+    const bool slab = row_lo >= 0;
     CK(cudaMemsetAsync(e->d_wcount, 0, sizeof(uint32_t) * (nt + 1), st));
-    wbin_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_spos, N, e->box, e->wp, e->tg, e->d_org, e->d_wcell_of, e->d_wcount); LAUNCHED(e);
+    if (slab) wbin_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_spos, N, e->box, e->wp, e->tg, e->d_org, e->d_wcell_of, e->d_wcount, row_lo, row_hi, row_wrap);
+    else wbin_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_spos, N, e->box, e->wp, e->tg, e->d_org, e->d_wcell_of, e->d_wcount);
+    LAUNCHED(e);
     CKRC(exclusive_scan(e, e->d_wcount, e->d_wstart, nt + 1, e->d_scan_tmp));
     CK(cudaMemsetAsync(e->d_wcount, 0, sizeof(uint32_t) * (nt + 1), st));
     // unordered fill into scratch (d_wcell_of is free again after the fill reads it), then rank sort per tile
     cell_fill_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_wcell_of, N, e->d_wstart, e->d_wcount, e->d_wtmp); LAUNCHED(e);
     cell_sort_block_kernel<<<nt, 128, 0, st>>>(e->d_wstart, e->d_wtmp, e->d_wperm); LAUNCHED(e);
-    wgather_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_spos, sF, e->d_org, e->d_wperm, e->d_perm, N, e->d_wpos, e->d_wF, e->d_worg, e->d_wid); LAUNCHED(e);
-    if (wt_tile_lo < 0) {
-        launch_wweights(e->wp.P, st, e->d_wpos, e->d_worg, N, e->box, e->wp, e->d_wwt); LAUNCHED(e);
-    } else {
-        // sharded call: W order is tile-sorted (x tile slowest), so the particles of a range of x-tile rows are one
-        // contiguous W range; its two ends come back through the pinned flag words
-        CK(cudaMemcpyAsync(e->h_nlinfo, e->d_wstart + wt_tile_lo, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(reinterpret_cast<uint32_t*>(e->h_nlinfo) + 1, e->d_wstart + wt_tile_hi, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    uint32_t nb = N;  // binned particles = d_wstart[nt]
+    if (slab) {
+        CK(cudaMemcpyAsync(e->h_nlinfo, e->d_wstart + nt, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        const uint32_t w0 = reinterpret_cast<uint32_t*>(e->h_nlinfo)[0], w1 = reinterpret_cast<uint32_t*>(e->h_nlinfo)[1];
-        if (w1 > w0) {
-            const size_t WS = (size_t)e->wp.P * e->wp.P + e->wp.P;
-            launch_wweights(e->wp.P, st, e->d_wpos + w0, e->d_worg + w0, w1 - w0, e->box, e->wp, e->d_wwt + (size_t)w0 * WS); LAUNCHED(e);
-        }
+        nb = reinterpret_cast<uint32_t*>(e->h_nlinfo)[0];
+    }
+    if (nb) {
+        wgather_kernel<<<nblk(nb, 256), 256, 0, st>>>(e->d_spos, sF, e->d_org, e->d_wperm, e->d_perm, nb, e->d_wpos, e->d_wF, e->d_worg, e->d_wid); LAUNCHED(e);
+        launch_wweights(e->wp.P, st, e->d_wpos, e->d_worg, nb, e->box, e->wp, e->d_wwt); LAUNCHED(e);
     }
     return PSE_OK;
 }
@@ -1402,23 +1403,12 @@ extern "C" int pse_shard_fwd(pse_engine* e, const float4* d_pos, const float4* d
     CKRC(ensure_neighbors(e, d_pos));
     gather_vec_kernel<<<nblk(e->N, 256), 256, 0, st>>>(d_F, e->d_perm, e->N, e->d_sx, (float4*)e->d_px); LAUNCHED(e);
     TileGrid tg = e->tg;
-    {
-        // Gaussian factor rows only for the particles this rank spreads or interpolates: origin tiles [tx0 - 1, tx1) in x
-        // (the previous tile row reaches into the slab); a wrap of the previous row (tx0 = 0) falls back to all rows
-        const int per_row = tg.nty * tg.ntz;
-        if (s->tx0 >= 1) CKRC(run_wbin(e, e->d_sx, (s->tx0 - 1) * per_row, s->tx1 * per_row));
-        else if (s->world > 1 && s->tx1 < tg.ntx - 1) {
-            CKRC(run_wbin(e, e->d_sx, 0, s->tx1 * per_row));
-            // + the last tile row of the grid
-            CK(cudaMemcpyAsync(e->h_nlinfo, e->d_wstart + (tg.ntx - 1) * per_row, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            const uint32_t w0 = reinterpret_cast<uint32_t*>(e->h_nlinfo)[0];
-            if (e->N > w0) {
-                const size_t WS = (size_t)wp.P * wp.P + wp.P;
-                launch_wweights(wp.P, st, e->d_wpos + w0, e->d_worg + w0, e->N - w0, e->box, e->wp, e->d_wwt + (size_t)w0 * WS); LAUNCHED(e);
-            }
-        } else CKRC(run_wbin(e, e->d_sx));
-    }
+    // only the particles this rank spreads or interpolates are binned: origin tile rows [tx0 - 1, tx1) in x (the previous
+    // row reaches into the slab; for the first slab it is the last row of the periodic grid)
+    const bool thin_last_row = wp.Nx - (tg.ntx - 1) * TILE < wp.P - 1;  // then the first slab is also reached from row ntx - 2
+    if (s->world > 1 && s->tx1 - s->tx0 + 1 < tg.ntx && !(s->tx0 == 0 && thin_last_row))
+        CKRC(run_wbin(e, e->d_sx, std::max(s->tx0 - 1, 0), s->tx1, s->tx0 == 0 ? tg.ntx - 1 : -1));
+    else CKRC(run_wbin(e, e->d_sx));
     tg.tile0 = s->tx0 * tg.nty * tg.ntz;
     const int ntiles = (s->tx1 - s->tx0) * tg.nty * tg.ntz;
     launch_spread_tile(wp.P, st, e->d_wF, e->d_worg, e->d_wwt, e->d_wstart, e->wp, tg, e->d_grid, ntiles); LAUNCHED(e);

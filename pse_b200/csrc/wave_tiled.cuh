@@ -31,14 +31,19 @@ struct TileGrid {
 };
 
 // ---- binning by support-origin tile --------------------------------------------------------------
+// row_lo/row_hi (x-tile rows, sharded calls only): particles whose origin tile lies outside rows [row_lo, row_hi) - and, when
+// row_wrap >= 0, outside row row_wrap - are left out of the binning altogether (cell_of = ~0).
 __global__ void wbin_kernel(const float4* __restrict__ spos, uint32_t N, PseBox box, WaveParams wp, TileGrid tg,
-                            int4* __restrict__ org, uint32_t* __restrict__ cell_of, uint32_t* __restrict__ count) {
+                            int4* __restrict__ org, uint32_t* __restrict__ cell_of, uint32_t* __restrict__ count,
+                            int row_lo = 0, int row_hi = 1 << 30, int row_wrap = -1) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= N) return;
     const float4 p = __ldg(spos + s);
     const Support o = support_origin(box, wp, p.x, p.y, p.z);
     const int x = wrap_node(o.x0, wp.Nx), y = wrap_node(o.y0, wp.Ny), z = wrap_node(o.z0, wp.Nz);
-    const uint32_t c = ((uint32_t)(x / TILE) * tg.nty + y / TILE) * tg.ntz + z / TILE;
+    const int trow = x / TILE;
+    if (!((trow >= row_lo && trow < row_hi) || trow == row_wrap)) { cell_of[s] = 0xffffffffu; return; }
+    const uint32_t c = ((uint32_t)trow * tg.nty + y / TILE) * tg.ntz + z / TILE;
     const int sx = (o.x0 - x) / wp.Nx + 1, sy = (o.y0 - y) / wp.Ny + 1, sz = (o.z0 - z) / wp.Nz + 1;  // in {0,1,2}
     org[s] = make_int4(x, y, z, sx | (sy << 2) | (sz << 4));
     cell_of[s] = c;
@@ -48,9 +53,9 @@ __global__ void wbin_kernel(const float4* __restrict__ spos, uint32_t N, PseBox 
 __global__ void wgather_kernel(const float4* __restrict__ spos, const float4* __restrict__ sF, const int4* __restrict__ org,
                                const uint32_t* __restrict__ wperm, const uint32_t* __restrict__ perm, uint32_t N,
                                float4* __restrict__ wpos, float4* __restrict__ wF, int4* __restrict__ worg,
-                               uint32_t* __restrict__ wid) {
+                               uint32_t* __restrict__ wid, const uint32_t* __restrict__ nbinned = nullptr) {
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= N) return;
+    if (w >= N || (nbinned && w >= __ldg(nbinned))) return;
     const uint32_t s = wperm[w];
     wid[w] = __ldg(perm + s);  // particle id of W slot w: interpolation writes U[id] without chasing two permutations
     wpos[w] = __ldg(spos + s);
