@@ -68,7 +68,7 @@ class ClockSampler(threading.Thread):
             while not self.stop_flag:
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 self.rows.append([str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx)] + ["Active" if r & b else "Not Active" for _, b in bits])
-                time.sleep(0.01)  # the timed region of the default run is ~80 ms
+                time.sleep(0.04)  # the timed region of the default run is ~80 ms; denser polling costs ~2 % of throughput
             return
         except Exception:
             pass
