@@ -473,3 +473,60 @@ def test_config5_eight_million_properties(cuda):
     d = torch.minimum(d, L - d)
     assert 2 <= m <= 20 and torch.isfinite(pos).all() and 0.01 < float(d.max()) < 1.0   # Brownian step ~ sqrt(2 kT M dt) ~ 0.05
     eng.close()
+
+
+# ---------------------------------------------------------------- multi-GPU logic on ONE device: virtual ranks in lockstep
+@pytest.mark.parametrize("g,xy", [(1, 0.0), (2, 0.0), (3, 0.3)])
+def test_sharded_mobility_virtual_ranks(cuda, g, xy):
+    """the slab decomposition (pse_shard_* phases: tile slabs, FFT passes on own planes, transposes, fused x pass,
+    halo planes, row-sharded SpMV) run as g virtual ranks on one GPU - the collectives of pse_b200/sharded.py are replayed with
+    tensor copies (all_to_all_single block order, halo from rank+1, sum over ranks) - against the single-domain engine."""
+    import ctypes
+    import torch
+    from pse_b200 import _lib, sharded as S
+    from pse_b200 import engine as E
+    from pse_b200.engine import _ptr
+    lib = _lib.lib
+    N, L = 30000, util.box_length(30000, 0.2)
+    cfg = E.make_config(N, L, xy=xy, T=1.0, dt=1e-3, seed=1)
+    pos = torch.from_numpy(util.lattice_positions(N, L, 4)).cuda(); F = torch.from_numpy(util.random_forces(N, 5)).cuda()
+    single = E.Engine(cfg)
+    Uref = single.mobility(pos, F).clone()
+    engs = [E.Engine(cfg) for _ in range(g)]
+    infos = []
+    for r, e in enumerate(engs):
+        info = _lib.pse_shard_info()
+        assert lib.pse_shard_setup(e._h, r, g, ctypes.byref(info)) == 0, lib.pse_last_error(e._h)
+        infos.append(info)
+    send = [S.split_sizes(i)[0] for i in infos]; recv = [S.split_sizes(i)[1] for i in infos]
+    f32 = dict(dtype=torch.float32, device="cuda")
+    buf_a = [torch.empty(max(sum(send[r]), 1), **f32) for r in range(g)]
+    buf_b = [torch.empty(max(sum(recv[r]), 1), **f32) for r in range(g)]
+    for r, e in enumerate(engs):
+        assert lib.pse_shard_fwd(e._h, _ptr(pos), _ptr(F), _ptr(buf_a[r])) == 0, lib.pse_last_error(e._h)
+    torch.cuda.synchronize()
+    off = lambda sizes, q: sum(sizes[:q])
+    for q in range(g):      # all_to_all_single: rank q receives, in rank order, the block every r addressed to q
+        for r in range(g):
+            assert send[r][q] == recv[q][r]
+            buf_b[q][off(recv[q], r): off(recv[q], r) + recv[q][r]] = buf_a[r][off(send[r], q): off(send[r], q) + send[r][q]]
+    for q, e in enumerate(engs):
+        assert lib.pse_shard_kspace(e._h, _ptr(buf_b[q]), _ptr(buf_b[q])) == 0, lib.pse_last_error(e._h)
+    torch.cuda.synchronize()
+    for r in range(g):      # the way back swaps the split tables
+        for q in range(g):
+            buf_a[r][off(send[r], q): off(send[r], q) + send[r][q]] = buf_b[q][off(recv[q], r): off(recv[q], r) + recv[q][r]]
+    halo_out = [torch.empty(int(infos[r].halo_floats), **f32) for r in range(g)]
+    for r, e in enumerate(engs):
+        assert lib.pse_shard_inv(e._h, _ptr(buf_a[r]), _ptr(halo_out[r])) == 0, lib.pse_last_error(e._h)
+    torch.cuda.synchronize()
+    U = torch.zeros_like(F)
+    for r, e in enumerate(engs):
+        dst, src = S.halo_peers(r, g)
+        Ur = torch.empty_like(F)
+        assert lib.pse_shard_finish(e._h, _ptr(halo_out[src].clone()), _ptr(Ur)) == 0, lib.pse_last_error(e._h)
+        torch.cuda.synchronize()
+        U += Ur
+    close(U, Uref, 2e-6)
+    for e in engs + [single]:
+        e.close()
