@@ -530,3 +530,38 @@ def test_sharded_mobility_virtual_ranks(cuda, g, xy):
     close(U, Uref, 2e-6)
     for e in engs + [single]:
         e.close()
+
+
+# ---------------------------------------------------------------- physics known-answers of SURVEY.md §4
+def test_xi_independence(cuda):
+    """"Changing value will not affect results, only speed" (examples/run.py:50): M.F at xi = 0.3, 0.5, 0.8 agrees within `error`."""
+    import torch
+    from pse_b200 import engine as E
+    N, L = 2000, util.box_length(2000, 0.1)
+    pos = torch.from_numpy(util.lattice_positions(N, L, 6)).cuda(); F = torch.from_numpy(util.random_forces(N, 7)).cuda()
+    U = {}
+    for xi in (0.3, 0.5, 0.8):
+        eng = E.Engine(E.make_config(N, L, xi=xi, error=1e-3, T=1.0, dt=1e-3, seed=1))
+        U[xi] = eng.mobility(pos, F).clone()
+        eng.close()
+    for xi in (0.3, 0.8):
+        l2, mx = util.rel_err(U[xi].cpu().numpy(), U[0.5].cpu().numpy())
+        assert l2 < 6e-3 and mx < 6e-3, (xi, l2, mx)   # each side is within 3x error of the dense sum (test above)
+
+
+def test_two_spheres_far_field(cuda):
+    """Two spheres d = 4a apart in a large periodic box: the pair mobility is the free-space RPY tensor minus the periodic
+    background 2.837297 a/L (same constant as the self term) up to O(d^2/L^3)."""
+    import torch
+    from pse_b200 import engine as E
+    L, d = 80.0, 4.0
+    pos = torch.tensor([[-d / 2, 0.3, -0.2, 0.0], [d / 2, 0.3, -0.2, 0.0]], dtype=torch.float32, device="cuda")
+    eng = E.Engine(E.make_config(2, L, xi=0.5, error=1e-3, T=1.0, dt=1e-3, seed=1))
+    par = 3.0 / (2 * d) - 1.0 / d**3 - 2.837297 / L      # along the line of centres
+    perp = 3.0 / (4 * d) + 1.0 / (2 * d**3) - 2.837297 / L
+    for axis, expect in ((0, par), (1, perp), (2, perp)):
+        F = torch.zeros((2, 4), dtype=torch.float32, device="cuda"); F[1, axis] = 1.0
+        U = eng.mobility(pos, F)
+        assert abs(float(U[0, axis]) - expect) < 3e-3, (axis, float(U[0, axis]), expect)
+        assert abs(float(U[1, axis]) - (1 - 2.837297 / L + 4 * math.pi / 3 / L**3)) < 3e-3
+    eng.close()
