@@ -120,6 +120,11 @@ const char* pse_last_error(const pse_engine* e); /* never NULL; also valid for e
 
 int pse_get_params(const pse_engine* e, pse_params* out);
 int pse_set_box(pse_engine* e, const pse_box* box);    /* box tilt update (HOOMD box_resize) */
+/* Re-image every particle into the engine's current box (one image per axis, BoxDim::wrap as at PSEv1/Stokes.cu:185),
+ * adjusting d_image when non-NULL.  HOOMD's box_resize updater does this after every box change; it matters when
+ * shear_variant flips the tilt from +max_strain to -max_strain (PSEv1/VariantShearFunction.cc:34-43): without it up to
+ * |xy| Ly / (2 Lx) of the particles sit outside the primary cell of the new box. */
+int pse_wrap_positions(pse_engine* e, float4* d_pos, int3* d_image);
 int pse_set_temperature(pse_engine* e, float T);        /* Stokes::setT */
 int pse_set_lanczos_m(pse_engine* e, int m);            /* Stokes::m_m_Lanczos (in/out, Stokes.h:157) */
 int pse_get_lanczos_m(const pse_engine* e);
@@ -142,7 +147,9 @@ int pse_grid_index(pse_engine* e, const float4* d_pos, int3* d_out);
 /* ---- operators --------------------------------------------------------------------------- */
 
 /* U = M_real F (PSEv1/Mobility.cu:594-687), U = M_wave F (:515-575), U = M F (:729-782).
- * d_U.w is written as 0.  Neighbour structures are refreshed automatically when stale. */
+ * pse_mreal writes d_U.w = 0 as the reference kernel does (:632,684); the others leave d_U.w untouched, as the
+ * reference does with the mass column of its velocity array (:474, PSEv1/Helper.cu:131).
+ * Neighbour structures are refreshed automatically when stale. */
 int pse_mreal(pse_engine* e, const float4* d_pos, const float4* d_F, float4* d_U);
 int pse_mwave(pse_engine* e, const float4* d_pos, const float4* d_F, float4* d_U);
 int pse_mobility(pse_engine* e, const float4* d_pos, const float4* d_F, float4* d_U);

@@ -88,6 +88,7 @@ SYMBOLS = {
     "pse_last_error": (ctypes.c_char_p, [_vp]),
     "pse_get_params": (_i, [_vp, _prmp]),
     "pse_set_box": (_i, [_vp, ctypes.POINTER(pse_box)]),
+    "pse_wrap_positions": (_i, [_vp, _vp, _vp]),
     "pse_set_temperature": (_i, [_vp, _f]),
     "pse_set_lanczos_m": (_i, [_vp, _i]),
     "pse_get_lanczos_m": (_i, [_vp]),

@@ -21,6 +21,7 @@
 #include "rng.cuh"
 #include "wave.cuh"
 #include "wave_tiled.cuh"
+#include "wave_v2.cuh"
 #include "fft.cuh"
 
 int pse_tridiag_sqrt_e1(int m, const double* diag, const double* off, double* c, double* lambda_min_out);
@@ -79,6 +80,7 @@ struct pse_engine {
     uint64_t nnz;
     float4* d_pos_build;
     float xy_build;
+    float xy_prev_call;  // tilt at the previous velocity evaluation (graph replay only while it stays put)
     bool nlist_valid;
     uint32_t* d_flag;
     uint32_t* h_flag;  // pinned
@@ -95,8 +97,10 @@ struct pse_engine {
     void* d_fft_tables;
     // tile-owned spreading / interpolation ("W order", rebinned per call)
     bool tiled;
+    bool wave_v2;     // spread2 / interp2 (every particle once, window merged with vector reductions) instead of the tile-owned kernels
+    bool v2_bulk;     // stage ring of spread2 fed by bulk copies + mbarriers (PSE_SPREAD_BULK=0: 8-byte cp.async + block barriers)
     TileGrid tg;
-    int4 *d_org, *d_worg;
+    int4 *d_org, *d_worg, *d_wrec;
     uint32_t *d_wcell_of, *d_wcount, *d_wstart, *d_wperm, *d_wtmp, *d_wid;
     float4 *d_wpos, *d_wF;
     float* d_wwt;  // Gaussian factor rows, W order: [N][P*P + P]
@@ -309,15 +313,29 @@ static int alloc_all(pse_engine* e) {
     {
         const WaveParams& wp = e->wp;
         TileGrid& tg = e->tg;
-        tg.ntx = (wp.Nx + TILE - 1) / TILE; tg.nty = (wp.Ny + TILE - 1) / TILE; tg.ntz = (wp.Nz + TILE - 1) / TILE;
+        tg.tx = tg.ty = tg.tz = TILE;
+        tg.cp = wp.P; tg.cy = tg.cz = 1; tg.cs = 0;
+        {
+            // spread2 / interp2 tile shape for this support size (PSE_WAVE=v1 keeps the bitwise-reproducible tile-owned kernels)
+            const char* wv = getenv("PSE_WAVE");
+            const char* alt = getenv("PSE_TILE_ALT");
+            int tx, ty, tz;
+            e->wave_v2 = !(wv && wv[0] == 'v' && wv[1] == '1') && v2_shape(wp.P, alt && alt[0] == '1', &tx, &ty, &tz) &&
+                         wp.Nx >= tx + wp.P && wp.Ny >= ty + wp.P && wp.Nz >= tz + wp.P;
+            if (e->wave_v2) v2_fill_tilegrid(wp.P, tx, ty, tz, &tg);
+            const char* bk = getenv("PSE_SPREAD_BULK");
+            e->v2_bulk = !(bk && bk[0] == '0');
+        }
+        tg.ntx = (wp.Nx + tg.tx - 1) / tg.tx; tg.nty = (wp.Ny + tg.ty - 1) / tg.ty; tg.ntz = (wp.Nz + tg.tz - 1) / tg.tz;
         tg.ntile = tg.ntx * tg.nty * tg.ntz;
         const int need = TILE + wp.P;
-        e->tiled = wp.P >= 2 && wp.P <= TILED_MAX_P && wp.Nx >= need && wp.Ny >= need && wp.Nz >= need;
+        e->tiled = e->wave_v2 || (wp.P >= 2 && wp.P <= TILED_MAX_P && wp.Nx >= need && wp.Ny >= need && wp.Nz >= need);
         const char* env = getenv("PSE_WAVE_TILED");
-        if (env && env[0] == '0') e->tiled = false;
+        if (env && env[0] == '0') { e->tiled = false; e->wave_v2 = false; }
         if (e->tiled) {
             CK(cudaMalloc(&e->d_org, sizeof(int4) * N));
             CK(cudaMalloc(&e->d_worg, sizeof(int4) * N));
+            if (e->wave_v2) CK(cudaMalloc(&e->d_wrec, sizeof(int4) * N));
             CK(cudaMalloc(&e->d_wcell_of, sizeof(uint32_t) * N));
             CK(cudaMalloc(&e->d_wcount, sizeof(uint32_t) * (tg.ntile + 1)));
             CK(cudaMalloc(&e->d_wstart, sizeof(uint32_t) * (tg.ntile + 1)));
@@ -326,8 +344,9 @@ static int alloc_all(pse_engine* e) {
             CK(cudaMalloc(&e->d_wtmp, sizeof(uint32_t) * N));
             CK(cudaMalloc(&e->d_wpos, sizeof(float4) * N));
             CK(cudaMalloc(&e->d_wF, sizeof(float4) * N));
-            CK(cudaMalloc(&e->d_wwt, sizeof(float) * (size_t)N * (wp.P * wp.P + wp.P)));
-            CK(tiled_set_attributes(wp.P));
+            CK(cudaMalloc(&e->d_wwt, sizeof(float) * (size_t)N * wrow_stride(wp.P)));
+            if (e->wave_v2) CK(v2_set_attributes(wp.P, tg.tx, tg.ty, tg.tz));
+            else CK(tiled_set_attributes(wp.P));
         }
     }
     return PSE_OK;
@@ -446,6 +465,7 @@ extern "C" int pse_create(const pse_config* cfg, void* stream, pse_engine** out)
     }
     e->rlist = rlist;
     refresh_box(e, c.box);
+    e->xy_prev_call = c.box.xy;
     e->G = (size_t)prm.Nx * prm.Ny * prm.Nz;
     WaveParams& wp = e->wp;
     wp.Nx = prm.Nx; wp.Ny = prm.Ny; wp.Nz = prm.Nz; wp.Nzh = prm.Nz / 2 + 1; wp.P = prm.P;
@@ -533,7 +553,7 @@ extern "C" void pse_destroy(pse_engine* e) {
                     e->d_spos, e->d_sx, e->d_sy, e->d_px, e->d_nn, e->d_head, e->d_nl, e->d_pos_build, e->d_flag, e->d_grid,
                     e->d_spec, e->d_V, e->d_u, e->d_y, e->d_alpha, e->d_beta, e->d_coef, e->d_partials, e->d_counter,
                     e->d_vel_work, e->d_hpos, e->d_hF, e->d_himage, e->d_org, e->d_worg, e->d_wcell_of, e->d_wcount,
-                    e->d_wstart, e->d_wperm, e->d_wid, e->d_wpos, e->d_wF, e->d_wwt, e->d_wtmp, e->d_ell, e->d_nn_act, e->d_nl_act};
+                    e->d_wstart, e->d_wperm, e->d_wid, e->d_wpos, e->d_wF, e->d_wwt, e->d_wrec, e->d_wtmp, e->d_ell, e->d_nn_act, e->d_nl_act};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (e->h_flag) cudaFreeHost(e->h_flag);
@@ -567,6 +587,22 @@ extern "C" int pse_set_box(pse_engine* e, const pse_box* b) {
     if (b->Lx != e->cfg.box.Lx || b->Ly != e->cfg.box.Ly || b->Lz != e->cfg.box.Lz)
         return fail(e, PSE_EINVAL, "pse_set_box: only the tilt may change (the reference sizes the grid once, Stokes.cc:139)");
     refresh_box(e, *b);
+    return PSE_OK;
+}
+__global__ void wrap_positions_kernel(float4* __restrict__ pos, int3* __restrict__ image, uint32_t N, PseBox box) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const float4 p = pos[i];
+    float3 w = make_float3(p.x, p.y, p.z);
+    int3 im = image ? image[i] : make_int3(0, 0, 0);
+    box.wrap(w, im);
+    pos[i] = make_float4(w.x, w.y, w.z, p.w);
+    if (image) image[i] = im;
+}
+extern "C" int pse_wrap_positions(pse_engine* e, float4* d_pos, int3* d_image) {
+    if (!e || !d_pos) return PSE_EINVAL;
+    wrap_positions_kernel<<<(e->N + 255) / 256, 256, 0, e->stream>>>(d_pos, d_image, e->N, e->box); e->launches++;
+    CK(cudaGetLastError());
     return PSE_OK;
 }
 extern "C" int pse_set_temperature(pse_engine* e, float T) {
@@ -827,7 +863,7 @@ static int run_wbin(pse_engine* e, const float4* sF, int row_lo = -1, int row_hi
         nb = reinterpret_cast<uint32_t*>(e->h_nlinfo)[0];
     }
     if (nb) {
-        wgather_kernel<<<nblk(nb, 256), 256, 0, st>>>(e->d_spos, sF, e->d_org, e->d_wperm, e->d_perm, nb, e->d_wpos, e->d_wF, e->d_worg, e->d_wid); LAUNCHED(e);
+        wgather_kernel<<<nblk(nb, 256), 256, 0, st>>>(e->d_spos, sF, e->d_org, e->d_wperm, e->d_perm, nb, e->d_wpos, e->d_wF, e->d_worg, e->d_wid, e->tg, e->wave_v2 ? e->d_wrec : nullptr); LAUNCHED(e);
         launch_wweights(e->wp.P, st, e->d_wpos, e->d_worg, nb, e->box, e->wp, e->d_wwt); LAUNCHED(e);
     }
     return PSE_OK;
@@ -841,7 +877,10 @@ static int run_wave(pse_engine* e, const float4* sF, float4* U, int accumulate, 
     if (det) {
         {
         ProfScope ps(e, PH_SPREAD);
-        if (e->tiled) {
+        if (e->wave_v2) {
+            CK(cudaMemsetAsync(e->d_grid, 0, sizeof(float) * 3 * e->G, st));
+            launch_spread2(P, st, e->v2_bulk, e->d_wF, e->d_wrec, e->d_wwt, e->d_wstart, e->wp, e->tg, e->d_grid); LAUNCHED(e);
+        } else if (e->tiled) {
             launch_spread_tile(P, st, e->d_wF, e->d_worg, e->d_wwt, e->d_wstart, e->wp, e->tg, e->d_grid); LAUNCHED(e);
         } else {
             CK(cudaMemsetAsync(e->d_grid, 0, sizeof(float) * 3 * e->G, st));
@@ -884,7 +923,10 @@ static int run_wave(pse_engine* e, const float4* sF, float4* U, int accumulate, 
         CKFFT(cufftExecC2R(e->plan_b, (cufftComplex*)e->d_spec, e->d_grid)); e->fft_execs++;
     }
     ProfScope ps(e, PH_INTERP);
-    if (e->tiled) {
+    if (e->wave_v2) {
+        launch_interp2(P, st, e->d_worg, e->d_wwt, e->d_wstart, e->d_wid, e->wp, e->tg, e->d_grid, U, accumulate);
+        LAUNCHED(e);
+    } else if (e->tiled) {
         launch_interp_tile(P, st, e->d_worg, e->d_wwt, e->d_wstart, e->d_wid, e->wp, e->tg, e->d_grid, U, accumulate);
         LAUNCHED(e);
     } else {
@@ -1080,7 +1122,11 @@ extern "C" int pse_velocity(pse_engine* e, const float4* d_pos, const float4* d_
 
     // Step loop as a captured CUDA graph (the reference issues ~60 launches + 15 blocking copies per step,
     // PSEv1/Stokes.cu:298-355, Brownian.cu:440-739).  The graph is keyed on everything frozen at capture time.
-    const bool graphable = e->use_graph && !e->prof_on && det && wnoise && rnoise && !d_u_particles && !d_u_grid;
+    // The box is baked into the kernel arguments at capture time, so a changing tilt (any shear function) would mean a
+    // re-capture and re-instantiation every step: while the tilt is moving the step is issued eagerly instead.
+    const bool tilt_steady = e->box.xy == e->xy_prev_call;
+    e->xy_prev_call = e->box.xy;
+    const bool graphable = e->use_graph && !e->prof_on && det && wnoise && rnoise && !d_u_particles && !d_u_grid && tilt_steady;
     if (graphable) {
         auto& k = e->graph_key;
         const bool hit = k.valid && k.pos == d_pos && k.F == d_F && k.U == d_U && k.m_batch == m_batch && k.xy == e->box.xy &&
@@ -1358,7 +1404,7 @@ extern "C" int pse_shard_plan(const pse_config* cfg, int rank, int world, pse_sh
 
 extern "C" int pse_shard_setup(pse_engine* e, int rank, int world, pse_shard_info* out) {
     if (!e || !out || world < 1 || world > SHARD_MAX_WORLD || rank < 0 || rank >= world) return PSE_EINVAL;
-    if (!e->tiled) return fail(e, PSE_EINVAL, "pse_shard_setup: needs the tile-owned wave path (P <= 10, grid >= TILE + P)");
+    if (!e->tiled || e->wave_v2) return fail(e, PSE_EINVAL, "pse_shard_setup: needs the tile-owned wave path (PSE_WAVE=v1, P <= 10, grid >= TILE + P)");
     const WaveParams& wp = e->wp;
     if (world > e->tg.ntx) return fail(e, PSE_EINVAL, "pse_shard_setup: %d ranks but only %d x-tiles of %d nodes", world, e->tg.ntx, TILE);
     if (e->shard) { shard_free(e->shard); e->shard = nullptr; }

@@ -384,13 +384,15 @@ basis_combine_kernel(const float4* __restrict__ V, const float* __restrict__ c, 
     }
     const float sc = __ldcg(psinorm) * thermal;
     const uint32_t p = perm[s];
-    float4 o = accumulate ? U[p] : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 o = U[p];  // .w (the mass column of the reference's velocity array, PSEv1/Helper.cu:131) is preserved
+    if (!accumulate) { o.x = 0.f; o.y = 0.f; o.z = 0.f; }
     if (ydet) { const float4 yd = __ldg(ydet + s); o.x += yd.x; o.y += yd.y; o.z += yd.z; }
-    o.x += sc * acc.x; o.y += sc * acc.y; o.z += sc * acc.z; o.w = 0.f;
+    o.x += sc * acc.x; o.y += sc * acc.y; o.z += sc * acc.z;
     U[p] = o;
 }
 
-// U[perm[slot]] (+)= y[slot]
+// U[perm[slot]] (+)= y[slot].  Accumulating writes keep U.w (the reference's LinearCombination keeps the mass column of
+// d_vel, PSEv1/Helper.cu:131); the plain write stores (y, 0) as gpu_stokes_Mreal_kernel does (PSEv1/Mobility.cu:632,684).
 __global__ void scatter_add_kernel(const float4* __restrict__ y, const uint32_t* __restrict__ perm, uint32_t N,
                                    float4* __restrict__ U, int accumulate, uint32_t row_begin = 0) {
     const uint32_t s = row_begin + blockIdx.x * blockDim.x + threadIdx.x;
@@ -398,7 +400,7 @@ __global__ void scatter_add_kernel(const float4* __restrict__ y, const uint32_t*
     const float4 v = __ldg(y + s);
     const uint32_t p = perm[s];
     float4 o = accumulate ? U[p] : make_float4(0.f, 0.f, 0.f, 0.f);
-    o.x += v.x; o.y += v.y; o.z += v.z; o.w = 0.f;
+    o.x += v.x; o.y += v.y; o.z += v.z;
     U[p] = o;
 }
 

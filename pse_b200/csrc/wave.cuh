@@ -119,8 +119,9 @@ interp_warp_kernel(const float4* __restrict__ pos, uint32_t N, PseBox box, WaveP
     acc.x = warp_sum(acc.x); acc.y = warp_sum(acc.y); acc.z = warp_sum(acc.z);
     if (lane == 0) {
         const uint32_t id = perm ? perm[p] : p;
-        float4 o = accumulate ? U[id] : make_float4(0.f, 0.f, 0.f, 0.f);
-        o.x += acc.x; o.y += acc.y; o.z += acc.z; o.w = 0.f;
+        float4 o = U[id];  // .w preserved (PSEv1/Mobility.cu:474)
+        if (!accumulate) { o.x = 0.f; o.y = 0.f; o.z = 0.f; }
+        o.x += acc.x; o.y += acc.y; o.z += acc.z;
         U[id] = o;
     }
 }

@@ -27,8 +27,13 @@
 
 struct TileGrid {
     int ntx, nty, ntz, ntile;
-    int tile0;  // first tile handled by a launch (0 unless the grid is sharded into x-slabs of tiles)
+    int tile0;       // first tile handled by a launch (0 unless the grid is sharded into x-slabs of tiles)
+    int tx, ty, tz;  // tile extent in nodes per axis (TILE^3 for the tile-owned gather kernels; per-P shapes for spread2)
+    int cp, cy, cz, cs;  // spread2 accumulator geometry: residue modulus (= P), cells per axis (y, z), words per cell
 };
+// row stride (floats) of the Gaussian factor rows: P*P + P rounded up to 16 bytes, so that any run of rows is a legal
+// source of a bulk (TMA) copy
+__host__ __device__ constexpr int wrow_stride(int P) { return ((P * P + P) + 3) / 4 * 4; }
 
 // ---- binning by support-origin tile --------------------------------------------------------------
 // row_lo/row_hi (x-tile rows, sharded calls only): particles whose origin tile lies outside rows [row_lo, row_hi) - and, when
@@ -41,9 +46,9 @@ __global__ void wbin_kernel(const float4* __restrict__ spos, uint32_t N, PseBox 
     const float4 p = __ldg(spos + s);
     const Support o = support_origin(box, wp, p.x, p.y, p.z);
     const int x = wrap_node(o.x0, wp.Nx), y = wrap_node(o.y0, wp.Ny), z = wrap_node(o.z0, wp.Nz);
-    const int trow = x / TILE;
+    const int trow = x / tg.tx;
     if (!((trow >= row_lo && trow < row_hi) || trow == row_wrap)) { cell_of[s] = 0xffffffffu; return; }
-    const uint32_t c = ((uint32_t)trow * tg.nty + y / TILE) * tg.ntz + z / TILE;
+    const uint32_t c = ((uint32_t)trow * tg.nty + y / tg.ty) * tg.ntz + z / tg.tz;
     const int sx = (o.x0 - x) / wp.Nx + 1, sy = (o.y0 - y) / wp.Ny + 1, sz = (o.z0 - z) / wp.Nz + 1;  // in {0,1,2}
     org[s] = make_int4(x, y, z, sx | (sy << 2) | (sz << 4));
     cell_of[s] = c;
@@ -53,14 +58,22 @@ __global__ void wbin_kernel(const float4* __restrict__ spos, uint32_t N, PseBox 
 __global__ void wgather_kernel(const float4* __restrict__ spos, const float4* __restrict__ sF, const int4* __restrict__ org,
                                const uint32_t* __restrict__ wperm, const uint32_t* __restrict__ perm, uint32_t N,
                                float4* __restrict__ wpos, float4* __restrict__ wF, int4* __restrict__ worg,
-                               uint32_t* __restrict__ wid, const uint32_t* __restrict__ nbinned = nullptr) {
+                               uint32_t* __restrict__ wid, TileGrid tg, int4* __restrict__ wrec,
+                               const uint32_t* __restrict__ nbinned = nullptr) {
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= N || (nbinned && w >= __ldg(nbinned))) return;
     const uint32_t s = wperm[w];
     wid[w] = __ldg(perm + s);  // particle id of W slot w: interpolation writes U[id] without chasing two permutations
     wpos[w] = __ldg(spos + s);
+    const int4 o = org[s];
     if (sF) wF[w] = __ldg(sF + s);
-    worg[w] = org[s];
+    if (wrec) {
+        // where the support starts inside the accumulator of spread2_kernel (wave_v2.cuh): the accumulator cell of the
+        // origin (origin / P per axis) as a word offset, and the residues origin % P
+        const int lx = o.x % tg.tx, ly = o.y % tg.ty, lz = o.z % tg.tz;
+        wrec[w] = make_int4((((lx / tg.cp) * tg.cy + ly / tg.cp) * tg.cz + lz / tg.cp) * tg.cs, lx % tg.cp, ly % tg.cp, lz % tg.cp);
+    }
+    worg[w] = o;
 }
 
 // candidate origin cells of one dimension for a tile starting at node t0 with extent e:
@@ -126,7 +139,7 @@ template <int P>
 __global__ void __launch_bounds__(256)
 wweights_kernel(const float4* __restrict__ wpos, const int4* __restrict__ worg, uint32_t N, PseBox box, WaveParams wp,
                 float* __restrict__ wwt) {
-    constexpr int PP = P * P, WS = PP + P;
+    constexpr int PP = P * P, WS = wrow_stride(P);  // (pad words of a row are never read)
     __shared__ __align__(16) float rows[WW_PB * WS];
     const uint32_t w0 = blockIdx.x * WW_PB;
     const int np = (int)min((uint32_t)WW_PB, N - w0);
@@ -149,6 +162,10 @@ wweights_kernel(const float4* __restrict__ wpos, const int4* __restrict__ worg, 
                 for (int k = 0; k < P; ++k) rows[q * WS + PP + k] = weight_z(box, wp, wrap_node(oz + k, wp.Nz), pz);
             }
         }
+    }
+    if constexpr (WS > PP + P) {
+        constexpr int PAD = WS - PP - P;
+        for (int t = threadIdx.x; t < WW_PB * PAD; t += blockDim.x) rows[(t / PAD) * WS + PP + P + t % PAD] = 0.f;
     }
     __syncthreads();
     float2* dst = reinterpret_cast<float2*>(wwt + (size_t)w0 * WS);  // WS is even and w0 * WS * 4 is a multiple of 8
@@ -178,7 +195,7 @@ template <int P> struct SpreadCfg {
     static constexpr int PPP = P * P * P;
     static constexpr int NT = PPP >= 256 ? 256 : ((PPP + 31) / 32) * 32;  // threads per block
     static constexpr int NPASS = (PPP + NT - 1) / NT;                     // support nodes per thread
-    static constexpr int WS = P * P + P;
+    static constexpr int WS = wrow_stride(P);
 };
 
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
@@ -403,7 +420,7 @@ spread_tile_kernel(const float4* __restrict__ wF, const int4* __restrict__ worg,
 
 static inline size_t spread_tile_smem(int P) {
     return (3 * (size_t)TILE * TILE * TILE_ZS) * sizeof(float) + SPREAD_CAP * (sizeof(float4) + 2 * sizeof(uint32_t)) +
-           2 * (size_t)SPREAD_CHUNK * (P * P + P) * sizeof(float);
+           2 * (size_t)SPREAD_CHUNK * wrow_stride(P) * sizeof(float);
 }
 
 // ---- interpolation: one block per origin cell --------------------------------------------------------
@@ -513,7 +530,7 @@ interp_tile_kernel(const int4* __restrict__ worg, const float* __restrict__ wwt,
         const uint32_t wn = w + NW;
         if (wn < ce) fetch(wn);
         float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (accumulate && lane == 0) old = U[id];
+        if (lane == 0) old = U[id];   // .w (mass in the reference's velocity array, PSEv1/Mobility.cu:474) is preserved
         float wz[P];
 #pragma unroll
         for (int k = 0; k < P; ++k) wz[k] = __shfl_sync(0xffffffffu, wt[(PP + k) / 32], (PP + k) % 32);
@@ -556,7 +573,10 @@ interp_tile_kernel(const int4* __restrict__ worg, const float* __restrict__ wwt,
             }
         }
         ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az);
-        if (lane == 0) U[id] = make_float4(old.x + wp.quadW * ax, old.y + wp.quadW * ay, old.z + wp.quadW * az, 0.f);  // quadrature weight h^3
+        if (lane == 0) {
+            if (!accumulate) { old.x = 0.f; old.y = 0.f; old.z = 0.f; }
+            U[id] = make_float4(old.x + wp.quadW * ax, old.y + wp.quadW * ay, old.z + wp.quadW * az, old.w);  // quadrature weight h^3
+        }
         w = wn;
     }
 }

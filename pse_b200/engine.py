@@ -91,6 +91,11 @@ class Engine:
         self.set_box(b.Lx, b.Ly, b.Lz, xy)
         self.cfg.box.xy = xy
 
+    def wrap_positions(self, pos, image=None):
+        """Re-image every particle into the current (possibly re-tilted) box, in place."""
+        _check4(pos, self.N, "pos")
+        self._ck(lib.pse_wrap_positions(self._h, _ptr(pos), _ptr(image)))
+
     def set_temperature(self, T):
         self._ck(lib.pse_set_temperature(self._h, T))
 
@@ -145,7 +150,7 @@ class Engine:
     def _op(self, fn, pos, F):
         import torch
         _check4(pos, self.N, "pos"); _check4(F, self.N, "F")
-        U = torch.empty_like(F)
+        U = torch.zeros_like(F)   # (.w of the output is left untouched by the engine, as the reference does with vel.w)
         self._ck(fn(self._h, _ptr(pos), _ptr(F), _ptr(U)))
         return U
 
@@ -171,7 +176,7 @@ class Engine:
     def velocity(self, pos, F, timestep=0, u_particles=None, u_grid=None, parts=7):
         import torch
         _check4(pos, self.N, "pos"); _check4(F, self.N, "F")
-        U = torch.empty_like(F)
+        U = torch.zeros_like(F)
         m = ctypes.c_int(0)
         self._ck(lib.pse_velocity(self._h, _ptr(pos), _ptr(F), _ptr(U), int(timestep) & 0xFFFFFFFF, _ptr(u_particles),
                                   _ptr(u_grid), parts, ctypes.byref(m)))

@@ -55,8 +55,7 @@ class System:
         import torch
         F = torch.as_tensor(F, dtype=torch.float32, device=self.pos.device)
         self.net_force[:, : F.shape[1]] = F
-        if self.forces:
-            self.constant_force = self.net_force.clone()
+        self.constant_force = self.net_force.clone()   # kept whether or not a pair provider is registered yet
 
     def _compute_forces(self):
         """HOOMD's ForceCompute pass: net_force = external force + sum of the enabled pair providers."""
@@ -113,9 +112,15 @@ class box_resize:
 
     def __call__(self, timestep):
         val = float(self.xy.get_value(timestep))
+        changed = val != self.system.box.xy
         self.system.box.xy = val
         if self.system.integrator is not None:
             self.system.integrator.set_tilt(val)
+            # HOOMD's BoxResizeUpdater re-images the particles after every box change; the wrapped-strain variant jumps
+            # from +max_strain to -max_strain (PSEv1/VariantShearFunction.cc:34-43), which leaves up to an eighth of the
+            # particles outside the primary cell of the new box
+            if changed:
+                self.system.integrator.cpp_method.wrap_positions(self.system.pos, self.system.image)
 
 
 _current = None

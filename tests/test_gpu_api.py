@@ -114,7 +114,7 @@ def test_pair_forces_match_numpy(cuda, xy):
 
 
 def test_pair_provider_drives_a_run_and_restart_roundtrip(cuda, tmp_path):
-    """A WCA suspension run through the HOOMD-shaped API, saved and reloaded: the reloaded system continues bit for bit."""
+    """A WCA suspension run through the HOOMD-shaped API, saved and reloaded: the reloaded system continues where the original would have."""
     import torch
     import pse_b200 as PSEv1
     N, L = 2000, util.box_length(2000, 0.3)
@@ -136,4 +136,8 @@ def test_pair_provider_drives_a_run_and_restart_roundtrip(cuda, tmp_path):
     pse2 = make(s2)
     pse2.cpp_method.lanczos_m = s2.restart_lanczos_m
     s2.run(3)
-    assert torch.equal(s.pos, s2.pos) and torch.equal(s.image, s2.image)
+    # (bit for bit with PSE_WAVE=v1; the default spreading merges its windows with float reductions whose order across
+    # blocks is not fixed, so two runs agree to round-off)
+    d = (s.pos[:, :3] - s2.pos[:, :3]).abs()
+    d = torch.minimum(d, L - d)
+    assert float(d.max()) < 2e-5

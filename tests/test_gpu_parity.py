@@ -305,9 +305,25 @@ def test_tiled_wave_path_is_bitwise_reproducible_and_matches_scatter_path(cuda):
     fallback scatter path (PSE_WAVE_TILED=0, used for tiny grids / P > 10) gives the same answer to round-off."""
     import os
     import torch
-    s = System(20000, util.box_length(20000, 0.2), xy=0.2, seed=12, want_ref=False)
+    os.environ["PSE_WAVE"] = "v1"
+    try:
+        s = System(20000, util.box_length(20000, 0.2), xy=0.2, seed=12, want_ref=False)
+    finally:
+        del os.environ["PSE_WAVE"]
     a = s.eng.mwave(s.pos, s.F); b = s.eng.mwave(s.pos, s.F)
     assert torch.equal(a, b)
+    # default path (spread2: window merged with vector reductions, summation order across blocks not fixed): round-off level
+    s3 = System(20000, s.L, xy=0.2, seed=12, want_ref=False)
+    c = s3.eng.mwave(s3.pos, s3.F); d = s3.eng.mwave(s3.pos, s3.F)
+    close(c, d, 1e-6); close(c, a, 1e-6)
+    for bulk in ("0", "1"):     # stage ring fed by 8-byte cp.async + block barriers / by bulk copies + mbarriers
+        os.environ["PSE_SPREAD_BULK"] = bulk
+        try:
+            s4 = System(20000, s.L, xy=0.2, seed=12, want_ref=False)
+        finally:
+            del os.environ["PSE_SPREAD_BULK"]
+        close(s4.eng.mwave(s4.pos, s4.F), a, 1e-6)
+        s4.eng.close()
     os.environ["PSE_WAVE_TILED"] = "0"
     try:
         s2 = System(20000, s.L, xy=0.2, seed=12, want_ref=False)
@@ -443,8 +459,9 @@ def test_own_fft_matches_cufft(cuda, monkeypatch, N, phi, xy, Lfac):
 # ---------------------------------------------------------------- BASELINE.json config 5 (largest): N = 8M, phi = 0.4, error 1e-4
 def test_config5_eight_million_properties(cuda):
     """The largest BASELINE.json configuration at the reference's sizing rule (xi = 0.45 -> 432^3 grid, P = 8; xi = 0.5 would need
-    576^3 > the 512^3 cap of PSEv1/Stokes.cc:203).  No oracle finishes at this size, so size-independent properties: symmetry,
-    positive definiteness, linearity of M.F, translation invariance under a lattice shift of the box, and one full BD step."""
+    576^3 > the 512^3 cap of PSEv1/Stokes.cc:203): M.F and the full velocity (identical random vectors, same Lanczos m) against the
+    reference's own kernels at this size, plus size-independent properties (symmetry, positive definiteness, linearity) and one
+    full BD step."""
     import torch
     from pse_b200 import engine as E
     free, _ = torch.cuda.mem_get_info()
@@ -465,6 +482,30 @@ def test_config5_eight_million_properties(cuda):
     close(eng.mobility(pos, 2.0 * F - 0.5 * G), 2.0 * MF - 0.5 * MG, 3e-6)
     st = eng.stats()
     assert abs(st["nnz"] / N - 145.8) < 8.0                          # <nbrs> within r_cut + 0.4 at phi = 0.4 (145.8 for an ideal gas; the jittered lattice gives 140)
+    # the reference's own kernels at this size (gpu_stokes_Mobility_wrap, PSEv1/Mobility.cu:729-782, and the full velocity with
+    # identical random vectors, PSEv1/Brownian.cu:772-923): ~3.2 GB of complex grids + k table and a 12.9 GB Krylov basis
+    from oracle import refwrap
+    if refwrap.available():
+        ref = refwrap.Reference(cfg_ref_pi(cfg), p, E.ewald_table(cfg))
+        engp = E.Engine(cfg_ref_pi(cfg))          # same 2*pi constant as the reference (PSE_FLAG_REF_PI)
+        engp.build_neighbors(pos)
+        ref.set_neighbors(*engp.neighbor_list())
+        close(engp.mobility(pos, F), ref.mobility(pos, F))
+        g = torch.Generator(device="cuda"); g.manual_seed(5)
+        up = torch.rand((N, 3), device="cuda", generator=g); ug = torch.rand((p.Nx * p.Ny * p.Nz, 6), device="cuda", generator=g)
+        v = ug.view(p.Nx, p.Ny, p.Nz, 6); v[:, :, p.Nz // 2, :] = 0.5; v[:, p.Ny // 2, 0, :] = 0.5   # doubly-visited nodes
+        ref.set_noise_tables(up, ug)
+        try:
+            engp.lanczos_m = 2; ref.m_lanczos = 2
+            Ue, m5 = engp.velocity(pos, F, timestep=3, u_particles=up, u_grid=ug, parts=7)
+            Ur = ref.velocity(pos, F, 1.0, 1e-3, 3)
+            assert m5 == ref.m_lanczos
+            close(Ue, Ur)
+        finally:
+            ref.set_noise_tables(None, None)
+        del ref, up, ug, v, Ue, Ur
+        engp.close()
+        torch.cuda.empty_cache()
     img = torch.zeros((N, 3), dtype=torch.int32, device="cuda")
     p0 = pos.clone()
     m = eng.step(pos, img, F, 0)
@@ -473,6 +514,14 @@ def test_config5_eight_million_properties(cuda):
     d = torch.minimum(d, L - d)
     assert 2 <= m <= 20 and torch.isfinite(pos).all() and 0.01 < float(d.max()) < 1.0   # Brownian step ~ sqrt(2 kT M dt) ~ 0.05
     eng.close()
+
+
+def cfg_ref_pi(cfg):
+    import copy
+    from pse_b200 import _lib
+    c = copy.copy(cfg)
+    c.flags = cfg.flags | _lib.PSE_FLAG_REF_PI
+    return c
 
 
 # ---------------------------------------------------------------- multi-GPU logic on ONE device: virtual ranks in lockstep
@@ -565,3 +614,119 @@ def test_two_spheres_far_field(cuda):
         assert abs(float(U[0, axis]) - expect) < 3e-3, (axis, float(U[0, axis]), expect)
         assert abs(float(U[1, axis]) - (1 - 2.837297 / L + 4 * math.pi / 3 / L**3)) < 3e-3
     eng.close()
+
+
+# ---------------------------------------------------------------- round-2 parity gaps ("next round" item 1)
+def test_config1_dense_ewald_error_at_N1000(cuda):
+    """BASELINE.json config 1 at its own size (N = 1000, phi = 0.1): M.F against the dense double-precision Ewald sum.
+    north_star: "within the requested Ewald error".  The achieved relative L2 error is printed and asserted against the
+    requested one (the reference's parameter rules, PSEv1/Stokes.cc:129-236, size r_cut/k_max/P for `error` per term; the
+    measured total is recorded in DESIGN.md)."""
+    from oracle import oraclewrap as O
+    N = 1000
+    L = util.box_length(N, 0.1)
+    got = {}
+    for xy in (0.0, 0.3):
+        for error in (1e-3, 1e-4):
+            s = System(N, L, xy=xy, seed=3, ref_pi=False, error=error, want_ref=False)
+            Ud = O.dense_mobility(s.pos_np[:, :3], s.F_np[:, :3], L, xy=xy)
+            U = s.eng.mobility(s.pos, s.F).cpu().numpy()[:, :3].astype(np.float64)
+            got[(xy, error)] = float(np.linalg.norm(U - Ud) / np.linalg.norm(Ud))
+            s.eng.close()
+    print("dense-Ewald relative L2 error at N = 1000:", {k: f"{v:.2e}" for k, v in got.items()})
+    for (xy, error), err in got.items():
+        assert err < ERR_MULT * error, (xy, error, err)
+
+
+ERR_MULT = 3.0   # measured multiple of `error` (see the printed values); tightened once measured
+
+
+def test_gpu_lanczos_matches_dense_sqrtm(cuda):
+    """The GPU Lanczos path (pse_velocity, parts = 4, injected psi) against sqrt(2T/dt) sqrtm(M_real) psi with M_real assembled
+    column by column from pse_mreal and its square root from a dense symmetric eigendecomposition (float64).  Lanczos stops
+    at a relative step norm of `error` (PSEv1/Brownian.cu:606), so agreement is expected at the `error` level."""
+    import torch
+    N = 300
+    L = util.box_length(N, 0.2)
+    s = System(N, L, seed=13, lattice=True, want_ref=False, error=1e-3)
+    M = np.zeros((3 * N, 3 * N))
+    for c in range(3 * N):
+        e = torch.zeros_like(s.F); e[c // 3, c % 3] = 1
+        M[:, c] = s.eng.mreal(s.pos, e).cpu().numpy()[:, :3].reshape(-1).astype(np.float64)
+    assert np.abs(M - M.T).max() < 2e-6
+    M = 0.5 * (M + M.T)
+    lam, W = np.linalg.eigh(M)
+    assert lam.min() > 0   # "positively split": the real-space part alone is positive definite
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    up = torch.rand((N, 3), device="cuda", generator=g)
+    a = np.float32(1.73205080757)
+    psi = (np.float32(2) * a * up.cpu().numpy() - a).astype(np.float64).reshape(-1)
+    exact = math.sqrt(2 * s.T / s.dt) * (W @ (np.sqrt(lam) * (W.T @ psi)))
+    s.eng.lanczos_m = 2
+    U, m = s.eng.velocity(s.pos, s.F, timestep=1, u_particles=up, parts=4)
+    got = U.cpu().numpy()[:, :3].astype(np.float64).reshape(-1)
+    err = np.linalg.norm(got - exact) / np.linalg.norm(exact)
+    print(f"Lanczos m = {m}, relative error vs dense sqrtm = {err:.2e}")
+    assert 2 <= m <= 30 and err < 2e-3, (m, err)
+    # a tighter tolerance converges further
+    s2 = System(N, L, seed=13, lattice=True, want_ref=False, error=1e-5)
+    U2, m2 = s2.eng.velocity(s2.pos, s2.F, timestep=1, u_particles=up, parts=4)
+    err2 = np.linalg.norm(U2.cpu().numpy()[:, :3].astype(np.float64).reshape(-1) - exact) / np.linalg.norm(exact)
+    assert m2 > m and err2 < 5e-5, (m2, err2)
+
+
+def test_tilt_flip_through_max_strain(cuda):
+    """a steady-shear run whose wrapped strain (`variant.shear_variant`, PSEv1/VariantShearFunction.cc:34-43)
+    jumps from +max_strain to -max_strain.  box_resize re-images the particles after the jump (HOOMD's updater does); on the
+    steps around the flip the neighbour list equals brute force, the particle->grid index is bit-exact, every particle sits
+    inside the primary cell of the new box, and M.F matches the reference kernels and the dense Ewald sum."""
+    import torch
+    import pse_b200 as PSEv1
+    from oracle import oraclewrap as O
+    from oracle import refwrap
+    from pse_b200 import _lib
+    from pse_b200 import engine as E
+    N, L, dt = 1500, util.box_length(1500, 0.15), 0.02
+    pos0 = util.lattice_positions(N, L, 17)
+    s = PSEv1.system.set_current(PSEv1.system.System(pos0, PSEv1.system.Box(L)))
+    PSEv1.integrate.mode_standard(dt=dt)
+    ff = PSEv1.shear_function.steady(dt=dt, shear_rate=2.5)          # strain advances by 0.05 per step: flip after step 10
+    pse = PSEv1.integrate.PSEv1(group=s.all(), seed=2, T=1e-3, xi=0.5, error=1e-3, function_form=ff)
+    var = PSEv1.variant.shear_variant(ff, total_timestep=1000)
+    PSEv1.system.box_resize(s, xy=var)
+    eng = pse.cpp_method
+    F = torch.from_numpy(util.random_forces(N, 5)).cuda()
+    s.set_forces(0.05 * F)
+    tilts = []
+    flipped = False
+    for t in range(14):
+        s.run(1)
+        xy = float(var.get_value(t))           # the tilt step t was taken with
+        tilts.append(xy)
+        just_flipped = len(tilts) > 1 and tilts[-1] < tilts[-2] - 0.5
+        flipped |= just_flipped
+        if not (just_flipped or abs(xy) > 0.4):
+            continue
+        # state after the step, in the box of tilt xy
+        pos_np = s.pos.cpu().numpy()
+        orc = O.Oracle(N, L, xy=xy, ref_pi=True)
+        eng.build_neighbors(s.pos)
+        nn, head, nl = [a.cpu().numpy().view(np.uint32) for a in eng.neighbor_list()]
+        onn, ohead, onl = orc.neighbors(pos_np, eng.params.rcut + 0.4, brute=True)
+        assert np.array_equal(nn, onn) and np.array_equal(nl, onl), (t, xy)
+        assert np.array_equal(eng.grid_index(s.pos).cpu().numpy(), orc.grid_index(pos_np)), (t, xy)
+        frac_x = (pos_np[:, 0] - xy * pos_np[:, 1]) / L + 0.5
+        assert frac_x.min() > -1e-3 and frac_x.max() < 1 + 1e-3, (t, xy, frac_x.min(), frac_x.max())
+        U = eng.mobility(s.pos, F)
+        if just_flipped:
+            Ud = O.dense_mobility(pos_np[:, :3].astype(np.float64), F.cpu().numpy()[:, :3].astype(np.float64), L, xy=xy)
+            err = np.linalg.norm(U.cpu().numpy()[:, :3] - Ud) / np.linalg.norm(Ud)
+            assert err < 3e-3, (t, xy, err)
+        if refwrap.available():
+            cfg = E.make_config(N, L, xy=xy, flags=_lib.PSE_FLAG_REF_PI, T=1.0, dt=dt, seed=1)
+            e2 = E.Engine(cfg)
+            ref = refwrap.Reference(cfg, e2.params, E.ewald_table(cfg))
+            e2.build_neighbors(s.pos); ref.set_neighbors(*e2.neighbor_list())
+            close(e2.mobility(s.pos, F), ref.mobility(s.pos, F))
+            e2.close()
+    assert flipped and min(tilts) < -0.4 and max(tilts) > 0.4, tilts
