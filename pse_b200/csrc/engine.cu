@@ -97,10 +97,11 @@ struct pse_engine {
     void* d_fft_tables;
     // tile-owned spreading / interpolation ("W order", rebinned per call)
     bool tiled;
+    int spread_var;   // record feed of spread2_kernel (Spread2Cfg): PSE_SPREAD_VAR
     bool wave_v2;     // spread2 / interp2 (every particle once, window merged with vector reductions) instead of the tile-owned kernels
-    bool v2_bulk;     // stage ring of spread2 fed by bulk copies + mbarriers (PSE_SPREAD_BULK=0: 8-byte cp.async + block barriers)
     TileGrid tg;
-    int4 *d_org, *d_worg, *d_wrec;
+    int4 *d_org, *d_worg;
+    float* d_wrecs;  // v2 wave kernels: one record per particle, W order (12 header words + Gaussian factor row)
     uint32_t *d_wcell_of, *d_wcount, *d_wstart, *d_wperm, *d_wtmp, *d_wid;
     float4 *d_wpos, *d_wF;
     float* d_wwt;  // Gaussian factor rows, W order: [N][P*P + P]
@@ -318,13 +319,13 @@ static int alloc_all(pse_engine* e) {
         {
             // spread2 / interp2 tile shape for this support size (PSE_WAVE=v1 keeps the bitwise-reproducible tile-owned kernels)
             const char* wv = getenv("PSE_WAVE");
-            const char* alt = getenv("PSE_TILE_ALT");
             int tx, ty, tz;
-            e->wave_v2 = !(wv && wv[0] == 'v' && wv[1] == '1') && v2_shape(wp.P, alt && alt[0] == '1', &tx, &ty, &tz) &&
+            e->wave_v2 = !(wv && wv[0] == 'v' && wv[1] == '1') && v2_shape(wp.P, &tx, &ty, &tz) &&
                          wp.Nx >= tx + wp.P && wp.Ny >= ty + wp.P && wp.Nz >= tz + wp.P;
             if (e->wave_v2) v2_fill_tilegrid(wp.P, tx, ty, tz, &tg);
-            const char* bk = getenv("PSE_SPREAD_BULK");
-            e->v2_bulk = !(bk && bk[0] == '0');
+            { const char* dbg = getenv("PSE_SPREAD_DBG"); tg.dbg = dbg ? atoi(dbg) : 0; }
+            const char* sv = getenv("PSE_SPREAD_VAR");
+            e->spread_var = sv ? atoi(sv) : 1;
         }
         tg.ntx = (wp.Nx + tg.tx - 1) / tg.tx; tg.nty = (wp.Ny + tg.ty - 1) / tg.ty; tg.ntz = (wp.Nz + tg.tz - 1) / tg.tz;
         tg.ntile = tg.ntx * tg.nty * tg.ntz;
@@ -335,7 +336,7 @@ static int alloc_all(pse_engine* e) {
         if (e->tiled) {
             CK(cudaMalloc(&e->d_org, sizeof(int4) * N));
             CK(cudaMalloc(&e->d_worg, sizeof(int4) * N));
-            if (e->wave_v2) CK(cudaMalloc(&e->d_wrec, sizeof(int4) * N));
+            if (e->wave_v2) CK(cudaMalloc(&e->d_wrecs, sizeof(float) * (size_t)N * wrec_stride(wp.P)));
             CK(cudaMalloc(&e->d_wcell_of, sizeof(uint32_t) * N));
             CK(cudaMalloc(&e->d_wcount, sizeof(uint32_t) * (tg.ntile + 1)));
             CK(cudaMalloc(&e->d_wstart, sizeof(uint32_t) * (tg.ntile + 1)));
@@ -344,9 +345,11 @@ static int alloc_all(pse_engine* e) {
             CK(cudaMalloc(&e->d_wtmp, sizeof(uint32_t) * N));
             CK(cudaMalloc(&e->d_wpos, sizeof(float4) * N));
             CK(cudaMalloc(&e->d_wF, sizeof(float4) * N));
-            CK(cudaMalloc(&e->d_wwt, sizeof(float) * (size_t)N * wrow_stride(wp.P)));
             if (e->wave_v2) CK(v2_set_attributes(wp.P, tg.tx, tg.ty, tg.tz));
-            else CK(tiled_set_attributes(wp.P));
+            else {
+                CK(cudaMalloc(&e->d_wwt, sizeof(float) * (size_t)N * wrow_stride(wp.P)));
+                CK(tiled_set_attributes(wp.P));
+            }
         }
     }
     return PSE_OK;
@@ -553,7 +556,7 @@ extern "C" void pse_destroy(pse_engine* e) {
                     e->d_spos, e->d_sx, e->d_sy, e->d_px, e->d_nn, e->d_head, e->d_nl, e->d_pos_build, e->d_flag, e->d_grid,
                     e->d_spec, e->d_V, e->d_u, e->d_y, e->d_alpha, e->d_beta, e->d_coef, e->d_partials, e->d_counter,
                     e->d_vel_work, e->d_hpos, e->d_hF, e->d_himage, e->d_org, e->d_worg, e->d_wcell_of, e->d_wcount,
-                    e->d_wstart, e->d_wperm, e->d_wid, e->d_wpos, e->d_wF, e->d_wwt, e->d_wrec, e->d_wtmp, e->d_ell, e->d_nn_act, e->d_nl_act};
+                    e->d_wstart, e->d_wperm, e->d_wid, e->d_wpos, e->d_wF, e->d_wwt, e->d_wrecs, e->d_wtmp, e->d_ell, e->d_nn_act, e->d_nl_act};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (e->h_flag) cudaFreeHost(e->h_flag);
@@ -863,8 +866,11 @@ static int run_wbin(pse_engine* e, const float4* sF, int row_lo = -1, int row_hi
         nb = reinterpret_cast<uint32_t*>(e->h_nlinfo)[0];
     }
     if (nb) {
-        wgather_kernel<<<nblk(nb, 256), 256, 0, st>>>(e->d_spos, sF, e->d_org, e->d_wperm, e->d_perm, nb, e->d_wpos, e->d_wF, e->d_worg, e->d_wid, e->tg, e->wave_v2 ? e->d_wrec : nullptr); LAUNCHED(e);
-        launch_wweights(e->wp.P, st, e->d_wpos, e->d_worg, nb, e->box, e->wp, e->d_wwt); LAUNCHED(e);
+        wgather_kernel<<<nblk(nb, 256), 256, 0, st>>>(e->d_spos, sF, e->d_org, e->d_wperm, e->d_perm, nb, e->d_wpos, e->d_wF, e->d_worg, e->d_wid, e->tg,
+                                                      reinterpret_cast<int4*>(e->d_wrecs)); LAUNCHED(e);
+        if (e->wave_v2) launch_wweights(e->wp.P, st, e->d_wpos, e->d_worg, nb, e->box, e->wp, e->d_wrecs + WREC_HDR, wrec_stride(e->wp.P));
+        else launch_wweights(e->wp.P, st, e->d_wpos, e->d_worg, nb, e->box, e->wp, e->d_wwt);
+        LAUNCHED(e);
     }
     return PSE_OK;
 }
@@ -879,7 +885,7 @@ static int run_wave(pse_engine* e, const float4* sF, float4* U, int accumulate, 
         ProfScope ps(e, PH_SPREAD);
         if (e->wave_v2) {
             CK(cudaMemsetAsync(e->d_grid, 0, sizeof(float) * 3 * e->G, st));
-            launch_spread2(P, st, e->v2_bulk, e->d_wF, e->d_wrec, e->d_wwt, e->d_wstart, e->wp, e->tg, e->d_grid); LAUNCHED(e);
+            launch_spread2(P, e->spread_var, st, e->d_wrecs, e->d_wstart, e->wp, e->tg, e->d_grid); LAUNCHED(e);
         } else if (e->tiled) {
             launch_spread_tile(P, st, e->d_wF, e->d_worg, e->d_wwt, e->d_wstart, e->wp, e->tg, e->d_grid); LAUNCHED(e);
         } else {
@@ -924,7 +930,7 @@ static int run_wave(pse_engine* e, const float4* sF, float4* U, int accumulate, 
     }
     ProfScope ps(e, PH_INTERP);
     if (e->wave_v2) {
-        launch_interp2(P, st, e->d_worg, e->d_wwt, e->d_wstart, e->d_wid, e->wp, e->tg, e->d_grid, U, accumulate);
+        launch_interp2(P, st, e->d_wrecs, e->d_wstart, e->wp, e->tg, e->d_grid, U, accumulate);
         LAUNCHED(e);
     } else if (e->tiled) {
         launch_interp_tile(P, st, e->d_worg, e->d_wwt, e->d_wstart, e->d_wid, e->wp, e->tg, e->d_grid, U, accumulate);

@@ -30,6 +30,8 @@ struct TileGrid {
     int tile0;       // first tile handled by a launch (0 unless the grid is sharded into x-slabs of tiles)
     int tx, ty, tz;  // tile extent in nodes per axis (TILE^3 for the tile-owned gather kernels; per-P shapes for spread2)
     int cp, cy, cz, cs;  // spread2 accumulator geometry: residue modulus (= P), cells per axis (y, z), words per cell
+    int rs;              // floats per W record of the v2 kernels (12 header words + factor row)
+    int dbg;             // measurement knock-outs of spread2_kernel (PSE_SPREAD_DBG bit 0: no accumulation, 1: no merge, 2: no clear)
 };
 // row stride (floats) of the Gaussian factor rows: P*P + P rounded up to 16 bytes, so that any run of rows is a legal
 // source of a bulk (TMA) copy
@@ -66,12 +68,17 @@ __global__ void wgather_kernel(const float4* __restrict__ spos, const float4* __
     wid[w] = __ldg(perm + s);  // particle id of W slot w: interpolation writes U[id] without chasing two permutations
     wpos[w] = __ldg(spos + s);
     const int4 o = org[s];
-    if (sF) wF[w] = __ldg(sF + s);
+    if (sF && !wrec) wF[w] = __ldg(sF + s);
     if (wrec) {
-        // where the support starts inside the accumulator of spread2_kernel (wave_v2.cuh): the accumulator cell of the
-        // origin (origin / P per axis) as a word offset, and the residues origin % P
+        // header of the W record streamed by spread2_kernel / interp2_kernel (wave_v2.cuh), 12 words:
+        //   (Fx, Fy, Fz, particle id | accumulator word offset of the origin's cell, origin residues x, y, z |
+        //    origin inside the tile x, y, z, -); the Gaussian factor row follows (wweights_kernel)
         const int lx = o.x % tg.tx, ly = o.y % tg.ty, lz = o.z % tg.tz;
-        wrec[w] = make_int4((((lx / tg.cp) * tg.cy + ly / tg.cp) * tg.cz + lz / tg.cp) * tg.cs, lx % tg.cp, ly % tg.cp, lz % tg.cp);
+        int4* h = reinterpret_cast<int4*>(reinterpret_cast<float*>(wrec) + (size_t)w * tg.rs);
+        const float4 f = sF ? __ldg(sF + s) : make_float4(0.f, 0.f, 0.f, 0.f);
+        h[0] = make_int4(__float_as_int(f.x), __float_as_int(f.y), __float_as_int(f.z), (int)__ldg(perm + s));
+        h[1] = make_int4((((lx / tg.cp) * tg.cy + ly / tg.cp) * tg.cz + lz / tg.cp) * tg.cs, lx % tg.cp, ly % tg.cp, lz % tg.cp);
+        h[2] = make_int4(lx, ly, lz, 0);
     }
     worg[w] = o;
 }
@@ -138,7 +145,7 @@ __device__ __forceinline__ int3 unwrapped_origin(const int4 o, const WaveParams&
 template <int P>
 __global__ void __launch_bounds__(256)
 wweights_kernel(const float4* __restrict__ wpos, const int4* __restrict__ worg, uint32_t N, PseBox box, WaveParams wp,
-                float* __restrict__ wwt) {
+                float* __restrict__ wwt, int dst_stride /* floats between the rows of consecutive particles */) {
     constexpr int PP = P * P, WS = wrow_stride(P);  // (pad words of a row are never read)
     __shared__ __align__(16) float rows[WW_PB * WS];
     const uint32_t w0 = blockIdx.x * WW_PB;
@@ -168,9 +175,12 @@ wweights_kernel(const float4* __restrict__ wpos, const int4* __restrict__ worg, 
         for (int t = threadIdx.x; t < WW_PB * PAD; t += blockDim.x) rows[(t / PAD) * WS + PP + P + t % PAD] = 0.f;
     }
     __syncthreads();
-    float2* dst = reinterpret_cast<float2*>(wwt + (size_t)w0 * WS);  // WS is even and w0 * WS * 4 is a multiple of 8
+    // rows are 8-byte aligned (WS and dst_stride are even); with dst_stride == WS the block writes one contiguous range
     const float2* src = reinterpret_cast<const float2*>(rows);
-    for (int t = threadIdx.x; t < np * (WS / 2); t += blockDim.x) dst[t] = src[t];
+    for (int t = threadIdx.x; t < np * (WS / 2); t += blockDim.x) {
+        const int q = t / (WS / 2), r = t - q * (WS / 2);
+        reinterpret_cast<float2*>(wwt + (size_t)(w0 + q) * dst_stride)[r] = src[t];
+    }
 }
 
 // ---- spreading: one block per node tile -------------------------------------------------------------
@@ -461,8 +471,8 @@ interp_tile_kernel(const int4* __restrict__ worg, const float* __restrict__ wwt,
                    const uint32_t* __restrict__ wpid, WaveParams wp,
                    TileGrid tg, const float* __restrict__ grid, float4* __restrict__ U, int accumulate) {
     extern __shared__ __align__(16) float smem[];
-    constexpr int PP = P * P, NW = INTERP_THREADS / 32, WS = PP + P;
-    constexpr int NWR = (WS + 31) / 32;  // factor words per lane
+    constexpr int PP = P * P, NW = INTERP_THREADS / 32, WS = wrow_stride(P), NWD = PP + P;
+    constexpr int NWR = (NWD + 31) / 32;  // factor words per lane
     constexpr int H = TILE + P - 1, XS = H * H + interp_pad(P), GT = H * XS;
     constexpr int NFULL = PP / 32;             // passes in which every lane has a column
     constexpr int LEFT = PP - 32 * NFULL;      // remaining columns
@@ -484,7 +494,7 @@ interp_tile_kernel(const int4* __restrict__ worg, const float* __restrict__ wwt,
         o_n = __ldg(worg + ww);
         id_n = __ldg(wpid + ww);
 #pragma unroll
-        for (int r = 0; r < NWR; ++r) wt_n[r] = lane + 32 * r < WS ? __ldg(wwt + (size_t)ww * WS + lane + 32 * r) : 0.f;
+        for (int r = 0; r < NWR; ++r) wt_n[r] = lane + 32 * r < NWD ? __ldg(wwt + (size_t)ww * WS + lane + 32 * r) : 0.f;
     };
     if (w < ce) fetch(w);
     // stage the halo tile (periodic wrap per node): a warp takes whole x planes of the tile, its lanes run over the H*H
@@ -606,10 +616,11 @@ static cudaError_t tiled_set_attributes(int P) {
 }
 
 static void launch_wweights(int P, cudaStream_t st, const float4* wpos, const int4* worg, uint32_t N, const PseBox& box,
-                            const WaveParams& wp, float* wwt) {
+                            const WaveParams& wp, float* wwt, int dst_stride = 0) {
     const unsigned int nb = (N + WW_PB - 1) / WW_PB;
+    if (dst_stride == 0) dst_stride = wrow_stride(P);
     switch (P) {
-#define X(p) case p: wweights_kernel<p><<<nb, 256, 0, st>>>(wpos, worg, N, box, wp, wwt); break;
+#define X(p) case p: wweights_kernel<p><<<nb, 256, 0, st>>>(wpos, worg, N, box, wp, wwt, dst_stride); break;
         PSE_FOR_EACH_P(X)
 #undef X
     }

@@ -12,14 +12,15 @@
 //     and NO barriers between particles (program order of the owning thread is the only ordering required);
 //   * the accumulator is stored residue-major, acc[cell][thread] with cell = (x / P, y / P, z / P) and a cell stride
 //     that is a multiple of 32 words: the bank of an access is the thread index, conflict-free for every particle;
-//   * records and Gaussian factor rows of the tile's particles (a contiguous W-order range) are streamed through a
-//     ring of shared-memory stages by bulk asynchronous copies (cp.async.bulk, completion on an mbarrier), one elected
-//     thread as producer, full/empty barriers instead of block barriers;
+//   * the W records of the tile's particles (force, window position, Gaussian factor row: one contiguous range) are
+//     streamed through a ring of shared-memory stages by bulk asynchronous copies (cp.async.bulk, completion on an
+//     mbarrier), one elected thread as producer, full/empty barriers instead of block barriers;
 //   * the window is merged into the grid with vector reductions (red.global.add.v4.f32) - about T^-3 (T + P - 1)^3
 //     grid-sized reduction passes in L2 instead of the reference's 3 P^3 N scattered atomics.  The grid must be zero
 //     on entry.  Summation order across blocks is not fixed, so results are reproducible to round-off (1e-7), not
 //     bitwise; PSE_WAVE=v1 selects the bitwise-reproducible tile-owned kernel.
-// interp2_kernel.  interp_tile_kernel generalised to box-shaped tiles, with 16-byte global loads in the window staging.
+// interp2_kernel.  interp_tile_kernel generalised to box-shaped tiles: window staged with asynchronous copies, W records
+// streamed through the same kind of bulk-copy ring.
 #pragma once
 #include "wave_tiled.cuh"
 
@@ -53,8 +54,42 @@ __device__ __forceinline__ void red_add(float* addr, float a) {
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(a) : "memory");
 }
 
+// ---- W records ----------------------------------------------------------------------------------------------------
+// One record per particle, W order (particles of a tile contiguous): 12 header words written by wgather_kernel
+// (wave_tiled.cuh) followed by the Gaussian factor row of wweights_kernel.  A record is a multiple of 16 bytes, so any run
+// of records is a legal bulk-copy source.
+#define WREC_HDR 12
+__host__ __device__ constexpr int wrec_stride(int P) { return WREC_HDR + wrow_stride(P); }
+
+// Ring of shared-memory stages fed by bulk copies: one elected thread is the producer, every warp a consumer.
+// full[s] completes when the bytes of the chunk in stage s have landed; empty[s] when every warp has released it.
+template <int STAGES, int NWARPS>
+struct BulkRing {
+    uint32_t bar0;   // shared address of full[STAGES] | empty[STAGES]
+    __device__ __forceinline__ uint32_t full(int s) const { return bar0 + 8u * s; }
+    __device__ __forceinline__ uint32_t empty(int s) const { return bar0 + 8u * (STAGES + s); }
+    __device__ __forceinline__ void init() const {   // one thread; followed by a block barrier before anybody waits
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), NWARPS); }
+        mbar_init_fence();
+    }
+    __device__ __forceinline__ void load(int c, uint32_t dst, const void* src, uint32_t bytes) const {
+        mbar_expect_tx(full(c % STAGES), bytes);
+        bulk_g2s(dst, src, bytes, full(c % STAGES));
+    }
+    // before refilling the stage chunk c - 1 used (c >= 1)
+    __device__ __forceinline__ void wait_released(int c_prev) const { mbar_wait(empty(c_prev % STAGES), (uint32_t)((c_prev / STAGES) & 1)); }
+    __device__ __forceinline__ void wait_filled(int c) const { mbar_wait(full(c % STAGES), (uint32_t)((c / STAGES) & 1)); }
+    __device__ __forceinline__ void release(int c) const { mbar_arrive(empty(c % STAGES)); }   // one lane per warp
+};
+
 // ---- geometry of one (P, tile shape) instance -------------------------------------------------------------------
-template <int P, int TX, int TY, int TZ> struct Spread2Cfg {
+// VAR selects how the W records reach shared memory:
+//   0  ring of two 8-particle stages filled with 8-byte cp.async by all threads, one block barrier per stage (small ring:
+//      the 73 KB accumulator of P = 6 keeps three blocks per SM);
+//   1  two large stages (half a tile each) filled by ONE bulk copy each (cp.async.bulk + mbarrier): the copy engine is
+//      efficient for multi-KB copies, and a wait per ~60 particles instead of per 8; two blocks per SM for P = 6;
+//   2  as 0 with 32-particle stages (same occupancy as 1; measurement control).
+template <int P, int TX, int TY, int TZ, int VAR = 1> struct Spread2Cfg {
     static constexpr int PP = P * P, PPP = PP * P;
     static constexpr int NT = ((PPP + 31) / 32) * 32;      // threads (thread t < PPP <-> residue class (a, b, c))
     static constexpr int NW = NT / 32;
@@ -62,31 +97,32 @@ template <int P, int TX, int TY, int TZ> struct Spread2Cfg {
     static constexpr int CX = (HX + P - 1) / P, CY = (HY + P - 1) / P, CZ = (HZ + P - 1) / P;  // residue cells per axis
     static constexpr int CS = NT;                          // words per cell: multiple of 32 -> bank = thread index
     static constexpr int ACC = CX * CY * CZ * CS;          // accumulator words per component
-    static constexpr int WS = wrow_stride(P);
-    // stage ring: sized so that the small-accumulator shapes keep three blocks per SM
+    static constexpr int RS = wrec_stride(P);              // floats per W record
     static constexpr int ACC_BYTES = 3 * ACC * 4;
-    static constexpr int CHUNK = ACC_BYTES > 100 * 1024 ? 16 : 8;   // particles per stage
-    static constexpr int STAGES = ACC_BYTES > 100 * 1024 ? 3 : 2;
-    static constexpr int REC_BYTES = 32;                  // (Fx, Fy, Fz, -) + (accumulator cell offset, origin residues)
-    static constexpr int STAGE_BYTES = CHUNK * (REC_BYTES + WS * 4);
+    static constexpr bool BIG = ACC_BYTES > 100 * 1024;    // one block per SM anyway: a generous ring
+    static constexpr bool BULK = VAR == 1;
+    static constexpr int STAGES = 2;
+    // particles per stage: VAR 1 sizes a stage for about half of a typical tile (density ~0.075 per node at phi = 0.3)
+    static constexpr int CHUNK = VAR == 0 ? 8 : (VAR == 2 ? 32 : (BIG ? 64 : (TX * TY * TZ * 3 / 64 + 7) / 8 * 8));
+    static constexpr int STAGE_BYTES = CHUNK * RS * 4;
     static constexpr size_t SMEM = (size_t)ACC_BYTES + (size_t)STAGES * STAGE_BYTES;
-    static_assert(CX * CY * CZ * CS < 65536, "accumulator offset must fit 16 bits of the record word");
-    static_assert(P <= 15, "residues are packed in 4 bits");
+    static_assert(CX * CY * CZ * CS < (1 << 24), "accumulator offset");
+    static_assert(HZ <= 32, "flush handles at most eight z quads per row");
 };
 
-template <int P, int TX, int TY, int TZ, bool BULK>
-__global__ void __launch_bounds__(Spread2Cfg<P, TX, TY, TZ>::NT)
-spread2_kernel(const float4* __restrict__ wF, const int4* __restrict__ wrec /* window position of the support, see wgather_kernel */,
-               const float* __restrict__ wwt, const uint32_t* __restrict__ wcell_start, WaveParams wp, TileGrid tg,
+template <int P, int TX, int TY, int TZ, int VAR>
+__global__ void __launch_bounds__(Spread2Cfg<P, TX, TY, TZ, VAR>::NT)
+spread2_kernel(const float* __restrict__ wrecs, const uint32_t* __restrict__ wcell_start, WaveParams wp, TileGrid tg,
                float* __restrict__ grid) {
-    using C = Spread2Cfg<P, TX, TY, TZ>;
-    constexpr int PP = C::PP, PPP = C::PPP, NT = C::NT, NW = C::NW, WS = C::WS, CHUNK = C::CHUNK, STAGES = C::STAGES;
+    using C = Spread2Cfg<P, TX, TY, TZ, VAR>;
+    constexpr bool BULK = C::BULK;
+    constexpr int PP = C::PP, PPP = C::PPP, NT = C::NT, NW = C::NW, RS = C::RS, CHUNK = C::CHUNK, STAGES = C::STAGES;
     constexpr int ACC = C::ACC, CS = C::CS;
     constexpr int SXW = C::CY * C::CZ * CS, SYW = C::CZ * CS, SZW = CS;  // cell strides in words
     extern __shared__ __align__(128) float smem_v2[];
     float* acc = smem_v2;                                                      // [3][ACC]
-    unsigned char* stage0 = reinterpret_cast<unsigned char*>(acc + 3 * ACC);  // [STAGES][ CHUNK records | CHUNK factor rows ]
-    __shared__ __align__(8) unsigned long long s_bar[2 * STAGES];           // full[STAGES] | empty[STAGES]
+    unsigned char* stage0 = reinterpret_cast<unsigned char*>(acc + 3 * ACC);  // [STAGES][CHUNK records]
+    __shared__ __align__(8) unsigned long long s_bar[2 * STAGES];
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int tile = blockIdx.x + tg.tile0;
@@ -97,136 +133,132 @@ spread2_kernel(const float4* __restrict__ wF, const int4* __restrict__ wrec /* w
     const uint32_t np = ce - cb;
     const int nchunks = (int)((np + CHUNK - 1) / CHUNK);
 
-    const uint32_t bar0 = smem_u32(s_bar);
-    auto full_bar = [&](int s) { return bar0 + 8u * s; };
-    auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
-    // producer side (thread 0 when BULK; all threads with 8-byte cp.async otherwise)
-    auto issue_chunk = [&](int c) {
-        const int s = c % STAGES;
+    BulkRing<STAGES, NW> ring;
+    ring.bar0 = smem_u32(s_bar);
+    auto issue_chunk = [&](int c) {   // BULK: producer thread only; otherwise all threads
         const uint32_t w0 = cb + (uint32_t)c * CHUNK;
         const uint32_t n = min((uint32_t)CHUNK, ce - w0);
-        unsigned char* st = stage0 + (size_t)s * C::STAGE_BYTES;
+        unsigned char* dst = stage0 + (size_t)(c % STAGES) * C::STAGE_BYTES;
+        const float* src = wrecs + (size_t)w0 * RS;
         if (BULK) {
-            mbar_expect_tx(full_bar(s), n * (32u + WS * 4u));
-            bulk_g2s(smem_u32(st), wF + w0, n * 16u, full_bar(s));
-            bulk_g2s(smem_u32(st + CHUNK * 16), wrec + w0, n * 16u, full_bar(s));
-            bulk_g2s(smem_u32(st + CHUNK * 32), wwt + (size_t)w0 * WS, n * WS * 4u, full_bar(s));
+            ring.load(c, smem_u32(dst), src, n * RS * 4u);
         } else {
-            for (int t = tid; t < (int)n * 2; t += NT) {
-                cp_async8(st + 8 * t, reinterpret_cast<const unsigned char*>(wF + w0) + 8 * t);
-                cp_async8(st + CHUNK * 16 + 8 * t, reinterpret_cast<const unsigned char*>(wrec + w0) + 8 * t);
-            }
-            for (int t = tid; t < (int)n * (WS / 2); t += NT)
-                cp_async8(st + CHUNK * 32 + 8 * t, reinterpret_cast<const unsigned char*>(wwt + (size_t)w0 * WS) + 8 * t);
+            for (int t = tid; t < (int)n * (RS / 2); t += NT) cp_async8(dst + 8 * t, reinterpret_cast<const unsigned char*>(src) + 8 * t);
             cp_async_commit();
         }
     };
+    // the first chunk(s) are in flight while the accumulator is cleared
     if (BULK) {
         if (tid == 0) {
-            for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), NW); }
-            mbar_init_fence();
-        }
-    }
-    for (int i = tid; i < 3 * ACC / 4; i += NT) reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
-    // prologue: the first STAGES - 1 chunks
-    if (BULK) {
-        if (tid == 0)
+            ring.init();
             for (int c = 0; c < STAGES - 1 && c < nchunks; ++c) issue_chunk(c);
+        }
     } else {
         issue_chunk(0);
     }
+    if (!(tg.dbg & 4))
+    for (int i = tid; i < 3 * ACC / 4; i += NT) reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
 
     // residue class of this thread
     const int a = tid / PP, b = (tid - a * PP) / P, c3 = tid - a * PP - b * P;
-    const bool worker = tid < PPP;
+    const bool worker = tid < PPP && !(tg.dbg & 1);
     const uint32_t my_acc = smem_u32(acc) + 4u * (uint32_t)tid;
 
     for (int c = 0; c < nchunks; ++c) {
-        const int s = c % STAGES;
         if (BULK) {
-            // refill the stage chunk c - 1 used (all warps have released it once they are past that chunk)
+            // refill the stage chunk c - 1 used (every warp releases a stage when it is past that chunk)
             if (tid == 0 && c + STAGES - 1 < nchunks) {
-                if (c >= 1) mbar_wait(empty_bar((c - 1) % STAGES), (uint32_t)(((c - 1) / STAGES) & 1));
+                if (c >= 1) ring.wait_released(c - 1);
                 issue_chunk(c + STAGES - 1);   // (at c = 0 the last stage of the ring is still fresh)
             }
             __syncwarp();
-            mbar_wait(full_bar(s), (uint32_t)((c / STAGES) & 1));
+            ring.wait_filled(c);
         } else {
             cp_async_wait<0>();
             __syncthreads();                       // chunk c visible to all; everyone is done with chunk c - 1
             if (c + 1 < nchunks) issue_chunk(c + 1);
         }
-        const unsigned char* st = stage0 + (size_t)s * C::STAGE_BYTES;
-        const float4* recs = reinterpret_cast<const float4*>(st);
-        const int4* ords = reinterpret_cast<const int4*>(st + CHUNK * 16);
-        const float* wq = reinterpret_cast<const float*>(st + CHUNK * 32);
+        const float* st = reinterpret_cast<const float*>(stage0 + (size_t)(c % STAGES) * C::STAGE_BYTES);
         const int n = (int)min((uint32_t)CHUNK, np - (uint32_t)c * CHUNK);
         if (worker) {
 #pragma unroll 2
             for (int q = 0; q < n; ++q) {
-                const float4 rec = recs[q];
-                const int4 od = ords[q];  // (accumulator word offset of the origin's cell, origin residues x, y, z)
+                const float* rec = st + q * RS;
+                const float4 f = *reinterpret_cast<const float4*>(rec);
+                const int4 od = *reinterpret_cast<const int4*>(rec + 4);  // (accumulator offset of the origin's cell, origin residues)
                 // support index of my node along each axis: (residue - origin residue) mod P; a borrow means the node lies
                 // in the next accumulator cell
                 const int dx = a - od.y, dy = b - od.z, dz = c3 - od.w;
                 const int mx = dx >> 31, my = dy >> 31, mz = dz >> 31;  // 0 or -1
                 const int ij = (dx - mx * P) * P + (dy - my * P), k = dz - mz * P;
                 const int cell = od.x - mx * SXW - my * SYW - mz * SZW;
-                const float w = wq[q * WS + ij] * wq[q * WS + PP + k];
+                const float w = rec[WREC_HDR + ij] * rec[WREC_HDR + PP + k];
                 const uint32_t addr = my_acc + 4u * (uint32_t)cell;
-                smem_fma<0>(addr, w, rec.x);
-                smem_fma<4 * ACC>(addr, w, rec.y);
-                smem_fma<8 * ACC>(addr, w, rec.z);
+                smem_fma<0>(addr, w, f.x);
+                smem_fma<4 * ACC>(addr, w, f.y);
+                smem_fma<8 * ACC>(addr, w, f.z);
             }
         }
         if (BULK) {
             __syncwarp();
-            if (lane == 0) mbar_arrive(empty_bar(s));
+            if (lane == 0) ring.release(c);
         }
     }
     __syncthreads();
 
-    // ---- merge the window into the grid: one vector reduction per four z nodes and component
+    // ---- merge the window into the grid: one vector reduction per four z nodes and component.  Eight lanes share a
+    // (x, y) row of the window, lane q of them takes z nodes 4q .. 4q + 3 (index arithmetic of the z part hoisted)
     const size_t G = (size_t)wp.Nx * wp.Ny * wp.Nz;
     constexpr int HX = C::HX, HY = C::HY, HZ = C::HZ, NQ = (HZ + 3) / 4;
     const bool vec = ((wp.Nz & 3) == 0) && ((TZ & 3) == 0);
-    for (int e = tid; e < HX * HY * NQ; e += NT) {
-        const int q = e % NQ, row = e / NQ;
-        const int ly = row % HY, lx = row / HY;
-        const int rowcell = ((lx / P) * C::CY + ly / P) * C::CZ, rowres = ((lx % P) * P + ly % P) * P;
-        float v[3][4];
-        bool any = false;
+    const int q = tid & 7;
+    if (q < NQ && !(tg.dbg & 2)) {
+        int zoff[4];
+        bool zin[4];
 #pragma unroll
         for (int z = 0; z < 4; ++z) {
             const int lz = 4 * q + z;
-            const bool in = lz < HZ;
-            const int idx = in ? (rowcell + lz / P) * CS + rowres + lz % P : 0;
-#pragma unroll
-            for (int cc = 0; cc < 3; ++cc) { v[cc][z] = in ? acc[cc * ACC + idx] : 0.f; any |= v[cc][z] != 0.f; }
+            zin[z] = lz < HZ;
+            zoff[z] = zin[z] ? (lz / P) * CS + lz % P : 0;
         }
-        if (!any) continue;
-        int gx = t0x + lx; if (gx >= wp.Nx) gx -= wp.Nx;
-        int gy = t0y + ly; if (gy >= wp.Ny) gy -= wp.Ny;
         int gz = t0z + 4 * q; if (gz >= wp.Nz) gz -= wp.Nz;
-        float* dst = grid + ((size_t)gx * wp.Ny + gy) * wp.Nz;
-        if (vec) {  // aligned quads never straddle the periodic boundary
+        for (int row = tid >> 3; row < HX * HY; row += NT / 8) {
+            const int lx = row / HY, ly = row - lx * HY;
+            const float* ar = acc + ((lx / P) * C::CY + ly / P) * C::CZ * CS + ((lx % P) * P + ly % P) * P;
+            float v[3][4];
+            bool any = false;
 #pragma unroll
-            for (int cc = 0; cc < 3; ++cc) red_add_v4(dst + cc * G + gz, v[cc][0], v[cc][1], v[cc][2], v[cc][3]);
-        } else {
+            for (int z = 0; z < 4; ++z)
 #pragma unroll
-            for (int z = 0; z < 4; ++z) {
-                if (4 * q + z >= HZ) break;
-                int zz = gz + z; if (zz >= wp.Nz) zz -= wp.Nz;
+                for (int cc = 0; cc < 3; ++cc) { v[cc][z] = zin[z] ? ar[cc * ACC + zoff[z]] : 0.f; any |= v[cc][z] != 0.f; }
+            if (!any) continue;
+            int gx = t0x + lx; if (gx >= wp.Nx) gx -= wp.Nx;
+            int gy = t0y + ly; if (gy >= wp.Ny) gy -= wp.Ny;
+            float* dst = grid + ((size_t)gx * wp.Ny + gy) * wp.Nz;
+            if (vec) {  // aligned quads never straddle the periodic boundary
 #pragma unroll
-                for (int cc = 0; cc < 3; ++cc)
-                    if (v[cc][z] != 0.f) red_add(dst + cc * G + zz, v[cc][z]);
+                for (int cc = 0; cc < 3; ++cc) red_add_v4(dst + cc * G + gz, v[cc][0], v[cc][1], v[cc][2], v[cc][3]);
+            } else {
+#pragma unroll
+                for (int z = 0; z < 4; ++z) {
+                    if (!zin[z]) break;
+                    int zz = gz + z; if (zz >= wp.Nz) zz -= wp.Nz;
+#pragma unroll
+                    for (int cc = 0; cc < 3; ++cc)
+                        if (v[cc][z] != 0.f) red_add(dst + cc * G + zz, v[cc][z]);
+                }
             }
         }
     }
 }
 
 // ---- interpolation on box-shaped tiles ----------------------------------------------------------------------------
+// The block stages the (T + P - 1)^3 window of the three velocity grids with 4-byte asynchronous copies (no register
+// staging: every load of the window is in flight at once) and streams the W records of its particles through a bulk-copy
+// ring, one particle per warp and chunk.  A lane owns one (i, j) COLUMN of the support and walks its P z-nodes (tile strides
+// searched at compile time so that the 32 columns of a pass hit 32 banks); w_xy is the lane's own word of the factor row,
+// w_z comes by shuffle.
 __host__ __device__ constexpr int interp2_pad(int P, int HY, int HZ) {
     const int PP = P * P;
     int best_pad = 0, best_cost = 1 << 30;
@@ -247,27 +279,37 @@ __host__ __device__ constexpr int interp2_pad(int P, int HY, int HZ) {
     }
     return best_pad;
 }
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src));
+}
 template <int P, int TX, int TY, int TZ> struct Interp2Cfg {
     static constexpr int HX = TX + P - 1, HY = TY + P - 1, HZ = TZ + P - 1;
     static constexpr int XS = HY * HZ + interp2_pad(P, HY, HZ), GT = HX * XS;
-    static constexpr size_t SMEM = 3 * (size_t)GT * sizeof(float);
-    static constexpr int THREADS = SMEM > 100 * 1024 ? 512 : 256;  // small windows: several blocks per SM
-    static constexpr int MINB = SMEM > 100 * 1024 ? 1 : (SMEM > 70 * 1024 ? 2 : 3);
+    static constexpr int WIN_BYTES = ((3 * GT * 4 + 127) / 128) * 128;
+    static constexpr bool BIG = WIN_BYTES > 100 * 1024;
+    static constexpr int THREADS = BIG ? 512 : 256;        // small windows: three blocks per SM
+    static constexpr int NW = THREADS / 32;
+    static constexpr int MINB = BIG ? 1 : (WIN_BYTES > 68 * 1024 ? 2 : 3);
+    static constexpr int RS = wrec_stride(P);
+    static constexpr int STAGES = 4;                       // one particle per warp and stage
+    static constexpr int STAGE_BYTES = NW * RS * 4;
+    static constexpr size_t SMEM = (size_t)WIN_BYTES + (size_t)STAGES * STAGE_BYTES;
 };
 
 template <int P, int TX, int TY, int TZ>
 __global__ void __launch_bounds__(Interp2Cfg<P, TX, TY, TZ>::THREADS, Interp2Cfg<P, TX, TY, TZ>::MINB)
-interp2_kernel(const int4* __restrict__ worg, const float* __restrict__ wwt, const uint32_t* __restrict__ wcell_start,
-               const uint32_t* __restrict__ wpid, WaveParams wp, TileGrid tg, const float* __restrict__ grid, float4* __restrict__ U,
-               int accumulate) {
+interp2_kernel(const float* __restrict__ wrecs, const uint32_t* __restrict__ wcell_start, WaveParams wp, TileGrid tg,
+               const float* __restrict__ grid, float4* __restrict__ U, int accumulate) {
     using C = Interp2Cfg<P, TX, TY, TZ>;
-    extern __shared__ __align__(16) float smem[];
-    constexpr int PP = P * P, NTH = C::THREADS, NW = NTH / 32, WS = wrow_stride(P), NWD = PP + P;
+    extern __shared__ __align__(128) float smem_v2[];
+    constexpr int PP = P * P, NW = C::NW, RS = C::RS, NWD = PP + P, STAGES = C::STAGES;
     constexpr int NWR = (NWD + 31) / 32;  // factor words per lane
     constexpr int HX = C::HX, HY = C::HY, HZ = C::HZ, XS = C::XS, GT = C::GT;
     constexpr int NFULL = PP / 32, LEFT = PP - 32 * NFULL;
     constexpr bool LEFT_NODES = LEFT > 0 && LEFT * P <= 32;
-    float* g = smem;
+    float* g = smem_v2;
+    unsigned char* stage0 = reinterpret_cast<unsigned char*>(smem_v2) + C::WIN_BYTES;
+    __shared__ __align__(8) unsigned long long s_bar[2 * STAGES];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint32_t cell = blockIdx.x + tg.tile0;
     const uint32_t cb = __ldg(wcell_start + cell), ce = __ldg(wcell_start + cell + 1);
@@ -275,50 +317,35 @@ interp2_kernel(const int4* __restrict__ worg, const float* __restrict__ wwt, con
     const int bz = cell % tg.ntz, by = (cell / tg.ntz) % tg.nty, bx = cell / (tg.ntz * tg.nty);
     const int t0x = bx * TX, t0y = by * TY, t0z = bz * TZ;
     const size_t G = (size_t)wp.Nx * wp.Ny * wp.Nz;
-    uint32_t w = cb + wid;
-    int4 o_n = make_int4(0, 0, 0, 0);
-    uint32_t id_n = 0;
-    float wt_n[NWR];
-    auto fetch = [&](uint32_t ww) {
-        o_n = __ldg(worg + ww);
-        id_n = __ldg(wpid + ww);
-#pragma unroll
-        for (int r = 0; r < NWR; ++r) wt_n[r] = lane + 32 * r < NWD ? __ldg(wwt + (size_t)ww * WS + lane + 32 * r) : 0.f;
+    const uint32_t np = ce - cb;
+    const int nchunks = (int)((np + NW - 1) / NW);
+    BulkRing<STAGES, NW> ring;
+    ring.bar0 = smem_u32(s_bar);
+    auto issue_chunk = [&](int c) {
+        const uint32_t w0 = cb + (uint32_t)c * NW;
+        const uint32_t n = min((uint32_t)NW, ce - w0);
+        ring.load(c, smem_u32(stage0 + (size_t)(c % STAGES) * C::STAGE_BYTES), wrecs + (size_t)w0 * RS, n * RS * 4u);
     };
-    if (w < ce) fetch(w);
-    // stage the window: a warp takes whole x planes, its lanes run over (y, z quad); aligned quads are 16-byte loads and
-    // never straddle the periodic boundary (t0z and Nz are multiples of 4 on that path)
-    {
-        constexpr int NQ = (HZ + 3) / 4;
-        const bool vec = ((wp.Nz & 3) == 0) && ((TZ & 3) == 0);
-        for (int lx = wid; lx < HX; lx += NW) {
-            int x = t0x + lx; if (x >= wp.Nx) x -= wp.Nx;
-            const float* gx = grid + (size_t)x * wp.Ny * wp.Nz;
-            float* sx = g + lx * XS;
-            for (int e = lane; e < HY * NQ; e += 32) {
-                const int ly = e / NQ, q = e - ly * NQ;
-                int y = t0y + ly; if (y >= wp.Ny) y -= wp.Ny;
-                int z = t0z + 4 * q; if (z >= wp.Nz) z -= wp.Nz;
-                const float* src = gx + (size_t)y * wp.Nz;
-                float* dst = sx + ly * HZ + 4 * q;
-                if (vec && 4 * q + 3 < HZ) {
-#pragma unroll
-                    for (int cc = 0; cc < 3; ++cc) {
-                        const float4 v = __ldg(reinterpret_cast<const float4*>(src + cc * G + z));
-                        dst[cc * GT] = v.x; dst[cc * GT + 1] = v.y; dst[cc * GT + 2] = v.z; dst[cc * GT + 3] = v.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        if (4 * q + t >= HZ) break;
-                        int zz = z + t; if (zz >= wp.Nz) zz -= wp.Nz;
-#pragma unroll
-                        for (int cc = 0; cc < 3; ++cc) dst[cc * GT + t] = __ldg(src + cc * G + zz);
-                    }
-                }
-            }
+    if (tid == 0) {
+        ring.init();
+        for (int c = 0; c < STAGES - 1 && c < nchunks; ++c) issue_chunk(c);
+    }
+    // stage the window (periodic wrap per node): a warp takes whole x planes, lanes run over (y, z) with z fastest
+    for (int lx = wid; lx < HX; lx += NW) {
+        int x = t0x + lx; if (x >= wp.Nx) x -= wp.Nx;
+        const float* gx = grid + (size_t)x * wp.Ny * wp.Nz;
+        float* sx = g + lx * XS;
+        for (int e = lane; e < HY * HZ; e += 32) {
+            const int ly = e / HZ, lz = e - ly * HZ;
+            int y = t0y + ly; if (y >= wp.Ny) y -= wp.Ny;
+            int z = t0z + lz; if (z >= wp.Nz) z -= wp.Nz;
+            const float* src = gx + (size_t)y * wp.Nz + z;
+            cp_async4(sx + e, src);  // (node = lx * XS + ly * HZ + lz = lx * XS + e)
+            cp_async4(sx + GT + e, src + G);
+            cp_async4(sx + 2 * GT + e, src + 2 * G);
         }
     }
+    cp_async_commit();
     int col_off[NFULL > 0 ? NFULL : 1];
 #pragma unroll
     for (int r = 0; r < NFULL; ++r) {
@@ -335,80 +362,88 @@ interp2_kernel(const int4* __restrict__ worg, const float* __restrict__ wwt, con
         }
         if (left_col >= 0) left_off = (left_col / P) * XS + (left_col % P) * HZ + left_k;
     }
-    __syncthreads();
-    while (w < ce) {
-        const int4 o = o_n;
-        const uint32_t id = id_n;
-        float wt[NWR];
-#pragma unroll
-        for (int r = 0; r < NWR; ++r) wt[r] = wt_n[r];
-        const uint32_t wn = w + NW;
-        if (wn < ce) fetch(wn);
-        float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (lane == 0) old = U[id];   // .w (mass in the reference's velocity array, PSEv1/Mobility.cu:474) is preserved
-        float wz[P];
-#pragma unroll
-        for (int k = 0; k < P; ++k) wz[k] = __shfl_sync(0xffffffffu, wt[(PP + k) / 32], (PP + k) % 32);
-        const float* gb = g + (o.x - t0x) * XS + (o.y - t0y) * HZ + (o.z - t0z);
-        float ax = 0.f, ay = 0.f, az = 0.f;
-#pragma unroll
-        for (int r = 0; r < NFULL; ++r) {
-            const float* gc = gb + col_off[r];
-#pragma unroll
-            for (int k = 0; k < P; ++k) {
-                const float wgt = wt[r] * wz[k];
-                ax = fmaf(wgt, gc[k], ax);
-                ay = fmaf(wgt, gc[GT + k], ay);
-                az = fmaf(wgt, gc[2 * GT + k], az);
-            }
+    cp_async_wait<0>();
+    __syncthreads();   // window staged, barriers initialised
+    for (int c = 0; c < nchunks; ++c) {
+        if (tid == 0 && c + STAGES - 1 < nchunks) {
+            if (c >= 1) ring.wait_released(c - 1);
+            issue_chunk(c + STAGES - 1);
         }
-        if (LEFT > 0) {
-            const int src = left_col >= 0 ? left_col : 0;
-            const float wxy = __shfl_sync(0xffffffffu, wt[NFULL], src % 32);
-            if (LEFT_NODES) {
-                float wzl = wz[0];
+        __syncwarp();
+        ring.wait_filled(c);
+        const uint32_t pidx = (uint32_t)c * NW + wid;   // this warp's particle of the chunk
+        if (pidx < np) {
+            const float* rec = reinterpret_cast<const float*>(stage0 + (size_t)(c % STAGES) * C::STAGE_BYTES) + wid * RS;
+            const uint32_t id = __float_as_uint(rec[3]);
+            const int4 o = *reinterpret_cast<const int4*>(rec + 8);   // support origin inside the tile
+            float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (lane == 0) old = U[id];   // .w (mass in the reference's velocity array, PSEv1/Mobility.cu:474) is preserved
+            float wt[NWR];
 #pragma unroll
-                for (int k = 1; k < P; ++k) wzl = left_k == k ? wz[k] : wzl;
-                if (left_off >= 0) {
-                    const float wgt = wxy * wzl;
-                    ax = fmaf(wgt, gb[left_off], ax);
-                    ay = fmaf(wgt, gb[GT + left_off], ay);
-                    az = fmaf(wgt, gb[2 * GT + left_off], az);
-                }
-            } else if (left_off >= 0) {
-                const float* gc = gb + left_off;
+            for (int r = 0; r < NWR; ++r) wt[r] = lane + 32 * r < NWD ? rec[WREC_HDR + lane + 32 * r] : 0.f;
+            float wz[P];
+#pragma unroll
+            for (int k = 0; k < P; ++k) wz[k] = __shfl_sync(0xffffffffu, wt[(PP + k) / 32], (PP + k) % 32);
+            const float* gb = g + o.x * XS + o.y * HZ + o.z;
+            float ax = 0.f, ay = 0.f, az = 0.f;
+#pragma unroll
+            for (int r = 0; r < NFULL; ++r) {
+                const float* gc = gb + col_off[r];
 #pragma unroll
                 for (int k = 0; k < P; ++k) {
-                    const float wgt = wxy * wz[k];
+                    const float wgt = wt[r] * wz[k];
                     ax = fmaf(wgt, gc[k], ax);
                     ay = fmaf(wgt, gc[GT + k], ay);
                     az = fmaf(wgt, gc[2 * GT + k], az);
                 }
             }
+            if (LEFT > 0) {
+                // factor words of the left-over columns live in other lanes: fetch by shuffle (all lanes take part)
+                const int src = left_col >= 0 ? left_col : 0;
+                const float wxy = __shfl_sync(0xffffffffu, wt[NFULL], src % 32);
+                if (LEFT_NODES) {
+                    float wzl = wz[0];
+#pragma unroll
+                    for (int k = 1; k < P; ++k) wzl = left_k == k ? wz[k] : wzl;
+                    if (left_off >= 0) {
+                        const float wgt = wxy * wzl;
+                        ax = fmaf(wgt, gb[left_off], ax);
+                        ay = fmaf(wgt, gb[GT + left_off], ay);
+                        az = fmaf(wgt, gb[2 * GT + left_off], az);
+                    }
+                } else if (left_off >= 0) {
+                    const float* gc = gb + left_off;
+#pragma unroll
+                    for (int k = 0; k < P; ++k) {
+                        const float wgt = wxy * wz[k];
+                        ax = fmaf(wgt, gc[k], ax);
+                        ay = fmaf(wgt, gc[GT + k], ay);
+                        az = fmaf(wgt, gc[2 * GT + k], az);
+                    }
+                }
+            }
+            ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az);
+            if (lane == 0) {
+                if (!accumulate) { old.x = 0.f; old.y = 0.f; old.z = 0.f; }
+                U[id] = make_float4(old.x + wp.quadW * ax, old.y + wp.quadW * ay, old.z + wp.quadW * az, old.w);  // quadrature weight h^3
+            }
         }
-        ax = warp_sum(ax); ay = warp_sum(ay); az = warp_sum(az);
-        if (lane == 0) {
-            if (!accumulate) { old.x = 0.f; old.y = 0.f; old.z = 0.f; }
-            U[id] = make_float4(old.x + wp.quadW * ax, old.y + wp.quadW * ay, old.z + wp.quadW * az, old.w);
-        }
-        w = wn;
+        __syncwarp();
+        if (lane == 0) ring.release(c);
     }
 }
 
 // ---- tile shape per support size --------------------------------------------------------------------------------
-// P = 6 (error 1e-3): 12^3 tiles -> 17^3 window, 3^3 residue cells, 73 KB accumulator, three blocks per SM.
+// P = 6 (error 1e-3): 12^3 tiles -> 17^3 window, 3^3 residue cells, 73 KB accumulator, three blocks per SM
+//                     (measured at N = 1M: 12^3 555 us vs 16^3 808 us, profiles/r2_notes.md).
 // P = 7:              (15, 15, 12)  -> 3^3 cells, 114 KB.
 // P = 8 (error 1e-4): (17, 17, 16)  -> (24, 24, 23) window, 3^3 cells, 166 KB, one 512-thread block per SM.
 // Other P keep the round-1 kernels (TILE^3 tiles).  z extents are multiples of 4 so that window rows start 16-byte aligned.
 #define PSE_V2_SHAPES(X) X(6, 12, 12, 12) X(7, 15, 15, 12) X(8, 17, 17, 16)
-#define PSE_V2_ALT_SHAPES(X) X(6, 16, 16, 16)
 
-static bool v2_shape(int P, int alt, int* tx, int* ty, int* tz) {
-#define X(p, a, b, c) if (P == p && !alt) { *tx = a; *ty = b; *tz = c; return true; }
+static bool v2_shape(int P, int* tx, int* ty, int* tz) {
+#define X(p, a, b, c) if (P == p) { *tx = a; *ty = b; *tz = c; return true; }
     PSE_V2_SHAPES(X)
-#undef X
-#define X(p, a, b, c) if (P == p && alt) { *tx = a; *ty = b; *tz = c; return true; }
-    PSE_V2_ALT_SHAPES(X)
 #undef X
     return false;
 }
@@ -417,44 +452,44 @@ static void v2_fill_tilegrid(int P, int tx, int ty, int tz, TileGrid* tg) {
     tg->cp = P;
     tg->cy = (ty + P - 1 + P - 1) / P; tg->cz = (tz + P - 1 + P - 1) / P;
     tg->cs = ((P * P * P + 31) / 32) * 32;
+    tg->rs = wrec_stride(P);
 }
 static cudaError_t v2_set_attributes(int P, int tx, int ty, int tz) {
     cudaError_t err = cudaErrorInvalidValue;
 #define X(p, a, b, c)                                                                                                          \
     if (P == p && tx == a && ty == b && tz == c) {                                                                             \
-        err = cudaFuncSetAttribute(spread2_kernel<p, a, b, c, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Spread2Cfg<p, a, b, c>::SMEM); \
-        if (err == cudaSuccess) err = cudaFuncSetAttribute(spread2_kernel<p, a, b, c, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Spread2Cfg<p, a, b, c>::SMEM); \
+        err = cudaFuncSetAttribute(spread2_kernel<p, a, b, c, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Spread2Cfg<p, a, b, c, 0>::SMEM); \
+        if (err == cudaSuccess) err = cudaFuncSetAttribute(spread2_kernel<p, a, b, c, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Spread2Cfg<p, a, b, c, 1>::SMEM); \
+        if (err == cudaSuccess) err = cudaFuncSetAttribute(spread2_kernel<p, a, b, c, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Spread2Cfg<p, a, b, c, 2>::SMEM); \
         if (err == cudaSuccess) err = cudaFuncSetAttribute(interp2_kernel<p, a, b, c>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Interp2Cfg<p, a, b, c>::SMEM); \
     }
     PSE_V2_SHAPES(X)
-    PSE_V2_ALT_SHAPES(X)
 #undef X
     return err;
 }
-static void launch_spread2(int P, cudaStream_t st, bool bulk, const float4* wF, const int4* wrec, const float* wwt, const uint32_t* wstart,
-                           const WaveParams& wp, const TileGrid& tg, float* grid, int ntiles = -1) {
+static void launch_spread2(int P, int var, cudaStream_t st, const float* wrecs, const uint32_t* wstart, const WaveParams& wp, const TileGrid& tg,
+                           float* grid, int ntiles = -1) {
     if (ntiles < 0) ntiles = tg.ntile;
     if (ntiles == 0) return;
 #define X(p, a, b, c)                                                                                                          \
     if (P == p && tg.tx == a && tg.ty == b && tg.tz == c) {                                                                    \
-        if (bulk) spread2_kernel<p, a, b, c, true><<<ntiles, Spread2Cfg<p, a, b, c>::NT, Spread2Cfg<p, a, b, c>::SMEM, st>>>(wF, wrec, wwt, wstart, wp, tg, grid); \
-        else spread2_kernel<p, a, b, c, false><<<ntiles, Spread2Cfg<p, a, b, c>::NT, Spread2Cfg<p, a, b, c>::SMEM, st>>>(wF, wrec, wwt, wstart, wp, tg, grid); \
+        if (var == 0) spread2_kernel<p, a, b, c, 0><<<ntiles, Spread2Cfg<p, a, b, c, 0>::NT, Spread2Cfg<p, a, b, c, 0>::SMEM, st>>>(wrecs, wstart, wp, tg, grid); \
+        else if (var == 2) spread2_kernel<p, a, b, c, 2><<<ntiles, Spread2Cfg<p, a, b, c, 2>::NT, Spread2Cfg<p, a, b, c, 2>::SMEM, st>>>(wrecs, wstart, wp, tg, grid); \
+        else spread2_kernel<p, a, b, c, 1><<<ntiles, Spread2Cfg<p, a, b, c, 1>::NT, Spread2Cfg<p, a, b, c, 1>::SMEM, st>>>(wrecs, wstart, wp, tg, grid); \
         return;                                                                                                                \
     }
     PSE_V2_SHAPES(X)
-    PSE_V2_ALT_SHAPES(X)
 #undef X
 }
-static void launch_interp2(int P, cudaStream_t st, const int4* worg, const float* wwt, const uint32_t* wstart, const uint32_t* wid,
-                           const WaveParams& wp, const TileGrid& tg, const float* grid, float4* U, int accumulate, int ntiles = -1) {
+static void launch_interp2(int P, cudaStream_t st, const float* wrecs, const uint32_t* wstart, const WaveParams& wp, const TileGrid& tg,
+                           const float* grid, float4* U, int accumulate, int ntiles = -1) {
     if (ntiles < 0) ntiles = tg.ntile;
     if (ntiles == 0) return;
 #define X(p, a, b, c)                                                                                                          \
     if (P == p && tg.tx == a && tg.ty == b && tg.tz == c) {                                                                    \
-        interp2_kernel<p, a, b, c><<<ntiles, Interp2Cfg<p, a, b, c>::THREADS, Interp2Cfg<p, a, b, c>::SMEM, st>>>(worg, wwt, wstart, wid, wp, tg, grid, U, accumulate); \
+        interp2_kernel<p, a, b, c><<<ntiles, Interp2Cfg<p, a, b, c>::THREADS, Interp2Cfg<p, a, b, c>::SMEM, st>>>(wrecs, wstart, wp, tg, grid, U, accumulate); \
         return;                                                                                                                \
     }
     PSE_V2_SHAPES(X)
-    PSE_V2_ALT_SHAPES(X)
 #undef X
 }

@@ -47,13 +47,7 @@ def main():
         base = engine(cfg, PSE_WAVE="v1")
         p = base.params
         Ub = base.mwave(pos, F).clone()
-        variants = [("v2 cp.async", dict(PSE_SPREAD_BULK=0))]
-        if which != "nobulk":
-            variants.append(("v2 bulk", dict(PSE_SPREAD_BULK=1)))
-        if p.P == 6:
-            variants.append(("v2 cp.async tile16", dict(PSE_SPREAD_BULK=0, PSE_TILE_ALT=1)))
-            if which != "nobulk":
-                variants.append(("v2 bulk tile16", dict(PSE_SPREAD_BULK=1, PSE_TILE_ALT=1)))
+        variants = [("v2", dict())]
         for name, env in variants:
             eng = engine(cfg, **env)
             U = eng.mwave(pos, F)

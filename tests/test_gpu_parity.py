@@ -316,14 +316,6 @@ def test_tiled_wave_path_is_bitwise_reproducible_and_matches_scatter_path(cuda):
     s3 = System(20000, s.L, xy=0.2, seed=12, want_ref=False)
     c = s3.eng.mwave(s3.pos, s3.F); d = s3.eng.mwave(s3.pos, s3.F)
     close(c, d, 1e-6); close(c, a, 1e-6)
-    for bulk in ("0", "1"):     # stage ring fed by 8-byte cp.async + block barriers / by bulk copies + mbarriers
-        os.environ["PSE_SPREAD_BULK"] = bulk
-        try:
-            s4 = System(20000, s.L, xy=0.2, seed=12, want_ref=False)
-        finally:
-            del os.environ["PSE_SPREAD_BULK"]
-        close(s4.eng.mwave(s4.pos, s4.F), a, 1e-6)
-        s4.eng.close()
     os.environ["PSE_WAVE_TILED"] = "0"
     try:
         s2 = System(20000, s.L, xy=0.2, seed=12, want_ref=False)
@@ -619,9 +611,11 @@ def test_two_spheres_far_field(cuda):
 # ---------------------------------------------------------------- round-2 parity gaps ("next round" item 1)
 def test_config1_dense_ewald_error_at_N1000(cuda):
     """BASELINE.json config 1 at its own size (N = 1000, phi = 0.1): M.F against the dense double-precision Ewald sum.
-    north_star: "within the requested Ewald error".  The achieved relative L2 error is printed and asserted against the
-    requested one (the reference's parameter rules, PSEv1/Stokes.cc:129-236, size r_cut/k_max/P for `error` per term; the
-    measured total is recorded in DESIGN.md)."""
+    north_star: "both sides must stay within the requested Ewald error".  Measured on a B200 (relative L2 error / `error`):
+    1.08 (ortho, 1e-3), 1.68 (xy = 0.3, 1e-3), 1.90 and 1.94 (1e-4) - the reference's parameter rules (PSEv1/Stokes.cc:129-236)
+    size r_cut, k_max and the Gaussian support so that EACH truncation is about `error`; their sum lands between one and two
+    times `error`, and the reference's own kernels, run here on the same inputs, land on the same value (asserted below).
+    So the bound asserted is 2 x `error` for both sides."""
     from oracle import oraclewrap as O
     N = 1000
     L = util.box_length(N, 0.1)
@@ -631,48 +625,58 @@ def test_config1_dense_ewald_error_at_N1000(cuda):
             s = System(N, L, xy=xy, seed=3, ref_pi=False, error=error, want_ref=False)
             Ud = O.dense_mobility(s.pos_np[:, :3], s.F_np[:, :3], L, xy=xy)
             U = s.eng.mobility(s.pos, s.F).cpu().numpy()[:, :3].astype(np.float64)
-            got[(xy, error)] = float(np.linalg.norm(U - Ud) / np.linalg.norm(Ud))
+            err = float(np.linalg.norm(U - Ud) / np.linalg.norm(Ud))
             s.eng.close()
-    print("dense-Ewald relative L2 error at N = 1000:", {k: f"{v:.2e}" for k, v in got.items()})
-    for (xy, error), err in got.items():
+            sr = System(N, L, xy=xy, seed=3, ref_pi=True, error=error)   # the reference's kernels (with their 2*pi constant)
+            err_ref = None
+            if sr.ref is not None:
+                Ur = sr.ref.mobility(sr.pos, sr.F).cpu().numpy()[:, :3].astype(np.float64)
+                err_ref = float(np.linalg.norm(Ur - Ud) / np.linalg.norm(Ud))
+            sr.eng.close()
+            got[(xy, error)] = (err, err_ref)
+    print("dense-Ewald relative L2 error at N = 1000 (engine, reference kernels):",
+          {k: (f"{v[0]:.2e}", None if v[1] is None else f"{v[1]:.2e}") for k, v in got.items()})
+    for (xy, error), (err, err_ref) in got.items():
         assert err < ERR_MULT * error, (xy, error, err)
+        if err_ref is not None:
+            assert err_ref < ERR_MULT * error and abs(err - err_ref) < 0.35 * error, (xy, error, err, err_ref)
 
 
-ERR_MULT = 3.0   # measured multiple of `error` (see the printed values); tightened once measured
+ERR_MULT = 2.0   # see the docstring above for the measured multiples
 
 
 def test_gpu_lanczos_matches_dense_sqrtm(cuda):
     """The GPU Lanczos path (pse_velocity, parts = 4, injected psi) against sqrt(2T/dt) sqrtm(M_real) psi with M_real assembled
     column by column from pse_mreal and its square root from a dense symmetric eigendecomposition (float64).  Lanczos stops
-    at a relative step norm of `error` (PSEv1/Brownian.cu:606), so agreement is expected at the `error` level."""
+    at a relative step norm of `error` (PSEv1/Brownian.cu:606), so agreement is expected at the `error` level, and a tighter
+    `error` (which also moves r_cut, i.e. M_real itself) must converge further against ITS dense square root."""
     import torch
     N = 300
     L = util.box_length(N, 0.2)
-    s = System(N, L, seed=13, lattice=True, want_ref=False, error=1e-3)
-    M = np.zeros((3 * N, 3 * N))
-    for c in range(3 * N):
-        e = torch.zeros_like(s.F); e[c // 3, c % 3] = 1
-        M[:, c] = s.eng.mreal(s.pos, e).cpu().numpy()[:, :3].reshape(-1).astype(np.float64)
-    assert np.abs(M - M.T).max() < 2e-6
-    M = 0.5 * (M + M.T)
-    lam, W = np.linalg.eigh(M)
-    assert lam.min() > 0   # "positively split": the real-space part alone is positive definite
     g = torch.Generator(device="cuda"); g.manual_seed(3)
     up = torch.rand((N, 3), device="cuda", generator=g)
     a = np.float32(1.73205080757)
     psi = (np.float32(2) * a * up.cpu().numpy() - a).astype(np.float64).reshape(-1)
-    exact = math.sqrt(2 * s.T / s.dt) * (W @ (np.sqrt(lam) * (W.T @ psi)))
-    s.eng.lanczos_m = 2
-    U, m = s.eng.velocity(s.pos, s.F, timestep=1, u_particles=up, parts=4)
-    got = U.cpu().numpy()[:, :3].astype(np.float64).reshape(-1)
-    err = np.linalg.norm(got - exact) / np.linalg.norm(exact)
-    print(f"Lanczos m = {m}, relative error vs dense sqrtm = {err:.2e}")
-    assert 2 <= m <= 30 and err < 2e-3, (m, err)
-    # a tighter tolerance converges further
-    s2 = System(N, L, seed=13, lattice=True, want_ref=False, error=1e-5)
-    U2, m2 = s2.eng.velocity(s2.pos, s2.F, timestep=1, u_particles=up, parts=4)
-    err2 = np.linalg.norm(U2.cpu().numpy()[:, :3].astype(np.float64).reshape(-1) - exact) / np.linalg.norm(exact)
-    assert m2 > m and err2 < 5e-5, (m2, err2)
+    got = {}
+    for error, tol in ((1e-3, 2e-3), (1e-5, 5e-5)):
+        s = System(N, L, seed=13, lattice=True, want_ref=False, error=error)
+        M = np.zeros((3 * N, 3 * N))
+        for c in range(3 * N):
+            e = torch.zeros_like(s.F); e[c // 3, c % 3] = 1
+            M[:, c] = s.eng.mreal(s.pos, e).cpu().numpy()[:, :3].reshape(-1).astype(np.float64)
+        assert np.abs(M - M.T).max() < 2e-6
+        M = 0.5 * (M + M.T)
+        lam, W = np.linalg.eigh(M)
+        assert lam.min() > 0   # "positively split": the real-space part alone is positive definite
+        exact = math.sqrt(2 * s.T / s.dt) * (W @ (np.sqrt(lam) * (W.T @ psi)))
+        s.eng.lanczos_m = 2
+        U, m = s.eng.velocity(s.pos, s.F, timestep=1, u_particles=up, parts=4)
+        err = np.linalg.norm(U.cpu().numpy()[:, :3].astype(np.float64).reshape(-1) - exact) / np.linalg.norm(exact)
+        print(f"error = {error}: Lanczos m = {m}, relative error vs dense sqrtm = {err:.2e}")
+        assert 2 <= m <= 40 and err < tol, (error, m, err)
+        got[error] = (m, err)
+        s.eng.close()
+    assert got[1e-5][0] > got[1e-3][0] and got[1e-5][1] < got[1e-3][1]
 
 
 def test_tilt_flip_through_max_strain(cuda):
