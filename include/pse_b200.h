@@ -212,28 +212,54 @@ int pse_set_profiling(pse_engine* e, int on);
 int pse_get_profile(pse_engine* e, double* ms_out, uint64_t* calls_out, int n);
 const char* pse_profile_phase_name(int i);
 
-/* ---- multi-GPU: slab-decomposed deterministic mobility (one engine per rank, replicated particle data) ------------
- * New work (the reference is single-GPU: "only one GPU is supported", PSEv1/Stokes.cc:104).  The engine exposes
- * the local phases; the caller issues the collectives between them on the buffers it owns:
- *   pse_shard_fwd     -> all-to-all (a2a_send_floats / a2a_recv_floats per peer, in floats)
- *   pse_shard_kspace  -> all-to-all back (roles of the two size arrays swapped)
- *   pse_shard_inv     -> send halo_floats to rank-1, receive from rank+1 (periodic)
- *   pse_shard_finish  -> all-reduce(SUM) of the N x float4 partial velocities
- * pse_b200/sharded.py does this with torch.distributed (NCCL). */
+/* ---- multi-GPU: slab decomposition of the WHOLE step (one engine per rank / GPU) -------------------------------------
+ * New work: the reference is single-GPU ("only one GPU is supported", PSEv1/Stokes.cc:104).
+ *
+ * After pse_shard_init every operator above (pse_mobility, pse_velocity, pse_step, pse_step_host ...) keeps its
+ * signature and meaning: each rank passes the SAME particle arrays and receives the SAME complete result, bit for bit.
+ * Inside, a rank works on its own particles only (a contiguous slot range: x layers of cells) and on its own x planes
+ * of the Fourier grid, and exchanges exactly what crosses a slab face; all collectives are issued from C++ on the
+ * engine's stream through the NCCL C API (bound with dlopen at run time, the copy the process already loaded):
+ *   real space   boundary rows of the multiplied vector to both neighbours before every Lanczos product
+ *                (ncclSend/ncclRecv), (alpha_j, |y|^2) in one two-float all-reduce per iteration;
+ *   wave space   halo planes added into the neighbours' planes after spreading and fetched before interpolation,
+ *                two all-to-all transposes (x slabs <-> y slabs) around the fused x pass;
+ *   velocities   one all-gather (N x 16 bytes in total) - positions stay replicated, no migration step.
+ * The step is issued eagerly (no CUDA graph) in this mode.  Needs the spread2/interp2 kernels (P = 6, 7, 8) and the
+ * engine's own FFT passes. */
 typedef struct {
     int rank, world;
-    int x0, x1;          /* own x planes of the grid */
-    int y0, y1;          /* own y rows in the transposed (k-space) layout */
-    uint32_t row0, row1; /* own rows (slots) of the real-space SpMV */
-    uint64_t a2a_send_floats[16], a2a_recv_floats[16];
-    uint64_t halo_floats;
+    int x0, x1;              /* own x planes of the grid */
+    int y0, y1;              /* own (stored) y rows of the transposed k-space layout */
+    int halo_left, halo_right; /* planes exchanged with the left / right neighbour */
+    int buffer_planes;       /* x planes of the local real-space buffer (own + halo + tile alignment) */
+    int layer0, layer1;      /* own x layers of cells (particle ownership) */
+    int halo_layers;         /* layers of cells whose vector rows come from each neighbour (0 before the first list build) */
+    uint32_t row0, row1;     /* own slots = rows of the real-space operator (0, 0 before the first list build) */
+    uint64_t a2a_send_bytes[16], a2a_recv_bytes[16]; /* forward transpose, per peer */
+    uint64_t bytes_sent;     /* payload this rank handed to the collectives since init */
+    uint64_t collectives;    /* collective calls issued since init */
 } pse_shard_info;
-int pse_shard_plan(const pse_config* cfg, int rank, int world, pse_shard_info* out); /* host only: the decomposition */
-int pse_shard_setup(pse_engine* e, int rank, int world, pse_shard_info* out);
-int pse_shard_fwd(pse_engine* e, const float4* d_pos, const float4* d_F, float* d_send);
-int pse_shard_kspace(pse_engine* e, const float* d_recv, float* d_send);
-int pse_shard_inv(pse_engine* e, const float* d_recv, float* d_halo_send);
-int pse_shard_finish(pse_engine* e, const float* d_halo_recv, float4* d_U);
+
+/* Host only (no GPU needed): the static part of the decomposition `cfg` gets on `world` ranks, as seen by `rank`.
+ * PSE_EINVAL when the grid is too small for that many slabs (a halo would reach past the adjacent rank). */
+int pse_shard_plan(const pse_config* cfg, int rank, int world, pse_shard_info* out);
+
+/* 128-byte NCCL unique id (ncclGetUniqueId); rank 0 creates it, the host layer broadcasts it to the other ranks. */
+int pse_comm_unique_id(uint8_t out[128]);
+
+/* In-process stand-in for the communicator: `world` engines of ONE process (one host thread each, any devices) exchange
+ * through device copies and a host barrier.  Used to run the multi-rank code path as virtual ranks on a single GPU in
+ * the parity tests; every collective is a host synchronisation point, so it says nothing about performance. */
+typedef struct pse_local_world pse_local_world;
+pse_local_world* pse_local_world_create(int world);
+void pse_local_world_destroy(pse_local_world* w);
+
+/* Turn `e` into rank `rank` of `world`.  Exactly one of nccl_uid128 (NCCL communicator over the ranks' GPUs; collective
+ * call: every rank must enter) and local (virtual ranks) is non-null; both may be null when world == 1.  Must be
+ * called before the first operator call.  Frees the single-GPU grids and allocates the rank's slabs. */
+int pse_shard_init(pse_engine* e, int rank, int world, const uint8_t* nccl_uid128, pse_local_world* local);
+int pse_shard_get_info(pse_engine* e, pse_shard_info* out);
 
 #ifdef __cplusplus
 }

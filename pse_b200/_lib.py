@@ -59,9 +59,18 @@ class pse_stats(ctypes.Structure):
 class pse_shard_info(ctypes.Structure):
     _fields_ = [
         ("rank", ctypes.c_int), ("world", ctypes.c_int), ("x0", ctypes.c_int), ("x1", ctypes.c_int),
-        ("y0", ctypes.c_int), ("y1", ctypes.c_int), ("row0", ctypes.c_uint32), ("row1", ctypes.c_uint32),
-        ("a2a_send_floats", ctypes.c_uint64 * 16), ("a2a_recv_floats", ctypes.c_uint64 * 16), ("halo_floats", ctypes.c_uint64),
+        ("y0", ctypes.c_int), ("y1", ctypes.c_int), ("halo_left", ctypes.c_int), ("halo_right", ctypes.c_int),
+        ("buffer_planes", ctypes.c_int), ("layer0", ctypes.c_int), ("layer1", ctypes.c_int), ("halo_layers", ctypes.c_int),
+        ("row0", ctypes.c_uint32), ("row1", ctypes.c_uint32),
+        ("a2a_send_bytes", ctypes.c_uint64 * 16), ("a2a_recv_bytes", ctypes.c_uint64 * 16),
+        ("bytes_sent", ctypes.c_uint64), ("collectives", ctypes.c_uint64),
     ]
+
+    def as_dict(self):
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        d["a2a_send_bytes"] = list(self.a2a_send_bytes)[: self.world]
+        d["a2a_recv_bytes"] = list(self.a2a_recv_bytes)[: self.world]
+        return d
 
 
 # every symbol include/pse_b200.h declares: name -> (restype, argtypes)
@@ -104,11 +113,11 @@ SYMBOLS = {
     "pse_pair_force": (_i, [_vp, _vp, ctypes.POINTER(pse_pair_params), _vp, _i]),
     "pse_get_stats": (_i, [_vp, ctypes.POINTER(pse_stats)]),
     "pse_shard_plan": (_i, [_cfgp, _i, _i, ctypes.POINTER(pse_shard_info)]),
-    "pse_shard_setup": (_i, [_vp, _i, _i, ctypes.POINTER(pse_shard_info)]),
-    "pse_shard_fwd": (_i, [_vp, _vp, _vp, _vp]),
-    "pse_shard_kspace": (_i, [_vp, _vp, _vp]),
-    "pse_shard_inv": (_i, [_vp, _vp, _vp]),
-    "pse_shard_finish": (_i, [_vp, _vp, _vp]),
+    "pse_comm_unique_id": (_i, [ctypes.POINTER(ctypes.c_uint8)]),
+    "pse_local_world_create": (_vp, [_i]),
+    "pse_local_world_destroy": (None, [_vp]),
+    "pse_shard_init": (_i, [_vp, _i, _i, ctypes.POINTER(ctypes.c_uint8), _vp]),
+    "pse_shard_get_info": (_i, [_vp, ctypes.POINTER(pse_shard_info)]),
     "pse_set_profiling": (_i, [_vp, _i]),
     "pse_get_profile": (_i, [_vp, ctypes.POINTER(_d), ctypes.POINTER(ctypes.c_uint64), _i]),
     "pse_profile_phase_name": (ctypes.c_char_p, [_i]),

@@ -71,17 +71,15 @@ __global__ void scan_block_kernel(const uint32_t* __restrict__ in, uint32_t* __r
     if (i < n) out[i] = incl - v;
     if (threadIdx.x == SCAN_BLOCK - 1) block_sums[blockIdx.x] = incl;
 }
-__global__ void scan_add_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ block_offs, uint32_t n,
-                                uint32_t* __restrict__ total_out) {
+__global__ void scan_add_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ block_offs, uint32_t n) {
     uint32_t i = blockIdx.x * SCAN_BLOCK + threadIdx.x;
     if (i < n) out[i] += block_offs[blockIdx.x];
-    if (total_out && i == n - 1) total_out[0] = 0;  // placeholder, real total written by caller kernel
 }
 
 // place particles into their cells (slot order inside a cell is made canonical afterwards)
 __global__ void cell_fill_kernel(const uint32_t* __restrict__ cell_of, uint32_t N, const uint32_t* __restrict__ cell_start,
-                                 uint32_t* __restrict__ cell_fill, uint32_t* __restrict__ perm) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+                                 uint32_t* __restrict__ cell_fill, uint32_t* __restrict__ perm, uint32_t begin = 0) {
+    uint32_t i = begin + blockIdx.x * blockDim.x + threadIdx.x;  // items [begin, N)
     if (i >= N) return;
     uint32_t c = cell_of[i];
     if (c == 0xffffffffu) return;  // not binned (sharded wave binning leaves out particles of other slabs)
@@ -186,8 +184,9 @@ __device__ __forceinline__ CellRange make_range(float f, float reach, int nc) {
 // (adjacent rows share cache lines).
 __global__ void nlist_kernel(const float4* __restrict__ spos, uint32_t N, PseBox box, CellGrid cg,
                              const uint32_t* __restrict__ cell_start, float rlist_sq, uint32_t cap, uint32_t* __restrict__ nn,
-                             uint32_t* __restrict__ nl, uint32_t* __restrict__ max_nn) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+                             uint32_t* __restrict__ nl, uint32_t* __restrict__ max_nn, uint32_t row_begin = 0) {
+    // rows [row_begin, N) (a slab-decomposed rank searches for its own rows only; scratch rows are relative to row_begin)
+    uint32_t i = row_begin + blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t count = 0;
     if (i < N) {
         float4 pi = __ldg(spos + i);
@@ -197,7 +196,7 @@ __global__ void nlist_kernel(const float4* __restrict__ spos, uint32_t N, PseBox
         CellRange rx = make_range(f.x, cg.reach_fx, cg.ncx);
         CellRange ry = make_range(f.y, cg.reach_fy, cg.ncy);
         CellRange rz = make_range(f.z, cg.reach_fz, cg.ncz);
-        uint32_t* __restrict__ row = nl + (size_t)i * cap;
+        uint32_t* __restrict__ row = nl + (size_t)(i - row_begin) * cap;
         for (int tx = 0; tx < rx.len; ++tx) {
             int cx = rx.at(tx);
             for (int ty = 0; ty < ry.len; ++ty) {
@@ -241,12 +240,12 @@ __global__ void nnz_kernel(const uint32_t* __restrict__ nn, uint32_t N, unsigned
 
 // ell[slot * cap + k] -> nl[head[slot] + k], 8 lanes per row
 __global__ void compact_rows_kernel(const uint32_t* __restrict__ ell, uint32_t cap, const uint32_t* __restrict__ nn,
-                                    const uint32_t* __restrict__ head, uint32_t N, uint32_t* __restrict__ nl) {
-    const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+                                    const uint32_t* __restrict__ head, uint32_t N, uint32_t* __restrict__ nl, uint32_t row_begin = 0) {
+    const uint32_t row = row_begin + ((blockIdx.x * blockDim.x + threadIdx.x) >> 3);
     const uint32_t sub = threadIdx.x & 7;
     if (row >= N) return;
     const uint32_t n = nn[row], h = head[row];
-    const uint32_t* __restrict__ src = ell + (size_t)row * cap;
+    const uint32_t* __restrict__ src = ell + (size_t)(row - row_begin) * cap;
     for (uint32_t k = sub; k < n; k += 8) nl[h + k] = __ldg(src + k);
 }
 
@@ -284,4 +283,11 @@ __global__ void export_rows_kernel(const uint32_t* __restrict__ nn, const uint32
         while (j > 0 && row[j - 1] > v) { row[j] = row[j - 1]; --j; }
         row[j] = v;
     }
+}
+
+// first slot of every x layer of cells: layer_start[cx] = cell_start[cx * ncy * ncz], cx in [0, ncx]  (slab bounds of the
+// multi-GPU decomposition are cut at layer boundaries; slots are x-major, so a range of layers is a contiguous slot range)
+__global__ void layer_start_kernel(const uint32_t* __restrict__ cell_start, int ncx, int layer_cells, uint32_t* __restrict__ out) {
+    const int cx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cx <= ncx) out[cx] = cell_start[(size_t)cx * layer_cells];
 }

@@ -23,6 +23,7 @@
 #include "wave_tiled.cuh"
 #include "wave_v2.cuh"
 #include "fft.cuh"
+#include "comm.cuh"
 
 int pse_tridiag_sqrt_e1(int m, const double* diag, const double* off, double* c, double* lambda_min_out);
 int pse_fit_rpy_cheb(double xi, double rcut, float* out, double* max_err_out);
@@ -33,11 +34,57 @@ static char g_create_error[512] = "no error";
 
 // phases for the optional CUDA-event profile (pse_set_profiling / pse_get_profile)
 enum Phase { PH_BIN = 0, PH_NLIST, PH_REORDER, PH_WBIN, PH_SPREAD, PH_FFT_FWD, PH_SCALE, PH_FFT_INV, PH_INTERP, PH_PRUNE, PH_SPMV,
-             PH_LANCZOS_SPMV, PH_LANCZOS_VEC, PH_COMBINE, PH_INTEGRATE, PH_COUNT };
+             PH_LANCZOS_SPMV, PH_LANCZOS_VEC, PH_COMBINE, PH_INTEGRATE, PH_COMM, PH_COUNT };
 static const char* kPhaseNames[PH_COUNT] = {"bin", "nlist", "reorder", "wave_bin", "spread", "fft_r2c", "scale", "fft_c2r",
-                                            "interp", "prune", "spmv", "lanczos_spmv", "lanczos_vec", "combine", "integrate"};
+                                            "interp", "prune", "spmv", "lanczos_spmv", "lanczos_vec", "combine", "integrate", "comm"};
 struct ProfSpan { int phase; cudaEvent_t a, b; };
-struct ShardState;
+// ---- multi-GPU slab decomposition of the whole step (new work: the reference is single-GPU, PSEv1/Stokes.cc:104) ---------------
+// One engine per rank / GPU.  Particle arrays at the C ABI stay replicated (every rank passes the same pos / F and gets the
+// same complete velocity back, so the plugin-facing calls are unchanged); every internal phase works on the rank's OWN
+// particles only - a contiguous range of slots, because slots are x-major cell order and ownership is cut at x layers of
+// cells - and exchanges exactly what crosses a slab face:
+//   real space   neighbour list, pruning, SpMV and the Lanczos vectors for the own rows; the multiplied vector's boundary rows
+//                go to the two neighbours before every product (ncclSend/ncclRecv); alpha_j and |y|^2 in ONE two-float
+//                all-reduce per iteration;
+//   wave space   own particles are spread into a local buffer of own planes + halo planes; halo planes are added into the
+//                neighbours' planes; z / y FFT passes on the own planes, all-to-all transpose to y slabs, fused x pass +
+//                scaling, all-to-all back, inverse passes; halo planes fetched from the neighbours; interpolation of the own
+//                particles;
+//   velocities   all-gathered in slot order (N x 16 B in total) so that every rank integrates every particle (positions stay
+//                replicated and bitwise identical, no position exchange, no migration step).
+// All collectives are issued from C++ on the engine's stream (comm.cuh), nothing goes through Python.
+#define SHARD_MAX_WORLD 16
+#define SHARD_DRIFT_NODES 2.0f
+struct ShardBounds { int xs[SHARD_MAX_WORLD + 1], ys[SHARD_MAX_WORLD + 1]; int world; };   // kernel argument: plane / y-row bounds
+struct ShardGeom {                        // identical on every rank (derived from replicated data only)
+    int world;
+    int X[SHARD_MAX_WORLD + 1];           // plane bounds: rank r transforms x planes [X[r], X[r + 1])
+    int YS[SHARD_MAX_WORLD + 1];          // stored y rows of the transposed (k-space) layout
+    int LB[SHARD_MAX_WORLD + 1];          // x layers of cells: particle ownership
+    int HL, HR;                           // halo planes exchanged with the left / right neighbour
+    // recomputed at every neighbour-list rebuild
+    int KH;                               // x layers of cells whose vector rows come from each neighbour
+    uint32_t ROW[SHARD_MAX_WORLD + 1];    // slot bounds
+    uint32_t SL1[SHARD_MAX_WORLD];        // a rank's first KH layers are rows [ROW[r], SL1[r])  (sent to its left neighbour)
+    uint32_t SR0[SHARD_MAX_WORLD];        // its last KH layers are rows [SR0[r], ROW[r + 1])    (sent to its right neighbour)
+};
+struct ShardState {
+    PseComm comm;
+    int rank, world;
+    ShardGeom g;
+    int BL, nown, xorg, nxa;              // own rank: planes in front of the own planes in the local buffer (>= HL, tile aligned)
+    size_t plane, Gl;                     // Ny * Nz, component stride of the local buffer
+    float2 *d_sloc, *d_tr;                // own x-slab of the spectrum / own y-slab after the transpose
+    float *d_a2a_a, *d_a2a_b;             // all-to-all blocks (x-slab side, y-slab side)
+    size_t a2a_send_off[SHARD_MAX_WORLD + 1], a2a_recv_off[SHARD_MAX_WORLD + 1];   // bytes, forward transpose
+    float *d_hsL, *d_hsR, *d_hrL, *d_hrR; // halo planes: send left / right, received from left / right
+    float4* d_uslot;                      // velocities in slot order (own rows computed, the rest all-gathered)
+    float4 *d_vsL, *d_vsR, *d_vrL, *d_vrR; // boundary rows of the multiplied vector: send left / right, received from left / right
+    size_t vcap;                          // rows each of them holds
+    uint32_t *d_layer_start, *h_layer_start;
+    uint64_t bytes_sent;                  // per-rank payload handed to the collectives since init (statistics)
+    uint64_t collectives;
+};
 static void shard_free(ShardState* s);
 
 struct pse_engine {
@@ -117,7 +164,11 @@ struct pse_engine {
     float4 *d_hpos, *d_hF;  // device staging for pse_step_host
     int3* d_himage;
     int num_sms;
-    struct ShardState* shard;  // multi-GPU slab decomposition of the deterministic mobility (pse_shard_*)
+    struct ShardState* shard;  // multi-GPU slab decomposition of the whole step (pse_shard_init); null = single GPU
+    uint32_t row0, row1;       // slots (rows) this engine works on: [0, N) unless slab-decomposed
+    size_t v_rows;             // rows per Krylov vector in d_V
+    size_t grid_planes;        // x planes allocated in d_grid (Nx unless slab-decomposed)
+    float* d_red2;             // slab-decomposed Lanczos: (alpha_j, |y|^2) partial sums -> all-reduced pair
     // per-step device scalars + captured step graph
     StepDev* d_stepdev;
     StepDev* h_stepdev;  // pinned
@@ -228,7 +279,7 @@ static int exclusive_scan(pse_engine* e, const uint32_t* in, uint32_t* out, uint
     if (nb > 1) {
         uint32_t* next = tmp + ((nb + 31) / 32) * 32;
         CKRC(exclusive_scan(e, tmp, tmp, nb, next));
-        scan_add_kernel<<<nb, SCAN_BLOCK, 0, e->stream>>>(out, tmp, n, nullptr);
+        scan_add_kernel<<<nb, SCAN_BLOCK, 0, e->stream>>>(out, tmp, n);
         LAUNCHED(e);
     }
     return PSE_OK;
@@ -240,20 +291,24 @@ static void refresh_box(pse_engine* e, const pse_box& b) {
     e->box = pse_make_box(b.Lx, b.Ly, b.Lz, b.xy);
 }
 
-static void setup_cell_grid(pse_engine* e) {
-    // cells of about half the list radius; the fractional x reach is widened by the tilt
-    const float target = e->rlist * 0.5f;
-    CellGrid& cg = e->cg;
-    cg.ncx = (int)fmaxf(1.f, floorf(e->box.Lx / target));
-    cg.ncy = (int)fmaxf(1.f, floorf(e->box.Ly / target));
-    cg.ncz = (int)fmaxf(1.f, floorf(e->box.Lz / target));
-    // bound the cell count by the number of particles (sparse systems) and by memory
-    while ((size_t)cg.ncx * cg.ncy * cg.ncz > e->cell_cap) {
-        if (cg.ncx >= cg.ncy && cg.ncx >= cg.ncz) cg.ncx = (cg.ncx + 1) / 2;
-        else if (cg.ncy >= cg.ncz) cg.ncy = (cg.ncy + 1) / 2;
-        else cg.ncz = (cg.ncz + 1) / 2;
+// cells of about half the list radius, bounded by `cell_cap` cells (sparse systems / memory); host-only so that the
+// multi-GPU planner (pse_shard_plan) sees the same x layers as the engine
+static void cell_grid_dims(float Lx, float Ly, float Lz, float rlist, size_t cell_cap, int* ncx, int* ncy, int* ncz) {
+    const float target = rlist * 0.5f;
+    int cx = (int)fmaxf(1.f, floorf(Lx / target)), cy = (int)fmaxf(1.f, floorf(Ly / target)), cz = (int)fmaxf(1.f, floorf(Lz / target));
+    while ((size_t)cx * cy * cz > cell_cap) {
+        if (cx >= cy && cx >= cz) cx = (cx + 1) / 2;
+        else if (cy >= cz) cy = (cy + 1) / 2;
+        else cz = (cz + 1) / 2;
     }
+    *ncx = cx; *ncy = cy; *ncz = cz;
+}
+static inline size_t cell_capacity(size_t N) { return std::max<size_t>(4096, 4 * N); }
+static void setup_cell_grid(pse_engine* e) {
+    CellGrid& cg = e->cg;
+    cell_grid_dims(e->box.Lx, e->box.Ly, e->box.Lz, e->rlist, e->cell_cap, &cg.ncx, &cg.ncy, &cg.ncz);
     cg.ncell = cg.ncx * cg.ncy * cg.ncz;
+    // the fractional x reach is widened by the tilt
     const float xy = fabsf(e->box.xy);
     const float safety = 1.0001f;
     cg.reach_fx = e->rlist * sqrtf(1.f + xy * xy) / e->box.Lx * safety + 1e-6f;
@@ -268,7 +323,7 @@ static int alloc_all(pse_engine* e) {
     const size_t N = e->N;
     const pse_params& p = e->prm;
     CK(cudaMalloc(&e->d_table, sizeof(float4) * (p.ewald_n + 1)));
-    e->cell_cap = std::max<size_t>(4096, 4 * N);
+    e->cell_cap = cell_capacity(N);
     CK(cudaMalloc(&e->d_cell_of, sizeof(uint32_t) * N));
     CK(cudaMalloc(&e->d_cell_count, sizeof(uint32_t) * (e->cell_cap + 1)));
     CK(cudaMalloc(&e->d_cell_start, sizeof(uint32_t) * (e->cell_cap + 1)));
@@ -290,20 +345,22 @@ static int alloc_all(pse_engine* e) {
     CK(cudaMalloc(&e->d_nlinfo, 2 * sizeof(unsigned long long)));
     CK(cudaMallocHost(&e->h_nlinfo, 2 * sizeof(unsigned long long)));
     CK(cudaMalloc(&e->d_pos_build, sizeof(float4) * N));
-    CK(cudaMalloc(&e->d_flag, sizeof(uint32_t)));
-    CK(cudaMallocHost(&e->h_flag, sizeof(uint32_t)));
+    CK(cudaMalloc(&e->d_flag, 2 * sizeof(uint32_t)));   // [0] largest squared displacement (bits), [1] slab-coverage guard
+    CK(cudaMemset(e->d_flag, 0, 2 * sizeof(uint32_t)));
+    CK(cudaMallocHost(&e->h_flag, 2 * sizeof(uint32_t)));
     CK(cudaEventCreateWithFlags(&e->flag_event, cudaEventDisableTiming));
-    CK(cudaMalloc(&e->d_grid, sizeof(float) * 3 * e->G));
-    CK(cudaMalloc(&e->d_spec, sizeof(float2) * 3 * e->Gh));
-    CK(cudaMalloc(&e->d_V, sizeof(float4) * N * LANCZOS_M_MAX));
+    // the real grids, the spectra and the Krylov basis are allocated at first use (ensure_wave_buffers / ensure_krylov):
+    // a slab-decomposed engine (pse_shard_init) only ever holds its own slab of each
+    e->d_grid = nullptr; e->d_spec = nullptr; e->d_V = nullptr; e->v_rows = 0; e->grid_planes = 0;
+    CK(cudaMalloc(&e->d_red2, 2 * sizeof(float)));
     CK(cudaMalloc(&e->d_u, sizeof(float4) * N));
     CK(cudaMalloc(&e->d_y, sizeof(float4) * N));
     CK(cudaMalloc(&e->d_alpha, sizeof(float) * (LANCZOS_M_MAX + 2)));
     CK(cudaMalloc(&e->d_beta, sizeof(float) * (LANCZOS_M_MAX + 2)));
     CK(cudaMalloc(&e->d_coef, sizeof(float) * (LANCZOS_M_MAX + 2)));
     CK(cudaMalloc(&e->d_partials, sizeof(float) * (N / 8 + 1024)));
-    CK(cudaMalloc(&e->d_counter, sizeof(unsigned int)));
-    CK(cudaMemset(e->d_counter, 0, sizeof(unsigned int)));
+    CK(cudaMalloc(&e->d_counter, 2 * sizeof(unsigned int)));
+    CK(cudaMemset(e->d_counter, 0, 2 * sizeof(unsigned int)));
     CK(cudaMallocHost(&e->h_ab, sizeof(float) * (3 * LANCZOS_M_MAX + 8)));  // + the combination coefficients
     CK(cudaMalloc(&e->d_vel_work, sizeof(float4) * N));
     CK(cudaMalloc(&e->d_stepdev, sizeof(StepDev)));
@@ -477,6 +534,7 @@ extern "C" int pse_create(const pse_config* cfg, void* stream, pse_engine** out)
     wp.hx = prm.hx; wp.hy = prm.hy; wp.hz = prm.hz;
     wp.prefac = prm.prefac; wp.expfac = prm.expfac; wp.quadW = prm.quadW;
     wp.xi = c.xi; wp.eta = prm.eta;
+    wp.xorg = 0; wp.nxa = prm.Nx; wp.nxw = prm.Nx;
     wp.two_pi_k = (c.flags & PSE_FLAG_REF_PI) ? (float)(2.0 * 3.1416926536) : (float)(2.0 * 3.14159265358979323846);
     e->Gh = (size_t)prm.Nx * prm.Ny * wp.Nzp;
     RealParams& rp = e->rp;
@@ -505,6 +563,7 @@ extern "C" int pse_create(const pse_config* cfg, void* stream, pse_engine** out)
         if (tpp) e->spmv_tpp = atoi(tpp);
     }
     e->m_lanczos = 2;  // PSEv1/Stokes.cc:132
+    e->row0 = 0; e->row1 = c.N;
     e->prof_pool = new std::vector<cudaEvent_t>();
     e->prof_spans = new std::vector<ProfSpan>();
 
@@ -555,7 +614,7 @@ extern "C" void pse_destroy(pse_engine* e) {
     void* bufs[] = {e->d_table, e->d_cell_of, e->d_cell_count, e->d_cell_start, e->d_scan_tmp, e->d_perm, e->d_slot_of,
                     e->d_spos, e->d_sx, e->d_sy, e->d_px, e->d_nn, e->d_head, e->d_nl, e->d_pos_build, e->d_flag, e->d_grid,
                     e->d_spec, e->d_V, e->d_u, e->d_y, e->d_alpha, e->d_beta, e->d_coef, e->d_partials, e->d_counter,
-                    e->d_vel_work, e->d_hpos, e->d_hF, e->d_himage, e->d_org, e->d_worg, e->d_wcell_of, e->d_wcount,
+                    e->d_vel_work, e->d_hpos, e->d_hF, e->d_himage, e->d_red2, e->d_org, e->d_worg, e->d_wcell_of, e->d_wcount,
                     e->d_wstart, e->d_wperm, e->d_wid, e->d_wpos, e->d_wF, e->d_wwt, e->d_wrecs, e->d_wtmp, e->d_ell, e->d_nn_act, e->d_nl_act};
     for (void* b : bufs)
         if (b) cudaFree(b);
@@ -625,7 +684,7 @@ extern "C" int pse_get_stats(pse_engine* e, pse_stats* out) {
     out->nnz_active = e->nnz;
     if (e->prune && e->pruned_valid && e->nlist_valid) {
         CK(cudaMemsetAsync(e->d_nlinfo, 0, sizeof(unsigned long long), e->stream));
-        nnz_kernel<<<e->num_sms, 256, 0, e->stream>>>(e->d_nn_act, e->N, e->d_nlinfo);
+        nnz_kernel<<<e->num_sms, 256, 0, e->stream>>>(e->d_nn_act + e->row0, e->row1 - e->row0, e->d_nlinfo);
         CK(cudaMemcpyAsync(e->h_nlinfo, e->d_nlinfo, sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
         CK(cudaStreamSynchronize(e->stream));
         out->nnz_active = e->h_nlinfo[0];
@@ -633,6 +692,26 @@ extern "C" int pse_get_stats(pse_engine* e, pse_stats* out) {
     out->nlist_builds = e->nlist_builds; out->lanczos_m = e->m_lanczos; out->lanczos_stepnorm = e->last_stepnorm;
     return PSE_OK;
 }
+
+// ---- lazily allocated big buffers ---------------------------------------------------------------------
+static int ensure_wave_buffers(pse_engine* e) {
+    if (e->d_grid) return PSE_OK;
+    if (e->shard) return fail(e, PSE_ECUDA, "slab buffers missing");   // allocated by pse_shard_init
+    CK(cudaMalloc(&e->d_grid, sizeof(float) * 3 * e->G));
+    CK(cudaMalloc(&e->d_spec, sizeof(float2) * 3 * e->Gh));
+    e->grid_planes = e->wp.Nx;
+    return PSE_OK;
+}
+static int ensure_krylov(pse_engine* e) {
+    const size_t rows = e->row1 - e->row0;
+    if (e->d_V && rows <= e->v_rows) return PSE_OK;
+    if (e->d_V) { CK(cudaStreamSynchronize(e->stream)); cudaFree(e->d_V); e->d_V = nullptr; }
+    e->v_rows = e->shard ? (size_t)(rows * 1.15) + 4096 : e->N;
+    CK(cudaMalloc(&e->d_V, sizeof(float4) * e->v_rows * LANCZOS_M_MAX));
+    e->nl_gen++;   // a captured graph holds the old pointer
+    return PSE_OK;
+}
+static int shard_update_geometry(pse_engine* e);
 
 // ---- binning + neighbour list ------------------------------------------------------------------
 extern "C" int pse_build_neighbors(pse_engine* e, const float4* d_pos) {
@@ -651,6 +730,9 @@ extern "C" int pse_build_neighbors(pse_engine* e, const float4* d_pos) {
     cell_sort_kernel<<<nblk(ncell, 128), 128, 0, st>>>(e->d_cell_start, ncell, e->d_perm); LAUNCHED(e);
     invert_perm_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_perm, N, e->d_slot_of); LAUNCHED(e);
     gather_pos_kernel<<<nblk(N, 256), 256, 0, st>>>(d_pos, e->d_perm, N, e->d_spos, (float4*)e->d_px); LAUNCHED(e);
+    // slab-decomposed: the binning above is replicated (identical on every rank); everything below is for the own rows
+    if (e->shard) CKRC(shard_update_geometry(e));
+    const uint32_t r0 = e->row0, r1 = e->row1, nrows = r1 - r0;
 
     delete ps;
     ps = new ProfScope(e, PH_NLIST);
@@ -662,21 +744,23 @@ extern "C" int pse_build_neighbors(pse_engine* e, const float4* d_pos) {
         e->nl_stride = (uint32_t)(((size_t)(1.5 * expect + 24.0) + 7) / 8 * 8);
         if (e->nl_stride > N) e->nl_stride = ((N + 7) / 8) * 8;
     }
-    CK(cudaMemsetAsync(e->d_nn + N, 0, sizeof(uint32_t), st));
+    CK(cudaMemsetAsync(e->d_nn + r1, 0, sizeof(uint32_t), st));   // (entry r1 closes the scan; with r1 < N it is another rank's row)
     for (int attempt = 0; attempt < 3; ++attempt) {
-        const size_t need = (size_t)N * e->nl_stride;
+        const size_t need = (size_t)std::max<uint32_t>(nrows, 1) * e->nl_stride;
         if (need > e->ell_cap) {
             if (e->d_ell) cudaFree(e->d_ell);
             e->d_ell = nullptr;
-            e->ell_cap = need;
+            e->ell_cap = need + need / 8;
             CK(cudaMalloc(&e->d_ell, sizeof(uint32_t) * e->ell_cap));
         }
         CK(cudaMemsetAsync(e->d_nlinfo, 0, 2 * sizeof(unsigned long long), st));
-        nlist_kernel<<<nblk(N, 128), 128, 0, st>>>(e->d_spos, N, e->box, cg, e->d_cell_start, rl2, e->nl_stride, e->d_nn, e->d_ell,
-                                                   (uint32_t*)(e->d_nlinfo + 1)); LAUNCHED(e);
-        CKRC(exclusive_scan(e, e->d_nn, e->d_head, N + 1, e->d_scan_tmp));
+        if (nrows) {
+            nlist_kernel<<<nblk(nrows, 128), 128, 0, st>>>(e->d_spos, r1, e->box, cg, e->d_cell_start, rl2, e->nl_stride, e->d_nn, e->d_ell,
+                                                           (uint32_t*)(e->d_nlinfo + 1), r0); LAUNCHED(e);
+        }
+        CKRC(exclusive_scan(e, e->d_nn + r0, e->d_head + r0, nrows + 1, e->d_scan_tmp));
         CK(cudaMemcpyAsync(e->h_nlinfo, e->d_nlinfo, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(e->h_flag, e->d_head + N, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(e->h_flag, e->d_head + r1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         const uint32_t max_nn = (uint32_t)e->h_nlinfo[1];
         e->nnz = *e->h_flag;
@@ -698,7 +782,9 @@ extern "C" int pse_build_neighbors(pse_engine* e, const float4* d_pos) {
         CK(cudaMalloc(&e->d_nl_act, sizeof(uint32_t) * e->nl_act_cap));
         e->nl_gen++;
     }
-    compact_rows_kernel<<<nblk((size_t)N * 8, 256), 256, 0, st>>>(e->d_ell, e->nl_stride, e->d_nn, e->d_head, N, e->d_nl); LAUNCHED(e);
+    if (nrows) {
+        compact_rows_kernel<<<nblk((size_t)nrows * 8, 256), 256, 0, st>>>(e->d_ell, e->nl_stride, e->d_nn, e->d_head, r1, e->d_nl, r0); LAUNCHED(e);
+    }
     CK(cudaMemcpyAsync(e->d_pos_build, d_pos, sizeof(float4) * N, cudaMemcpyDeviceToDevice, st));
     delete ps;
     e->xy_build = e->box.xy;
@@ -714,13 +800,17 @@ static bool stale_from_bits(const pse_engine* e, uint32_t bits) {
     float r2;
     memcpy(&r2, &bits, 4);
     const float drift = fabsf(e->box.xy - e->xy_build) * e->rlist;
-    return 2.f * sqrtf(r2) + drift > e->cfg.r_buff;
+    if (2.f * sqrtf(r2) + drift > e->cfg.r_buff) return true;
+    // slab-decomposed: a rank's particles must keep their Gaussian supports inside its local grid buffer, whose halo was
+    // sized for a drift of SHARD_DRIFT_NODES nodes of the sheared frame at |y| = Ly / 2 (shard_static_geometry)
+    if (e->shard && fabsf(e->box.xy - e->xy_build) * 0.5f * e->box.Ly > SHARD_DRIFT_NODES * e->wp.hx) return true;
+    return false;
 }
 static int launch_disp_check(pse_engine* e, const float4* d_pos) {
     ProfScope ps(e, PH_REORDER);
     CK(cudaMemsetAsync(e->d_flag, 0, sizeof(uint32_t), e->stream));
     max_disp_kernel<<<nblk(e->N, 256), 256, 0, e->stream>>>(d_pos, e->d_pos_build, e->N, e->box, e->d_flag); LAUNCHED(e);
-    CK(cudaMemcpyAsync(e->h_flag, e->d_flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(e->h_flag, e->d_flag, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaEventRecord(e->flag_event, e->stream));
     e->flag_pending = true;
     return PSE_OK;
@@ -732,6 +822,7 @@ static int ensure_neighbors(pse_engine* e, const float4* d_pos) {
         CKRC(launch_disp_check(e, d_pos));
         CK(cudaEventSynchronize(e->flag_event));
         e->flag_pending = false;
+        if (e->h_flag[1]) return fail(e, PSE_EINVAL, "slab decomposition: a particle's Gaussian support left the rank's grid buffer (halo too thin)");
         rebuild = stale_from_bits(e, *e->h_flag);
     }
     if (rebuild) {
@@ -748,8 +839,8 @@ static int ensure_neighbors(pse_engine* e, const float4* d_pos) {
 static int ensure_pruned(pse_engine* e) {
     if (!e->prune || e->pruned_valid) return PSE_OK;
     ProfScope ps(e, PH_PRUNE);
-    prune_kernel<<<persistent_grid(e, nblk((size_t)e->N * 8, 256), 8), 256, 0, e->stream>>>(e->d_spos, e->N, e->d_nn, e->d_head, e->d_nl, e->rp,
-                                                                                         e->box, e->d_nn_act, e->d_nl_act); LAUNCHED(e);
+    prune_kernel<<<persistent_grid(e, nblk((size_t)(e->row1 - e->row0) * 8, 256), 8), 256, 0, e->stream>>>(e->d_spos, e->row1, e->d_nn, e->d_head, e->d_nl, e->rp,
+                                                                                         e->box, e->d_nn_act, e->d_nl_act, e->row0); LAUNCHED(e);
     e->pruned_valid = true;
     return PSE_OK;
 }
@@ -758,6 +849,7 @@ extern "C" int pse_neighbor_list(pse_engine* e, uint32_t* d_n_neigh, uint32_t* d
                                  size_t cap, size_t* nnz_out) {
     if (!e) return PSE_EINVAL;
     if (!e->nlist_valid) return fail(e, PSE_EINVAL, "pse_neighbor_list: no list built yet");
+    if (e->shard && e->shard->world > 1) return fail(e, PSE_EINVAL, "pse_neighbor_list: a slab-decomposed engine holds the rows of its own slab only");
     if (nnz_out) *nnz_out = e->nnz;
     if (!d_n_neigh && !d_headlist && !d_nlist) return PSE_OK;
     const uint32_t N = e->N;
@@ -789,36 +881,36 @@ extern "C" int pse_grid_index(pse_engine* e, const float4* d_pos, int3* d_out) {
 // ---- building blocks (slot order) -----------------------------------------------------------------
 template <int TPP, int MODE, bool PRUNED>
 static void launch_spmv_tpp(pse_engine* e, float4* y, const LanczosArgs& la) {
-    const unsigned int work = nblk((size_t)e->N * TPP, 256);
+    const unsigned int work = nblk((size_t)(e->row1 - e->row0) * TPP, 256);   // rows [row0, row1): all of them unless slab-decomposed
     const uint32_t* nn = PRUNED ? e->d_nn_act : e->d_nn;
     const uint32_t* nl = PRUNED ? e->d_nl_act : e->d_nl;
     if (e->spmv_table_mode == TABLE_POLY) {
         spmv_kernel<TPP, MODE, TABLE_POLY, PRUNED><<<persistent_grid(e, work, e->spmv_bps > 0 ? e->spmv_bps : 8), 256, 0, e->stream>>>(
-            e->d_px, y, e->N, nn, e->d_head, nl, e->d_table, e->cheb, e->rp, e->box, la);
+            e->d_px, y, e->row1, nn, e->d_head, nl, e->d_table, e->cheb, e->rp, e->box, la, e->row0);
     } else if (e->spmv_table_mode == TABLE_SHARED) {
         const size_t sm = spmv_table_smem(e);
         int bps = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (sm + 1024)));
         if (e->spmv_bps > 0) bps = std::min(bps, e->spmv_bps);
         cudaFuncSetAttribute(spmv_kernel<TPP, MODE, TABLE_SHARED, PRUNED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         spmv_kernel<TPP, MODE, TABLE_SHARED, PRUNED><<<persistent_grid(e, work, bps), 256, sm, e->stream>>>(
-            e->d_px, y, e->N, nn, e->d_head, nl, e->d_table, e->cheb, e->rp, e->box, la);
+            e->d_px, y, e->row1, nn, e->d_head, nl, e->d_table, e->cheb, e->rp, e->box, la, e->row0);
     } else {
         spmv_kernel<TPP, MODE, TABLE_GLOBAL, PRUNED><<<persistent_grid(e, work, e->spmv_bps > 0 ? e->spmv_bps : 8), 256, 0, e->stream>>>(
-            e->d_px, y, e->N, nn, e->d_head, nl, e->d_table, e->cheb, e->rp, e->box, la);
+            e->d_px, y, e->row1, nn, e->d_head, nl, e->d_table, e->cheb, e->rp, e->box, la, e->row0);
     }
     LAUNCHED(e);
 }
 // first Lanczos product of a full step with M_real F riding along (poly / global table modes, pruned lists)
 static bool launch_spmv_dual(pse_engine* e, float4* y, const LanczosArgs& la, const float4* x2, float4* y2) {
     if (!e->prune || !e->spmv_dual || e->spmv_tpp != 4 || e->spmv_table_mode == TABLE_SHARED) return false;
-    const unsigned int work = nblk((size_t)e->N * 4, 256);
+    const unsigned int work = nblk((size_t)(e->row1 - e->row0) * 4, 256);
     const unsigned int grid = persistent_grid(e, work, e->spmv_bps > 0 ? e->spmv_bps : 8);
     if (e->spmv_table_mode == TABLE_POLY)
-        spmv_kernel<4, SPMV_LANCZOS, TABLE_POLY, true, true><<<grid, 256, 0, e->stream>>>(e->d_px, y, e->N, e->d_nn_act, e->d_head, e->d_nl_act, e->d_table,
-                                                                                     e->cheb, e->rp, e->box, la, 0, x2, y2);
+        spmv_kernel<4, SPMV_LANCZOS, TABLE_POLY, true, true><<<grid, 256, 0, e->stream>>>(e->d_px, y, e->row1, e->d_nn_act, e->d_head, e->d_nl_act, e->d_table,
+                                                                                     e->cheb, e->rp, e->box, la, e->row0, x2, y2);
     else
-        spmv_kernel<4, SPMV_LANCZOS, TABLE_GLOBAL, true, true><<<grid, 256, 0, e->stream>>>(e->d_px, y, e->N, e->d_nn_act, e->d_head, e->d_nl_act, e->d_table,
-                                                                                       e->cheb, e->rp, e->box, la, 0, x2, y2);
+        spmv_kernel<4, SPMV_LANCZOS, TABLE_GLOBAL, true, true><<<grid, 256, 0, e->stream>>>(e->d_px, y, e->row1, e->d_nn_act, e->d_head, e->d_nl_act, e->d_table,
+                                                                                       e->cheb, e->rp, e->box, la, e->row0, x2, y2);
     LAUNCHED(e);
     return true;
 }
@@ -941,26 +1033,35 @@ static int run_wave(pse_engine* e, const float4* sF, float4* U, int accumulate, 
     return PSE_OK;
 }
 
-// one Lanczos iteration j (two kernels)
-static void lanczos_iteration(pse_engine* e, int j, bool dual = false) {
-    const uint32_t N = e->N;
-    float4* Vj = e->d_V + (size_t)j * N;
+// one Lanczos iteration j (two kernels).  Slab-decomposed engines work on rows [row0, row1) of every vector (V holds the own
+// rows only) and add two exchanges: the boundary rows of u_j from both neighbours before the product, and the all-reduce
+// of (alpha_j, |y|^2) after it.
+static int shard_exchange_px(pse_engine* e);
+static int shard_allreduce2(pse_engine* e);
+static int lanczos_iteration(pse_engine* e, int j, bool dual = false) {
+    const uint32_t r0 = e->row0, r1 = e->row1;
+    const bool multi = e->shard && e->shard->world > 1;
+    float4* Vj = e->d_V + (size_t)j * e->v_rows - r0;   // indexed by row
     LanczosArgs la;
     la.beta_j = e->d_beta + j;
-    la.v_prev = j > 0 ? e->d_V + (size_t)(j - 1) * N : nullptr;
+    la.v_prev = j > 0 ? e->d_V + (size_t)(j - 1) * e->v_rows - r0 : nullptr;
     la.v_out = Vj;
     la.alpha_out = e->d_alpha + j;
     la.partials = e->d_partials;
     la.counter = e->d_counter;
     la.first = j == 0;
+    la.red2 = multi ? e->d_red2 : nullptr;
+    if (multi && j > 0) CKRC(shard_exchange_px(e));   // (u_0 = psi is generated for every row on every rank)
     {
     ProfScope ps(e, PH_LANCZOS_SPMV);
     if (!(dual && launch_spmv_dual(e, e->d_y, la, e->d_sx, e->d_sy))) launch_spmv<SPMV_LANCZOS>(e, e->d_y, la);
     }
+    if (multi) CKRC(shard_allreduce2(e));
     ProfScope ps(e, PH_LANCZOS_VEC);
-    lanczos_update_kernel<<<persistent_grid(e, nblk(N, 256), 8), 256, 0, e->stream>>>(e->d_y, Vj, e->d_px, N, e->d_alpha + j, e->d_beta + j + 1,
-                                                               e->d_partials, e->d_counter);
+    lanczos_update_kernel<<<persistent_grid(e, nblk(r1 - r0, 256), 8), 256, 0, e->stream>>>(e->d_y, Vj, e->d_px, r1, e->d_alpha + j, e->d_beta + j + 1,
+                                                               e->d_partials, e->d_counter, r0, la.red2, e->d_alpha + j);
     LAUNCHED(e);
+    return PSE_OK;
 }
 
 static int solve_coeffs(pse_engine* e, int m, const float* alpha, const float* beta, std::vector<double>& c) {
@@ -993,15 +1094,15 @@ static int lanczos_batch(pse_engine* e, const float* d_u_particles, int m, bool 
     }
     float* alpha = e->h_ab;
     float* beta = e->h_ab + LANCZOS_M_MAX + 1;
-    for (int j = 0; j < m; ++j) lanczos_iteration(e, j, dual && j == 0);
+    for (int j = 0; j < m; ++j) CKRC(lanczos_iteration(e, j, dual && j == 0));
     CK(cudaMemcpyAsync(alpha, e->d_alpha, sizeof(float) * m, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(beta, e->d_beta, sizeof(float) * (m + 1), cudaMemcpyDeviceToHost, st));
     return PSE_OK;
 }
 
 // host side: tridiagonal solves, adaptive iterations until the step norm drops below `error`, final combination
-static int lanczos_finish(pse_engine* e, float4* U, int accumulate, int m, int* m_out, const float4* ydet) {
-    const uint32_t N = e->N;
+// (slab-decomposed: U is the slot-ordered velocity buffer and `perm` is null)
+static int lanczos_finish(pse_engine* e, float4* U, int accumulate, int m, int* m_out, const float4* ydet, const uint32_t* perm) {
     cudaStream_t st = e->stream;
     float* alpha = e->h_ab;
     float* beta = e->h_ab + LANCZOS_M_MAX + 1;
@@ -1017,7 +1118,7 @@ static int lanczos_finish(pse_engine* e, float4* U, int accumulate, int m, int* 
     while (!broke && stepnorm > e->cfg.error && m < LANCZOS_M_MAX) {  // PSEv1/Brownian.cu:606-736
         ++m;
         const int j = m - 1;
-        lanczos_iteration(e, j);
+        CKRC(lanczos_iteration(e, j));
         CK(cudaMemcpyAsync(alpha + j, e->d_alpha + j, sizeof(float), cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(beta + j + 1, e->d_beta + j + 1, sizeof(float), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -1039,7 +1140,10 @@ static int lanczos_finish(pse_engine* e, float4* U, int accumulate, int m, int* 
     CK(cudaMemcpyAsync(e->d_coef, hc, sizeof(float) * m, cudaMemcpyHostToDevice, st));
     const float thermal = sqrtf((float)(2.0 * e->cfg.T / e->cfg.dt));  // PSEv1/Brownian.cu:739
     ProfScope ps(e, PH_COMBINE);
-    basis_combine_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_V, e->d_coef, m, N, (size_t)N, e->d_beta, thermal, e->d_perm, U, accumulate, ydet); LAUNCHED(e);
+    if (e->row1 > e->row0) {
+        basis_combine_kernel<<<nblk(e->row1 - e->row0, 256), 256, 0, st>>>(e->d_V - e->row0, e->d_coef, m, e->row1, e->v_rows, e->d_beta, thermal, perm, U,
+                                                                        accumulate, ydet, e->row0); LAUNCHED(e);
+    }
     e->m_lanczos = m;
     e->last_stepnorm = (float)stepnorm;
     if (m_out) *m_out = m;
@@ -1047,8 +1151,15 @@ static int lanczos_finish(pse_engine* e, float4* U, int accumulate, int m, int* 
 }
 
 // ---- public operators -----------------------------------------------------------------------------
+static int upload_stepdev(pse_engine* e, uint32_t timestep);
+// parts of a velocity evaluation on a slab-decomposed engine (shard.inl)
+enum { SV_DET_WAVE = 1, SV_DET_REAL = 2, SV_WNOISE = 4, SV_RNOISE = 8 };
+static int shard_velocity(pse_engine* e, const float4* d_pos, const float4* d_F, float4* d_U, uint32_t timestep, const float* d_u_particles,
+                          const float* d_u_grid, unsigned what, int* m_out);
+
 extern "C" int pse_mreal(pse_engine* e, const float4* d_pos, const float4* d_F, float4* d_U) {
     if (!e || !d_pos || !d_F || !d_U) return PSE_EINVAL;
+    if (e->shard) return shard_velocity(e, d_pos, d_F, d_U, 0u, nullptr, nullptr, SV_DET_REAL, nullptr);
     CKRC(ensure_neighbors(e, d_pos));
     gather_vec_kernel<<<nblk(e->N, 256), 256, 0, e->stream>>>(d_F, e->d_perm, e->N, nullptr, (float4*)e->d_px); LAUNCHED(e);
     CKRC(run_spmv_plain(e, e->d_sy));
@@ -1059,6 +1170,8 @@ extern "C" int pse_mreal(pse_engine* e, const float4* d_pos, const float4* d_F, 
 
 extern "C" int pse_mwave(pse_engine* e, const float4* d_pos, const float4* d_F, float4* d_U) {
     if (!e || !d_pos || !d_F || !d_U) return PSE_EINVAL;
+    if (e->shard) return shard_velocity(e, d_pos, d_F, d_U, 0u, nullptr, nullptr, SV_DET_WAVE, nullptr);
+    CKRC(ensure_wave_buffers(e));
     CKRC(ensure_neighbors(e, d_pos));
     gather4_kernel<<<nblk(e->N, 256), 256, 0, e->stream>>>(d_F, e->d_perm, e->N, e->d_sx); LAUNCHED(e);
     CKRC(run_wave(e, e->d_sx, d_U, 0, true, false, nullptr));
@@ -1120,7 +1233,14 @@ extern "C" int pse_velocity(pse_engine* e, const float4* d_pos, const float4* d_
     const bool det = parts & 1u;
     const bool thermal = e->cfg.T > 0.f;  // PSEv1/Brownian.cu:855,885
     const bool wnoise = (parts & 2u) && thermal, rnoise = (parts & 4u) && thermal;
+    if (e->shard) {
+        if (m_out) *m_out = e->m_lanczos;
+        return shard_velocity(e, d_pos, d_F, d_U, timestep, d_u_particles, d_u_grid,
+                              (det ? SV_DET_WAVE | SV_DET_REAL : 0u) | (wnoise ? SV_WNOISE : 0u) | (rnoise ? SV_RNOISE : 0u), m_out);
+    }
+    if (det || wnoise) CKRC(ensure_wave_buffers(e));
     CKRC(ensure_neighbors(e, d_pos));  // host decision (list still valid?) happens before the fixed part
+    if (rnoise) CKRC(ensure_krylov(e));
     if (e->wait_F) { e->wait_F = false; CK(cudaStreamWaitEvent(st, e->ev_F, 0)); }
     CKRC(upload_stepdev(e, timestep));
     const int m_batch = lanczos_batch_size(e);
@@ -1161,7 +1281,7 @@ extern "C" int pse_velocity(pse_engine* e, const float4* d_pos, const float4* d_
     } else {
         CKRC(velocity_fixed_part(e, d_F, d_U, det, wnoise, rnoise, d_u_particles, d_u_grid, m_batch));
     }
-    if (rnoise) CKRC(lanczos_finish(e, d_U, (det || wnoise) ? 1 : 0, m_batch, m_out, det ? e->d_sy : nullptr));
+    if (rnoise) CKRC(lanczos_finish(e, d_U, (det || wnoise) ? 1 : 0, m_batch, m_out, det ? e->d_sy : nullptr, e->d_perm));
     CK(cudaGetLastError());
     return PSE_OK;
 }
@@ -1180,6 +1300,7 @@ extern "C" int pse_pair_force(pse_engine* e, const float4* d_pos, const pse_pair
         return fail(e, PSE_EINVAL, "pse_pair_force: r_cut %g outside (0, %g] (the neighbour list is complete up to the real-space cutoff)",
                     pp.rcut, e->prm.rcut);
     pp.rcut_sq = pp.rcut * pp.rcut;
+    if (e->shard && e->shard->world > 1) return fail(e, PSE_EINVAL, "pse_pair_force: a slab-decomposed engine holds the rows of its own slab only");
     CKRC(ensure_neighbors(e, d_pos));
     pair_force_kernel<<<nblk((size_t)e->N * 8, 256), 256, 0, e->stream>>>(e->d_spos, e->N, e->d_nn, e->d_head, e->d_nl, e->d_perm, pp, e->box,
                                                                       d_F, accumulate); LAUNCHED(e);
@@ -1283,301 +1404,4 @@ extern "C" int pse_test_fft_plan(int N, int* radix_out /* FFT_MAX_PASSES */, int
     return PSE_OK;
 }
 
-// ===================================================================================================
-// Multi-GPU: slab decomposition of the deterministic mobility U = M F (first stage).
-// One engine per rank; particle data are replicated (every rank is handed the same positions / forces),
-// the WORK is sharded:
-//   wave space   x-slabs of node tiles: tile-owned spreading of the own slab (no halo add: the gather form
-//                reads whatever particles reach the tile), 2-D (y,z) R2C per own x plane, all-to-all transpose
-//                to y-slabs, 1-D FFT along x, scaling, inverse 1-D, all-to-all back, 2-D C2R, P-1 halo planes
-//                from the next rank, interpolation of the particles whose support origin lies in the own slab;
-//   real space   contiguous slot ranges (x-slabs, since slots are in x-major cell order): pruning + SpMV of the
-//                own rows.
-// Each rank accumulates its contributions into a zero-initialised U (particle-id order); one all-reduce(SUM)
-// completes M F everywhere.  The collectives themselves (2 all-to-all, 1 neighbour exchange, 1 all-reduce) are
-// issued by the host layer with torch.distributed/NCCL on the buffers exposed here (pse_b200/sharded.py).
-// ===================================================================================================
-#define SHARD_MAX_WORLD 16
-struct ShardBounds { int xs[SHARD_MAX_WORLD + 1], ys[SHARD_MAX_WORLD + 1]; int world; };
-struct ShardState {
-    int rank, world;
-    ShardBounds b;
-    int tx0, tx1, x0, x1, y0, y1;
-    uint32_t row0, row1;
-    cufftHandle p2f, p2b, p1;
-    bool have2d, have1d;
-    float2 *d_sloc, *d_tr;
-    float* d_stage;       // own real planes, component stride padded so every cuFFT base is aligned
-    size_t stage_stride;
-};
-static void shard_free(ShardState* s) {
-    if (!s) return;
-    if (s->have2d) { cufftDestroy(s->p2f); cufftDestroy(s->p2b); }
-    if (s->have1d) cufftDestroy(s->p1);
-    if (s->d_sloc) cudaFree(s->d_sloc);
-    if (s->d_stage) cudaFree(s->d_stage);
-    if (s->d_tr) cudaFree(s->d_tr);
-    delete s;
-}
-
-// slab layout  s[c][xl][y][kz]  <->  per-destination blocks  [q][c][xl][y - ys[q]][kz]
-__global__ void shard_slab_blocks_kernel(float2* __restrict__ slab, float2* __restrict__ blocks, ShardBounds b, int nxl, int Ny, int Nzp,
-                                         int to_blocks) {
-    const size_t n = (size_t)3 * nxl * Ny * Nzp;
-    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
-        const int kz = (int)(t % Nzp);
-        const int y = (int)((t / Nzp) % Ny);
-        const int xl = (int)((t / ((size_t)Nzp * Ny)) % nxl);
-        const int c = (int)(t / ((size_t)Nzp * Ny * nxl));
-        int q = 0;
-        while (y >= b.ys[q + 1]) ++q;
-        const int nyl = b.ys[q + 1] - b.ys[q];
-        const size_t off = (size_t)3 * nxl * Nzp * b.ys[q] + (((size_t)c * nxl + xl) * nyl + (y - b.ys[q])) * Nzp + kz;
-        if (to_blocks) blocks[off] = slab[t]; else slab[t] = blocks[off];
-    }
-}
-// transposed layout  t[c][x][yl][kz]  <->  per-source blocks  [r][c][x - xs[r]][yl][kz]
-__global__ void shard_trans_blocks_kernel(float2* __restrict__ tr, float2* __restrict__ blocks, ShardBounds b, int Nx, int nyl, int Nzp,
-                                          int to_blocks) {
-    const size_t n = (size_t)3 * Nx * nyl * Nzp;
-    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
-        const int kz = (int)(t % Nzp);
-        const int yl = (int)((t / Nzp) % nyl);
-        const int x = (int)((t / ((size_t)Nzp * nyl)) % Nx);
-        const int c = (int)(t / ((size_t)Nzp * nyl * Nx));
-        int r = 0;
-        while (x >= b.xs[r + 1]) ++r;
-        const int nxr = b.xs[r + 1] - b.xs[r];
-        const size_t off = (size_t)3 * nyl * Nzp * b.xs[r] + (((size_t)c * nxr + (x - b.xs[r])) * nyl + yl) * Nzp + kz;
-        if (to_blocks) blocks[off] = tr[t]; else tr[t] = blocks[off];
-    }
-}
-// g[c][x0 + i][y][z], i < nplanes  <->  contiguous halo buffer [c][i][y][z]   (x wrapped)
-__global__ void shard_halo_kernel(float* __restrict__ grid, float* __restrict__ halo, size_t G, int Nx, size_t plane, int xfirst, int nplanes,
-                                  int to_halo) {
-    const size_t n = (size_t)3 * nplanes * plane;
-    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
-        const size_t in_plane = t % plane;
-        const int i = (int)((t / plane) % nplanes);
-        const int c = (int)(t / (plane * nplanes));
-        const int x = (xfirst + i) % Nx;
-        const size_t gi = (size_t)c * G + (size_t)x * plane + in_plane;
-        if (to_halo) halo[t] = grid[gi]; else grid[gi] = halo[t];
-    }
-}
-
-// slab bounds of every rank: x planes in whole tiles, y rows and SpMV rows in even shares
-static int shard_bounds(int Nx, int Ny, int ntx, uint32_t N, int world, ShardBounds* b, int* tb, uint32_t* rows) {
-    if (world < 1 || world > SHARD_MAX_WORLD || world > ntx) return PSE_EINVAL;
-    b->world = world;
-    for (int r = 0; r <= world; ++r) {
-        tb[r] = (int)(((long long)ntx * r) / world);
-        b->xs[r] = std::min(tb[r] * TILE, Nx);
-        b->ys[r] = (int)(((long long)Ny * r) / world);
-        rows[r] = (uint32_t)(((unsigned long long)N * r) / world);
-    }
-    b->xs[world] = Nx;
-    return PSE_OK;
-}
-static void shard_fill_info(const ShardBounds& b, const int* tb, const uint32_t* rows, int rank, int Ny, int Nz, int Nzp, int P,
-                            pse_shard_info* out) {
-    memset(out, 0, sizeof(*out));
-    const int world = b.world;
-    out->rank = rank; out->world = world;
-    out->x0 = b.xs[rank]; out->x1 = b.xs[rank + 1]; out->y0 = b.ys[rank]; out->y1 = b.ys[rank + 1];
-    out->row0 = rows[rank]; out->row1 = rows[rank + 1];
-    const int nxl = out->x1 - out->x0, nyl = out->y1 - out->y0;
-    for (int q = 0; q < world; ++q) {
-        out->a2a_send_floats[q] = (uint64_t)2 * 3 * nxl * (b.ys[q + 1] - b.ys[q]) * Nzp;
-        out->a2a_recv_floats[q] = (uint64_t)2 * 3 * (b.xs[q + 1] - b.xs[q]) * nyl * Nzp;
-    }
-    out->halo_floats = (uint64_t)3 * (P - 1) * Ny * Nz;
-    (void)tb;
-}
-
-// host-only: the decomposition a given configuration gets (no GPU needed; used by the CPU tests)
-extern "C" int pse_shard_plan(const pse_config* cfg, int rank, int world, pse_shard_info* out) {
-    if (!cfg || !out || rank < 0 || rank >= world) return PSE_EINVAL;
-    pse_params p;
-    int rc = pse_derive_params(cfg, &p);
-    if (rc != PSE_OK) return rc;
-    ShardBounds b; int tb[SHARD_MAX_WORLD + 1]; uint32_t rows[SHARD_MAX_WORLD + 1];
-    rc = shard_bounds(p.Nx, p.Ny, (p.Nx + TILE - 1) / TILE, cfg->N, world, &b, tb, rows);
-    if (rc != PSE_OK) return rc;
-    shard_fill_info(b, tb, rows, rank, p.Ny, p.Nz, p.Nz / 2 + 1, p.P, out);
-    return PSE_OK;
-}
-
-extern "C" int pse_shard_setup(pse_engine* e, int rank, int world, pse_shard_info* out) {
-    if (!e || !out || world < 1 || world > SHARD_MAX_WORLD || rank < 0 || rank >= world) return PSE_EINVAL;
-    if (!e->tiled || e->wave_v2) return fail(e, PSE_EINVAL, "pse_shard_setup: needs the tile-owned wave path (PSE_WAVE=v1, P <= 10, grid >= TILE + P)");
-    const WaveParams& wp = e->wp;
-    if (world > e->tg.ntx) return fail(e, PSE_EINVAL, "pse_shard_setup: %d ranks but only %d x-tiles of %d nodes", world, e->tg.ntx, TILE);
-    if (e->shard) { shard_free(e->shard); e->shard = nullptr; }
-    ShardState* s = new ShardState();
-    memset(s, 0, sizeof(*s));
-    s->rank = rank; s->world = world;
-    int tb[SHARD_MAX_WORLD + 1]; uint32_t rows[SHARD_MAX_WORLD + 1];
-    if (shard_bounds(wp.Nx, wp.Ny, e->tg.ntx, e->N, world, &s->b, tb, rows) != PSE_OK) { delete s; return PSE_EINVAL; }
-    s->tx0 = tb[rank]; s->tx1 = tb[rank + 1];
-    s->x0 = s->b.xs[rank]; s->x1 = s->b.xs[rank + 1];
-    s->y0 = s->b.ys[rank]; s->y1 = s->b.ys[rank + 1];
-    s->row0 = rows[rank]; s->row1 = rows[rank + 1];
-    const int nxl = s->x1 - s->x0, nyl = s->y1 - s->y0;
-    if (nxl < wp.P - 1) { delete s; return fail(e, PSE_EINVAL, "pse_shard_setup: slab thinner than the halo"); }
-    e->shard = s;
-    CK(cudaMalloc(&s->d_sloc, sizeof(float2) * 3 * (size_t)nxl * wp.Ny * wp.Nzp));
-    // cuFFT wants the real side of an R2C/C2R 8-byte aligned; the own planes of an odd grid are not, so they are staged
-    s->stage_stride = (((size_t)nxl * wp.Ny * wp.Nz + 3) / 4) * 4;
-    CK(cudaMalloc(&s->d_stage, sizeof(float) * 3 * s->stage_stride));
-    CK(cudaMalloc(&s->d_tr, sizeof(float2) * 3 * (size_t)wp.Nx * std::max(nyl, 1) * wp.Nzp));
-    int n2[2] = {wp.Ny, wp.Nz}, re[2] = {wp.Ny, wp.Nz}, ce[2] = {wp.Ny, wp.Nzp};
-    CKFFT(cufftPlanMany(&s->p2f, 2, n2, re, 1, wp.Ny * wp.Nz, ce, 1, wp.Ny * wp.Nzp, CUFFT_R2C, nxl));
-    CKFFT(cufftPlanMany(&s->p2b, 2, n2, ce, 1, wp.Ny * wp.Nzp, re, 1, wp.Ny * wp.Nz, CUFFT_C2R, nxl));
-    s->have2d = true;
-    cufftSetStream(s->p2f, e->stream); cufftSetStream(s->p2b, e->stream);
-    if (nyl > 0) {
-        int n1[1] = {wp.Nx}, em[1] = {wp.Nx};
-        CKFFT(cufftPlanMany(&s->p1, 1, n1, em, nyl * wp.Nzp, 1, em, nyl * wp.Nzp, 1, CUFFT_C2C, nyl * wp.Nzp));
-        s->have1d = true;
-        cufftSetStream(s->p1, e->stream);
-    }
-    shard_fill_info(s->b, tb, rows, rank, wp.Ny, wp.Nz, wp.Nzp, wp.P, out);
-    return PSE_OK;
-}
-
-// phase 1: bin, spread the own slab, 2-D R2C of the own planes, pack for the forward transpose
-extern "C" int pse_shard_fwd(pse_engine* e, const float4* d_pos, const float4* d_F, float* d_send) {
-    if (!e || !e->shard || !d_pos || !d_F || !d_send) return PSE_EINVAL;
-    ShardState* s = e->shard;
-    const WaveParams& wp = e->wp;
-    cudaStream_t st = e->stream;
-    CKRC(ensure_neighbors(e, d_pos));
-    gather_vec_kernel<<<nblk(e->N, 256), 256, 0, st>>>(d_F, e->d_perm, e->N, e->d_sx, (float4*)e->d_px); LAUNCHED(e);
-    TileGrid tg = e->tg;
-    // only the particles this rank spreads or interpolates are binned: origin tile rows [tx0 - 1, tx1) in x (the previous
-    // row reaches into the slab; for the first slab it is the last row of the periodic grid)
-    const bool thin_last_row = wp.Nx - (tg.ntx - 1) * TILE < wp.P - 1;  // then the first slab is also reached from row ntx - 2
-    if (s->world > 1 && s->tx1 - s->tx0 + 1 < tg.ntx && !(s->tx0 == 0 && thin_last_row))
-        CKRC(run_wbin(e, e->d_sx, std::max(s->tx0 - 1, 0), s->tx1, s->tx0 == 0 ? tg.ntx - 1 : -1));
-    else CKRC(run_wbin(e, e->d_sx));
-    tg.tile0 = s->tx0 * tg.nty * tg.ntz;
-    const int ntiles = (s->tx1 - s->tx0) * tg.nty * tg.ntz;
-    launch_spread_tile(wp.P, st, e->d_wF, e->d_worg, e->d_wwt, e->d_wstart, e->wp, tg, e->d_grid, ntiles); LAUNCHED(e);
-    const int nxl = s->x1 - s->x0;
-    const size_t plane = (size_t)wp.Ny * wp.Nz;
-    if (e->own_fft) {  // z and y passes of the own planes (fft.cuh); the y index leaves in digit-reversed order
-        const uint32_t nrows = (uint32_t)nxl * wp.Ny;
-        for (int c = 0; c < 3; ++c) {
-            fft_z_forward_kernel<<<nblk(nrows, 2 * FFT_Z_COLS), FFT_THREADS, fft_smem_bytes(wp.Nz, FFT_Z_COLS + 1), st>>>(
-                e->d_grid + c * e->G + s->x0 * plane, s->d_sloc + (size_t)c * nxl * wp.Ny * wp.Nzp, e->fft_ax[2], nrows, wp.Nzp); LAUNCHED(e);
-        }
-        fft_y_kernel<false><<<dim3(nblk(wp.Nzh, FFT_Y_COLS), 3 * nxl), FFT_THREADS, fft_smem_bytes(wp.Ny, FFT_Y_CP), st>>>(
-            s->d_sloc, e->fft_ax[1], wp.Nzh, wp.Nzp); LAUNCHED(e);
-    } else {
-        for (int c = 0; c < 3; ++c) {
-            CK(cudaMemcpyAsync(s->d_stage + c * s->stage_stride, e->d_grid + c * e->G + s->x0 * plane, sizeof(float) * nxl * plane,
-                               cudaMemcpyDeviceToDevice, st));
-            CKFFT(cufftExecR2C(s->p2f, s->d_stage + c * s->stage_stride, (cufftComplex*)(s->d_sloc + (size_t)c * nxl * wp.Ny * wp.Nzp)));
-        }
-    }
-    e->fft_execs++;
-    shard_slab_blocks_kernel<<<e->num_sms * 8, 256, 0, st>>>(s->d_sloc, (float2*)d_send, s->b, nxl, wp.Ny, wp.Nzp, 1); LAUNCHED(e);
-    CK(cudaGetLastError());
-    return PSE_OK;
-}
-
-// phase 2: unpack to y-slabs, FFT along x, Green's-function scaling, inverse along x, pack for the way back
-extern "C" int pse_shard_kspace(pse_engine* e, const float* d_recv, float* d_send) {
-    if (!e || !e->shard || !d_recv || !d_send) return PSE_EINVAL;
-    ShardState* s = e->shard;
-    const WaveParams& wp = e->wp;
-    cudaStream_t st = e->stream;
-    const int nyl = s->y1 - s->y0;
-    if (nyl > 0) {
-        shard_trans_blocks_kernel<<<e->num_sms * 8, 256, 0, st>>>(s->d_tr, (float2*)d_recv, s->b, wp.Nx, nyl, wp.Nzp, 0); LAUNCHED(e);
-        const size_t comp = (size_t)wp.Nx * nyl * wp.Nzp;
-        CKRC(upload_stepdev(e, 0));
-        if (e->own_fft) {  // x forward + scaling + x inverse of the own stored-y rows in one kernel
-            fft_x_scale_kernel<<<dim3(nblk(wp.Nzh, FFT_X_COLS), nyl), FFT_THREADS, fft_smem_bytes(wp.Nx, FFT_X_CP), st>>>(
-                s->d_tr, e->fft_ax[0], e->fft_ax[1].freq_of, e->wp, e->box, 1, 0, e->d_stepdev, nullptr, s->y0, nyl); LAUNCHED(e);
-        } else {
-            for (int c = 0; c < 3; ++c) CKFFT(cufftExecC2C(s->p1, (cufftComplex*)(s->d_tr + c * comp), (cufftComplex*)(s->d_tr + c * comp), CUFFT_FORWARD));
-            scale_kernel<<<dim3(nyl, wp.Nx), 128, 0, st>>>(s->d_tr, e->wp, e->box, 1, 0, e->d_stepdev, nullptr, s->y0, nyl); LAUNCHED(e);
-            for (int c = 0; c < 3; ++c) CKFFT(cufftExecC2C(s->p1, (cufftComplex*)(s->d_tr + c * comp), (cufftComplex*)(s->d_tr + c * comp), CUFFT_INVERSE));
-        }
-        e->fft_execs += 2;
-        shard_trans_blocks_kernel<<<e->num_sms * 8, 256, 0, st>>>(s->d_tr, (float2*)d_send, s->b, wp.Nx, nyl, wp.Nzp, 1); LAUNCHED(e);
-    }
-    CK(cudaGetLastError());
-    return PSE_OK;
-}
-
-// phase 3: unpack to the own x-slab, 2-D C2R, export the first P-1 planes for the previous rank
-extern "C" int pse_shard_inv(pse_engine* e, const float* d_recv, float* d_halo_send) {
-    if (!e || !e->shard || !d_recv || !d_halo_send) return PSE_EINVAL;
-    ShardState* s = e->shard;
-    const WaveParams& wp = e->wp;
-    cudaStream_t st = e->stream;
-    const int nxl = s->x1 - s->x0;
-    const size_t plane = (size_t)wp.Ny * wp.Nz;
-    shard_slab_blocks_kernel<<<e->num_sms * 8, 256, 0, st>>>(s->d_sloc, (float2*)d_recv, s->b, nxl, wp.Ny, wp.Nzp, 0); LAUNCHED(e);
-    if (e->own_fft) {
-        const uint32_t nrows = (uint32_t)nxl * wp.Ny;
-        fft_y_kernel<true><<<dim3(nblk(wp.Nzh, FFT_Y_COLS), 3 * nxl), FFT_THREADS, fft_smem_bytes(wp.Ny, FFT_Y_CP), st>>>(
-            s->d_sloc, e->fft_ax[1], wp.Nzh, wp.Nzp); LAUNCHED(e);
-        for (int c = 0; c < 3; ++c) {
-            fft_z_inverse_kernel<<<nblk(nrows, 2 * FFT_Z_COLS), FFT_THREADS, fft_smem_bytes(wp.Nz, FFT_Z_COLS + 1), st>>>(
-                s->d_sloc + (size_t)c * nxl * wp.Ny * wp.Nzp, e->d_grid + c * e->G + s->x0 * plane, e->fft_ax[2], nrows, wp.Nzp); LAUNCHED(e);
-        }
-    } else {
-        for (int c = 0; c < 3; ++c) {
-            CKFFT(cufftExecC2R(s->p2b, (cufftComplex*)(s->d_sloc + (size_t)c * nxl * wp.Ny * wp.Nzp), s->d_stage + c * s->stage_stride));
-            CK(cudaMemcpyAsync(e->d_grid + c * e->G + s->x0 * plane, s->d_stage + c * s->stage_stride, sizeof(float) * nxl * plane,
-                               cudaMemcpyDeviceToDevice, st));
-        }
-    }
-    e->fft_execs++;
-    shard_halo_kernel<<<e->num_sms * 4, 256, 0, st>>>(e->d_grid, d_halo_send, e->G, wp.Nx, plane, s->x0, wp.P - 1, 1); LAUNCHED(e);
-    CK(cudaGetLastError());
-    return PSE_OK;
-}
-
-// phase 4: import the halo planes of the next rank, interpolate the own particles, real-space SpMV of the own rows.
-// d_U (particle-id order) receives this rank's partial result; sum over ranks = M F.
-extern "C" int pse_shard_finish(pse_engine* e, const float* d_halo_recv, float4* d_U) {
-    if (!e || !e->shard || !d_halo_recv || !d_U) return PSE_EINVAL;
-    ShardState* s = e->shard;
-    const WaveParams& wp = e->wp;
-    cudaStream_t st = e->stream;
-    const size_t plane = (size_t)wp.Ny * wp.Nz;
-    shard_halo_kernel<<<e->num_sms * 4, 256, 0, st>>>(e->d_grid, const_cast<float*>(d_halo_recv), e->G, wp.Nx, plane, s->x1 % wp.Nx, wp.P - 1, 0); LAUNCHED(e);
-    CK(cudaMemsetAsync(d_U, 0, sizeof(float4) * e->N, st));
-    TileGrid tg = e->tg;
-    tg.tile0 = s->tx0 * tg.nty * tg.ntz;
-    const int ntiles = (s->tx1 - s->tx0) * tg.nty * tg.ntz;
-    launch_interp_tile(wp.P, st, e->d_worg, e->d_wwt, e->d_wstart, e->d_wid, e->wp, tg, e->d_grid, d_U, 0, ntiles); LAUNCHED(e);
-    // real space, own rows only
-    const uint32_t nrows = s->row1 - s->row0;
-    if (nrows) {
-        const uint32_t* nn = e->d_nn; const uint32_t* nl = e->d_nl;
-        if (e->prune) {
-            prune_kernel<<<persistent_grid(e, nblk((size_t)nrows * 8, 256), 8), 256, 0, st>>>(e->d_spos, s->row1, e->d_nn, e->d_head, e->d_nl, e->rp,
-                                                                                         e->box, e->d_nn_act, e->d_nl_act, s->row0); LAUNCHED(e);
-            nn = e->d_nn_act; nl = e->d_nl_act;
-            e->pruned_valid = false;  // only a row range is pruned
-        }
-        LanczosArgs la = {};
-        const unsigned int work = nblk((size_t)nrows * 4, 256);
-        if (e->prune)
-            spmv_kernel<4, SPMV_PLAIN, TABLE_GLOBAL, true><<<persistent_grid(e, work, 8), 256, 0, st>>>(e->d_px, e->d_sy, s->row1, nn, e->d_head, nl, e->d_table,
-                                                                                                  e->cheb, e->rp, e->box, la, s->row0);
-        else
-            spmv_kernel<4, SPMV_PLAIN, TABLE_GLOBAL, false><<<persistent_grid(e, work, 8), 256, 0, st>>>(e->d_px, e->d_sy, s->row1, nn, e->d_head, nl, e->d_table,
-                                                                                                   e->cheb, e->rp, e->box, la, s->row0);
-        LAUNCHED(e);
-        scatter_add_kernel<<<nblk(nrows, 256), 256, 0, st>>>(e->d_sy, e->d_perm, s->row1, d_U, 1, s->row0); LAUNCHED(e);
-    }
-    CK(cudaGetLastError());
-    return PSE_OK;
-}
+#include "shard.inl"

@@ -184,6 +184,10 @@ struct LanczosArgs {
     float* partials;
     unsigned int* counter;
     int first;             // j == 0
+    // slab-decomposed Lanczos: the kernel also reduces |y|^2 of its rows; both partial sums go to red2[0..1], the host
+    // layer all-reduces the pair over ranks and lanczos_update_kernel forms beta_{j+1}^2 = |y|^2 - alpha_j^2
+    // (|y - alpha v|^2 for a unit v with v.y = alpha): ONE two-float all-reduce per iteration.
+    float* red2;
 };
 
 // y = M x            (PLAIN:   x = F, y = U)
@@ -226,7 +230,7 @@ spmv_kernel(const PX* __restrict__ px, float4* __restrict__ y, uint32_t N,
     if constexpr (TABLE == TABLE_SHARED) table.t = stab;
     else if constexpr (TABLE == TABLE_POLY) { table.c = cheb; table.t = gtable; }
     else table.t = gtable;
-    float part = 0.f;
+    float part = 0.f, part2 = 0.f;
     float beta = 0.f, s = 0.f;
     if (MODE == SPMV_LANCZOS) {
         beta = __ldcg(la.beta_j);
@@ -326,13 +330,21 @@ spmv_kernel(const PX* __restrict__ px, float4* __restrict__ y, uint32_t N,
                 la.v_out[row] = make_float4(v.x, v.y, v.z, 0.f);
                 y[row] = make_float4(mv.x, mv.y, mv.z, 0.f);
                 part += v.x * mv.x + v.y * mv.y + v.z * mv.z;
+                part2 += mv.x * mv.x + mv.y * mv.y + mv.z * mv.z;
             }
         }
     }
     if (MODE == SPMV_LANCZOS) {
         __shared__ float red[32];
         const float tot = block_sum(part, red);
-        grid_sum_finish(tot, la.partials, la.counter, la.alpha_out, red);
+        if (la.red2) {
+            const float tot2 = block_sum(part2, red);
+            grid_sum_finish(tot, la.partials, la.counter, la.red2, red);
+            __syncthreads();   // (the "last block" flag of the first reduction is shared memory)
+            grid_sum_finish(tot2, la.partials + gridDim.x, la.counter + 1, la.red2 + 1, red);
+        } else {
+            grid_sum_finish(tot, la.partials, la.counter, la.alpha_out, red);
+        }
     }
 }
 
@@ -341,18 +353,37 @@ spmv_kernel(const PX* __restrict__ px, float4* __restrict__ y, uint32_t N,
 __global__ void __launch_bounds__(256)
 lanczos_update_kernel(const float4* __restrict__ y, const float4* __restrict__ vj, PX* __restrict__ px, uint32_t N,
                       const float* __restrict__ alpha_j, float* __restrict__ beta_next, float* partials,
-                      unsigned int* counter) {
+                      unsigned int* counter, uint32_t row_begin = 0, const float* __restrict__ red2 = nullptr,
+                      float* __restrict__ alpha_store = nullptr) {
     __shared__ float red[32];
     float part = 0.f;
-    const float a = __ldcg(alpha_j);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+    // slab-decomposed: rows [row_begin, N); alpha_j and |y|^2 arrive all-reduced in red2, no second reduction needed
+    const float a = red2 ? __ldcg(red2) : __ldcg(alpha_j);
+    for (uint32_t i = row_begin + blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
         const float4 yy = __ldg(y + i), v = __ldg(vj + i);
         float3 w = make_float3(yy.x - a * v.x, yy.y - a * v.y, yy.z - a * v.z);
         px[i].x = make_float4(w.x, w.y, w.z, 0.f);
         part += w.x * w.x + w.y * w.y + w.z * w.z;
     }
+    if (red2) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            *alpha_store = a;
+            *beta_next = sqrtf(fmaxf(__ldcg(red2 + 1) - a * a, 0.f));
+        }
+        return;
+    }
     float tot = block_sum(part, red);
     grid_sum_finish(tot, partials, counter, beta_next, red, /*take_sqrt=*/true);
+}
+
+// boundary rows of the vector being multiplied <-> contiguous exchange buffers (slab-decomposed SpMV halo)
+__global__ void pack_px_kernel(const PX* __restrict__ px, uint32_t row0, uint32_t n, float4* __restrict__ buf) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) buf[i] = px[row0 + i].x;
+}
+__global__ void unpack_px_kernel(PX* __restrict__ px, uint32_t row0, uint32_t n, const float4* __restrict__ buf) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) px[row0 + i].x = buf[i];
 }
 
 // |px.x|^2 (or its square root) over xyz -> *out (deterministic)
@@ -373,8 +404,9 @@ dot_px_kernel(const PX* __restrict__ px, uint32_t N, float* out, float* partials
 __global__ void __launch_bounds__(256)
 basis_combine_kernel(const float4* __restrict__ V, const float* __restrict__ c, int m, uint32_t N, size_t stride,
                      const float* __restrict__ psinorm, float thermal, const uint32_t* __restrict__ perm,
-                     float4* __restrict__ U, int accumulate, const float4* __restrict__ ydet /* slot-ordered M_real F or null */) {
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+                     float4* __restrict__ U, int accumulate, const float4* __restrict__ ydet /* slot-ordered M_real F or null */,
+                     uint32_t row_begin = 0) {
+    const uint32_t s = row_begin + blockIdx.x * blockDim.x + threadIdx.x;   // rows [row_begin, N); V is indexed by row
     if (s >= N) return;
     float3 acc = make_float3(0.f, 0.f, 0.f);
     for (int k = 0; k < m; ++k) {
@@ -383,7 +415,7 @@ basis_combine_kernel(const float4* __restrict__ V, const float* __restrict__ c, 
         acc.x += v.x * ck; acc.y += v.y * ck; acc.z += v.z * ck;
     }
     const float sc = __ldcg(psinorm) * thermal;
-    const uint32_t p = perm[s];
+    const uint32_t p = perm ? perm[s] : s;   // (null: slot order, slab-decomposed engines)
     float4 o = U[p];  // .w (the mass column of the reference's velocity array, PSEv1/Helper.cu:131) is preserved
     if (!accumulate) { o.x = 0.f; o.y = 0.f; o.z = 0.f; }
     if (ydet) { const float4 yd = __ldg(ydet + s); o.x += yd.x; o.y += yd.y; o.z += yd.z; }
@@ -398,7 +430,7 @@ __global__ void scatter_add_kernel(const float4* __restrict__ y, const uint32_t*
     const uint32_t s = row_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= N) return;
     const float4 v = __ldg(y + s);
-    const uint32_t p = perm[s];
+    const uint32_t p = perm ? perm[s] : s;
     float4 o = accumulate ? U[p] : make_float4(0.f, 0.f, 0.f, 0.f);
     o.x += v.x; o.y += v.y; o.z += v.z;
     U[p] = o;

@@ -20,6 +20,10 @@ struct WaveParams {
     float prefac, expfac, quadW;
     float xi, eta;
     float two_pi_k;  // 2*pi used for wave vectors (reference typo or exact)
+    // Real-grid buffer addressed by the spread2 / interp2 kernels.  Single GPU: the whole grid (xorg = 0, nxa = nxw = Nx).
+    // Slab-decomposed: the rank's local buffer of nxa x planes starting at global plane xorg (own planes + halo planes on
+    // both sides, indexed without periodic wrap: nxw = "never").
+    int xorg, nxa, nxw;
 };
 
 // ---- particle -> grid assignment (bit-exact contract) ------------------------------------------

@@ -42,8 +42,9 @@ __host__ __device__ constexpr int wrow_stride(int P) { return ((P * P + P) + 3) 
 // row_wrap >= 0, outside row row_wrap - are left out of the binning altogether (cell_of = ~0).
 __global__ void wbin_kernel(const float4* __restrict__ spos, uint32_t N, PseBox box, WaveParams wp, TileGrid tg,
                             int4* __restrict__ org, uint32_t* __restrict__ cell_of, uint32_t* __restrict__ count,
-                            int row_lo = 0, int row_hi = 1 << 30, int row_wrap = -1) {
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+                            int row_lo = 0, int row_hi = 1 << 30, int row_wrap = -1, uint32_t slot_begin = 0) {
+    // slots [slot_begin, N) are binned (slab-decomposed calls pass the rank's own slot range)
+    const uint32_t s = slot_begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= N) return;
     const float4 p = __ldg(spos + s);
     const Support o = support_origin(box, wp, p.x, p.y, p.z);
@@ -65,7 +66,10 @@ __global__ void wgather_kernel(const float4* __restrict__ spos, const float4* __
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= N || (nbinned && w >= __ldg(nbinned))) return;
     const uint32_t s = wperm[w];
-    wid[w] = __ldg(perm + s);  // particle id of W slot w: interpolation writes U[id] without chasing two permutations
+    // particle id of W slot w: interpolation writes U[id] without chasing two permutations (perm == null: the slot itself,
+    // slab-decomposed engines collect velocities in slot order)
+    const uint32_t id = perm ? __ldg(perm + s) : s;
+    wid[w] = id;
     wpos[w] = __ldg(spos + s);
     const int4 o = org[s];
     if (sF && !wrec) wF[w] = __ldg(sF + s);
@@ -76,7 +80,7 @@ __global__ void wgather_kernel(const float4* __restrict__ spos, const float4* __
         const int lx = o.x % tg.tx, ly = o.y % tg.ty, lz = o.z % tg.tz;
         int4* h = reinterpret_cast<int4*>(reinterpret_cast<float*>(wrec) + (size_t)w * tg.rs);
         const float4 f = sF ? __ldg(sF + s) : make_float4(0.f, 0.f, 0.f, 0.f);
-        h[0] = make_int4(__float_as_int(f.x), __float_as_int(f.y), __float_as_int(f.z), (int)__ldg(perm + s));
+        h[0] = make_int4(__float_as_int(f.x), __float_as_int(f.y), __float_as_int(f.z), (int)id);
         h[1] = make_int4((((lx / tg.cp) * tg.cy + ly / tg.cp) * tg.cz + lz / tg.cp) * tg.cs, lx % tg.cp, ly % tg.cp, lz % tg.cp);
         h[2] = make_int4(lx, ly, lz, 0);
     }

@@ -209,7 +209,8 @@ spread2_kernel(const float* __restrict__ wrecs, const uint32_t* __restrict__ wce
 
     // ---- merge the window into the grid: one vector reduction per four z nodes and component.  Eight lanes share a
     // (x, y) row of the window, lane q of them takes z nodes 4q .. 4q + 3 (index arithmetic of the z part hoisted)
-    const size_t G = (size_t)wp.Nx * wp.Ny * wp.Nz;
+    const size_t G = (size_t)wp.nxa * wp.Ny * wp.Nz;   // component stride of the (local) grid buffer
+    int relx = t0x - wp.xorg; if (relx < 0) relx += wp.Nx;
     constexpr int HX = C::HX, HY = C::HY, HZ = C::HZ, NQ = (HZ + 3) / 4;
     const bool vec = ((wp.Nz & 3) == 0) && ((TZ & 3) == 0);
     const int q = tid & 7;
@@ -233,7 +234,8 @@ spread2_kernel(const float* __restrict__ wrecs, const uint32_t* __restrict__ wce
 #pragma unroll
                 for (int cc = 0; cc < 3; ++cc) { v[cc][z] = zin[z] ? ar[cc * ACC + zoff[z]] : 0.f; any |= v[cc][z] != 0.f; }
             if (!any) continue;
-            int gx = t0x + lx; if (gx >= wp.Nx) gx -= wp.Nx;
+            int gx = relx + lx; if (gx >= wp.nxw) gx -= wp.Nx;
+            if (gx >= wp.nxa) continue;   // (slab buffer: only ever rows nobody spread into, or an undersized halo)
             int gy = t0y + ly; if (gy >= wp.Ny) gy -= wp.Ny;
             float* dst = grid + ((size_t)gx * wp.Ny + gy) * wp.Nz;
             if (vec) {  // aligned quads never straddle the periodic boundary
@@ -316,7 +318,8 @@ interp2_kernel(const float* __restrict__ wrecs, const uint32_t* __restrict__ wce
     if (cb == ce) return;
     const int bz = cell % tg.ntz, by = (cell / tg.ntz) % tg.nty, bx = cell / (tg.ntz * tg.nty);
     const int t0x = bx * TX, t0y = by * TY, t0z = bz * TZ;
-    const size_t G = (size_t)wp.Nx * wp.Ny * wp.Nz;
+    const size_t G = (size_t)wp.nxa * wp.Ny * wp.Nz;   // component stride of the (local) grid buffer
+    int relx = t0x - wp.xorg; if (relx < 0) relx += wp.Nx;
     const uint32_t np = ce - cb;
     const int nchunks = (int)((np + NW - 1) / NW);
     BulkRing<STAGES, NW> ring;
@@ -332,7 +335,8 @@ interp2_kernel(const float* __restrict__ wrecs, const uint32_t* __restrict__ wce
     }
     // stage the window (periodic wrap per node): a warp takes whole x planes, lanes run over (y, z) with z fastest
     for (int lx = wid; lx < HX; lx += NW) {
-        int x = t0x + lx; if (x >= wp.Nx) x -= wp.Nx;
+        int x = relx + lx; if (x >= wp.nxw) x -= wp.Nx;
+        if (x >= wp.nxa) continue;   // (slab buffer: window planes no particle of this rank reaches)
         const float* gx = grid + (size_t)x * wp.Ny * wp.Nz;
         float* sx = g + lx * XS;
         for (int e = lane; e < HY * HZ; e += 32) {

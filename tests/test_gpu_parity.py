@@ -516,61 +516,64 @@ def cfg_ref_pi(cfg):
     return c
 
 
-# ---------------------------------------------------------------- multi-GPU logic on ONE device: virtual ranks in lockstep
+# ---------------------------------------------------------------- multi-GPU logic on ONE device: virtual ranks
+@pytest.mark.timeout(600, method="thread")
 @pytest.mark.parametrize("g,xy", [(1, 0.0), (2, 0.0), (3, 0.3)])
-def test_sharded_mobility_virtual_ranks(cuda, g, xy):
-    """the slab decomposition (pse_shard_* phases: tile slabs, FFT passes on own planes, transposes, fused x pass,
-    halo planes, row-sharded SpMV) run as g virtual ranks on one GPU - the collectives of pse_b200/sharded.py are replayed with
-    tensor copies (all_to_all_single block order, halo from rank+1, sum over ranks) - against the single-domain engine."""
-    import ctypes
+def test_sharded_step_virtual_ranks(cuda, g, xy):
+    """the slab decomposition of the WHOLE step (own-row neighbour list / pruning / SpMV / Lanczos with vector
+    halo rows and the two-float all-reduce, own-plane spreading with halo-plane reduction, FFT passes + transposes + fused x
+    pass, halo fetch, interpolation, velocity all-gather) run as g virtual ranks on one GPU (pse_local_world: the collectives
+    become device copies + a host barrier inside the library) against the single-domain engine: every operator, injected
+    noise, and three full steps with list rebuilds."""
     import torch
-    from pse_b200 import _lib, sharded as S
-    from pse_b200 import engine as E
-    from pse_b200.engine import _ptr
-    lib = _lib.lib
+    from pse_b200 import engine as E, sharded as S
     N, L = 30000, util.box_length(30000, 0.2)
     cfg = E.make_config(N, L, xy=xy, T=1.0, dt=1e-3, seed=1)
     pos = torch.from_numpy(util.lattice_positions(N, L, 4)).cuda(); F = torch.from_numpy(util.random_forces(N, 5)).cuda()
     single = E.Engine(cfg)
-    Uref = single.mobility(pos, F).clone()
-    engs = [E.Engine(cfg) for _ in range(g)]
-    infos = []
-    for r, e in enumerate(engs):
-        info = _lib.pse_shard_info()
-        assert lib.pse_shard_setup(e._h, r, g, ctypes.byref(info)) == 0, lib.pse_last_error(e._h)
-        infos.append(info)
-    send = [S.split_sizes(i)[0] for i in infos]; recv = [S.split_sizes(i)[1] for i in infos]
-    f32 = dict(dtype=torch.float32, device="cuda")
-    buf_a = [torch.empty(max(sum(send[r]), 1), **f32) for r in range(g)]
-    buf_b = [torch.empty(max(sum(recv[r]), 1), **f32) for r in range(g)]
-    for r, e in enumerate(engs):
-        assert lib.pse_shard_fwd(e._h, _ptr(pos), _ptr(F), _ptr(buf_a[r])) == 0, lib.pse_last_error(e._h)
+    p = single.params
+    gen = torch.Generator(device="cuda"); gen.manual_seed(3)
+    up = torch.rand((N, 3), device="cuda", generator=gen); ug = torch.rand((p.Nx * p.Ny * p.Nz, 6), device="cuda", generator=gen)
+    ref = {"mf": single.mobility(pos, F).clone(), "mreal": single.mreal(pos, F).clone(), "mwave": single.mwave(pos, F).clone()}
+    single.lanczos_m = 4
+    ref["vel"], ref["m"] = single.velocity(pos, F, 7, up, ug)
+    ref["wn"], _ = single.velocity(pos, F, 7, up, ug, parts=2)
+    ps, img = pos.clone(), torch.zeros((N, 3), dtype=torch.int32, device="cuda")
+    for t in range(3):
+        single.step(ps, img, F, t)
     torch.cuda.synchronize()
-    off = lambda sizes, q: sum(sizes[:q])
-    for q in range(g):      # all_to_all_single: rank q receives, in rank order, the block every r addressed to q
-        for r in range(g):
-            assert send[r][q] == recv[q][r]
-            buf_b[q][off(recv[q], r): off(recv[q], r) + recv[q][r]] = buf_a[r][off(send[r], q): off(send[r], q) + send[r][q]]
-    for q, e in enumerate(engs):
-        assert lib.pse_shard_kspace(e._h, _ptr(buf_b[q]), _ptr(buf_b[q])) == 0, lib.pse_last_error(e._h)
+    lw = S.LocalWorld(cfg, g)
+
+    def work(r, e):
+        out = {"mf": e.mobility(pos, F), "mreal": e.mreal(pos, F), "mwave": e.mwave(pos, F)}
+        e.lanczos_m = 4
+        out["vel"], out["m"] = e.velocity(pos, F, 7, up, ug)
+        out["wn"], _ = e.velocity(pos, F, 7, up, ug, parts=2)
+        q, im = pos.clone(), torch.zeros((N, 3), dtype=torch.int32, device="cuda")
+        for t in range(3):
+            e.step(q, im, F, t)
+        out["pos"], out["img"] = q, im
+        out["info"] = e.shard_info().as_dict()
+        return out
+    outs = lw.run(work)
     torch.cuda.synchronize()
-    for r in range(g):      # the way back swaps the split tables
-        for q in range(g):
-            buf_a[r][off(send[r], q): off(send[r], q) + send[r][q]] = buf_b[q][off(recv[q], r): off(recv[q], r) + recv[q][r]]
-    halo_out = [torch.empty(int(infos[r].halo_floats), **f32) for r in range(g)]
-    for r, e in enumerate(engs):
-        assert lib.pse_shard_inv(e._h, _ptr(buf_a[r]), _ptr(halo_out[r])) == 0, lib.pse_last_error(e._h)
-    torch.cuda.synchronize()
-    U = torch.zeros_like(F)
-    for r, e in enumerate(engs):
-        dst, src = S.halo_peers(r, g)
-        Ur = torch.empty_like(F)
-        assert lib.pse_shard_finish(e._h, _ptr(halo_out[src].clone()), _ptr(Ur)) == 0, lib.pse_last_error(e._h)
-        torch.cuda.synchronize()
-        U += Ur
-    close(U, Uref, 2e-6)
-    for e in engs + [single]:
-        e.close()
+    for r, o in enumerate(outs):
+        for k in ("mf", "mreal", "mwave", "vel", "wn"):
+            l2, mx = util.rel_err(o[k].cpu().numpy(), ref[k].cpu().numpy())
+            assert l2 < 5e-6 and mx < 1e-5, (g, r, k, l2, mx)
+        assert o["m"] == ref["m"]
+        d = (o["pos"][:, :3] - ps[:, :3]).abs().max().item()
+        assert d < 2e-5 and torch.equal(o["img"], img), (g, r, d)
+        assert torch.equal(o["pos"], outs[0]["pos"])        # replicated state stays bitwise identical across ranks
+        assert torch.equal(o["vel"], outs[0]["vel"])
+    infos = [o["info"] for o in outs]
+    assert infos[0]["row0"] == 0 and infos[-1]["row1"] == N and infos[0]["x0"] == 0 and infos[-1]["x1"] == p.Nx
+    for r in range(g - 1):
+        assert infos[r]["row1"] == infos[r + 1]["row0"] and infos[r]["x1"] == infos[r + 1]["x0"]
+    if g > 1:
+        assert all(i["collectives"] > 0 and i["bytes_sent"] > 0 for i in infos)
+        assert all(i["buffer_planes"] < p.Nx for i in infos)   # a rank holds its slab of the grid only
+    lw.close(); single.close()
 
 
 # ---------------------------------------------------------------- physics known-answers of SURVEY.md §4

@@ -111,8 +111,9 @@ def test_replica_logic_world_size_2_gloo(tmp_path):
 
 
 def test_shard_plan_all_to_all_is_consistent_world_3_gloo(tmp_path):
-    """Slab decomposition of the multi-GPU mobility (pse_b200/sharded.py): the per-peer split sizes every rank derives
-    must agree pairwise, cover the grid, and drive a real (gloo, CPU) all_to_all_single there and back; halo ring."""
+    """Slab decomposition of the multi-GPU step (pse_b200/sharded.py): the static plan every rank derives on its own must
+    tile the grid and the cell layers, the per-peer transpose sizes must agree pairwise and drive a real (gloo, CPU)
+    all_to_all_single there and back, ring neighbours must be mutual; too many ranks are refused on every rank alike."""
     script = tmp_path / "w.py"
     script.write_text(textwrap.dedent(f"""
         import os, sys
@@ -122,19 +123,22 @@ def test_shard_plan_all_to_all_is_consistent_world_3_gloo(tmp_path):
         from tests import util
         dist.init_process_group("gloo")
         rank, world = dist.get_rank(), dist.get_world_size()
-        cfg = E.make_config(100000, util.box_length(100000, 0.2))       # 125^3 grid: 8 x-tiles, uneven slabs
-        info = S.plan(cfg, rank, world)
-        send, recv = S.split_sizes(info)
+        cfg = E.make_config(100000, util.box_length(100000, 0.2))       # 125^3 grid, P = 6: uneven slabs
+        info = S.plan(cfg, rank, world).as_dict()
         allinfo = [None] * world
-        dist.all_gather_object(allinfo, (info.x0, info.x1, info.y0, info.y1, info.row0, info.row1, send, recv))
-        assert allinfo[0][0] == 0 and allinfo[-1][1] == 125 and allinfo[0][2] == 0 and allinfo[-1][3] == 125
-        assert allinfo[0][4] == 0 and allinfo[-1][5] == 100000
+        dist.all_gather_object(allinfo, info)
+        assert allinfo[0]["x0"] == 0 and allinfo[-1]["x1"] == 125 and allinfo[0]["y0"] == 0 and allinfo[-1]["y1"] == 125
+        assert allinfo[0]["layer0"] == 0
         for r in range(world - 1):
-            assert allinfo[r][1] == allinfo[r + 1][0] and allinfo[r][3] == allinfo[r + 1][2] and allinfo[r][5] == allinfo[r + 1][4]
-            assert allinfo[r][0] % 16 == 0                              # slabs are whole tiles
+            assert allinfo[r]["x1"] == allinfo[r + 1]["x0"] and allinfo[r]["y1"] == allinfo[r + 1]["y0"]
+            assert allinfo[r]["layer1"] == allinfo[r + 1]["layer0"]
         for r in range(world):
+            i = allinfo[r]
+            assert i["x1"] - i["x0"] >= max(i["halo_left"], i["halo_right"])          # halos reach the adjacent slab only
+            assert i["x1"] - i["x0"] + i["halo_left"] + i["halo_right"] <= i["buffer_planes"] < 125
             for q in range(world):
-                assert allinfo[r][6][q] == allinfo[q][7][r]            # what r sends to q is what q expects from r
+                assert i["a2a_send_bytes"][q] == allinfo[q]["a2a_recv_bytes"][r]    # what r sends to q is what q expects from r
+        send = [n // 4 for n in info["a2a_send_bytes"]]; recv = [n // 4 for n in info["a2a_recv_bytes"]]
         a = torch.cat([torch.full((n,), float(rank * 100 + q)) for q, n in enumerate(send)])
         b = torch.empty(sum(recv))
         dist.all_to_all_single(b, a, recv, send)
@@ -144,12 +148,11 @@ def test_shard_plan_all_to_all_is_consistent_world_3_gloo(tmp_path):
         back = torch.empty(sum(send))
         dist.all_to_all_single(back, b, send, recv)                     # the way back swaps the roles
         assert torch.equal(back, a)
-        dst, src = S.halo_peers(rank, world)
         peers = [None] * world
-        dist.all_gather_object(peers, (dst, src))
-        assert all(peers[peers[r][0]][1] == r for r in range(world))    # my destination expects me as its source
+        dist.all_gather_object(peers, S.ring_peers(rank, world))
+        assert all(peers[peers[r][0]][1] == r and peers[peers[r][1]][0] == r for r in range(world))
         try:
-            S.plan(E.make_config(1000, 34.7), rank, 8)                  # 36^3 grid has 3 x-tiles: 8 ranks refused
+            S.plan(E.make_config(1000, 34.7), rank, 8)                  # 36^3 grid: 8 slabs would be thinner than their halos
             raise SystemExit("expected an error")
         except E.PSEError:
             pass
