@@ -221,7 +221,7 @@ const char* pse_profile_phase_name(int i);
  * of the Fourier grid, and exchanges exactly what crosses a slab face; all collectives are issued from C++ on the
  * engine's stream through the NCCL C API (bound with dlopen at run time, the copy the process already loaded):
  *   real space   boundary rows of the multiplied vector to both neighbours before every Lanczos product
- *                (ncclSend/ncclRecv), (alpha_j, |y|^2) in one two-float all-reduce per iteration;
+ *                (ncclSend/ncclRecv), (v.y, |y|^2, |v|^2) in one three-word (double) all-reduce per iteration;
  *   wave space   halo planes added into the neighbours' planes after spreading and fetched before interpolation,
  *                two all-to-all transposes (x slabs <-> y slabs) around the fused x pass;
  *   velocities   one all-gather (N x 16 bytes in total) - positions stay replicated, no migration step.

@@ -15,7 +15,7 @@
 struct pse_nccl_comm_opaque;
 typedef pse_nccl_comm_opaque* pse_nccl_comm_t;
 struct pse_nccl_uid { char internal[128]; };   // ncclUniqueId
-enum { PSE_NCCL_CHAR = 0, PSE_NCCL_FLOAT = 7 };  // ncclChar / ncclFloat32
+enum { PSE_NCCL_CHAR = 0, PSE_NCCL_FLOAT = 7, PSE_NCCL_DOUBLE = 8 };  // ncclChar / ncclFloat32 / ncclFloat64
 enum { PSE_NCCL_SUM = 0 };
 
 struct NcclApi {
@@ -64,11 +64,13 @@ static NcclApi* nccl_api(char* err, size_t errlen) {
 // addressed to this rank (device copies on the own stream), synchronise, host barrier.  Deterministic, slow, and only there
 // so that the multi-rank code path can be checked against the single-domain engine on ONE GPU (tests/test_gpu_parity.py).
 #define PSE_COMM_MAX_WORLD 16
+#define PSE_PEER_NBUF 6   // buffers a rank exposes to its peers: pad, px, uslot, grid, sloc, tr
 struct pse_local_world {
     int world;
     pthread_barrier_t bar;
+    void* ptrs[PSE_COMM_MAX_WORLD][PSE_PEER_NBUF];   // peer-memory transport: plain pointers (one process, one address space)
     struct Desc { const void* a; const void* b; const size_t* off; } desc[PSE_COMM_MAX_WORLD];
-    float red[PSE_COMM_MAX_WORLD][64];
+    double red[PSE_COMM_MAX_WORLD][64];
 };
 
 // One communicator on one stream.  world == 1 needs no transport at all: every exchange degenerates to a device copy.
@@ -117,20 +119,20 @@ struct PseComm {
         pthread_barrier_wait(&lw->bar);
         return rc;
     }
-    // sum of n floats over ranks, in place (identical bits on every rank)
-    int allreduce_sum(float* d, size_t n, cudaStream_t st) {
+    // sum of n doubles over ranks, in place (identical bits on every rank)
+    int allreduce_sum(double* d, size_t n, cudaStream_t st) {
         if (world == 1) return 0;
         if (lw) {
-            if (n > 64) { snprintf(err, sizeof(err), "local all-reduce handles at most 64 floats"); return -1; }
-            int rc = cu(cudaMemcpyAsync(lw->red[rank], d, n * sizeof(float), cudaMemcpyDeviceToHost, st), "local all-reduce");
+            if (n > 64) { snprintf(err, sizeof(err), "local all-reduce handles at most 64 words"); return -1; }
+            int rc = cu(cudaMemcpyAsync(lw->red[rank], d, n * sizeof(double), cudaMemcpyDeviceToHost, st), "local all-reduce");
             if (lw_open(nullptr, nullptr, nullptr, st)) rc = -1;
-            float sum[64];
-            for (size_t i = 0; i < n; ++i) { float a = 0.f; for (int q = 0; q < world; ++q) a += lw->red[q][i]; sum[i] = a; }
-            if (!rc) rc = cu(cudaMemcpyAsync(d, sum, n * sizeof(float), cudaMemcpyHostToDevice, st), "local all-reduce");
+            double sum[64];
+            for (size_t i = 0; i < n; ++i) { double a = 0.0; for (int q = 0; q < world; ++q) a += lw->red[q][i]; sum[i] = a; }
+            if (!rc) rc = cu(cudaMemcpyAsync(d, sum, n * sizeof(double), cudaMemcpyHostToDevice, st), "local all-reduce");
             if (lw_close(st)) rc = -1;
             return rc;
         }
-        return ck(api->AllReduce(d, d, n, PSE_NCCL_FLOAT, PSE_NCCL_SUM, comm, st), "ncclAllReduce");
+        return ck(api->AllReduce(d, d, n, PSE_NCCL_DOUBLE, PSE_NCCL_SUM, comm, st), "ncclAllReduce");
     }
     // In-place all-gather of unequal blocks: block q of `buf` (bytes off[q] .. off[q + 1]) is owned by rank q and ends up
     // on every rank.

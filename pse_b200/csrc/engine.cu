@@ -24,19 +24,23 @@
 #include "wave_v2.cuh"
 #include "fft.cuh"
 #include "comm.cuh"
+#include "peer.cuh"
 
 int pse_tridiag_sqrt_e1(int m, const double* diag, const double* off, double* c, double* lambda_min_out);
 int pse_fit_rpy_cheb(double xi, double rcut, float* out, double* max_err_out);
 
 #define LANCZOS_M_MAX 100  // PSEv1/Brownian.cu:397
+#define DOTS_BLOCKS 592    // grid of lanczos_dots_kernel (4 blocks per SM)
 
 static char g_create_error[512] = "no error";
 
 // phases for the optional CUDA-event profile (pse_set_profiling / pse_get_profile)
 enum Phase { PH_BIN = 0, PH_NLIST, PH_REORDER, PH_WBIN, PH_SPREAD, PH_FFT_FWD, PH_SCALE, PH_FFT_INV, PH_INTERP, PH_PRUNE, PH_SPMV,
-             PH_LANCZOS_SPMV, PH_LANCZOS_VEC, PH_COMBINE, PH_INTEGRATE, PH_COMM, PH_COUNT };
+             PH_LANCZOS_SPMV, PH_LANCZOS_VEC, PH_COMBINE, PH_INTEGRATE, PH_COMM_TRANS, PH_COMM_HALO, PH_COMM_VEC, PH_COMM_RED, PH_COMM_GATHER,
+             PH_COUNT };
 static const char* kPhaseNames[PH_COUNT] = {"bin", "nlist", "reorder", "wave_bin", "spread", "fft_r2c", "scale", "fft_c2r",
-                                            "interp", "prune", "spmv", "lanczos_spmv", "lanczos_vec", "combine", "integrate", "comm"};
+                                            "interp", "prune", "spmv", "lanczos_spmv", "lanczos_vec", "combine", "integrate", "comm_transpose", "comm_grid_halo",
+                                            "comm_vector_halo", "comm_allreduce", "comm_gather"};
 struct ProfSpan { int phase; cudaEvent_t a, b; };
 // ---- multi-GPU slab decomposition of the whole step (new work: the reference is single-GPU, PSEv1/Stokes.cc:104) ---------------
 // One engine per rank / GPU.  Particle arrays at the C ABI stay replicated (every rank passes the same pos / F and gets the
@@ -44,7 +48,7 @@ struct ProfSpan { int phase; cudaEvent_t a, b; };
 // particles only - a contiguous range of slots, because slots are x-major cell order and ownership is cut at x layers of
 // cells - and exchanges exactly what crosses a slab face:
 //   real space   neighbour list, pruning, SpMV and the Lanczos vectors for the own rows; the multiplied vector's boundary rows
-//                go to the two neighbours before every product (ncclSend/ncclRecv); alpha_j and |y|^2 in ONE two-float
+//                go to the two neighbours before every product (ncclSend/ncclRecv); (v.y, |y|^2, |v|^2) in ONE three-word (double)
 //                all-reduce per iteration;
 //   wave space   own particles are spread into a local buffer of own planes + halo planes; halo planes are added into the
 //                neighbours' planes; z / y FFT passes on the own planes, all-to-all transpose to y slabs, fused x pass +
@@ -52,7 +56,9 @@ struct ProfSpan { int phase; cudaEvent_t a, b; };
 //                particles;
 //   velocities   all-gathered in slot order (N x 16 B in total) so that every rank integrates every particle (positions stay
 //                replicated and bitwise identical, no position exchange, no migration step).
-// All collectives are issued from C++ on the engine's stream (comm.cuh), nothing goes through Python.
+// All exchanges are issued from C++ on the engine's stream, nothing goes through Python.  Default transport: kernels that
+// read the peers' buffers directly over NVLink behind a device-side flag barrier (peer.cuh; pointers from CUDA IPC handles
+// exchanged once); PSE_COMM=coll selects the NCCL collectives of comm.cuh (pack, ncclSend/ncclRecv, unpack) instead.
 #define SHARD_MAX_WORLD 16
 #define SHARD_DRIFT_NODES 2.0f
 struct ShardBounds { int xs[SHARD_MAX_WORLD + 1], ys[SHARD_MAX_WORLD + 1]; int world; };   // kernel argument: plane / y-row bounds
@@ -84,6 +90,17 @@ struct ShardState {
     uint32_t *d_layer_start, *h_layer_start;
     uint64_t bytes_sent;                  // per-rank payload handed to the collectives since init (statistics)
     uint64_t collectives;
+    // peer-memory transport (peer.cuh)
+    bool use_peer, peer_ready;
+    PeerSync psync;
+    unsigned char* d_pad;                 // own flag / reduction pad
+    uint32_t epoch, red_count;            // synchronisation points / pair reductions issued so far (same sequence on every rank)
+    const PX* peer_px[SHARD_MAX_WORLD];
+    const float4* peer_uslot[SHARD_MAX_WORLD];
+    const float* peer_grid[SHARD_MAX_WORLD];
+    const float2 *peer_sloc[SHARD_MAX_WORLD], *peer_tr[SHARD_MAX_WORLD];
+    void* ipc_opened[SHARD_MAX_WORLD][PSE_PEER_NBUF];
+    int BLq[SHARD_MAX_WORLD], nxaq[SHARD_MAX_WORLD];   // layout of every rank's local real-space buffer
 };
 static void shard_free(ShardState* s);
 
@@ -168,7 +185,7 @@ struct pse_engine {
     uint32_t row0, row1;       // slots (rows) this engine works on: [0, N) unless slab-decomposed
     size_t v_rows;             // rows per Krylov vector in d_V
     size_t grid_planes;        // x planes allocated in d_grid (Nx unless slab-decomposed)
-    float* d_red2;             // slab-decomposed Lanczos: (alpha_j, |y|^2) partial sums -> all-reduced pair
+    double* d_red2;            // slab-decomposed Lanczos: (v.y, |y|^2, |v|^2) partial sums -> all-reduced | per-block partials
     // per-step device scalars + captured step graph
     StepDev* d_stepdev;
     StepDev* h_stepdev;  // pinned
@@ -352,7 +369,7 @@ static int alloc_all(pse_engine* e) {
     // the real grids, the spectra and the Krylov basis are allocated at first use (ensure_wave_buffers / ensure_krylov):
     // a slab-decomposed engine (pse_shard_init) only ever holds its own slab of each
     e->d_grid = nullptr; e->d_spec = nullptr; e->d_V = nullptr; e->v_rows = 0; e->grid_planes = 0;
-    CK(cudaMalloc(&e->d_red2, 2 * sizeof(float)));
+    CK(cudaMalloc(&e->d_red2, (4 + 3 * DOTS_BLOCKS) * sizeof(double)));
     CK(cudaMalloc(&e->d_u, sizeof(float4) * N));
     CK(cudaMalloc(&e->d_y, sizeof(float4) * N));
     CK(cudaMalloc(&e->d_alpha, sizeof(float) * (LANCZOS_M_MAX + 2)));
@@ -822,6 +839,7 @@ static int ensure_neighbors(pse_engine* e, const float4* d_pos) {
         CKRC(launch_disp_check(e, d_pos));
         CK(cudaEventSynchronize(e->flag_event));
         e->flag_pending = false;
+        if (e->h_flag[1] & 2u) return fail(e, PSE_ECUDA, "slab decomposition: a peer rank did not arrive at a synchronisation point within 10 s");
         if (e->h_flag[1]) return fail(e, PSE_EINVAL, "slab decomposition: a particle's Gaussian support left the rank's grid buffer (halo too thin)");
         rebuild = stale_from_bits(e, *e->h_flag);
     }
@@ -1050,16 +1068,22 @@ static int lanczos_iteration(pse_engine* e, int j, bool dual = false) {
     la.partials = e->d_partials;
     la.counter = e->d_counter;
     la.first = j == 0;
-    la.red2 = multi ? e->d_red2 : nullptr;
     if (multi && j > 0) CKRC(shard_exchange_px(e));   // (u_0 = psi is generated for every row on every rank)
     {
     ProfScope ps(e, PH_LANCZOS_SPMV);
     if (!(dual && launch_spmv_dual(e, e->d_y, la, e->d_sx, e->d_sy))) launch_spmv<SPMV_LANCZOS>(e, e->d_y, la);
     }
-    if (multi) CKRC(shard_allreduce2(e));
+    if (multi) {
+        {
+            ProfScope ps(e, PH_LANCZOS_VEC);
+            const unsigned int gd = std::min<unsigned int>(DOTS_BLOCKS, std::max(1u, nblk(r1 - r0, 256)));
+            lanczos_dots_kernel<<<gd, 256, 0, e->stream>>>(e->d_y, Vj, r0, r1, e->d_red2 + 4, e->d_counter + 1, e->d_red2); LAUNCHED(e);
+        }
+        CKRC(shard_allreduce2(e));
+    }
     ProfScope ps(e, PH_LANCZOS_VEC);
     lanczos_update_kernel<<<persistent_grid(e, nblk(r1 - r0, 256), 8), 256, 0, e->stream>>>(e->d_y, Vj, e->d_px, r1, e->d_alpha + j, e->d_beta + j + 1,
-                                                               e->d_partials, e->d_counter, r0, la.red2, e->d_alpha + j);
+                                                               e->d_partials, e->d_counter, r0, multi ? e->d_red2 : nullptr, e->d_alpha + j);
     LAUNCHED(e);
     return PSE_OK;
 }

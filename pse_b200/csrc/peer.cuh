@@ -1,0 +1,148 @@
+// Peer-memory transport of the slab-decomposed step: every exchange is ONE kernel that reads the neighbours' buffers
+// directly over NVLink (pointers obtained with cudaIpcOpenMemHandle, or plain pointers when the ranks are engines of one
+// process), preceded by a device-side barrier on flags in peer memory.  No packing, no staging buffers, no host
+// involvement: an exchange costs the barrier (a few microseconds) plus the NVLink transfer itself, where the same
+// exchange through ncclSend/ncclRecv costs two pack/unpack passes over HBM and a collective launch (measured at N = 1M
+// on 2 GPUs: 1.3 ms of a 3.5 ms step in collectives, profiles/r2_multi_gpu.md).
+// The reference is single-GPU (PSEv1/Stokes.cc:104): everything here is new work.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define PEER_MAX 16
+// one per rank, in that rank's memory:  flags[PEER_MAX] (arrival epochs, written by the peers) | red[2][PEER_MAX][4]
+#define PEER_PAD_RED_OFF 256
+#define PEER_PAD_BYTES (PEER_PAD_RED_OFF + 2 * PEER_MAX * 4 * 8)
+struct PeerSync {
+    int rank, world;
+    unsigned char* pad[PEER_MAX];   // pad[q]: rank q's pad as addressable from this rank
+    uint32_t* err;                  // own error word (read by the host with the displacement check)
+};
+template <class T> struct PeerPtrs { T* p[PEER_MAX]; };
+struct PeerBounds { uint32_t row[PEER_MAX + 1]; };
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// arrival of every rank at synchronisation point `epoch`: thread q tells rank q, then waits for rank q.
+// A rank that never arrives (host-side error on that rank) must not hang the GPU: after ~10 s the wait gives up and
+// raises the error word, which the host reads with the next displacement check.
+__device__ __forceinline__ void peer_arrive_and_wait(const PeerSync& ps, uint32_t epoch) {
+    const int q = threadIdx.x;
+    if (q < ps.world) {
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<uint32_t*>(ps.pad[q]) + ps.rank, epoch);
+        const uint32_t* mine = reinterpret_cast<const uint32_t*>(ps.pad[ps.rank]) + q;
+        const long long t0 = clock64();
+        while ((int)(ld_acquire_sys(mine) - epoch) < 0) {
+            if (clock64() - t0 > (20ll << 30)) { atomicOr(ps.err, 2u); break; }
+            __nanosleep(64);
+        }
+    }
+}
+__global__ void peer_barrier_kernel(PeerSync ps, uint32_t epoch) {
+    peer_arrive_and_wait(ps, epoch);
+}
+// sum of three doubles over ranks, in place; every rank adds the contributions in rank order -> identical bits
+__global__ void peer_allreduce3_kernel(PeerSync ps, uint32_t epoch, uint32_t parity, double* __restrict__ v) {
+    const int q = threadIdx.x;
+    if (q < ps.world) {
+        double* slot = reinterpret_cast<double*>(ps.pad[q] + PEER_PAD_RED_OFF) + ((size_t)parity * PEER_MAX + ps.rank) * 4;
+        slot[0] = v[0]; slot[1] = v[1]; slot[2] = v[2];
+    }
+    peer_arrive_and_wait(ps, epoch);
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        const double* mine = reinterpret_cast<const double*>(ps.pad[ps.rank] + PEER_PAD_RED_OFF) + (size_t)parity * PEER_MAX * 4;
+        double a = 0.0;
+        for (int r = 0; r < ps.world; ++r) a += mine[4 * r + threadIdx.x];
+        v[threadIdx.x] = a;
+    }
+}
+
+struct PeerSlabs { int xs[PEER_MAX + 1], ys[PEER_MAX + 1]; };
+__device__ __forceinline__ void peer_copy_row(float2* __restrict__ dst, const float2* __restrict__ src, int n, int lane) {
+    if ((n & 1) == 0) {
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        for (int i = lane; i < n / 2; i += 32) d4[i] = s4[i];
+    } else {
+        for (int i = lane; i < n; i += 32) dst[i] = src[i];
+    }
+}
+// transpose x slabs -> y slabs:  tr[c][x][yl][kz] = sloc_{owner(x)}[c][x - xs][y0 + yl][kz]   (one warp per kz row)
+__global__ void __launch_bounds__(256)
+peer_pull_trans_kernel(float2* __restrict__ tr, PeerPtrs<const float2> sloc, PeerSlabs b, int Nx, int Ny, int y0, int nyl, int Nzp) {
+    const int lane = threadIdx.x & 31, nw = gridDim.x * (blockDim.x >> 5), w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int nrow = 3 * Nx * nyl;
+    for (int row = w; row < nrow; row += nw) {
+        const int yl = row % nyl, x = (row / nyl) % Nx, c = row / (nyl * Nx);
+        int r = 0;
+        while (x >= b.xs[r + 1]) ++r;
+        const float2* src = sloc.p[r] + (((size_t)c * (b.xs[r + 1] - b.xs[r]) + (x - b.xs[r])) * Ny + (y0 + yl)) * Nzp;
+        peer_copy_row(tr + (size_t)row * Nzp, src, Nzp, lane);
+    }
+}
+// and back:  sloc[c][xl][y][kz] = tr_{owner(y)}[c][x0 + xl][y - ys][kz]
+__global__ void __launch_bounds__(256)
+peer_pull_slab_kernel(float2* __restrict__ sloc, PeerPtrs<const float2> tr, PeerSlabs b, int Nx, int Ny, int x0, int nxl, int Nzp) {
+    const int lane = threadIdx.x & 31, nw = gridDim.x * (blockDim.x >> 5), w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int nrow = 3 * nxl * Ny;
+    for (int row = w; row < nrow; row += nw) {
+        const int y = row % Ny, xl = (row / Ny) % nxl, c = row / (Ny * nxl);
+        int q = 0;
+        while (y >= b.ys[q + 1]) ++q;
+        const float2* src = tr.p[q] + (((size_t)c * Nx + (x0 + xl)) * (b.ys[q + 1] - b.ys[q]) + (y - b.ys[q])) * Nzp;
+        peer_copy_row(sloc + (size_t)row * Nzp, src, Nzp, lane);
+    }
+}
+// planes [p_dst, p_dst + n) of my real-space buffer (+)= planes [p_src, ..) of a peer's buffer (component strides differ)
+__global__ void __launch_bounds__(256)
+peer_planes_kernel(float* __restrict__ grid, size_t Gl, const float* __restrict__ peer, size_t Glp, size_t plane, int p_dst, int p_src, int n, int add) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((plane & 3) == 0) {
+        const size_t p4 = plane / 4, tot = (size_t)3 * n * p4;
+        for (size_t t = t0; t < tot; t += stride) {
+            const size_t k = t % p4;
+            const int i = (int)((t / p4) % n), c = (int)(t / (p4 * n));
+            float4* d = reinterpret_cast<float4*>(grid + c * Gl + (size_t)(p_dst + i) * plane) + k;
+            const float4 v = reinterpret_cast<const float4*>(peer + c * Glp + (size_t)(p_src + i) * plane)[k];
+            if (add) { float4 o = *d; o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w; *d = o; }
+            else *d = v;
+        }
+    } else {
+        const size_t tot = (size_t)3 * n * plane;
+        for (size_t t = t0; t < tot; t += stride) {
+            const size_t k = t % plane;
+            const int i = (int)((t / plane) % n), c = (int)(t / (plane * n));
+            float* d = grid + c * Gl + (size_t)(p_dst + i) * plane + k;
+            const float v = peer[c * Glp + (size_t)(p_src + i) * plane + k];
+            *d = add ? *d + v : v;
+        }
+    }
+}
+// boundary rows of the vector about to be multiplied, straight from the owners' records (16 of every 32 bytes)
+__global__ void peer_pull_px_kernel(float4* __restrict__ px /* stride 2 */, const float4* __restrict__ peerA, uint32_t a0, uint32_t na,
+                                    const float4* __restrict__ peerB, uint32_t b0, uint32_t nb) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < na) px[2 * (size_t)(a0 + i) + 1] = peerA[2 * (size_t)(a0 + i) + 1];
+    else if (i < na + nb) { const uint32_t j = i - na; px[2 * (size_t)(b0 + j) + 1] = peerB[2 * (size_t)(b0 + j) + 1]; }
+}
+// velocities: every rank reads every row from its owner and scatters it to particle-id order (the caller's .w is kept)
+__global__ void peer_gather_scatter_kernel(PeerPtrs<const float4> uslot, PeerBounds rows, int world, const uint32_t* __restrict__ perm,
+                                           uint32_t N, float4* __restrict__ U) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= N) return;
+    int r = 0;
+    while (r + 1 < world && s >= rows.row[r + 1]) ++r;
+    const float4 v = uslot.p[r][s];
+    const uint32_t p = perm[s];
+    float4 o = U[p];
+    o.x = v.x; o.y = v.y; o.z = v.z;
+    U[p] = o;
+}

@@ -184,10 +184,6 @@ struct LanczosArgs {
     float* partials;
     unsigned int* counter;
     int first;             // j == 0
-    // slab-decomposed Lanczos: the kernel also reduces |y|^2 of its rows; both partial sums go to red2[0..1], the host
-    // layer all-reduces the pair over ranks and lanczos_update_kernel forms beta_{j+1}^2 = |y|^2 - alpha_j^2
-    // (|y - alpha v|^2 for a unit v with v.y = alpha): ONE two-float all-reduce per iteration.
-    float* red2;
 };
 
 // y = M x            (PLAIN:   x = F, y = U)
@@ -230,7 +226,7 @@ spmv_kernel(const PX* __restrict__ px, float4* __restrict__ y, uint32_t N,
     if constexpr (TABLE == TABLE_SHARED) table.t = stab;
     else if constexpr (TABLE == TABLE_POLY) { table.c = cheb; table.t = gtable; }
     else table.t = gtable;
-    float part = 0.f, part2 = 0.f;
+    float part = 0.f;
     float beta = 0.f, s = 0.f;
     if (MODE == SPMV_LANCZOS) {
         beta = __ldcg(la.beta_j);
@@ -330,21 +326,13 @@ spmv_kernel(const PX* __restrict__ px, float4* __restrict__ y, uint32_t N,
                 la.v_out[row] = make_float4(v.x, v.y, v.z, 0.f);
                 y[row] = make_float4(mv.x, mv.y, mv.z, 0.f);
                 part += v.x * mv.x + v.y * mv.y + v.z * mv.z;
-                part2 += mv.x * mv.x + mv.y * mv.y + mv.z * mv.z;
             }
         }
     }
     if (MODE == SPMV_LANCZOS) {
         __shared__ float red[32];
         const float tot = block_sum(part, red);
-        if (la.red2) {
-            const float tot2 = block_sum(part2, red);
-            grid_sum_finish(tot, la.partials, la.counter, la.red2, red);
-            __syncthreads();   // (the "last block" flag of the first reduction is shared memory)
-            grid_sum_finish(tot2, la.partials + gridDim.x, la.counter + 1, la.red2 + 1, red);
-        } else {
-            grid_sum_finish(tot, la.partials, la.counter, la.alpha_out, red);
-        }
+        grid_sum_finish(tot, la.partials, la.counter, la.alpha_out, red);
     }
 }
 
@@ -353,12 +341,14 @@ spmv_kernel(const PX* __restrict__ px, float4* __restrict__ y, uint32_t N,
 __global__ void __launch_bounds__(256)
 lanczos_update_kernel(const float4* __restrict__ y, const float4* __restrict__ vj, PX* __restrict__ px, uint32_t N,
                       const float* __restrict__ alpha_j, float* __restrict__ beta_next, float* partials,
-                      unsigned int* counter, uint32_t row_begin = 0, const float* __restrict__ red2 = nullptr,
+                      unsigned int* counter, uint32_t row_begin = 0, const double* __restrict__ red2 = nullptr,
                       float* __restrict__ alpha_store = nullptr) {
     __shared__ float red[32];
     float part = 0.f;
-    // slab-decomposed: rows [row_begin, N); alpha_j and |y|^2 arrive all-reduced in red2, no second reduction needed
-    const float a = red2 ? __ldcg(red2) : __ldcg(alpha_j);
+    // slab-decomposed: rows [row_begin, N); (v.y, |y|^2, |v|^2) arrive all-reduced in red2 (lanczos_dots_kernel), no second
+    // reduction needed: |y - a v|^2 = |y|^2 - a^2 (2 - |v|^2) with a = v.y, exactly, for the stored float vectors
+    const double ad = red2 ? __ldcg(red2) : 0.0;
+    const float a = red2 ? (float)ad : __ldcg(alpha_j);
     for (uint32_t i = row_begin + blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
         const float4 yy = __ldg(y + i), v = __ldg(vj + i);
         float3 w = make_float3(yy.x - a * v.x, yy.y - a * v.y, yy.z - a * v.z);
@@ -368,12 +358,56 @@ lanczos_update_kernel(const float4* __restrict__ y, const float4* __restrict__ v
     if (red2) {
         if (blockIdx.x == 0 && threadIdx.x == 0) {
             *alpha_store = a;
-            *beta_next = sqrtf(fmaxf(__ldcg(red2 + 1) - a * a, 0.f));
+            *beta_next = (float)sqrt(fmax(__ldcg(red2 + 1) - ad * ad * (2.0 - __ldcg(red2 + 2)), 0.0));
         }
         return;
     }
     float tot = block_sum(part, red);
     grid_sum_finish(tot, partials, counter, beta_next, red, /*take_sqrt=*/true);
+}
+
+// slab-decomposed Lanczos: (v.y, |y|^2, |v|^2) over the rank's rows [r0, r1), in double (the combination above cancels two to
+// three digits); the three sums are all-reduced over ranks in ONE exchange per iteration.  Deterministic: the block that
+// arrives last adds the per-block partials in index order.
+__global__ void __launch_bounds__(256)
+lanczos_dots_kernel(const float4* __restrict__ y, const float4* __restrict__ v, uint32_t r0, uint32_t r1, double* __restrict__ partials /* [3][gridDim.x] */,
+                    unsigned int* __restrict__ counter, double* __restrict__ out3) {
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (uint32_t i = r0 + blockIdx.x * blockDim.x + threadIdx.x; i < r1; i += gridDim.x * blockDim.x) {
+        const float4 yy = __ldg(y + i), vv = __ldg(v + i);
+        a += (double)vv.x * yy.x + (double)vv.y * yy.y + (double)vv.z * yy.z;
+        b += (double)yy.x * yy.x + (double)yy.y * yy.y + (double)yy.z * yy.z;
+        c += (double)vv.x * vv.x + (double)vv.y * vv.y + (double)vv.z * vv.z;
+    }
+    __shared__ double sm[3][8];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    if (lane == 0) { sm[0][wid] = a; sm[1][wid] = b; sm[2][wid] = c; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < 3; ++k) {
+            double t = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sm[k][w];
+            partials[(size_t)k * gridDim.x + blockIdx.x] = t;
+        }
+        __threadfence();
+        is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (is_last && wid < 3) {   // warp k adds the partials of sum k: lane-strided, then a fixed shuffle tree
+        __threadfence();
+        double t = 0.0;
+        for (unsigned int i = lane; i < gridDim.x; i += 32) t += __ldcg(partials + (size_t)wid * gridDim.x + i);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) out3[wid] = t;
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) *counter = 0u;
 }
 
 // boundary rows of the vector being multiplied <-> contiguous exchange buffers (slab-decomposed SpMV halo)

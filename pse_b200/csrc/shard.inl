@@ -72,6 +72,10 @@ __global__ void shard_scatter_kernel(const float4* __restrict__ uslot, const uin
 static void shard_free(ShardState* s) {
     if (!s) return;
     s->comm.destroy();
+    for (int q = 0; q < SHARD_MAX_WORLD; ++q)
+        for (int k = 0; k < PSE_PEER_NBUF; ++k)
+            if (s->ipc_opened[q][k]) cudaIpcCloseMemHandle(s->ipc_opened[q][k]);
+    if (s->d_pad) cudaFree(s->d_pad);
     void* bufs[] = {s->d_sloc, s->d_tr, s->d_a2a_a, s->d_a2a_b, s->d_hsL, s->d_hsR, s->d_hrL, s->d_hrR, s->d_uslot, s->d_layer_start,
                     s->d_vsL, s->d_vsR, s->d_vrL, s->d_vrR};
     for (void* b : bufs)
@@ -120,6 +124,15 @@ static int shard_static_geometry(const pse_config& cfg, const pse_params& prm, i
     }
     return PSE_OK;
 }
+// local real-space buffer of rank q: first global plane, own planes' offset, planes held
+static void shard_rank_layout(const ShardGeom& g, int q, int Nx, int tile_x, int* xorg, int* BL, int* nxa) {
+    if (g.world == 1) { *xorg = 0; *BL = 0; *nxa = Nx; return; }
+    int lo = g.X[q] - g.HL; if (lo < 0) lo += Nx;
+    *xorg = (lo / tile_x) * tile_x;      // tile aligned: no tile an own particle is binned to starts before the buffer
+    int bl = g.X[q] - *xorg; if (bl < 0) bl += Nx;
+    *BL = bl;
+    *nxa = bl + (g.X[q + 1] - g.X[q]) + g.HR;
+}
 static void shard_fill_info(const ShardGeom& g, int rank, const pse_params& prm, int Nzp, int tile_x, pse_shard_info* out) {
     memset(out, 0, sizeof(*out));
     out->rank = rank; out->world = g.world;
@@ -127,13 +140,8 @@ static void shard_fill_info(const ShardGeom& g, int rank, const pse_params& prm,
     out->halo_left = g.HL; out->halo_right = g.HR;
     out->layer0 = g.LB[rank]; out->layer1 = g.LB[rank + 1];
     const int nown = out->x1 - out->x0, nyl = out->y1 - out->y0;
-    if (g.world == 1) out->buffer_planes = prm.Nx;
-    else {
-        int lo = g.X[rank] - g.HL; if (lo < 0) lo += prm.Nx;
-        const int xorg = (lo / tile_x) * tile_x;
-        int bl = g.X[rank] - xorg; if (bl < 0) bl += prm.Nx;
-        out->buffer_planes = bl + nown + g.HR;
-    }
+    int xorg, bl;
+    shard_rank_layout(g, rank, prm.Nx, tile_x, &xorg, &bl, &out->buffer_planes);
     for (int q = 0; q < g.world; ++q) {
         out->a2a_send_bytes[q] = (uint64_t)8 * 3 * nown * (g.YS[q + 1] - g.YS[q]) * Nzp;
         out->a2a_recv_bytes[q] = (uint64_t)8 * 3 * (g.X[q + 1] - g.X[q]) * nyl * Nzp;
@@ -208,14 +216,10 @@ extern "C" int pse_shard_init(pse_engine* e, int rank, int world, const uint8_t*
     WaveParams& wp = e->wp;
     s->plane = (size_t)wp.Ny * wp.Nz;
     s->nown = g.X[rank + 1] - g.X[rank];
-    if (world == 1) { s->BL = 0; s->xorg = 0; s->nxa = wp.Nx; wp.nxw = wp.Nx; }
-    else {
-        int lo = g.X[rank] - g.HL; if (lo < 0) lo += wp.Nx;
-        s->xorg = (lo / e->tg.tx) * e->tg.tx;      // tile aligned: no tile an own particle is binned to starts before the buffer
-        s->BL = g.X[rank] - s->xorg; if (s->BL < 0) s->BL += wp.Nx;
-        s->nxa = s->BL + s->nown + g.HR;
-        wp.nxw = 1 << 30;                          // the local buffer is indexed without periodic wrap
-    }
+    for (int q = 0; q < world; ++q) { int xo; shard_rank_layout(g, q, wp.Nx, e->tg.tx, &xo, &s->BLq[q], &s->nxaq[q]); }
+    shard_rank_layout(g, rank, wp.Nx, e->tg.tx, &s->xorg, &s->BL, &s->nxa);
+    wp.nxw = world == 1 ? wp.Nx : 1 << 30;         // a slab buffer is indexed without periodic wrap
+    { const char* env = getenv("PSE_COMM"); s->use_peer = world > 1 && !(env && env[0] == 'c'); }
     wp.xorg = s->xorg; wp.nxa = s->nxa;
     s->Gl = (size_t)s->nxa * s->plane;
     // the single-GPU grids / basis are allocated lazily, so there is normally nothing to free here
@@ -243,6 +247,8 @@ extern "C" int pse_shard_init(pse_engine* e, int rank, int world, const uint8_t*
     }
     CK(cudaMalloc(&s->d_uslot, sizeof(float4) * e->N));
     CK(cudaMemset(s->d_uslot, 0, sizeof(float4) * e->N));
+    CK(cudaMalloc(&s->d_pad, PEER_PAD_BYTES));
+    CK(cudaMemset(s->d_pad, 0, PEER_PAD_BYTES));
     CK(cudaMalloc(&s->d_layer_start, sizeof(uint32_t) * (e->cg.ncx + 2)));
     CK(cudaMallocHost(&s->h_layer_start, sizeof(uint32_t) * (e->cg.ncx + 2)));
     e->use_graph = false;   // the collectives make the step topology a host matter: issued eagerly
@@ -293,29 +299,125 @@ static int shard_update_geometry(pse_engine* e) {
 // ---- the exchanges -----------------------------------------------------------------------------------------------------------
 #define CKCOMM(call) do { if ((call) != 0) return fail(e, PSE_ECUDA, "%s", s->comm.err); s->collectives++; } while (0)
 
+// Peer-memory transport: exchange the addresses of the buffers the peers read (once, at the first evaluation: a collective
+// step).  Separate processes: CUDA IPC handles, all-gathered through the NCCL communicator; one process: plain pointers.
+struct IpcPack { cudaIpcMemHandle_t h[PSE_PEER_NBUF]; };
+static int shard_connect_peers(pse_engine* e) {
+    ShardState* s = e->shard;
+    if (!s->use_peer || s->peer_ready) return PSE_OK;
+    const int W = s->world, me = s->rank;
+    cudaStream_t st = e->stream;
+    void* mine[PSE_PEER_NBUF] = {s->d_pad, e->d_px, s->d_uslot, e->d_grid, s->d_sloc, s->d_tr};
+    void* theirs[SHARD_MAX_WORLD][PSE_PEER_NBUF];
+    if (s->comm.lw) {
+        pse_local_world* lw = s->comm.lw;
+        for (int k = 0; k < PSE_PEER_NBUF; ++k) lw->ptrs[me][k] = mine[k];
+        CK(cudaStreamSynchronize(st));
+        pthread_barrier_wait(&lw->bar);
+        for (int q = 0; q < W; ++q) for (int k = 0; k < PSE_PEER_NBUF; ++k) theirs[q][k] = lw->ptrs[q][k];
+        pthread_barrier_wait(&lw->bar);
+    } else {
+        IpcPack* d_packs = nullptr;
+        std::vector<IpcPack> packs(W);
+        bool ok = true;
+        for (int k = 0; k < PSE_PEER_NBUF; ++k) ok &= cudaIpcGetMemHandle(&packs[me].h[k], mine[k]) == cudaSuccess;
+        if (!ok) { cudaGetLastError(); memset(&packs[me], 0, sizeof(IpcPack)); }
+        CK(cudaMalloc(&d_packs, sizeof(IpcPack) * W));
+        CK(cudaMemcpyAsync(d_packs + me, &packs[me], sizeof(IpcPack), cudaMemcpyHostToDevice, st));
+        size_t off[SHARD_MAX_WORLD + 1];
+        for (int q = 0; q <= W; ++q) off[q] = sizeof(IpcPack) * q;
+        if (s->comm.allgatherv(d_packs, off, st) != 0) { cudaFree(d_packs); return fail(e, PSE_ECUDA, "%s", s->comm.err); }
+        CK(cudaMemcpyAsync(packs.data(), d_packs, sizeof(IpcPack) * W, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (int q = 0; q < W && ok; ++q) {
+            if (q == me) { for (int k = 0; k < PSE_PEER_NBUF; ++k) theirs[q][k] = mine[k]; continue; }
+            IpcPack zero; memset(&zero, 0, sizeof(zero));
+            if (!memcmp(&packs[q], &zero, sizeof(zero))) { ok = false; break; }
+            for (int k = 0; k < PSE_PEER_NBUF && ok; ++k) {
+                void* ptr = nullptr;
+                if (cudaIpcOpenMemHandle(&ptr, packs[q].h[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+                s->ipc_opened[q][k] = ptr;
+                theirs[q][k] = ptr;
+            }
+        }
+        // everybody or nobody: a rank that could not map a peer takes all ranks back to the NCCL collectives
+        double* d_ok = reinterpret_cast<double*>(d_packs);
+        const double mine_ok = ok ? 0.0 : 1.0;
+        CK(cudaMemcpyAsync(d_ok, &mine_ok, sizeof(double), cudaMemcpyHostToDevice, st));
+        if (s->comm.allreduce_sum(d_ok, 1, st) != 0) { cudaFree(d_packs); return fail(e, PSE_ECUDA, "%s", s->comm.err); }
+        double failed = 0.0;
+        CK(cudaMemcpyAsync(&failed, d_ok, sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        cudaFree(d_packs);
+        if (failed != 0.0) {
+            fprintf(stderr, "pse_b200: CUDA IPC mapping of peer buffers failed on %d rank(s); using NCCL collectives\n", (int)failed);
+            s->use_peer = false;
+            return PSE_OK;
+        }
+    }
+    s->psync.rank = me; s->psync.world = W; s->psync.err = e->d_flag + 1;
+    for (int q = 0; q < W; ++q) {
+        s->psync.pad[q] = static_cast<unsigned char*>(theirs[q][0]);
+        s->peer_px[q] = static_cast<const PX*>(theirs[q][1]);
+        s->peer_uslot[q] = static_cast<const float4*>(theirs[q][2]);
+        s->peer_grid[q] = static_cast<const float*>(theirs[q][3]);
+        s->peer_sloc[q] = static_cast<const float2*>(theirs[q][4]);
+        s->peer_tr[q] = static_cast<const float2*>(theirs[q][5]);
+    }
+    s->peer_ready = true;
+    return PSE_OK;
+}
+// Every rank has finished everything issued before this point.  Between processes: flags in peer memory, device side, no
+// host involvement.  Virtual ranks of one process share a GPU and a CUDA context, where a kernel spinning on a flag can
+// starve the very work it waits for (lazy module loading and allocator calls synchronise the context): there the barrier
+// is taken on the host - the pull kernels and the pointer logic they exercise are the same.
+static void shard_peer_barrier(pse_engine* e) {
+    ShardState* s = e->shard;
+    s->collectives++;
+    if (s->comm.lw) {
+        cudaStreamSynchronize(e->stream);
+        pthread_barrier_wait(&s->comm.lw->bar);
+        return;
+    }
+    peer_barrier_kernel<<<1, 32, 0, e->stream>>>(s->psync, ++s->epoch); LAUNCHED(e);
+}
+
 // boundary rows of the vector about to be multiplied: my first KH layers go to the left neighbour, my last KH layers to the
 // right one; theirs arrive in the rows they occupy in the (global) slot numbering
 static int shard_exchange_px(pse_engine* e) {
     ShardState* s = e->shard;
     const ShardGeom& g = s->g;
-    ProfScope ps(e, PH_COMM);
+    ProfScope ps(e, PH_COMM_VEC);
     cudaStream_t st = e->stream;
     const int r = s->rank, left = (r + g.world - 1) % g.world, right = (r + 1) % g.world;
     const uint32_t nsL = g.SL1[r] - g.ROW[r], nsR = g.ROW[r + 1] - g.SR0[r];
     const uint32_t nrR = g.SL1[right] - g.ROW[right], nrL = g.ROW[left + 1] - g.SR0[left];
+    s->bytes_sent += ((uint64_t)nsL + nsR) * 16;
+    if (s->use_peer) {
+        shard_peer_barrier(e);
+        if (nrR + nrL) {
+            peer_pull_px_kernel<<<nblk(nrR + nrL, 256), 256, 0, st>>>((float4*)e->d_px, (const float4*)s->peer_px[right], g.ROW[right], nrR,
+                                                                     (const float4*)s->peer_px[left], g.SR0[left], nrL); LAUNCHED(e);
+        }
+        return PSE_OK;
+    }
     if (nsL) { pack_px_kernel<<<nblk(nsL, 256), 256, 0, st>>>(e->d_px, g.ROW[r], nsL, s->d_vsL); LAUNCHED(e); }
     if (nsR) { pack_px_kernel<<<nblk(nsR, 256), 256, 0, st>>>(e->d_px, g.SR0[r], nsR, s->d_vsR); LAUNCHED(e); }
     CKCOMM(s->comm.ring_exchange(s->d_vsL, (size_t)nsL * 16, s->d_vrR, (size_t)nrR * 16, s->d_vsR, (size_t)nsR * 16, s->d_vrL, (size_t)nrL * 16, st));
-    s->bytes_sent += ((uint64_t)nsL + nsR) * 16;
     if (nrR) { unpack_px_kernel<<<nblk(nrR, 256), 256, 0, st>>>(e->d_px, g.ROW[right], nrR, s->d_vrR); LAUNCHED(e); }
     if (nrL) { unpack_px_kernel<<<nblk(nrL, 256), 256, 0, st>>>(e->d_px, g.SR0[left], nrL, s->d_vrL); LAUNCHED(e); }
     return PSE_OK;
 }
 static int shard_allreduce2(pse_engine* e) {
     ShardState* s = e->shard;
-    ProfScope ps(e, PH_COMM);
-    CKCOMM(s->comm.allreduce_sum(e->d_red2, 2, e->stream));
-    s->bytes_sent += 8;
+    ProfScope ps(e, PH_COMM_RED);
+    s->bytes_sent += 24 * (s->world - 1);
+    if (s->use_peer && !s->comm.lw) {
+        peer_allreduce3_kernel<<<1, 32, 0, e->stream>>>(s->psync, ++s->epoch, (s->red_count++) & 1u, e->d_red2); LAUNCHED(e);
+        s->collectives++;
+        return PSE_OK;
+    }
+    CKCOMM(s->comm.allreduce_sum(e->d_red2, 3, e->stream));
     return PSE_OK;
 }
 // spreading: what my particles put on planes outside my slab is added into the owners' planes
@@ -323,14 +425,24 @@ static int shard_halo_reduce(pse_engine* e) {
     ShardState* s = e->shard;
     const ShardGeom& g = s->g;
     if (g.world == 1) return PSE_OK;
-    ProfScope ps(e, PH_COMM);
+    ProfScope ps(e, PH_COMM_HALO);
     cudaStream_t st = e->stream;
     const unsigned int gb = e->num_sms * 8;
+    const size_t bL = sizeof(float) * 3 * g.HL * s->plane, bR = sizeof(float) * 3 * g.HR * s->plane;
+    s->bytes_sent += bL + bR;
+    if (s->use_peer) {
+        const int left = (s->rank + g.world - 1) % g.world, right = (s->rank + 1) % g.world;
+        shard_peer_barrier(e);
+        // the right neighbour's left halo lands on my last HL planes, the left neighbour's right halo on my first HR planes
+        peer_planes_kernel<<<gb, 256, 0, st>>>(e->d_grid, s->Gl, s->peer_grid[right], (size_t)s->nxaq[right] * s->plane, s->plane,
+                                                s->BL + s->nown - g.HL, s->BLq[right] - g.HL, g.HL, 1); LAUNCHED(e);
+        peer_planes_kernel<<<gb, 256, 0, st>>>(e->d_grid, s->Gl, s->peer_grid[left], (size_t)s->nxaq[left] * s->plane, s->plane,
+                                                s->BL, s->BLq[left] + (g.X[left + 1] - g.X[left]), g.HR, 1); LAUNCHED(e);
+        return PSE_OK;
+    }
     shard_planes_kernel<<<gb, 256, 0, st>>>(e->d_grid, s->d_hsL, s->Gl, s->plane, s->BL - g.HL, g.HL, 0); LAUNCHED(e);
     shard_planes_kernel<<<gb, 256, 0, st>>>(e->d_grid, s->d_hsR, s->Gl, s->plane, s->BL + s->nown, g.HR, 0); LAUNCHED(e);
-    const size_t bL = sizeof(float) * 3 * g.HL * s->plane, bR = sizeof(float) * 3 * g.HR * s->plane;
     CKCOMM(s->comm.ring_exchange(s->d_hsL, bL, s->d_hrR, bL, s->d_hsR, bR, s->d_hrL, bR, st));
-    s->bytes_sent += bL + bR;
     // from the right neighbour: its left halo = my last HL planes; from the left neighbour: its right halo = my first HR planes
     shard_planes_kernel<<<gb, 256, 0, st>>>(e->d_grid, s->d_hrR, s->Gl, s->plane, s->BL + s->nown - g.HL, g.HL, 2); LAUNCHED(e);
     shard_planes_kernel<<<gb, 256, 0, st>>>(e->d_grid, s->d_hrL, s->Gl, s->plane, s->BL, g.HR, 2); LAUNCHED(e);
@@ -341,15 +453,24 @@ static int shard_halo_fetch(pse_engine* e) {
     ShardState* s = e->shard;
     const ShardGeom& g = s->g;
     if (g.world == 1) return PSE_OK;
-    ProfScope ps(e, PH_COMM);
+    ProfScope ps(e, PH_COMM_HALO);
     cudaStream_t st = e->stream;
     const unsigned int gb = e->num_sms * 8;
+    const size_t bL = sizeof(float) * 3 * g.HL * s->plane, bR = sizeof(float) * 3 * g.HR * s->plane;
+    s->bytes_sent += bL + bR;
+    if (s->use_peer) {
+        const int left = (s->rank + g.world - 1) % g.world, right = (s->rank + 1) % g.world;
+        shard_peer_barrier(e);
+        peer_planes_kernel<<<gb, 256, 0, st>>>(e->d_grid, s->Gl, s->peer_grid[right], (size_t)s->nxaq[right] * s->plane, s->plane,
+                                                s->BL + s->nown, s->BLq[right], g.HR, 0); LAUNCHED(e);
+        peer_planes_kernel<<<gb, 256, 0, st>>>(e->d_grid, s->Gl, s->peer_grid[left], (size_t)s->nxaq[left] * s->plane, s->plane,
+                                                s->BL - g.HL, s->BLq[left] + (g.X[left + 1] - g.X[left]) - g.HL, g.HL, 0); LAUNCHED(e);
+        return PSE_OK;
+    }
     // to the left neighbour: my first HR planes (its right halo); to the right neighbour: my last HL planes (its left halo)
     shard_planes_kernel<<<gb, 256, 0, st>>>(e->d_grid, s->d_hsL, s->Gl, s->plane, s->BL, g.HR, 0); LAUNCHED(e);
     shard_planes_kernel<<<gb, 256, 0, st>>>(e->d_grid, s->d_hsR, s->Gl, s->plane, s->BL + s->nown - g.HL, g.HL, 0); LAUNCHED(e);
-    const size_t bL = sizeof(float) * 3 * g.HL * s->plane, bR = sizeof(float) * 3 * g.HR * s->plane;
     CKCOMM(s->comm.ring_exchange(s->d_hsL, bR, s->d_hrR, bR, s->d_hsR, bL, s->d_hrL, bL, st));
-    s->bytes_sent += bL + bR;
     shard_planes_kernel<<<gb, 256, 0, st>>>(e->d_grid, s->d_hrR, s->Gl, s->plane, s->BL + s->nown, g.HR, 1); LAUNCHED(e);
     shard_planes_kernel<<<gb, 256, 0, st>>>(e->d_grid, s->d_hrL, s->Gl, s->plane, s->BL - g.HL, g.HL, 1); LAUNCHED(e);
     return PSE_OK;
@@ -389,6 +510,10 @@ static int shard_wave(pse_engine* e, const float4* sF, bool det, bool noise, con
     ShardBounds b;
     b.world = g.world;
     for (int r = 0; r <= g.world; ++r) { b.xs[r] = g.X[r]; b.ys[r] = g.YS[r]; }
+    PeerSlabs pb;
+    PeerPtrs<const float2> pp_sloc, pp_tr;
+    for (int r = 0; r <= g.world; ++r) { pb.xs[r] = g.X[r]; pb.ys[r] = g.YS[r]; }
+    for (int r = 0; r < g.world; ++r) { pp_sloc.p[r] = s->peer_sloc[r]; pp_tr.p[r] = s->peer_tr[r]; }
     CKRC(shard_wbin(e, det ? sF : nullptr));
     if (det) {
         {
@@ -407,8 +532,14 @@ static int shard_wave(pse_engine* e, const float4* sF, bool det, bool noise, con
                 s->d_sloc, e->fft_ax[1], wp.Nzh, wp.Nzp); LAUNCHED(e);
             e->fft_execs++;
         }
-        ProfScope ps(e, PH_COMM);   // transpose: x slabs -> y slabs
-        if (g.world > 1) {
+        ProfScope ps(e, PH_COMM_TRANS);   // transpose: x slabs -> y slabs
+        if (s->use_peer) {
+            shard_peer_barrier(e);
+            s->bytes_sent += s->a2a_recv_off[g.world] - (s->a2a_recv_off[s->rank + 1] - s->a2a_recv_off[s->rank]);
+            if (nyl > 0) {
+                peer_pull_trans_kernel<<<e->num_sms * 8, 256, 0, st>>>(s->d_tr, pp_sloc, pb, wp.Nx, wp.Ny, g.YS[s->rank], nyl, wp.Nzp); LAUNCHED(e);
+            }
+        } else if (g.world > 1) {
             shard_slab_blocks_kernel<<<e->num_sms * 8, 256, 0, st>>>(s->d_sloc, (float2*)s->d_a2a_a, b, nown, wp.Ny, wp.Nzp, 1); LAUNCHED(e);
             CKCOMM(s->comm.alltoallv(s->d_a2a_a, s->a2a_send_off, s->d_a2a_b, s->a2a_recv_off, st));
             s->bytes_sent += s->a2a_send_off[g.world] - (s->a2a_send_off[s->rank + 1] - s->a2a_send_off[s->rank]);
@@ -424,8 +555,12 @@ static int shard_wave(pse_engine* e, const float4* sF, bool det, bool noise, con
         e->fft_execs++;
     }
     {
-        ProfScope ps(e, PH_COMM);    // transpose back: y slabs -> x slabs
-        if (g.world > 1) {
+        ProfScope ps(e, PH_COMM_TRANS);    // transpose back: y slabs -> x slabs
+        if (s->use_peer) {
+            shard_peer_barrier(e);
+            s->bytes_sent += s->a2a_send_off[g.world] - (s->a2a_send_off[s->rank + 1] - s->a2a_send_off[s->rank]);
+            peer_pull_slab_kernel<<<e->num_sms * 8, 256, 0, st>>>(s->d_sloc, pp_tr, pb, wp.Nx, wp.Ny, g.X[s->rank], nown, wp.Nzp); LAUNCHED(e);
+        } else if (g.world > 1) {
             if (nyl > 0) { shard_trans_blocks_kernel<<<e->num_sms * 8, 256, 0, st>>>(s->d_tr, (float2*)s->d_a2a_b, b, wp.Nx, nyl, wp.Nzp, 1); LAUNCHED(e); }
             CKCOMM(s->comm.alltoallv(s->d_a2a_b, s->a2a_recv_off, s->d_a2a_a, s->a2a_send_off, st));
             s->bytes_sent += s->a2a_recv_off[g.world] - (s->a2a_recv_off[s->rank + 1] - s->a2a_recv_off[s->rank]);
@@ -458,6 +593,7 @@ static int shard_velocity(pse_engine* e, const float4* d_pos, const float4* d_F,
     cudaStream_t st = e->stream;
     const uint32_t N = e->N;
     const bool wdet = what & SV_DET_WAVE, rdet = what & SV_DET_REAL, wnoise = what & SV_WNOISE, rnoise = what & SV_RNOISE;
+    CKRC(shard_connect_peers(e));
     CKRC(ensure_neighbors(e, d_pos));   // replicated decision (identical positions on every rank); the build covers the own rows
     if (rnoise) CKRC(ensure_krylov(e));
     if (e->wait_F) { e->wait_F = false; CK(cudaStreamWaitEvent(st, e->ev_F, 0)); }
@@ -481,13 +617,23 @@ static int shard_velocity(pse_engine* e, const float4* d_pos, const float4* d_F,
     }
     if (!acc && nrows) CK(cudaMemsetAsync(s->d_uslot + r0, 0, sizeof(float4) * nrows, st));
     {
-        ProfScope ps(e, PH_COMM);   // every rank gets every velocity: positions stay replicated and bitwise identical
-        size_t off[SHARD_MAX_WORLD + 1];
-        for (int r = 0; r <= g.world; ++r) off[r] = (size_t)g.ROW[r] * sizeof(float4);
-        CKCOMM(s->comm.allgatherv(s->d_uslot, off, st));
+        ProfScope ps(e, PH_COMM_GATHER);   // every rank gets every velocity: positions stay replicated and bitwise identical
         s->bytes_sent += (uint64_t)(g.world - 1) * nrows * sizeof(float4);
+        if (s->use_peer) {
+            PeerPtrs<const float4> pu;
+            PeerBounds rb;
+            for (int r = 0; r < g.world; ++r) pu.p[r] = s->peer_uslot[r];
+            for (int r = 0; r <= g.world; ++r) rb.row[r] = g.ROW[r];
+            shard_peer_barrier(e);
+            peer_gather_scatter_kernel<<<nblk(N, 256), 256, 0, st>>>(pu, rb, g.world, e->d_perm, N, d_U); LAUNCHED(e);
+            shard_peer_barrier(e);   // nobody rewrites a buffer a peer may still be reading
+        } else {
+            size_t off[SHARD_MAX_WORLD + 1];
+            for (int r = 0; r <= g.world; ++r) off[r] = (size_t)g.ROW[r] * sizeof(float4);
+            if (g.world > 1) CKCOMM(s->comm.allgatherv(s->d_uslot, off, st));
+            shard_scatter_kernel<<<nblk(N, 256), 256, 0, st>>>(s->d_uslot, e->d_perm, N, d_U); LAUNCHED(e);
+        }
     }
-    shard_scatter_kernel<<<nblk(N, 256), 256, 0, st>>>(s->d_uslot, e->d_perm, N, d_U); LAUNCHED(e);
     CK(cudaGetLastError());
     return PSE_OK;
 }

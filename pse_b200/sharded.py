@@ -4,7 +4,7 @@ One process per GPU.  After `pse_shard_init` (include/pse_b200.h) every operator
 each rank passes the same particle arrays and receives the same complete result.  Inside, a rank owns a contiguous range
 of x layers of cells (its particles: neighbour list, pruning, SpMV rows, Lanczos vectors, spreading, interpolation) and
 the x planes of the Fourier grid those layers cover; what crosses a slab face is exchanged by collectives the C++ engine
-issues itself on its stream through the NCCL C API (vector halo rows per Lanczos product, one two-float all-reduce per
+issues itself on its stream through the NCCL C API (vector halo rows per Lanczos product, one three-word (double) all-reduce per
 iteration, grid halo planes, two all-to-all transposes, one all-gather of the velocities).  Python only hands over the
 128-byte NCCL unique id, broadcast with torch.distributed.
 

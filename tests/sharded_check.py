@@ -70,6 +70,13 @@ for N, phi, xy in cases:
     t_mf_sh = timeit(lambda: sh.mobility(pos, F)); t_mf_1 = timeit(lambda: single.mobility(pos, F))
     t_st_sh = timeit(step_sh, 20); t_st_1 = timeit(step_1, 20)
     info = sh.shard_info().as_dict()
+    if os.environ.get("PSE_PROF"):
+        sh.set_profiling(True)
+        for _ in range(10):
+            step_sh()
+        prof = sh.profile(); sh.set_profiling(False)
+        if rank == 0:
+            print("phases (us/step, sharded rank 0):", {k: round(v[0] / 10 * 1e3, 1) for k, v in prof.items() if v[1]}, flush=True)
     if rank == 0:
         print(json.dumps({"N": N, "grid": int(p.Nx), "P": int(p.P), "xy": xy, "world": world, "mf_rel_l2": e_mf[0], "mf_rel_max": e_mf[1],
                           "vel_rel_l2": e_v[0], "vel_rel_max": e_v[1], "m": [res["sharded"][2], res["single"][2]], "pos_maxdiff_3steps": dpos,
