@@ -40,7 +40,33 @@ def lib():
         _lib.orc_real_fg.restype = None
         _lib.orc_real_fg.argtypes = [ctypes.c_double, ctypes.c_double, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
         _lib.orc_dense_mobility.argtypes = [ctypes.c_int] + [ctypes.c_double] * 4 + [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_double] * 3 + [ctypes.c_void_p]
+        _lib.orc_set_spteqr.argtypes = [ctypes.c_void_p]
     return _lib
+
+
+_blas = None
+
+
+def use_lapacke(on=True):
+    """Route the Lanczos tridiagonal solve through LAPACKE_spteqr as the reference does (PSEv1/Brownian.cu:540), bound from
+    the OpenBLAS that ships with scipy (the library the compiled reference links, oracle/Makefile).  Returns True if bound."""
+    global _blas
+    if not on:
+        lib().orc_set_spteqr(None)
+        return False
+    if _blas is None:
+        import glob
+        import scipy
+        cands = glob.glob(os.path.join(os.path.dirname(os.path.dirname(scipy.__file__)), "scipy.libs", "libscipy_openblas*.so"))
+        if not cands:
+            return False
+        _blas = ctypes.CDLL(cands[0])
+    try:
+        fn = ctypes.cast(_blas.scipy_LAPACKE_spteqr, ctypes.c_void_p)
+    except AttributeError:
+        return False
+    lib().orc_set_spteqr(fn)
+    return True
 
 
 def _f(a):

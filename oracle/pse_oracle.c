@@ -513,7 +513,30 @@ int orc_mwave(const orc_config* c, const orc_params* p, const float* pos4, const
  * Symmetric tridiagonal eigen-solve (cyclic Jacobi on the dense m x m matrix, m <= 100) and
  * c = W Lambda^{1/2} W^T e_1.  Stands in for LAPACKE_spteqr + PSEv1/Brownian.cu:568-582.
  * ---------------------------------------------------------------------------------------- */
+/* The reference's own route (PSEv1/Brownian.cu:540-582): LAPACKE_spteqr(LAPACK_ROW_MAJOR, 'I', m, alpha, &beta[1], W, m)
+ * in single precision, then Tm = W (Lambda^{1/2} W^T e_1).  The LAPACKE entry point is bound at run time from the
+ * OpenBLAS that ships with scipy (orc_set_spteqr; oracle/oraclewrap.py) - the same library the compiled reference links. */
+typedef int (*orc_spteqr_fn)(int layout, char compz, int n, float* d, float* e, float* z, int ldz);
+static orc_spteqr_fn g_spteqr = 0;
+void orc_set_spteqr(void* fn) { g_spteqr = (orc_spteqr_fn)fn; }
+int orc_have_spteqr(void) { return g_spteqr != 0; }
+static int tridiag_sqrt_e1_lapacke(int m, const double* alpha, const double* beta, double* cvec) {
+    float d[101], e[101];
+    float* W = (float*)calloc((size_t)m * m, sizeof(float));
+    for (int i = 0; i < m; ++i) d[i] = (float)alpha[i];
+    for (int i = 1; i < m; ++i) e[i - 1] = (float)beta[i];
+    int info = g_spteqr(101 /* LAPACK_ROW_MAJOR */, 'I', m, d, e, W, m);
+    if (info != 0) { free(W); return -6; }
+    for (int i = 0; i < m; ++i) {
+        float acc = 0.f;
+        for (int k = 0; k < m; ++k) acc += W[m * i + k] * (sqrtf(d[k]) * W[k]);   /* Brownian.cu:568-582 */
+        cvec[i] = acc;
+    }
+    free(W);
+    return 0;
+}
 static int tridiag_sqrt_e1(int m, const double* alpha, const double* beta /* beta[1..m-1] couple i-1,i */, double* cvec) {
+    if (g_spteqr) return tridiag_sqrt_e1_lapacke(m, alpha, beta, cvec);
     double* A = (double*)calloc((size_t)m * m, sizeof(double));
     double* V = (double*)calloc((size_t)m * m, sizeof(double));
     for (int i = 0; i < m; ++i) { A[i * m + i] = alpha[i]; V[i * m + i] = 1.0; }
