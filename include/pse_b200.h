@@ -191,6 +191,17 @@ int pse_pair_force(pse_engine* e, const float4* d_pos, const pse_pair_params* pr
 int pse_step_host(pse_engine* e, float* h_pos4, int* h_image3, const float* h_F4, float* h_vel4, uint32_t timestep,
                   float shear_rate, int* m_lanczos_out);
 
+/* Pipelined form of pse_step_host.  The state (positions, images) stays on the device between calls; a call uploads
+ * the step's forces (overlapped with the position-only head of the step), runs the step and STARTS the download of the
+ * new state into h_pos4 / h_image3 (/ h_vel4) on a copy stream, which proceeds while the next call computes.
+ * Double-buffer the host arrays (or call pse_wait) before reading them.  PSE_HOST_STATE_IN: h_pos4 / h_image3 are read
+ * first and replace the device state (implied on the first call and after an error).  Replaces the synchronous
+ * d_pos/d_net_force hand-over of Stokes::integrateStepOne (PSEv1/Stokes.cc:436-470) for host-resident callers. */
+#define PSE_HOST_STATE_IN 1u
+int pse_step_host_async(pse_engine* e, float* h_pos4, int* h_image3, const float* h_F4, float* h_vel4, uint32_t timestep,
+                        float shear_rate, uint32_t flags, int* m_lanczos_out);
+int pse_wait(pse_engine* e); /* blocks until the outputs of the last pse_step_host_async are on the host */
+
 /* ---- introspection ---------------------------------------------------------------------- */
 
 typedef struct {

@@ -14,6 +14,7 @@ PSE_OK = 0
 PSE_EINVAL, PSE_ENODEVICE, PSE_ECUDA, PSE_EGRID, PSE_ENOMEM, PSE_EEIGEN, PSE_ECAPACITY = -1, -2, -3, -4, -5, -6, -7
 PSE_FLAG_REF_PI = 1
 PSE_FLAG_LIFT_GRID_CAP = 2
+PSE_HOST_STATE_IN = 1
 
 
 class pse_box(ctypes.Structure):
@@ -110,6 +111,8 @@ SYMBOLS = {
     "pse_velocity": (_i, [_vp, _vp, _vp, _vp, _u32, _vp, _vp, _u32, ctypes.POINTER(_i)]),
     "pse_step": (_i, [_vp, _vp, _vp, _vp, _vp, _u32, _f, ctypes.POINTER(_i)]),
     "pse_step_host": (_i, [_vp, _vp, _vp, _vp, _vp, _u32, _f, ctypes.POINTER(_i)]),
+    "pse_step_host_async": (_i, [_vp, _vp, _vp, _vp, _vp, _u32, _f, _u32, ctypes.POINTER(_i)]),
+    "pse_wait": (_i, [_vp]),
     "pse_pair_force": (_i, [_vp, _vp, ctypes.POINTER(pse_pair_params), _vp, _i]),
     "pse_get_stats": (_i, [_vp, ctypes.POINTER(pse_stats)]),
     "pse_shard_plan": (_i, [_cfgp, _i, _i, ctypes.POINTER(pse_shard_info)]),

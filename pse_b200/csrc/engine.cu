@@ -114,9 +114,13 @@ struct pse_engine {
     cudaStream_t stream, own_stream;
     cudaStream_t stream2;         // second stream: the real-space branch of a step runs beside the wave-space branch
     cudaEvent_t ev_fork, ev_join;
-    cudaStream_t stream_h2d;      // pse_step_host: forces and images are uploaded beside the position-only head of the step
-    cudaEvent_t ev_F, ev_img;
+    cudaStream_t stream_h2d;      // pse_step_host*: forces and images are uploaded beside the position-only head of the step
+    cudaStream_t stream_d2h;      // ... and the new state goes back to the host beside the NEXT step's compute
+    cudaEvent_t ev_F, ev_img, ev_step, ev_out;
     bool wait_F, wait_img;        // uploads in flight that the next consumer on `stream` has to wait for
+    bool wait_out;                // a download of the device-resident state is in flight: integrate must not overwrite it yet
+    bool host_state_valid;        // d_hpos / d_himage hold the state of the host-driven run
+    bool out_has_vel;             // the download in flight also reads d_vel_work
     bool overlap;
     uint32_t N;
     size_t G, Gh;
@@ -135,6 +139,7 @@ struct pse_engine {
     uint32_t *d_nn_act, *d_nl_act;  // per-step pruned list (pairs inside r_cut at the current positions)
     size_t nl_act_cap;
     bool prune, pruned_valid;
+    bool wbin_valid;               // W order / records / factor rows current for the positions of this call
     size_t nl_cap;
     uint32_t nl_stride;            // row stride of the fixed-stride search output
     uint32_t* d_ell;
@@ -281,6 +286,26 @@ extern "C" int pse_get_profile(pse_engine* e, double* ms_out, uint64_t* calls_ou
 extern "C" const char* pse_profile_phase_name(int i) { return (i >= 0 && i < PH_COUNT) ? kPhaseNames[i] : ""; }
 
 static inline unsigned int nblk(size_t n, int b) { return (unsigned int)((n + b - 1) / b); }
+
+// Control words between host and device travel in KERNELS, not through the copy engines: a few bytes written to / read
+// from pinned host memory (device-addressable under unified addressing).  A cudaMemcpyAsync of 4 bytes on the compute
+// stream queues on the same DMA engine as the bulk transfers of pse_step_host_async and would wait behind 16-28 MB of them
+// (measured: 0.5 ms per step).
+__global__ void words_copy_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+__global__ void words2_copy_kernel(uint32_t* __restrict__ dst_a, const uint32_t* __restrict__ src_a, int na, uint32_t* __restrict__ dst_b,
+                                   const uint32_t* __restrict__ src_b, int nb) {
+    for (int i = threadIdx.x; i < na; i += blockDim.x) dst_a[i] = src_a[i];
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) dst_b[i] = src_b[i];
+}
+struct CoefArg { float c[LANCZOS_M_MAX + 2]; };
+__global__ void coef_store_kernel(float* __restrict__ dst, CoefArg a, int m) {
+    for (int i = threadIdx.x; i < m; i += blockDim.x) dst[i] = a.c[i];
+}
+__global__ void stepdev_store_kernel(StepDev* __restrict__ dst, StepDev v) { *dst = v; }
+#define WORDS(p) reinterpret_cast<uint32_t*>(p)
+#define CWORDS(p) reinterpret_cast<const uint32_t*>(p)
 
 // persistent launch: a whole number of waves of resident blocks
 static inline unsigned int persistent_grid(const pse_engine* e, size_t work_blocks, int blocks_per_sm) {
@@ -645,8 +670,11 @@ extern "C" void pse_destroy(pse_engine* e) {
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     if (e->ev_join) cudaEventDestroy(e->ev_join);
     if (e->stream_h2d) cudaStreamDestroy(e->stream_h2d);
+    if (e->stream_d2h) cudaStreamDestroy(e->stream_d2h);
     if (e->ev_F) cudaEventDestroy(e->ev_F);
     if (e->ev_img) cudaEventDestroy(e->ev_img);
+    if (e->ev_step) cudaEventDestroy(e->ev_step);
+    if (e->ev_out) cudaEventDestroy(e->ev_out);
     if (e->h_nlinfo) cudaFreeHost(e->h_nlinfo);
     if (e->d_nlinfo) cudaFree(e->d_nlinfo);
     if (e->h_ab) cudaFreeHost(e->h_ab);
@@ -776,8 +804,7 @@ extern "C" int pse_build_neighbors(pse_engine* e, const float4* d_pos) {
                                                            (uint32_t*)(e->d_nlinfo + 1), r0); LAUNCHED(e);
         }
         CKRC(exclusive_scan(e, e->d_nn + r0, e->d_head + r0, nrows + 1, e->d_scan_tmp));
-        CK(cudaMemcpyAsync(e->h_nlinfo, e->d_nlinfo, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(e->h_flag, e->d_head + r1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        words2_copy_kernel<<<1, 32, 0, st>>>(WORDS(e->h_nlinfo), CWORDS(e->d_nlinfo), 4, e->h_flag, e->d_head + r1, 1); LAUNCHED(e);
         CK(cudaStreamSynchronize(st));
         const uint32_t max_nn = (uint32_t)e->h_nlinfo[1];
         e->nnz = *e->h_flag;
@@ -827,7 +854,7 @@ static int launch_disp_check(pse_engine* e, const float4* d_pos) {
     ProfScope ps(e, PH_REORDER);
     CK(cudaMemsetAsync(e->d_flag, 0, sizeof(uint32_t), e->stream));
     max_disp_kernel<<<nblk(e->N, 256), 256, 0, e->stream>>>(d_pos, e->d_pos_build, e->N, e->box, e->d_flag); LAUNCHED(e);
-    CK(cudaMemcpyAsync(e->h_flag, e->d_flag, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    words_copy_kernel<<<1, 32, 0, e->stream>>>(e->h_flag, e->d_flag, 2); LAUNCHED(e);
     CK(cudaEventRecord(e->flag_event, e->stream));
     e->flag_pending = true;
     return PSE_OK;
@@ -850,6 +877,7 @@ static int ensure_neighbors(pse_engine* e, const float4* d_pos) {
         gather_pos_kernel<<<nblk(e->N, 256), 256, 0, e->stream>>>(d_pos, e->d_perm, e->N, e->d_spos, (float4*)e->d_px); LAUNCHED(e);
     }
     e->pruned_valid = false;
+    e->wbin_valid = false;
     return PSE_OK;
 }
 
@@ -951,37 +979,33 @@ static int run_spmv_plain(pse_engine* e, float4* y) {
     return PSE_OK;
 }
 
-// bin the (slot-ordered) particles by the tile of their support origin and gather the W-order records
-// Bin the (slot-ordered) particles by the tile of their support origin and gather the W-order records and factor rows.
-// Sharded calls pass the x-tile rows they need ([row_lo, row_hi) plus row_wrap, the row before row 0): everything else -
-// binning, sorting, gathering, factor rows - then only sees that slab's particles.
-static int run_wbin(pse_engine* e, const float4* sF, int row_lo = -1, int row_hi = -1, int row_wrap = -1) {
+// Bin the (slot-ordered) particles by the tile of their support origin and gather the W-order records and factor rows:
+// everything that depends on the positions only, valid until the positions change (ensure_neighbors).
+static int run_wbin(pse_engine* e) {
+    if (e->wbin_valid) return PSE_OK;
     ProfScope ps(e, PH_WBIN);
     cudaStream_t st = e->stream;
     const uint32_t N = e->N, nt = e->tg.ntile;
-    const bool slab = row_lo >= 0;
     CK(cudaMemsetAsync(e->d_wcount, 0, sizeof(uint32_t) * (nt + 1), st));
-    if (slab) wbin_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_spos, N, e->box, e->wp, e->tg, e->d_org, e->d_wcell_of, e->d_wcount, row_lo, row_hi, row_wrap);
-    else wbin_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_spos, N, e->box, e->wp, e->tg, e->d_org, e->d_wcell_of, e->d_wcount);
-    LAUNCHED(e);
+    wbin_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_spos, N, e->box, e->wp, e->tg, e->d_org, e->d_wcell_of, e->d_wcount); LAUNCHED(e);
     CKRC(exclusive_scan(e, e->d_wcount, e->d_wstart, nt + 1, e->d_scan_tmp));
     CK(cudaMemsetAsync(e->d_wcount, 0, sizeof(uint32_t) * (nt + 1), st));
     // unordered fill into scratch (d_wcell_of is free again after the fill reads it), then rank sort per tile
     cell_fill_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_wcell_of, N, e->d_wstart, e->d_wcount, e->d_wtmp); LAUNCHED(e);
     cell_sort_block_kernel<<<nt, 128, 0, st>>>(e->d_wstart, e->d_wtmp, e->d_wperm); LAUNCHED(e);
-    uint32_t nb = N;  // binned particles = d_wstart[nt]
-    if (slab) {
-        CK(cudaMemcpyAsync(e->h_nlinfo, e->d_wstart + nt, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        nb = reinterpret_cast<uint32_t*>(e->h_nlinfo)[0];
-    }
-    if (nb) {
-        wgather_kernel<<<nblk(nb, 256), 256, 0, st>>>(e->d_spos, sF, e->d_org, e->d_wperm, e->d_perm, nb, e->d_wpos, e->d_wF, e->d_worg, e->d_wid, e->tg,
-                                                      reinterpret_cast<int4*>(e->d_wrecs)); LAUNCHED(e);
-        if (e->wave_v2) launch_wweights(e->wp.P, st, e->d_wpos, e->d_worg, nb, e->box, e->wp, e->d_wrecs + WREC_HDR, wrec_stride(e->wp.P));
-        else launch_wweights(e->wp.P, st, e->d_wpos, e->d_worg, nb, e->box, e->wp, e->d_wwt);
-        LAUNCHED(e);
-    }
+    wgather_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_spos, nullptr, e->d_org, e->d_wperm, e->d_perm, N, e->d_wpos, e->d_wF, e->d_worg, e->d_wid, e->tg,
+                                                 reinterpret_cast<int4*>(e->d_wrecs), nullptr, 1); LAUNCHED(e);
+    if (e->wave_v2) launch_wweights(e->wp.P, st, e->d_wpos, e->d_worg, N, e->box, e->wp, e->d_wrecs + WREC_HDR, wrec_stride(e->wp.P));
+    else launch_wweights(e->wp.P, st, e->d_wpos, e->d_worg, N, e->box, e->wp, e->d_wwt);
+    LAUNCHED(e);
+    e->wbin_valid = true;
+    return PSE_OK;
+}
+// the forces of the call into the W records (spreading reads them from there)
+static int run_wforce(pse_engine* e, const float4* sF) {
+    ProfScope ps(e, PH_WBIN);
+    wgather_kernel<<<nblk(e->N, 256), 256, 0, e->stream>>>(e->d_spos, sF, e->d_org, e->d_wperm, e->d_perm, e->N, e->d_wpos, e->d_wF, e->d_worg, e->d_wid, e->tg,
+                                                        reinterpret_cast<int4*>(e->d_wrecs), nullptr, 2); LAUNCHED(e);
     return PSE_OK;
 }
 
@@ -989,7 +1013,10 @@ static int run_wbin(pse_engine* e, const float4* sF, int row_lo = -1, int row_hi
 static int run_wave(pse_engine* e, const float4* sF, float4* U, int accumulate, bool det, bool noise, const float* d_u_grid) {
     cudaStream_t st = e->stream;
     const int P = e->wp.P;
-    if (e->tiled) CKRC(run_wbin(e, det ? sF : nullptr));
+    if (e->tiled) {
+        CKRC(run_wbin(e));
+        if (det) CKRC(run_wforce(e, sF));
+    }
     if (det) {
         {
         ProfScope ps(e, PH_SPREAD);
@@ -1119,8 +1146,7 @@ static int lanczos_batch(pse_engine* e, const float* d_u_particles, int m, bool 
     float* alpha = e->h_ab;
     float* beta = e->h_ab + LANCZOS_M_MAX + 1;
     for (int j = 0; j < m; ++j) CKRC(lanczos_iteration(e, j, dual && j == 0));
-    CK(cudaMemcpyAsync(alpha, e->d_alpha, sizeof(float) * m, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(beta, e->d_beta, sizeof(float) * (m + 1), cudaMemcpyDeviceToHost, st));
+    words2_copy_kernel<<<1, 128, 0, st>>>(WORDS(alpha), CWORDS(e->d_alpha), m, WORDS(beta), CWORDS(e->d_beta), m + 1); LAUNCHED(e);
     return PSE_OK;
 }
 
@@ -1143,8 +1169,7 @@ static int lanczos_finish(pse_engine* e, float4* U, int accumulate, int m, int* 
         ++m;
         const int j = m - 1;
         CKRC(lanczos_iteration(e, j));
-        CK(cudaMemcpyAsync(alpha + j, e->d_alpha + j, sizeof(float), cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(beta + j + 1, e->d_beta + j + 1, sizeof(float), cudaMemcpyDeviceToHost, st));
+        words2_copy_kernel<<<1, 32, 0, st>>>(WORDS(alpha + j), CWORDS(e->d_alpha + j), 1, WORDS(beta + j + 1), CWORDS(e->d_beta + j + 1), 1); LAUNCHED(e);
         CK(cudaStreamSynchronize(st));
         if (beta[j + 1] < 1e-8f) { m = j; break; }
         CKRC(solve_coeffs(e, m, alpha, beta, c));
@@ -1159,9 +1184,11 @@ static int lanczos_finish(pse_engine* e, float4* U, int accumulate, int m, int* 
     }
     c = c_prev;
     m = (int)c.size();
-    float* hc = e->h_ab + 2 * LANCZOS_M_MAX + 4;  // pinned: the copy needs no host synchronisation (the next write to it
-    for (int i = 0; i < m; ++i) hc[i] = (float)c[i];  // comes after the next step's alpha/beta read-back sync)
-    CK(cudaMemcpyAsync(e->d_coef, hc, sizeof(float) * m, cudaMemcpyHostToDevice, st));
+    {
+        CoefArg ca;   // by value in the launch: no copy engine, no host buffer to keep alive
+        for (int i = 0; i < m; ++i) ca.c[i] = (float)c[i];
+        coef_store_kernel<<<1, 128, 0, st>>>(e->d_coef, ca, m); LAUNCHED(e);
+    }
     const float thermal = sqrtf((float)(2.0 * e->cfg.T / e->cfg.dt));  // PSEv1/Brownian.cu:739
     ProfScope ps(e, PH_COMBINE);
     if (e->row1 > e->row0) {
@@ -1207,7 +1234,7 @@ extern "C" int pse_mwave(pse_engine* e, const float4* d_pos, const float4* d_F, 
 static int upload_stepdev(pse_engine* e, uint32_t timestep) {
     e->h_stepdev->key = timestep + e->prm.seed_hashed;  // PSEv1/Brownian.cu:117,176
     e->h_stepdev->noise_fac = sqrtf((float)(2.0 * e->cfg.T / e->cfg.dt / e->wp.quadW));  // PSEv1/Brownian.cu:198
-    CK(cudaMemcpyAsync(e->d_stepdev, e->h_stepdev, sizeof(StepDev), cudaMemcpyHostToDevice, e->stream));
+    stepdev_store_kernel<<<1, 1, 0, e->stream>>>(e->d_stepdev, *e->h_stepdev); LAUNCHED(e);
     return PSE_OK;
 }
 
@@ -1265,6 +1292,23 @@ extern "C" int pse_velocity(pse_engine* e, const float4* d_pos, const float4* d_
     if (det || wnoise) CKRC(ensure_wave_buffers(e));
     CKRC(ensure_neighbors(e, d_pos));  // host decision (list still valid?) happens before the fixed part
     if (rnoise) CKRC(ensure_krylov(e));
+    // everything that needs the positions only runs first: forces still in flight from the host (pse_step_host_async) are
+    // waited for after it
+    {
+        const bool need_prune = (det || rnoise) && e->prune && !e->pruned_valid, need_wbin = (det || wnoise) && e->tiled && !e->wbin_valid;
+        const bool fork = need_prune && need_wbin && e->overlap && !e->prof_on && e->stream2;
+        if (fork) {   // pruning (L1 gathers) beside the binning / factor rows (HBM streaming)
+            CK(cudaEventRecord(e->ev_fork, st));
+            CK(cudaStreamWaitEvent(e->stream2, e->ev_fork, 0));
+            e->stream = e->stream2;
+            const int rc = ensure_pruned(e);
+            e->stream = st;
+            if (rc != PSE_OK) return rc;
+            CK(cudaEventRecord(e->ev_join, e->stream2));
+        } else if (need_prune) CKRC(ensure_pruned(e));
+        if (need_wbin) CKRC(run_wbin(e));
+        if (fork) CK(cudaStreamWaitEvent(st, e->ev_join, 0));
+    }
     if (e->wait_F) { e->wait_F = false; CK(cudaStreamWaitEvent(st, e->ev_F, 0)); }
     CKRC(upload_stepdev(e, timestep));
     const int m_batch = lanczos_batch_size(e);
@@ -1284,7 +1328,6 @@ extern "C" int pse_velocity(pse_engine* e, const float4* d_pos, const float4* d_
         if (!hit) {
             if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
             k.valid = false;
-            e->pruned_valid = false;
             cudaGraph_t graph = nullptr;
             const uint64_t l0 = e->launches;
             CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
@@ -1301,7 +1344,6 @@ extern "C" int pse_velocity(pse_engine* e, const float4* d_pos, const float4* d_
         else e->launches += e->graph_nodes;  // kernels replayed by the graph
         CK(cudaGraphLaunch(e->graph_exec, st));
         e->graph_launches++;
-        e->pruned_valid = true;
     } else {
         CKRC(velocity_fixed_part(e, d_F, d_U, det, wnoise, rnoise, d_u_particles, d_u_grid, m_batch));
     }
@@ -1354,6 +1396,7 @@ extern "C" int pse_step(pse_engine* e, float4* d_pos, int3* d_image, const float
     float4* vel = d_vel ? d_vel : e->d_vel_work;
     CKRC(pse_velocity(e, d_pos, d_F, vel, timestep, nullptr, nullptr, 7u, m_out));
     if (e->wait_img) { e->wait_img = false; CK(cudaStreamWaitEvent(e->stream, e->ev_img, 0)); }
+    if (e->wait_out) { e->wait_out = false; CK(cudaStreamWaitEvent(e->stream, e->ev_out, 0)); }
     {
         ProfScope ps(e, PH_INTEGRATE);
         integrate_kernel<<<nblk(e->N, 256), 256, 0, e->stream>>>(d_pos, d_image, vel, e->N, e->box, e->cfg.dt, shear_rate); LAUNCHED(e);
@@ -1362,8 +1405,13 @@ extern "C" int pse_step(pse_engine* e, float4* d_pos, int3* d_image, const float
     return PSE_OK;
 }
 
-extern "C" int pse_step_host(pse_engine* e, float* h_pos4, int* h_image3, const float* h_F4, float* h_vel4, uint32_t timestep,
-                             float shear_rate, int* m_out) {
+// Host-buffer entry points.  The state of a host-driven run (positions, images) lives on the device between calls; what
+// crosses PCIe every step is the step's input (forces, 16 N bytes up) and its result (positions + images, 28 N bytes down),
+// and both transfers are hidden: the forces arrive on a copy stream while the position-only head of the step runs
+// (neighbour-list check / rebuild, pruning, wave-space binning and Gaussian factors), the result leaves on a second copy
+// stream while the NEXT step computes.  pse_wait blocks until the last result is on the host.
+extern "C" int pse_step_host_async(pse_engine* e, float* h_pos4, int* h_image3, const float* h_F4, float* h_vel4, uint32_t timestep,
+                                   float shear_rate, uint32_t flags, int* m_out) {
     if (!e || !h_pos4 || !h_F4) return PSE_EINVAL;
     const size_t N = e->N;
     cudaStream_t st = e->stream;
@@ -1374,25 +1422,52 @@ extern "C" int pse_step_host(pse_engine* e, float* h_pos4, int* h_image3, const 
     }
     if (!e->stream_h2d) {
         CK(cudaStreamCreateWithFlags(&e->stream_h2d, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&e->stream_d2h, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&e->ev_F, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&e->ev_img, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&e->ev_step, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming));
+        CK(cudaEventRecord(e->ev_step, st));
     }
-    // positions first, on the compute stream; forces and images follow on the copy stream while the neighbour-list check
-    // (and rebuild) runs, and are waited for where they are first read (pse_velocity / integrate_kernel).  The previous
-    // call ended with a stream synchronisation, so nothing is still reading the staging buffers.
-    CK(cudaMemcpyAsync(e->d_hpos, h_pos4, sizeof(float4) * N, cudaMemcpyHostToDevice, st));
+    // (the velocity scratch is rewritten early in a step: a pending download of it has to finish first)
+    if (e->wait_out && e->out_has_vel) { e->wait_out = false; CK(cudaStreamWaitEvent(st, e->ev_out, 0)); }
+    // the forces of this step: staged behind the previous step's last kernels (which may still be reading the staging buffer)
+    CK(cudaStreamWaitEvent(e->stream_h2d, e->ev_step, 0));
     CK(cudaMemcpyAsync(e->d_hF, h_F4, sizeof(float4) * N, cudaMemcpyHostToDevice, e->stream_h2d));
     CK(cudaEventRecord(e->ev_F, e->stream_h2d));
-    if (h_image3) CK(cudaMemcpyAsync(e->d_himage, h_image3, sizeof(int3) * N, cudaMemcpyHostToDevice, e->stream_h2d));
-    else CK(cudaMemsetAsync(e->d_himage, 0, sizeof(int3) * N, e->stream_h2d));
-    CK(cudaEventRecord(e->ev_img, e->stream_h2d));
-    e->wait_F = e->wait_img = true;
-    CKRC(pse_step(e, e->d_hpos, e->d_himage, e->d_hF, h_vel4 ? e->d_vel_work : nullptr, timestep, shear_rate, m_out));
-    CK(cudaMemcpyAsync(h_pos4, e->d_hpos, sizeof(float4) * N, cudaMemcpyDeviceToHost, st));
-    if (h_image3) CK(cudaMemcpyAsync(h_image3, e->d_himage, sizeof(int3) * N, cudaMemcpyDeviceToHost, st));
-    if (h_vel4) CK(cudaMemcpyAsync(h_vel4, e->d_vel_work, sizeof(float4) * N, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    e->wait_F = true;
+    if ((flags & PSE_HOST_STATE_IN) || !e->host_state_valid) {
+        // the caller's positions / images replace the device state (first call, or the host changed them)
+        if (e->wait_out) { e->wait_out = false; CK(cudaStreamWaitEvent(st, e->ev_out, 0)); }
+        CK(cudaMemcpyAsync(e->d_hpos, h_pos4, sizeof(float4) * N, cudaMemcpyHostToDevice, st));
+        if (h_image3) CK(cudaMemcpyAsync(e->d_himage, h_image3, sizeof(int3) * N, cudaMemcpyHostToDevice, e->stream_h2d));
+        else CK(cudaMemsetAsync(e->d_himage, 0, sizeof(int3) * N, e->stream_h2d));
+        CK(cudaEventRecord(e->ev_img, e->stream_h2d));
+        e->wait_img = true;
+        e->host_state_valid = true;
+    }
+    const int rc = pse_step(e, e->d_hpos, e->d_himage, e->d_hF, h_vel4 ? e->d_vel_work : nullptr, timestep, shear_rate, m_out);
+    if (rc != PSE_OK) { e->host_state_valid = false; return rc; }
+    CK(cudaEventRecord(e->ev_step, st));
+    CK(cudaStreamWaitEvent(e->stream_d2h, e->ev_step, 0));
+    CK(cudaMemcpyAsync(h_pos4, e->d_hpos, sizeof(float4) * N, cudaMemcpyDeviceToHost, e->stream_d2h));
+    if (h_image3) CK(cudaMemcpyAsync(h_image3, e->d_himage, sizeof(int3) * N, cudaMemcpyDeviceToHost, e->stream_d2h));
+    if (h_vel4) CK(cudaMemcpyAsync(h_vel4, e->d_vel_work, sizeof(float4) * N, cudaMemcpyDeviceToHost, e->stream_d2h));
+    CK(cudaEventRecord(e->ev_out, e->stream_d2h));
+    e->wait_out = true;   // the next integrate waits for this download before it overwrites the state
+    e->out_has_vel = h_vel4 != nullptr;
     return PSE_OK;
+}
+extern "C" int pse_wait(pse_engine* e) {
+    if (!e) return PSE_EINVAL;
+    if (e->ev_out) CK(cudaEventSynchronize(e->ev_out));
+    return PSE_OK;
+}
+// synchronous form: state in, one step, state out, wait
+extern "C" int pse_step_host(pse_engine* e, float* h_pos4, int* h_image3, const float* h_F4, float* h_vel4, uint32_t timestep,
+                             float shear_rate, int* m_out) {
+    CKRC(pse_step_host_async(e, h_pos4, h_image3, h_F4, h_vel4, timestep, shear_rate, PSE_HOST_STATE_IN, m_out));
+    return pse_wait(e);
 }
 
 // test hook: host tridiagonal square root (compared against numpy in the CPU tests)

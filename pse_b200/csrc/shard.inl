@@ -274,7 +274,7 @@ static int shard_update_geometry(pse_engine* e) {
     cudaStream_t st = e->stream;
     const CellGrid& cg = e->cg;
     layer_start_kernel<<<nblk(cg.ncx + 1, 128), 128, 0, st>>>(e->d_cell_start, cg.ncx, cg.ncy * cg.ncz, s->d_layer_start); LAUNCHED(e);
-    CK(cudaMemcpyAsync(s->h_layer_start, s->d_layer_start, sizeof(uint32_t) * (cg.ncx + 1), cudaMemcpyDeviceToHost, st));
+    words_copy_kernel<<<1, 128, 0, st>>>(s->h_layer_start, s->d_layer_start, cg.ncx + 1); LAUNCHED(e);
     CK(cudaStreamSynchronize(st));
     const uint32_t* ls = s->h_layer_start;
     g.KH = g.world > 1 ? (int)ceilf(cg.reach_fx * cg.ncx) + 1 : 0;

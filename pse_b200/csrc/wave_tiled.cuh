@@ -58,33 +58,41 @@ __global__ void wbin_kernel(const float4* __restrict__ spos, uint32_t N, PseBox 
     atomicAdd(count + c, 1u);
 }
 
+// part bit 0: everything that depends on the positions only (wpos, worg, wid, record header words 3 .. 11);
+// part bit 1: the force (wF / record header words 0 .. 2).  Split so that a step can bin and weight while its forces are
+// still on their way from the host (pse_step_host_async).
 __global__ void wgather_kernel(const float4* __restrict__ spos, const float4* __restrict__ sF, const int4* __restrict__ org,
                                const uint32_t* __restrict__ wperm, const uint32_t* __restrict__ perm, uint32_t N,
                                float4* __restrict__ wpos, float4* __restrict__ wF, int4* __restrict__ worg,
                                uint32_t* __restrict__ wid, TileGrid tg, int4* __restrict__ wrec,
-                               const uint32_t* __restrict__ nbinned = nullptr) {
+                               const uint32_t* __restrict__ nbinned = nullptr, int part = 3) {
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= N || (nbinned && w >= __ldg(nbinned))) return;
     const uint32_t s = wperm[w];
     // particle id of W slot w: interpolation writes U[id] without chasing two permutations (perm == null: the slot itself,
     // slab-decomposed engines collect velocities in slot order)
     const uint32_t id = perm ? __ldg(perm + s) : s;
-    wid[w] = id;
-    wpos[w] = __ldg(spos + s);
-    const int4 o = org[s];
-    if (sF && !wrec) wF[w] = __ldg(sF + s);
-    if (wrec) {
-        // header of the W record streamed by spread2_kernel / interp2_kernel (wave_v2.cuh), 12 words:
-        //   (Fx, Fy, Fz, particle id | accumulator word offset of the origin's cell, origin residues x, y, z |
-        //    origin inside the tile x, y, z, -); the Gaussian factor row follows (wweights_kernel)
-        const int lx = o.x % tg.tx, ly = o.y % tg.ty, lz = o.z % tg.tz;
-        int4* h = reinterpret_cast<int4*>(reinterpret_cast<float*>(wrec) + (size_t)w * tg.rs);
-        const float4 f = sF ? __ldg(sF + s) : make_float4(0.f, 0.f, 0.f, 0.f);
-        h[0] = make_int4(__float_as_int(f.x), __float_as_int(f.y), __float_as_int(f.z), (int)id);
-        h[1] = make_int4((((lx / tg.cp) * tg.cy + ly / tg.cp) * tg.cz + lz / tg.cp) * tg.cs, lx % tg.cp, ly % tg.cp, lz % tg.cp);
-        h[2] = make_int4(lx, ly, lz, 0);
+    int4* h = wrec ? reinterpret_cast<int4*>(reinterpret_cast<float*>(wrec) + (size_t)w * tg.rs) : nullptr;
+    if (part & 1) {
+        wid[w] = id;
+        wpos[w] = __ldg(spos + s);
+        const int4 o = org[s];
+        if (h) {
+            // header of the W record streamed by spread2_kernel / interp2_kernel (wave_v2.cuh), 12 words:
+            //   (Fx, Fy, Fz, particle id | accumulator word offset of the origin's cell, origin residues x, y, z |
+            //    origin inside the tile x, y, z, -); the Gaussian factor row follows (wweights_kernel)
+            const int lx = o.x % tg.tx, ly = o.y % tg.ty, lz = o.z % tg.tz;
+            h[0] = make_int4(0, 0, 0, (int)id);   // (zero force until the force part runs)
+            h[1] = make_int4((((lx / tg.cp) * tg.cy + ly / tg.cp) * tg.cz + lz / tg.cp) * tg.cs, lx % tg.cp, ly % tg.cp, lz % tg.cp);
+            h[2] = make_int4(lx, ly, lz, 0);
+        }
+        worg[w] = o;
     }
-    worg[w] = o;
+    if (part & 2) {
+        const float4 f = sF ? __ldg(sF + s) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (h) h[0] = make_int4(__float_as_int(f.x), __float_as_int(f.y), __float_as_int(f.z), (int)id);   // one 16-byte store
+        else if (sF) wF[w] = f;
+    }
 }
 
 // candidate origin cells of one dimension for a tile starting at node t0 with extent e:

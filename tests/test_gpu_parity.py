@@ -300,6 +300,33 @@ def test_stale_list_is_rebuilt_and_host_step_matches_device_step(cuda):
     assert np.abs(ph - pd.cpu().numpy()).max() < 1e-5 and np.array_equal(ih, im.cpu().numpy())
 
 
+def test_pipelined_host_steps_match_device_steps(cuda):
+    """pse_step_host_async / pse_wait (device-resident state, forces up and state down on copy streams beside the compute,
+    double-buffered host arrays) against the same steps through the device entry point: same trajectories, including
+    list rebuilds, a state re-upload in the middle (PSE_HOST_STATE_IN) and a velocity download."""
+    import torch
+    N, L = 20000, util.box_length(20000, 0.2)
+    a = System(N, L, seed=4, lattice=True, want_ref=False)
+    b = System(N, L, seed=4, lattice=True, want_ref=False)
+    pd = a.pos.clone(); im = torch.zeros((N, 3), dtype=torch.int32, device="cuda"); vd = torch.zeros_like(a.F)
+    hp = [a.pos_np.copy(), a.pos_np.copy()]; hi = [np.zeros((N, 3), dtype=np.int32) for _ in range(2)]
+    hv = np.zeros((N, 4), dtype=np.float32)
+    Fs = [util.random_forces(N, 50 + t) for t in range(8)]
+    a.eng.lanczos_m = 3; b.eng.lanczos_m = 3
+    for t in range(8):
+        a.eng.step(pd, im, torch.from_numpy(Fs[t]).cuda(), t, shear_rate=0.1, vel=vd)
+        if t == 4:       # the host edits the state: it must be taken from the host arrays again
+            b.eng.wait()
+            hp[t & 1][:] = hp[(t - 1) & 1]; hi[t & 1][:] = hi[(t - 1) & 1]
+        b.eng.step_host_async(hp[t & 1], hi[t & 1], Fs[t], t, shear_rate=0.1, vel_np=hv if t == 7 else None, state_in=(t == 4))
+    b.eng.wait()
+    assert a.eng.stats()["nlist_builds"] >= 2
+    # (spreading merges tile windows with floating-point reductions in arbitrary order: equal to round-off, not bitwise)
+    assert np.abs(hp[7 & 1] - pd.cpu().numpy()).max() < 2e-5 and np.array_equal(hi[7 & 1], im.cpu().numpy())
+    assert np.abs(hv[:, :3] - vd.cpu().numpy()[:, :3]).max() < 2e-4 * np.abs(hv[:, :3]).max()
+    a.eng.close(); b.eng.close()
+
+
 def test_tiled_wave_path_is_bitwise_reproducible_and_matches_scatter_path(cuda):
     """The tile-owned spreading has a fixed summation order (no atomics): repeated runs are bitwise equal; the
     fallback scatter path (PSE_WAVE_TILED=0, used for tiny grids / P > 10) gives the same answer to round-off."""
