@@ -60,7 +60,7 @@ struct ProfSpan { int phase; cudaEvent_t a, b; };
 // read the peers' buffers directly over NVLink behind a device-side flag barrier (peer.cuh; pointers from CUDA IPC handles
 // exchanged once); PSE_COMM=coll selects the NCCL collectives of comm.cuh (pack, ncclSend/ncclRecv, unpack) instead.
 #define SHARD_MAX_WORLD 16
-#define SHARD_DRIFT_NODES 2.0f
+#define SHARD_DRIFT_NODES 1.0f
 struct ShardBounds { int xs[SHARD_MAX_WORLD + 1], ys[SHARD_MAX_WORLD + 1]; int world; };   // kernel argument: plane / y-row bounds
 struct ShardGeom {                        // identical on every rank (derived from replicated data only)
     int world;
@@ -94,7 +94,7 @@ struct ShardState {
     bool use_peer, peer_ready;
     PeerSync psync;
     unsigned char* d_pad;                 // own flag / reduction pad
-    uint32_t epoch, red_count;            // synchronisation points / pair reductions issued so far (same sequence on every rank)
+    uint32_t epoch[2], red_count;         // synchronisation points per channel / reductions issued so far (same sequence on every rank)
     const PX* peer_px[SHARD_MAX_WORLD];
     const float4* peer_uslot[SHARD_MAX_WORLD];
     const float* peer_grid[SHARD_MAX_WORLD];

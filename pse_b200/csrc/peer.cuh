@@ -10,11 +10,13 @@
 #include <stdint.h>
 
 #define PEER_MAX 16
-// one per rank, in that rank's memory:  flags[PEER_MAX] (arrival epochs, written by the peers) | red[2][PEER_MAX][4]
+// one per rank, in that rank's memory:  flags[2 channels][PEER_MAX] (arrival epochs, written by the peers) | red[2][PEER_MAX][4]
+// Two channels: the wave-space and the real-space branch of a step run on two streams and synchronise independently.
 #define PEER_PAD_RED_OFF 256
 #define PEER_PAD_BYTES (PEER_PAD_RED_OFF + 2 * PEER_MAX * 4 * 8)
 struct PeerSync {
     int rank, world;
+    int chan;                       // synchronisation channel (0 wave space / velocities, 1 real space)
     unsigned char* pad[PEER_MAX];   // pad[q]: rank q's pad as addressable from this rank
     uint32_t* err;                  // own error word (read by the host with the displacement check)
 };
@@ -36,8 +38,8 @@ __device__ __forceinline__ void peer_arrive_and_wait(const PeerSync& ps, uint32_
     const int q = threadIdx.x;
     if (q < ps.world) {
         __threadfence_system();
-        st_release_sys(reinterpret_cast<uint32_t*>(ps.pad[q]) + ps.rank, epoch);
-        const uint32_t* mine = reinterpret_cast<const uint32_t*>(ps.pad[ps.rank]) + q;
+        st_release_sys(reinterpret_cast<uint32_t*>(ps.pad[q]) + ps.chan * PEER_MAX + ps.rank, epoch);
+        const uint32_t* mine = reinterpret_cast<const uint32_t*>(ps.pad[ps.rank]) + ps.chan * PEER_MAX + q;
         const long long t0 = clock64();
         while ((int)(ld_acquire_sys(mine) - epoch) < 0) {
             if (clock64() - t0 > (20ll << 30)) { atomicOr(ps.err, 2u); break; }

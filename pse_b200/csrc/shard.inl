@@ -86,9 +86,10 @@ static void shard_free(ShardState* s) {
 
 // ---- static geometry: identical on every rank, derived from the configuration only ------------------------------------------
 // x layers of cells are dealt out evenly; a rank transforms the x planes its layers cover; halo widths cover the Gaussian
-// support (P / 2 to the left, P / 2 + 1 to the right of a particle's node, one more for the layer/plane rounding) plus the
-// motion the Verlet buffer allows between two list rebuilds (r_buff / 2 in the sheared frame) plus the tilt drift
-// SHARD_DRIFT_NODES that forces a rebuild (stale_from_bits).
+// support ((P - 1) / 2 nodes to the left and (P + 1) / 2 to the right of a particle's node, PSEv1/Mobility.cu:173-214; one
+// more on the right because the last layer's particles can sit on the first plane of the next slab) plus the motion the
+// Verlet buffer allows between two list rebuilds (r_buff / 2 in the sheared frame), the tilt drift SHARD_DRIFT_NODES that
+// forces a rebuild (stale_from_bits) and one node for float rounding; shard_cover_kernel guards the assumption.
 static int shard_static_geometry(const pse_config& cfg, const pse_params& prm, int world, int tile_x, ShardGeom* g, char* err, size_t errlen) {
     memset(g, 0, sizeof(*g));
     g->world = world;
@@ -106,8 +107,8 @@ static int shard_static_geometry(const pse_config& cfg, const pse_params& prm, i
     if (world == 1) { g->HL = g->HR = 0; return PSE_OK; }
     const float ms = fabsf(cfg.max_strain);
     const int dn = (int)ceilf(0.5f * r_buff * sqrtf(1.f + ms * ms) / prm.hx) + (int)SHARD_DRIFT_NODES + 1;
-    g->HL = prm.P / 2 + dn;
-    g->HR = prm.P / 2 + 2 + dn;
+    g->HL = (prm.P - 1) / 2 + dn;
+    g->HR = (prm.P + 1) / 2 + 1 + dn;
     // the search reach in layers at the largest tilt (shard_update_geometry recomputes it for the current one)
     const float reach = rlist * sqrtf(1.f + ms * ms) / cfg.box.Lx * 1.0001f + 1e-6f;
     const int kh = (int)ceilf(reach * ncx) + 1;
@@ -371,7 +372,7 @@ static int shard_connect_peers(pse_engine* e) {
 // host involvement.  Virtual ranks of one process share a GPU and a CUDA context, where a kernel spinning on a flag can
 // starve the very work it waits for (lazy module loading and allocator calls synchronise the context): there the barrier
 // is taken on the host - the pull kernels and the pointer logic they exercise are the same.
-static void shard_peer_barrier(pse_engine* e) {
+static void shard_peer_barrier(pse_engine* e, int chan) {
     ShardState* s = e->shard;
     s->collectives++;
     if (s->comm.lw) {
@@ -379,7 +380,9 @@ static void shard_peer_barrier(pse_engine* e) {
         pthread_barrier_wait(&s->comm.lw->bar);
         return;
     }
-    peer_barrier_kernel<<<1, 32, 0, e->stream>>>(s->psync, ++s->epoch); LAUNCHED(e);
+    PeerSync ps = s->psync;
+    ps.chan = chan;
+    peer_barrier_kernel<<<1, 32, 0, e->stream>>>(ps, ++s->epoch[chan]); LAUNCHED(e);
 }
 
 // boundary rows of the vector about to be multiplied: my first KH layers go to the left neighbour, my last KH layers to the
@@ -394,7 +397,7 @@ static int shard_exchange_px(pse_engine* e) {
     const uint32_t nrR = g.SL1[right] - g.ROW[right], nrL = g.ROW[left + 1] - g.SR0[left];
     s->bytes_sent += ((uint64_t)nsL + nsR) * 16;
     if (s->use_peer) {
-        shard_peer_barrier(e);
+        shard_peer_barrier(e, 1);
         if (nrR + nrL) {
             peer_pull_px_kernel<<<nblk(nrR + nrL, 256), 256, 0, st>>>((float4*)e->d_px, (const float4*)s->peer_px[right], g.ROW[right], nrR,
                                                                      (const float4*)s->peer_px[left], g.SR0[left], nrL); LAUNCHED(e);
@@ -413,7 +416,9 @@ static int shard_allreduce2(pse_engine* e) {
     ProfScope ps(e, PH_COMM_RED);
     s->bytes_sent += 24 * (s->world - 1);
     if (s->use_peer && !s->comm.lw) {
-        peer_allreduce3_kernel<<<1, 32, 0, e->stream>>>(s->psync, ++s->epoch, (s->red_count++) & 1u, e->d_red2); LAUNCHED(e);
+        PeerSync ps = s->psync;
+        ps.chan = 1;
+        peer_allreduce3_kernel<<<1, 32, 0, e->stream>>>(ps, ++s->epoch[1], (s->red_count++) & 1u, e->d_red2); LAUNCHED(e);
         s->collectives++;
         return PSE_OK;
     }
@@ -432,7 +437,7 @@ static int shard_halo_reduce(pse_engine* e) {
     s->bytes_sent += bL + bR;
     if (s->use_peer) {
         const int left = (s->rank + g.world - 1) % g.world, right = (s->rank + 1) % g.world;
-        shard_peer_barrier(e);
+        shard_peer_barrier(e, 0);
         // the right neighbour's left halo lands on my last HL planes, the left neighbour's right halo on my first HR planes
         peer_planes_kernel<<<gb, 256, 0, st>>>(e->d_grid, s->Gl, s->peer_grid[right], (size_t)s->nxaq[right] * s->plane, s->plane,
                                                 s->BL + s->nown - g.HL, s->BLq[right] - g.HL, g.HL, 1); LAUNCHED(e);
@@ -460,7 +465,7 @@ static int shard_halo_fetch(pse_engine* e) {
     s->bytes_sent += bL + bR;
     if (s->use_peer) {
         const int left = (s->rank + g.world - 1) % g.world, right = (s->rank + 1) % g.world;
-        shard_peer_barrier(e);
+        shard_peer_barrier(e, 0);
         peer_planes_kernel<<<gb, 256, 0, st>>>(e->d_grid, s->Gl, s->peer_grid[right], (size_t)s->nxaq[right] * s->plane, s->plane,
                                                 s->BL + s->nown, s->BLq[right], g.HR, 0); LAUNCHED(e);
         peer_planes_kernel<<<gb, 256, 0, st>>>(e->d_grid, s->Gl, s->peer_grid[left], (size_t)s->nxaq[left] * s->plane, s->plane,
@@ -534,7 +539,7 @@ static int shard_wave(pse_engine* e, const float4* sF, bool det, bool noise, con
         }
         ProfScope ps(e, PH_COMM_TRANS);   // transpose: x slabs -> y slabs
         if (s->use_peer) {
-            shard_peer_barrier(e);
+            shard_peer_barrier(e, 0);
             s->bytes_sent += s->a2a_recv_off[g.world] - (s->a2a_recv_off[s->rank + 1] - s->a2a_recv_off[s->rank]);
             if (nyl > 0) {
                 peer_pull_trans_kernel<<<e->num_sms * 8, 256, 0, st>>>(s->d_tr, pp_sloc, pb, wp.Nx, wp.Ny, g.YS[s->rank], nyl, wp.Nzp); LAUNCHED(e);
@@ -557,7 +562,7 @@ static int shard_wave(pse_engine* e, const float4* sF, bool det, bool noise, con
     {
         ProfScope ps(e, PH_COMM_TRANS);    // transpose back: y slabs -> x slabs
         if (s->use_peer) {
-            shard_peer_barrier(e);
+            shard_peer_barrier(e, 0);
             s->bytes_sent += s->a2a_send_off[g.world] - (s->a2a_send_off[s->rank + 1] - s->a2a_send_off[s->rank]);
             peer_pull_slab_kernel<<<e->num_sms * 8, 256, 0, st>>>(s->d_sloc, pp_tr, pb, wp.Nx, wp.Ny, g.X[s->rank], nown, wp.Nzp); LAUNCHED(e);
         } else if (g.world > 1) {
@@ -601,17 +606,35 @@ static int shard_velocity(pse_engine* e, const float4* d_pos, const float4* d_F,
     const uint32_t r0 = e->row0, r1 = e->row1, nrows = r1 - r0;
     // forces in slot order (replicated pass over N: every rank reads its halo rows from the same array)
     if (wdet || rdet) { gather_vec_kernel<<<nblk(N, 256), 256, 0, st>>>(d_F, e->d_perm, N, e->d_sx, (float4*)e->d_px); LAUNCHED(e); }
-    int acc = 0;
-    if (wdet || wnoise) { CKRC(shard_wave(e, e->d_sx, wdet, wnoise, d_u_grid)); acc = 1; }
+    // The real-space branch (prune, M_real F, Lanczos with its vector halos and reductions: channel 1) and the wave-space
+    // branch (bin, spread, FFTs, transposes, grid halos, interpolate: channel 0) touch disjoint buffers until they meet in the
+    // velocity, so they are issued on two streams: the kernels of one branch fill the gaps the other leaves while it waits
+    // for its neighbours.  Profiling keeps them serial so that the per-phase times stay meaningful.
+    const bool wave = wdet || wnoise, real = rdet || rnoise;
+    const bool fork = wave && real && g.world > 1 && s->use_peer && e->overlap && !e->prof_on && e->stream2;
     const int m_batch = lanczos_batch_size(e);
     const bool dual = rdet && rnoise && spmv_dual_available(e);
-    if (rdet && !dual) CKRC(run_spmv_plain(e, e->d_sy));
+    int rc = PSE_OK;
+    if (fork) {
+        CK(cudaEventRecord(e->ev_fork, st));
+        CK(cudaStreamWaitEvent(e->stream2, e->ev_fork, 0));
+        e->stream = e->stream2;
+    }
+    if (rdet && !dual) rc = run_spmv_plain(e, e->d_sy);
+    if (rc == PSE_OK && rnoise) rc = lanczos_batch(e, d_u_particles, m_batch, dual);
+    if (fork) {
+        e->stream = st;
+        if (rc == PSE_OK) CK(cudaEventRecord(e->ev_join, e->stream2));
+    }
+    if (rc != PSE_OK) return rc;
+    int acc = 0;
+    if (wave) { CKRC(shard_wave(e, e->d_sx, wdet, wnoise, d_u_grid)); acc = 1; }
+    if (fork) CK(cudaStreamWaitEvent(st, e->ev_join, 0));
     if (rdet && !rnoise) {
         if (nrows) { scatter_add_kernel<<<nblk(nrows, 256), 256, 0, st>>>(e->d_sy, nullptr, r1, s->d_uslot, acc, r0); LAUNCHED(e); }
         acc = 1;
     }
     if (rnoise) {
-        CKRC(lanczos_batch(e, d_u_particles, m_batch, dual));
         CKRC(lanczos_finish(e, s->d_uslot, acc, m_batch, m_out, rdet ? e->d_sy : nullptr, nullptr));
         acc = 1;
     }
@@ -624,9 +647,9 @@ static int shard_velocity(pse_engine* e, const float4* d_pos, const float4* d_F,
             PeerBounds rb;
             for (int r = 0; r < g.world; ++r) pu.p[r] = s->peer_uslot[r];
             for (int r = 0; r <= g.world; ++r) rb.row[r] = g.ROW[r];
-            shard_peer_barrier(e);
+            shard_peer_barrier(e, 0);
             peer_gather_scatter_kernel<<<nblk(N, 256), 256, 0, st>>>(pu, rb, g.world, e->d_perm, N, d_U); LAUNCHED(e);
-            shard_peer_barrier(e);   // nobody rewrites a buffer a peer may still be reading
+            shard_peer_barrier(e, 0);   // nobody rewrites a buffer a peer may still be reading
         } else {
             size_t off[SHARD_MAX_WORLD + 1];
             for (int r = 0; r <= g.world; ++r) off[r] = (size_t)g.ROW[r] * sizeof(float4);
