@@ -380,8 +380,8 @@ def main():
     eng.wait()
     barrier()
     t0 = time.perf_counter()
-    for i in range(KE):
-        eng.step_host_async(hp[i & 1], hi[i & 1], hf, step_no); step_no += 1
+    for i in range(KE):   # (slab-decomposed: every rank uploads the forces, rank 0 downloads the result)
+        eng.step_host_async(hp[i & 1], hi[i & 1], hf, step_no, state_out=(rank == 0)); step_no += 1
     eng.wait()
     torch.cuda.synchronize()
     t_e2e = max_over_ranks(time.perf_counter() - t0)
@@ -395,7 +395,7 @@ def main():
     t_sync = max_over_ranks(time.perf_counter() - t0)
     line["e2e"] = {"value": KE / t_e2e, "unit": "steps/s", "h2d_bytes_per_step": 16 * N, "d2h_bytes_per_step": 28 * N,
                    "api": "pse_step_host_async + pse_wait (C ABI, pinned host buffers, device-resident state: forces in, positions + images out every step, "
-                          "copies overlapped with compute)" + (", every rank" if world > 1 else ""),
+                          "copies overlapped with compute)" + ("; forces uploaded on every rank, result downloaded on rank 0" if world > 1 else ""),
                    "synchronous": {"value": KS / t_sync, "h2d_bytes_per_step": 44 * N, "d2h_bytes_per_step": 28 * N,
                                    "api": "pse_step_host (positions + images + forces in, positions + images out, blocking)"}}
 

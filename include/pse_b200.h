@@ -198,6 +198,8 @@ int pse_step_host(pse_engine* e, float* h_pos4, int* h_image3, const float* h_F4
  * first and replace the device state (implied on the first call and after an error).  Replaces the synchronous
  * d_pos/d_net_force hand-over of Stokes::integrateStepOne (PSEv1/Stokes.cc:436-470) for host-resident callers. */
 #define PSE_HOST_STATE_IN 1u
+#define PSE_HOST_NO_STATE_OUT 2u /* leave h_pos4 / h_image3 alone (slab-decomposed runs: every rank holds the same state on its
+                                    device, one of them downloading it is enough) */
 int pse_step_host_async(pse_engine* e, float* h_pos4, int* h_image3, const float* h_F4, float* h_vel4, uint32_t timestep,
                         float shear_rate, uint32_t flags, int* m_lanczos_out);
 int pse_wait(pse_engine* e); /* blocks until the outputs of the last pse_step_host_async are on the host */

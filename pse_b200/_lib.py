@@ -15,6 +15,7 @@ PSE_EINVAL, PSE_ENODEVICE, PSE_ECUDA, PSE_EGRID, PSE_ENOMEM, PSE_EEIGEN, PSE_ECA
 PSE_FLAG_REF_PI = 1
 PSE_FLAG_LIFT_GRID_CAP = 2
 PSE_HOST_STATE_IN = 1
+PSE_HOST_NO_STATE_OUT = 2
 
 
 class pse_box(ctypes.Structure):

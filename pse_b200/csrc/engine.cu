@@ -1450,8 +1450,10 @@ extern "C" int pse_step_host_async(pse_engine* e, float* h_pos4, int* h_image3, 
     if (rc != PSE_OK) { e->host_state_valid = false; return rc; }
     CK(cudaEventRecord(e->ev_step, st));
     CK(cudaStreamWaitEvent(e->stream_d2h, e->ev_step, 0));
-    CK(cudaMemcpyAsync(h_pos4, e->d_hpos, sizeof(float4) * N, cudaMemcpyDeviceToHost, e->stream_d2h));
-    if (h_image3) CK(cudaMemcpyAsync(h_image3, e->d_himage, sizeof(int3) * N, cudaMemcpyDeviceToHost, e->stream_d2h));
+    if (!(flags & PSE_HOST_NO_STATE_OUT)) {
+        CK(cudaMemcpyAsync(h_pos4, e->d_hpos, sizeof(float4) * N, cudaMemcpyDeviceToHost, e->stream_d2h));
+        if (h_image3) CK(cudaMemcpyAsync(h_image3, e->d_himage, sizeof(int3) * N, cudaMemcpyDeviceToHost, e->stream_d2h));
+    }
     if (h_vel4) CK(cudaMemcpyAsync(h_vel4, e->d_vel_work, sizeof(float4) * N, cudaMemcpyDeviceToHost, e->stream_d2h));
     CK(cudaEventRecord(e->ev_out, e->stream_d2h));
     e->wait_out = true;   // the next integrate waits for this download before it overwrites the state

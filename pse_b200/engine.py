@@ -197,14 +197,15 @@ class Engine:
                                    float(shear_rate), ctypes.byref(m)))
         return m.value
 
-    def step_host_async(self, pos_np, image_np, F_np, timestep, shear_rate=0.0, vel_np=None, state_in=False):
+    def step_host_async(self, pos_np, image_np, F_np, timestep, shear_rate=0.0, vel_np=None, state_in=False, state_out=True):
         """Pipelined host step: the state stays on the device between calls, forces go up and the new state comes down on
         copy streams beside the compute.  `pos_np` / `image_np` are OUTPUTS (inputs too with state_in=True / on the first
         call); they are valid after wait() - alternate two sets of host arrays to keep the pipeline full."""
         m = ctypes.c_int(0)
         vp = lambda a: ctypes.c_void_p(0 if a is None else a.ctypes.data)
         self._ck(lib.pse_step_host_async(self._h, vp(pos_np), vp(image_np), vp(F_np), vp(vel_np), int(timestep) & 0xFFFFFFFF,
-                                         float(shear_rate), _lib.PSE_HOST_STATE_IN if state_in else 0, ctypes.byref(m)))
+                                         float(shear_rate), (_lib.PSE_HOST_STATE_IN if state_in else 0) | (0 if state_out else _lib.PSE_HOST_NO_STATE_OUT),
+                                         ctypes.byref(m)))
         return m.value
 
     def wait(self):
