@@ -139,6 +139,7 @@ struct pse_engine {
     uint32_t *d_nn_act, *d_nl_act;  // per-step pruned list (pairs inside r_cut at the current positions)
     size_t nl_act_cap;
     bool prune, pruned_valid;
+    bool csr_valid;                // d_nl holds the packed copy of the buffered list (made on demand)
     bool wbin_valid;               // W order / records / factor rows current for the positions of this call
     size_t nl_cap;
     uint32_t nl_stride;            // row stride of the fixed-stride search output
@@ -757,6 +758,7 @@ static int ensure_krylov(pse_engine* e) {
     return PSE_OK;
 }
 static int shard_update_geometry(pse_engine* e);
+static int ensure_csr(pse_engine* e);
 
 // ---- binning + neighbour list ------------------------------------------------------------------
 extern "C" int pse_build_neighbors(pse_engine* e, const float4* d_pos) {
@@ -826,9 +828,10 @@ extern "C" int pse_build_neighbors(pse_engine* e, const float4* d_pos) {
         CK(cudaMalloc(&e->d_nl_act, sizeof(uint32_t) * e->nl_act_cap));
         e->nl_gen++;
     }
-    if (nrows) {
-        compact_rows_kernel<<<nblk((size_t)nrows * 8, 256), 256, 0, st>>>(e->d_ell, e->nl_stride, e->d_nn, e->d_head, r1, e->d_nl, r0); LAUNCHED(e);
-    }
+    // The fixed-stride search output is what the per-step pruning reads; the packed (CSR) copy of the buffered list is only
+    // made when somebody walks it directly (unpruned SpMV, pair forces, export): ensure_csr.
+    e->csr_valid = false;
+    if (!e->prune) CKRC(ensure_csr(e));
     CK(cudaMemcpyAsync(e->d_pos_build, d_pos, sizeof(float4) * N, cudaMemcpyDeviceToDevice, st));
     delete ps;
     e->xy_build = e->box.xy;
@@ -836,6 +839,16 @@ extern "C" int pse_build_neighbors(pse_engine* e, const float4* d_pos) {
     e->flag_pending = false;
     e->nlist_builds++;
     CK(cudaGetLastError());
+    return PSE_OK;
+}
+
+static int ensure_csr(pse_engine* e) {
+    if (e->csr_valid) return PSE_OK;
+    const uint32_t nrows = e->row1 - e->row0;
+    if (nrows) {
+        compact_rows_kernel<<<nblk((size_t)nrows * 8, 256), 256, 0, e->stream>>>(e->d_ell, e->nl_stride, e->d_nn, e->d_head, e->row1, e->d_nl, e->row0); LAUNCHED(e);
+    }
+    e->csr_valid = true;
     return PSE_OK;
 }
 
@@ -885,8 +898,8 @@ static int ensure_neighbors(pse_engine* e, const float4* d_pos) {
 static int ensure_pruned(pse_engine* e) {
     if (!e->prune || e->pruned_valid) return PSE_OK;
     ProfScope ps(e, PH_PRUNE);
-    prune_kernel<<<persistent_grid(e, nblk((size_t)(e->row1 - e->row0) * 8, 256), 8), 256, 0, e->stream>>>(e->d_spos, e->row1, e->d_nn, e->d_head, e->d_nl, e->rp,
-                                                                                         e->box, e->d_nn_act, e->d_nl_act, e->row0); LAUNCHED(e);
+    prune_kernel<<<persistent_grid(e, nblk((size_t)(e->row1 - e->row0) * 8, 256), 8), 256, 0, e->stream>>>(e->d_spos, e->row1, e->d_nn, e->d_head, e->d_ell, e->rp,
+                                                                                         e->box, e->d_nn_act, e->d_nl_act, e->row0, e->nl_stride); LAUNCHED(e);
     e->pruned_valid = true;
     return PSE_OK;
 }
@@ -898,6 +911,7 @@ extern "C" int pse_neighbor_list(pse_engine* e, uint32_t* d_n_neigh, uint32_t* d
     if (e->shard && e->shard->world > 1) return fail(e, PSE_EINVAL, "pse_neighbor_list: a slab-decomposed engine holds the rows of its own slab only");
     if (nnz_out) *nnz_out = e->nnz;
     if (!d_n_neigh && !d_headlist && !d_nlist) return PSE_OK;
+    CKRC(ensure_csr(e));
     const uint32_t N = e->N;
     uint32_t *nn_id = nullptr, *head_id = nullptr;
     CK(cudaMalloc(&nn_id, sizeof(uint32_t) * (N + 1)));
@@ -1368,6 +1382,7 @@ extern "C" int pse_pair_force(pse_engine* e, const float4* d_pos, const pse_pair
     pp.rcut_sq = pp.rcut * pp.rcut;
     if (e->shard && e->shard->world > 1) return fail(e, PSE_EINVAL, "pse_pair_force: a slab-decomposed engine holds the rows of its own slab only");
     CKRC(ensure_neighbors(e, d_pos));
+    CKRC(ensure_csr(e));
     pair_force_kernel<<<nblk((size_t)e->N * 8, 256), 256, 0, e->stream>>>(e->d_spos, e->N, e->d_nn, e->d_head, e->d_nl, e->d_perm, pp, e->box,
                                                                       d_F, accumulate); LAUNCHED(e);
     CK(cudaGetLastError());

@@ -139,7 +139,7 @@ __device__ __forceinline__ void ld_px(const PX* ptr, float4& p, float4& x) {
 __global__ void __launch_bounds__(256)
 prune_kernel(const float4* __restrict__ spos, uint32_t N, const uint32_t* __restrict__ nn, const uint32_t* __restrict__ head,
              const uint32_t* __restrict__ nl, RealParams rp, PseBox box, uint32_t* __restrict__ nn_act, uint32_t* __restrict__ nl_act,
-             uint32_t row_begin = 0) {
+             uint32_t row_begin = 0, uint32_t ell_stride = 0 /* != 0: nl holds fixed-stride rows relative to row_begin (search output) */) {
     const int sub = threadIdx.x & 7;
     const int grp = (threadIdx.x & 31) >> 3;  // group inside the warp
     for (uint32_t row0 = row_begin + blockIdx.x * 32; row0 < N; row0 += gridDim.x * 32) {
@@ -147,7 +147,11 @@ prune_kernel(const float4* __restrict__ spos, uint32_t N, const uint32_t* __rest
         const bool live = row < N;
         uint32_t n = 0, h = 0;
         float4 pi = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (live) { n = __ldg(nn + row); h = __ldg(head + row); pi = __ldg(spos + row); }
+        const uint32_t* __restrict__ src = nl;
+        if (live) {
+            n = __ldg(nn + row); h = __ldg(head + row); pi = __ldg(spos + row);
+            src = ell_stride ? nl + (size_t)(row - row_begin) * ell_stride : nl + h;
+        }
         // all 32 lanes iterate together (ballot needs convergence): trip count = longest row in the warp
         uint32_t nmax = n;
 #pragma unroll
@@ -158,7 +162,7 @@ prune_kernel(const float4* __restrict__ spos, uint32_t N, const uint32_t* __rest
             bool in = false;
             uint32_t j = 0;
             if (k < n) {
-                j = __ldg(nl + h + k);
+                j = __ldg(src + k);
                 const float4 pj = __ldg(spos + j);
                 const float3 dl = make_float3(PSE_SUB(pi.x, pj.x), PSE_SUB(pi.y, pj.y), PSE_SUB(pi.z, pj.z));
                 const float3 r = box.min_image_fast(dl);
