@@ -387,6 +387,8 @@ def main():
     t_e2e = max_over_ranks(time.perf_counter() - t0)
     assert np.isfinite(hp[(KE - 1) & 1]).all()
     KS = max(K // 2, 1)
+    eng.step_host_async(hp[0], hi[0], hf, step_no); step_no += 1     # (untimed: every rank's host arrays hold the common state again)
+    eng.wait()
     barrier()
     t0 = time.perf_counter()
     for _ in range(KS):
@@ -398,6 +400,26 @@ def main():
                           "copies overlapped with compute)" + ("; forces uploaded on every rank, result downloaded on rank 0" if world > 1 else ""),
                    "synchronous": {"value": KS / t_sync, "h2d_bytes_per_step": 44 * N, "d2h_bytes_per_step": 28 * N,
                                    "api": "pse_step_host (positions + images + forces in, positions + images out, blocking)"}}
+
+    # steady shear (the plugin's main use case): the tilt moves every step, so the captured step graph is not replayed and the
+    # step is issued eagerly; same suspension, shear rate 1, tilt advanced by rate * dt per step as box_resize would
+    if world == 1:
+        qs, ims = pos.clone(), img.clone()
+        xy = 0.0
+        with torch.cuda.stream(stream):
+            for _ in range(3):
+                xy += dt; eng.set_tilt(xy); eng.step(qs, ims, F, step_no, shear_rate=1.0); step_no += 1
+            torch.cuda.synchronize()
+            a0, b0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(stream)
+            for _ in range(K):
+                xy += dt; eng.set_tilt(xy); eng.step(qs, ims, F, step_no, shear_rate=1.0); step_no += 1
+            b0.record(stream)
+            torch.cuda.synchronize()
+        line["sheared"] = {"value": K / (a0.elapsed_time(b0) * 1e-3), "unit": "steps/s",
+                           "note": "same suspension under steady shear (rate 1, tilt changing every step: eager launches instead of graph replay)"}
+        eng.set_tilt(0.0)
+        del qs, ims
 
     # deterministic M.F time (second half of the BASELINE metric)
     barrier()

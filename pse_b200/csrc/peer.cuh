@@ -103,17 +103,22 @@ peer_pull_slab_kernel(float2* __restrict__ sloc, PeerPtrs<const float2> tr, Peer
         peer_copy_row(sloc + (size_t)row * Nzp, src, Nzp, lane);
     }
 }
-// planes [p_dst, p_dst + n) of my real-space buffer (+)= planes [p_src, ..) of a peer's buffer (component strides differ)
+// planes [p_dst, p_dst + n) of my real-space buffer (+)= planes [p_src, ..) of a peer's buffer (component strides differ);
+// one launch serves both neighbours: blocks with odd index take job B
+struct PeerPlaneJob { const float* peer; size_t Glp; int p_dst, p_src, n; };
 __global__ void __launch_bounds__(256)
-peer_planes_kernel(float* __restrict__ grid, size_t Gl, const float* __restrict__ peer, size_t Glp, size_t plane, int p_dst, int p_src, int n, int add) {
-    const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+peer_planes_kernel(float* __restrict__ grid, size_t Gl, size_t plane, PeerPlaneJob ja, PeerPlaneJob jb, int add) {
+    const PeerPlaneJob j = (blockIdx.x & 1) ? jb : ja;
+    const float* __restrict__ peer = j.peer;
+    const size_t stride = (size_t)(gridDim.x >> 1) * blockDim.x, t0 = (size_t)(blockIdx.x >> 1) * blockDim.x + threadIdx.x;
+    const int n = j.n;
     if ((plane & 3) == 0) {
         const size_t p4 = plane / 4, tot = (size_t)3 * n * p4;
         for (size_t t = t0; t < tot; t += stride) {
             const size_t k = t % p4;
             const int i = (int)((t / p4) % n), c = (int)(t / (p4 * n));
-            float4* d = reinterpret_cast<float4*>(grid + c * Gl + (size_t)(p_dst + i) * plane) + k;
-            const float4 v = reinterpret_cast<const float4*>(peer + c * Glp + (size_t)(p_src + i) * plane)[k];
+            float4* d = reinterpret_cast<float4*>(grid + c * Gl + (size_t)(j.p_dst + i) * plane) + k;
+            const float4 v = reinterpret_cast<const float4*>(peer + c * j.Glp + (size_t)(j.p_src + i) * plane)[k];
             if (add) { float4 o = *d; o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w; *d = o; }
             else *d = v;
         }
@@ -122,8 +127,8 @@ peer_planes_kernel(float* __restrict__ grid, size_t Gl, const float* __restrict_
         for (size_t t = t0; t < tot; t += stride) {
             const size_t k = t % plane;
             const int i = (int)((t / plane) % n), c = (int)(t / (plane * n));
-            float* d = grid + c * Gl + (size_t)(p_dst + i) * plane + k;
-            const float v = peer[c * Glp + (size_t)(p_src + i) * plane + k];
+            float* d = grid + c * Gl + (size_t)(j.p_dst + i) * plane + k;
+            const float v = peer[c * j.Glp + (size_t)(j.p_src + i) * plane + k];
             *d = add ? *d + v : v;
         }
     }

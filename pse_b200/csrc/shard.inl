@@ -439,10 +439,16 @@ static int shard_halo_reduce(pse_engine* e) {
         const int left = (s->rank + g.world - 1) % g.world, right = (s->rank + 1) % g.world;
         shard_peer_barrier(e, 0);
         // the right neighbour's left halo lands on my last HL planes, the left neighbour's right halo on my first HR planes
-        peer_planes_kernel<<<gb, 256, 0, st>>>(e->d_grid, s->Gl, s->peer_grid[right], (size_t)s->nxaq[right] * s->plane, s->plane,
-                                                s->BL + s->nown - g.HL, s->BLq[right] - g.HL, g.HL, 1); LAUNCHED(e);
-        peer_planes_kernel<<<gb, 256, 0, st>>>(e->d_grid, s->Gl, s->peer_grid[left], (size_t)s->nxaq[left] * s->plane, s->plane,
-                                                s->BL, s->BLq[left] + (g.X[left + 1] - g.X[left]), g.HR, 1); LAUNCHED(e);
+        // (distinct planes because a slab is at least as thick as either halo: one launch adds both)
+        const PeerPlaneJob ja = {s->peer_grid[right], (size_t)s->nxaq[right] * s->plane, s->BL + s->nown - g.HL, s->BLq[right] - g.HL, g.HL};
+        const PeerPlaneJob jb = {s->peer_grid[left], (size_t)s->nxaq[left] * s->plane, s->BL, s->BLq[left] + (g.X[left + 1] - g.X[left]), g.HR};
+        if (s->nown >= g.HL + g.HR) {
+            peer_planes_kernel<<<2 * gb, 256, 0, st>>>(e->d_grid, s->Gl, s->plane, ja, jb, 1); LAUNCHED(e);
+        } else {   // the two target ranges overlap: one after the other
+            const PeerPlaneJob none = {nullptr, 0, 0, 0, 0};
+            peer_planes_kernel<<<2 * gb, 256, 0, st>>>(e->d_grid, s->Gl, s->plane, ja, none, 1); LAUNCHED(e);
+            peer_planes_kernel<<<2 * gb, 256, 0, st>>>(e->d_grid, s->Gl, s->plane, jb, none, 1); LAUNCHED(e);
+        }
         return PSE_OK;
     }
     shard_planes_kernel<<<gb, 256, 0, st>>>(e->d_grid, s->d_hsL, s->Gl, s->plane, s->BL - g.HL, g.HL, 0); LAUNCHED(e);
@@ -466,10 +472,9 @@ static int shard_halo_fetch(pse_engine* e) {
     if (s->use_peer) {
         const int left = (s->rank + g.world - 1) % g.world, right = (s->rank + 1) % g.world;
         shard_peer_barrier(e, 0);
-        peer_planes_kernel<<<gb, 256, 0, st>>>(e->d_grid, s->Gl, s->peer_grid[right], (size_t)s->nxaq[right] * s->plane, s->plane,
-                                                s->BL + s->nown, s->BLq[right], g.HR, 0); LAUNCHED(e);
-        peer_planes_kernel<<<gb, 256, 0, st>>>(e->d_grid, s->Gl, s->peer_grid[left], (size_t)s->nxaq[left] * s->plane, s->plane,
-                                                s->BL - g.HL, s->BLq[left] + (g.X[left + 1] - g.X[left]) - g.HL, g.HL, 0); LAUNCHED(e);
+        const PeerPlaneJob ja = {s->peer_grid[right], (size_t)s->nxaq[right] * s->plane, s->BL + s->nown, s->BLq[right], g.HR};
+        const PeerPlaneJob jb = {s->peer_grid[left], (size_t)s->nxaq[left] * s->plane, s->BL - g.HL, s->BLq[left] + (g.X[left + 1] - g.X[left]) - g.HL, g.HL};
+        peer_planes_kernel<<<2 * gb, 256, 0, st>>>(e->d_grid, s->Gl, s->plane, ja, jb, 0); LAUNCHED(e);
         return PSE_OK;
     }
     // to the left neighbour: my first HR planes (its right halo); to the right neighbour: my last HL planes (its left halo)
