@@ -7,6 +7,7 @@
 // Stokes::integrateStepOne (PSEv1/Stokes.cc:429-523).
 #include <cuda_runtime.h>
 #include <cufft.h>
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: named ranges per phase for timelines (no cost without a tool attached)
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -251,6 +252,7 @@ struct ProfScope {
     cudaEvent_t b;
     bool on;
     ProfScope(pse_engine* eng, int phase) : e(eng), b(nullptr), on(eng->prof_on) {
+        nvtxRangePushA(kPhaseNames[phase]);
         if (!on) return;
         auto& pool = *e->prof_pool;
         while (pool.size() < e->prof_used + 2) { cudaEvent_t ev; cudaEventCreate(&ev); pool.push_back(ev); }
@@ -259,7 +261,7 @@ struct ProfScope {
         cudaEventRecord(a, e->stream);
         e->prof_spans->push_back({phase, a, b});
     }
-    ~ProfScope() { if (on) cudaEventRecord(b, e->stream); }
+    ~ProfScope() { if (on) cudaEventRecord(b, e->stream); nvtxRangePop(); }
 };
 static void prof_collect(pse_engine* e) {
     if (!e->prof_spans || e->prof_spans->empty()) return;

@@ -81,25 +81,25 @@ def test_integrator_refuses_to_run_without_cuda():
     assert PSEv1.integrate.PSE is PSEv1.integrate.PSEv1
 
 
-def test_replica_logic_world_size_2_gloo(tmp_path):
-    """bench.py's multi-GPU path (independent replicas): aggregate = all units / slowest rank, seeds distinct."""
+def test_nccl_id_hand_over_world_size_2_gloo(tmp_path):
+    """The only thing the host layer does for the slab-decomposed engine (pse_b200/sharded.py): rank 0 creates the 128-byte
+    NCCL unique id through the C ABI (pse_comm_unique_id binds the NCCL the process already loaded) and broadcasts it; every
+    rank must end up with the same bytes.  Ring neighbours are mutual.  (CPU, gloo.)"""
     script = tmp_path / "w.py"
     script.write_text(textwrap.dedent(f"""
         import os, sys
         sys.path.insert(0, {ROOT!r})
-        import torch.distributed as dist
-        from pse_b200 import replicas as R
+        import torch, torch.distributed as dist
+        from pse_b200 import sharded as S
         dist.init_process_group("gloo")
-        rank, world, local = R.rank_world()
-        assert world == 2 and dist.get_world_size() == 2
-        secs = 1.0 + rank                      # rank 1 is slower
-        thr = R.aggregate_throughput(10, secs)
-        assert abs(thr - 20 / 2.0) < 1e-12, thr
-        assert R.max_over_ranks(rank) == 1.0 and R.sum_over_ranks(1) == 2.0
-        seeds = R.replica_seeds(0, rank)
-        gathered = [None, None]
-        dist.all_gather_object(gathered, seeds)
-        assert len(set(gathered[0]) | set(gathered[1])) == 6 or gathered[0] != gathered[1]
+        rank, world = dist.get_rank(), dist.get_world_size()
+        uid = bytes(S.nccl_unique_id())
+        assert len(uid) == 128 and any(uid)
+        got = [None] * world
+        dist.all_gather_object(got, uid)
+        assert got[0] == got[1]
+        l, r = S.ring_peers(rank, world)
+        assert l == r == 1 - rank                # two ranks: both neighbours are the other rank
         dist.barrier(); dist.destroy_process_group()
         open(os.path.join({str(tmp_path)!r}, f"ok_{{rank}}"), "w").write("ok")
     """))
