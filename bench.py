@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--phi", type=float, default=0.3)
     ap.add_argument("--error", type=float, default=1e-3)
     ap.add_argument("--xi", type=float, default=0.5)
-    ap.add_argument("--r-buff", type=float, default=0.8)
+    ap.add_argument("--r-buff", type=float, default=1.6)   # Verlet buffer of the engine's list: measured optimum of the rebuild / pruning trade-off (profiles/r2_notes.md)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-N", type=int, default=1000000)
     ap.add_argument("--config5", action="store_true", help="also time BASELINE.json configs[4] (N = 8M, 432^3); default with 8 ranks")

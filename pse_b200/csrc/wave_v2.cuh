@@ -281,6 +281,9 @@ __host__ __device__ constexpr int interp2_pad(int P, int HY, int HZ) {
     }
     return best_pad;
 }
+__device__ __forceinline__ void cp_async4s(uint32_t smem_addr, const void* gmem_src) {   // shared-window address
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr), "l"(gmem_src));
+}
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src));
 }
@@ -333,20 +336,34 @@ interp2_kernel(const float* __restrict__ wrecs, const uint32_t* __restrict__ wce
         ring.init();
         for (int c = 0; c < STAGES - 1 && c < nchunks; ++c) issue_chunk(c);
     }
-    // stage the window (periodic wrap per node): a warp takes whole x planes, lanes run over (y, z) with z fastest
+    // stage the window (periodic wrap per node): a warp takes whole x planes, lanes run over (y, z) with z fastest.  The
+    // (y, z) part of a node's address is the same in every plane: each lane works out its NE offsets once, the plane loop
+    // is then one address add and three 4-byte asynchronous copies per node (the index arithmetic was a third of the
+    // kernel's instructions)
+    constexpr int NE = (HY * HZ + 31) / 32;
+    int poff[NE];
+#pragma unroll
+    for (int t = 0; t < NE; ++t) {
+        const int e = lane + 32 * t;
+        const int ly = e / HZ, lz = e - ly * HZ;
+        int y = t0y + ly; if (y >= wp.Ny) y -= wp.Ny;
+        int z = t0z + lz; if (z >= wp.Nz) z -= wp.Nz;
+        poff[t] = e < HY * HZ ? y * wp.Nz + z : -1;
+    }
+    const uint32_t g_sh = smem_u32(g) + 4u * (uint32_t)lane;
     for (int lx = wid; lx < HX; lx += NW) {
         int x = relx + lx; if (x >= wp.nxw) x -= wp.Nx;
         if (x >= wp.nxa) continue;   // (slab buffer: window planes no particle of this rank reaches)
         const float* gx = grid + (size_t)x * wp.Ny * wp.Nz;
-        float* sx = g + lx * XS;
-        for (int e = lane; e < HY * HZ; e += 32) {
-            const int ly = e / HZ, lz = e - ly * HZ;
-            int y = t0y + ly; if (y >= wp.Ny) y -= wp.Ny;
-            int z = t0z + lz; if (z >= wp.Nz) z -= wp.Nz;
-            const float* src = gx + (size_t)y * wp.Nz + z;
-            cp_async4(sx + e, src);  // (node = lx * XS + ly * HZ + lz = lx * XS + e)
-            cp_async4(sx + GT + e, src + G);
-            cp_async4(sx + 2 * GT + e, src + 2 * G);
+        const uint32_t sx = g_sh + 4u * (uint32_t)(lx * XS);
+#pragma unroll
+        for (int t = 0; t < NE; ++t) {
+            if (poff[t] < 0) continue;
+            const float* src = gx + poff[t];
+            const uint32_t dst = sx + 128u * t;   // (node = lx * XS + ly * HZ + lz = lx * XS + e)
+            cp_async4s(dst, src);
+            cp_async4s(dst + 4u * GT, src + G);
+            cp_async4s(dst + 8u * GT, src + 2 * G);
         }
     }
     cp_async_commit();
