@@ -93,6 +93,7 @@ struct ShardState {
     uint64_t collectives;
     // peer-memory transport (peer.cuh)
     bool use_peer, peer_ready;
+    bool push;                            // spectrum transposes as pushes (remote stores) instead of pulls
     PeerSync psync;
     unsigned char* d_pad;                 // own flag / reduction pad
     uint32_t epoch[2], red_count;         // synchronisation points per channel / reductions issued so far (same sequence on every rank)

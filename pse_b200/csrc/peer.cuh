@@ -68,26 +68,39 @@ __global__ void peer_allreduce3_kernel(PeerSync ps, uint32_t epoch, uint32_t par
 }
 
 struct PeerSlabs { int xs[PEER_MAX + 1], ys[PEER_MAX + 1]; };
-__device__ __forceinline__ void peer_copy_row(float2* __restrict__ dst, const float2* __restrict__ src, int n, int lane) {
+// Two rows per warp and trip, all loads issued before the first store: a load from a peer takes ~2 us over NVLink, so the
+// bytes in flight per SM, not the instruction count, set the rate of these kernels.
+__device__ __forceinline__ void peer_copy_rows2(float2* __restrict__ dst0, const float2* __restrict__ src0, float2* __restrict__ dst1,
+                                                const float2* __restrict__ src1, int n, int lane) {
     if ((n & 1) == 0) {
-        const float4* s4 = reinterpret_cast<const float4*>(src);
-        float4* d4 = reinterpret_cast<float4*>(dst);
-        for (int i = lane; i < n / 2; i += 32) d4[i] = s4[i];
+        const float4 *a = reinterpret_cast<const float4*>(src0), *b = reinterpret_cast<const float4*>(src1);
+        float4 *da = reinterpret_cast<float4*>(dst0), *db = reinterpret_cast<float4*>(dst1);
+        const int n4 = n / 2;
+        for (int i = lane; i < n4; i += 64) {
+            const bool two = i + 32 < n4;
+            const float4 v0 = a[i], w0 = src1 ? b[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 v1 = two ? a[i + 32] : v0, w1 = (two && src1) ? b[i + 32] : w0;
+            da[i] = v0; if (src1) db[i] = w0;
+            if (two) { da[i + 32] = v1; if (src1) db[i + 32] = w1; }
+        }
     } else {
-        for (int i = lane; i < n; i += 32) dst[i] = src[i];
+        for (int i = lane; i < n; i += 32) { dst0[i] = src0[i]; if (src1) dst1[i] = src1[i]; }
     }
 }
-// transpose x slabs -> y slabs:  tr[c][x][yl][kz] = sloc_{owner(x)}[c][x - xs][y0 + yl][kz]   (one warp per kz row)
+// transpose x slabs -> y slabs:  tr[c][x][yl][kz] = sloc_{owner(x)}[c][x - xs][y0 + yl][kz]   (one warp per pair of kz rows)
 __global__ void __launch_bounds__(256)
 peer_pull_trans_kernel(float2* __restrict__ tr, PeerPtrs<const float2> sloc, PeerSlabs b, int Nx, int Ny, int y0, int nyl, int Nzp) {
     const int lane = threadIdx.x & 31, nw = gridDim.x * (blockDim.x >> 5), w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int nrow = 3 * Nx * nyl;
-    for (int row = w; row < nrow; row += nw) {
+    auto src_of = [&](int row) {
         const int yl = row % nyl, x = (row / nyl) % Nx, c = row / (nyl * Nx);
         int r = 0;
         while (x >= b.xs[r + 1]) ++r;
-        const float2* src = sloc.p[r] + (((size_t)c * (b.xs[r + 1] - b.xs[r]) + (x - b.xs[r])) * Ny + (y0 + yl)) * Nzp;
-        peer_copy_row(tr + (size_t)row * Nzp, src, Nzp, lane);
+        return sloc.p[r] + (((size_t)c * (b.xs[r + 1] - b.xs[r]) + (x - b.xs[r])) * Ny + (y0 + yl)) * Nzp;
+    };
+    for (int row = 2 * w; row < nrow; row += 2 * nw) {
+        const bool two = row + 1 < nrow;
+        peer_copy_rows2(tr + (size_t)row * Nzp, src_of(row), tr + (size_t)(row + 1) * Nzp, two ? src_of(row + 1) : nullptr, Nzp, lane);
     }
 }
 // and back:  sloc[c][xl][y][kz] = tr_{owner(y)}[c][x0 + xl][y - ys][kz]
@@ -95,12 +108,48 @@ __global__ void __launch_bounds__(256)
 peer_pull_slab_kernel(float2* __restrict__ sloc, PeerPtrs<const float2> tr, PeerSlabs b, int Nx, int Ny, int x0, int nxl, int Nzp) {
     const int lane = threadIdx.x & 31, nw = gridDim.x * (blockDim.x >> 5), w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int nrow = 3 * nxl * Ny;
-    for (int row = w; row < nrow; row += nw) {
+    auto src_of = [&](int row) {
         const int y = row % Ny, xl = (row / Ny) % nxl, c = row / (Ny * nxl);
         int q = 0;
         while (y >= b.ys[q + 1]) ++q;
-        const float2* src = tr.p[q] + (((size_t)c * Nx + (x0 + xl)) * (b.ys[q + 1] - b.ys[q]) + (y - b.ys[q])) * Nzp;
-        peer_copy_row(sloc + (size_t)row * Nzp, src, Nzp, lane);
+        return tr.p[q] + (((size_t)c * Nx + (x0 + xl)) * (b.ys[q + 1] - b.ys[q]) + (y - b.ys[q])) * Nzp;
+    };
+    for (int row = 2 * w; row < nrow; row += 2 * nw) {
+        const bool two = row + 1 < nrow;
+        peer_copy_rows2(sloc + (size_t)row * Nzp, src_of(row), sloc + (size_t)(row + 1) * Nzp, two ? src_of(row + 1) : nullptr, Nzp, lane);
+    }
+}
+// The same two transposes as PUSHES: a rank reads its own rows and stores them into the owners' buffers (posted writes over
+// NVLink need no round trip; measured against the pulls in profiles/r2_scaling.md).  The barrier that follows makes the
+// stores visible before anybody reads them.
+__global__ void __launch_bounds__(256)
+peer_push_trans_kernel(const float2* __restrict__ sloc, PeerPtrs<float2> tr, PeerSlabs b, int Nx, int Ny, int x0, int nxl, int Nzp) {
+    const int lane = threadIdx.x & 31, nw = gridDim.x * (blockDim.x >> 5), w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int nrow = 3 * nxl * Ny;
+    auto dst_of = [&](int row) {
+        const int y = row % Ny, xl = (row / Ny) % nxl, c = row / (Ny * nxl);
+        int q = 0;
+        while (y >= b.ys[q + 1]) ++q;
+        return tr.p[q] + (((size_t)c * Nx + (x0 + xl)) * (b.ys[q + 1] - b.ys[q]) + (y - b.ys[q])) * Nzp;
+    };
+    for (int row = 2 * w; row < nrow; row += 2 * nw) {
+        const bool two = row + 1 < nrow;
+        peer_copy_rows2(dst_of(row), sloc + (size_t)row * Nzp, two ? dst_of(row + 1) : nullptr, two ? sloc + (size_t)(row + 1) * Nzp : nullptr, Nzp, lane);
+    }
+}
+__global__ void __launch_bounds__(256)
+peer_push_slab_kernel(const float2* __restrict__ tr, PeerPtrs<float2> sloc, PeerSlabs b, int Nx, int Ny, int y0, int nyl, int Nzp) {
+    const int lane = threadIdx.x & 31, nw = gridDim.x * (blockDim.x >> 5), w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int nrow = 3 * Nx * nyl;
+    auto dst_of = [&](int row) {
+        const int yl = row % nyl, x = (row / nyl) % Nx, c = row / (nyl * Nx);
+        int r = 0;
+        while (x >= b.xs[r + 1]) ++r;
+        return sloc.p[r] + (((size_t)c * (b.xs[r + 1] - b.xs[r]) + (x - b.xs[r])) * Ny + (y0 + yl)) * Nzp;
+    };
+    for (int row = 2 * w; row < nrow; row += 2 * nw) {
+        const bool two = row + 1 < nrow;
+        peer_copy_rows2(dst_of(row), tr + (size_t)row * Nzp, two ? dst_of(row + 1) : nullptr, two ? tr + (size_t)(row + 1) * Nzp : nullptr, Nzp, lane);
     }
 }
 // planes [p_dst, p_dst + n) of my real-space buffer (+)= planes [p_src, ..) of a peer's buffer (component strides differ);

@@ -221,6 +221,7 @@ extern "C" int pse_shard_init(pse_engine* e, int rank, int world, const uint8_t*
     shard_rank_layout(g, rank, wp.Nx, e->tg.tx, &s->xorg, &s->BL, &s->nxa);
     wp.nxw = world == 1 ? wp.Nx : 1 << 30;         // a slab buffer is indexed without periodic wrap
     { const char* env = getenv("PSE_COMM"); s->use_peer = world > 1 && !(env && env[0] == 'c'); }
+    { const char* env = getenv("PSE_TRANSPOSE"); s->push = env && env[0] == 'p' && env[1] == 'u' && env[2] == 's'; }   // "push": remote stores (measured equal)
     wp.xorg = s->xorg; wp.nxa = s->nxa;
     s->Gl = (size_t)s->nxa * s->plane;
     // the single-GPU grids / basis are allocated lazily, so there is normally nothing to free here
@@ -523,7 +524,11 @@ static int shard_wave(pse_engine* e, const float4* sF, bool det, bool noise, con
     PeerSlabs pb;
     PeerPtrs<const float2> pp_sloc, pp_tr;
     for (int r = 0; r <= g.world; ++r) { pb.xs[r] = g.X[r]; pb.ys[r] = g.YS[r]; }
-    for (int r = 0; r < g.world; ++r) { pp_sloc.p[r] = s->peer_sloc[r]; pp_tr.p[r] = s->peer_tr[r]; }
+    PeerPtrs<float2> pw_sloc, pw_tr;
+    for (int r = 0; r < g.world; ++r) {
+        pp_sloc.p[r] = s->peer_sloc[r]; pp_tr.p[r] = s->peer_tr[r];
+        pw_sloc.p[r] = const_cast<float2*>(s->peer_sloc[r]); pw_tr.p[r] = const_cast<float2*>(s->peer_tr[r]);
+    }
     CKRC(shard_wbin(e, det ? sF : nullptr));
     if (det) {
         {
@@ -543,7 +548,12 @@ static int shard_wave(pse_engine* e, const float4* sF, bool det, bool noise, con
             e->fft_execs++;
         }
         ProfScope ps(e, PH_COMM_TRANS);   // transpose: x slabs -> y slabs
-        if (s->use_peer) {
+        if (s->use_peer && s->push) {
+            // (the peers' y slabs are free: everybody passed the barrier that ended the previous evaluation)
+            s->bytes_sent += s->a2a_send_off[g.world] - (s->a2a_send_off[s->rank + 1] - s->a2a_send_off[s->rank]);
+            peer_push_trans_kernel<<<e->num_sms * 8, 256, 0, st>>>(s->d_sloc, pw_tr, pb, wp.Nx, wp.Ny, g.X[s->rank], nown, wp.Nzp); LAUNCHED(e);
+            shard_peer_barrier(e, 0);
+        } else if (s->use_peer) {
             shard_peer_barrier(e, 0);
             s->bytes_sent += s->a2a_recv_off[g.world] - (s->a2a_recv_off[s->rank + 1] - s->a2a_recv_off[s->rank]);
             if (nyl > 0) {
@@ -566,7 +576,13 @@ static int shard_wave(pse_engine* e, const float4* sF, bool det, bool noise, con
     }
     {
         ProfScope ps(e, PH_COMM_TRANS);    // transpose back: y slabs -> x slabs
-        if (s->use_peer) {
+        if (s->use_peer && s->push) {
+            // (the peers' x slabs are free: every rank finished pushing out of its own before the barrier above;
+            // without a deterministic part nothing was pushed and the x slabs were last read before the previous end barrier)
+            s->bytes_sent += s->a2a_recv_off[g.world] - (s->a2a_recv_off[s->rank + 1] - s->a2a_recv_off[s->rank]);
+            if (nyl > 0) { peer_push_slab_kernel<<<e->num_sms * 8, 256, 0, st>>>(s->d_tr, pw_sloc, pb, wp.Nx, wp.Ny, g.YS[s->rank], nyl, wp.Nzp); LAUNCHED(e); }
+            shard_peer_barrier(e, 0);
+        } else if (s->use_peer) {
             shard_peer_barrier(e, 0);
             s->bytes_sent += s->a2a_send_off[g.world] - (s->a2a_send_off[s->rank + 1] - s->a2a_send_off[s->rank]);
             peer_pull_slab_kernel<<<e->num_sms * 8, 256, 0, st>>>(s->d_sloc, pp_tr, pb, wp.Nx, wp.Ny, g.X[s->rank], nown, wp.Nzp); LAUNCHED(e);
