@@ -40,7 +40,10 @@ def parse():
     ap.add_argument("--phi", type=float, default=0.3)
     ap.add_argument("--error", type=float, default=1e-3)
     ap.add_argument("--xi", type=float, default=0.5)
-    ap.add_argument("--r-buff", type=float, default=1.6)   # Verlet buffer of the engine's list: measured optimum of the rebuild / pruning trade-off (profiles/r2_notes.md)
+    # Verlet buffer of the engine's list.  Measured at config 3 (profiles/r2_notes.md): 1.6 gives 3 % more steps/s (rebuilds every ~10
+    # steps instead of ~3) but 13 % slower stand-alone M.F calls (every call prunes the longer rows); 0.8 balances the two metrics.
+    ap.add_argument("--r-buff", type=float, default=0.8)
+    ap.add_argument("--ref-r-buff", type=float, default=0.4, help="buffer of the list handed to the reference arm (HOOMD 2.x default r_buff)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-N", type=int, default=1000000)
     ap.add_argument("--config5", action="store_true", help="also time BASELINE.json configs[4] (N = 8M, 432^3); default with 8 ranks")
@@ -229,7 +232,9 @@ def main():
         if not refwrap.available():
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libpse_ref.so not built (reference sources absent at build time)"}))
             return
-        cfg = E.make_config(N, L, xi=args.xi, error=args.error, T=T, dt=dt, seed=1, r_buff=args.r_buff)
+        # the list the reference kernels walk is the BUFFERED list (they test the cutoff per pair, PSEv1/Mobility.cu:652), so its
+        # buffer is the reference's own default (HOOMD 2.x nlist r_buff = 0.4), not this engine's tuning
+        cfg = E.make_config(N, L, xi=args.xi, error=args.error, T=T, dt=dt, seed=1, r_buff=args.ref_r_buff)
         eng = E.Engine(cfg)
         p = eng.params
         pos_np, F_np = util.lattice_positions(N, L, seed=0), util.random_forces(N, seed=100)
@@ -237,7 +242,7 @@ def main():
         img = torch.zeros((N, 3), dtype=torch.int32, device="cuda")
         # the reference plugin's own kernels (compiled unmodified for sm_100a); HOOMD's neighbour list is not in the
         # reference tree, so the list comes from the engine's builder, rebuilt every step OUTSIDE the timed spans
-        cfg_r = E.make_config(N, L, xi=args.xi, error=args.error, T=T, dt=dt, seed=1, r_buff=args.r_buff, flags=1)
+        cfg_r = E.make_config(N, L, xi=args.xi, error=args.error, T=T, dt=dt, seed=1, r_buff=args.ref_r_buff, flags=1)
         ref = refwrap.Reference(cfg_r, p, E.ewald_table(cfg_r))
         vel = torch.zeros_like(F); vel[:, 3] = 1.0
         acc = torch.zeros((N, 3), device="cuda")
