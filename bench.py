@@ -426,10 +426,22 @@ def main():
         eng.set_tilt(0.0)
         del qs, ims
 
-    # deterministic M.F time (second half of the BASELINE metric)
+    # deterministic M.F time (second half of the BASELINE metric): `mf_us` with positions that change from call to call (two
+    # configurations alternate, a displacement of 1e-3 radii: everything position-dependent is redone every call), and
+    # `mf_us_fixed_positions` for the operator applied again at an unchanged configuration (iterative solvers), where the
+    # pruned list, the wave-space binning and the Gaussian factor rows of the previous call are reused
     barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pos2 = pos.clone(); pos2[:, 0] += 1e-3
     with torch.cuda.stream(stream):
+        eng.mobility(pos, F); eng.mobility(pos2, F)
+        barrier()
+        a.record(stream)
+        for i in range(10):
+            eng.mobility(pos2 if i & 1 else pos, F)
+        b.record(stream)
+        torch.cuda.synchronize()
+        line["mf_us"] = max_over_ranks(a.elapsed_time(b) / 10 * 1e3)
         eng.mobility(pos, F)
         barrier()
         a.record(stream)
@@ -437,7 +449,8 @@ def main():
             eng.mobility(pos, F)
         b.record(stream)
     torch.cuda.synchronize()
-    line["mf_us"] = max_over_ranks(a.elapsed_time(b) / 10 * 1e3)
+    line["mf_us_fixed_positions"] = max_over_ranks(a.elapsed_time(b) / 10 * 1e3)
+    del pos2
     if world == 1:
         b_mf = 120.0 * G + 64.0 * N + 56.0 * N + 4.0 * nnz
         line["roofline"]["mf"] = {"us": line["mf_us"], "algorithmic_MB": b_mf / 1e6, "frac": b_mf / (line["mf_us"] * 1e-6) / 1e9 / peak}

@@ -249,19 +249,29 @@ __global__ void compact_rows_kernel(const uint32_t* __restrict__ ell, uint32_t c
     for (uint32_t k = sub; k < n; k += 8) nl[h + k] = __ldg(src + k);
 }
 
-// largest squared displacement since the list was built (staleness test); result via atomicMax on bits
-__global__ void max_disp_kernel(const float4* __restrict__ pos, const float4* __restrict__ pos_build, uint32_t N,
-                                PseBox box, uint32_t* __restrict__ max_bits) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+// One pass in slot order at the head of every call: gathers the caller's positions into the slot-ordered arrays (plain copy
+// + the .p half of the SpMV records) and, on the way,
+//   flags[0]  largest squared displacement since the list was built (staleness test; atomicMax on the bits);
+//   flags[2]  != 0 when some particle is not bit for bit where the previous call had it - when nothing moved, the
+//             position-only work of the previous call (pruned list, wave-space binning, Gaussian factor rows) is still
+//             valid and is not repeated (the operator applied again at a fixed configuration).
+__global__ void check_and_gather_kernel(const float4* __restrict__ pos, const uint32_t* __restrict__ perm, uint32_t N, PseBox box,
+                                        const float4* __restrict__ spos_build, float4* __restrict__ spos, float4* __restrict__ px /* stride 2 */,
+                                        uint32_t* __restrict__ flags) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     float r2 = 0.f;
-    if (i < N) {
-        float4 a = __ldg(pos + i), b = __ldg(pos_build + i);
-        float3 d = box.min_image(make_float3(a.x - b.x, a.y - b.y, a.z - b.z));
+    bool moved = false;
+    if (s < N) {
+        const float4 a = __ldg(pos + __ldg(perm + s)), b = __ldg(spos_build + s), l = spos[s];
+        const float3 d = box.min_image(make_float3(a.x - b.x, a.y - b.y, a.z - b.z));
         r2 = d.x * d.x + d.y * d.y + d.z * d.z;
+        moved = __float_as_uint(a.x) != __float_as_uint(l.x) || __float_as_uint(a.y) != __float_as_uint(l.y) || __float_as_uint(a.z) != __float_as_uint(l.z);
+        if (moved) { spos[s] = a; px[2 * (size_t)s] = a; }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) r2 = fmaxf(r2, __shfl_xor_sync(0xffffffffu, r2, o));
-    if ((threadIdx.x & 31) == 0 && r2 > 0.f) atomicMax(max_bits, __float_as_uint(r2));
+    if ((threadIdx.x & 31) == 0 && r2 > 0.f) atomicMax(flags, __float_as_uint(r2));
+    if (__any_sync(0xffffffffu, moved) && (threadIdx.x & 31) == 0) flags[2] = 1u;
 }
 
 // ---- export in the reference layout (particle ids, rows ascending by id) --------------------

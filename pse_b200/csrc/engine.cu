@@ -153,6 +153,8 @@ struct pse_engine {
     float4* d_pos_build;
     float xy_build;
     float xy_prev_call;  // tilt at the previous velocity evaluation (graph replay only while it stays put)
+    float xy_spos;       // tilt the slot-ordered positions / pruned list / W records were made for
+    bool reuse_static;   // keep them when a call finds every particle where the previous call left it (PSE_REUSE=0 turns it off)
     bool nlist_valid;
     uint32_t* d_flag;
     uint32_t* h_flag;  // pinned
@@ -391,9 +393,9 @@ static int alloc_all(pse_engine* e) {
     CK(cudaMalloc(&e->d_nlinfo, 2 * sizeof(unsigned long long)));
     CK(cudaMallocHost(&e->h_nlinfo, 2 * sizeof(unsigned long long)));
     CK(cudaMalloc(&e->d_pos_build, sizeof(float4) * N));
-    CK(cudaMalloc(&e->d_flag, 2 * sizeof(uint32_t)));   // [0] largest squared displacement (bits), [1] slab-coverage guard
-    CK(cudaMemset(e->d_flag, 0, 2 * sizeof(uint32_t)));
-    CK(cudaMallocHost(&e->h_flag, 2 * sizeof(uint32_t)));
+    CK(cudaMalloc(&e->d_flag, 4 * sizeof(uint32_t)));   // [0] largest squared displacement (bits), [1] slab guards, [2] moved since the last call
+    CK(cudaMemset(e->d_flag, 0, 4 * sizeof(uint32_t)));
+    CK(cudaMallocHost(&e->h_flag, 4 * sizeof(uint32_t)));
     CK(cudaEventCreateWithFlags(&e->flag_event, cudaEventDisableTiming));
     // the real grids, the spectra and the Krylov basis are allocated at first use (ensure_wave_buffers / ensure_krylov):
     // a slab-decomposed engine (pse_shard_init) only ever holds its own slab of each
@@ -608,6 +610,7 @@ extern "C" int pse_create(const pse_config* cfg, void* stream, pse_engine** out)
         const char* tpp = getenv("PSE_SPMV_TPP");
         if (tpp) e->spmv_tpp = atoi(tpp);
     }
+    { const char* v = getenv("PSE_REUSE"); e->reuse_static = v ? atoi(v) != 0 : true; }
     e->m_lanczos = 2;  // PSEv1/Stokes.cc:132
     e->row0 = 0; e->row1 = c.N;
     e->prof_pool = new std::vector<cudaEvent_t>();
@@ -835,9 +838,12 @@ extern "C" int pse_build_neighbors(pse_engine* e, const float4* d_pos) {
     // made when somebody walks it directly (unpruned SpMV, pair forces, export): ensure_csr.
     e->csr_valid = false;
     if (!e->prune) CKRC(ensure_csr(e));
-    CK(cudaMemcpyAsync(e->d_pos_build, d_pos, sizeof(float4) * N, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(e->d_pos_build, e->d_spos, sizeof(float4) * N, cudaMemcpyDeviceToDevice, st));   // slot order
     delete ps;
     e->xy_build = e->box.xy;
+    e->xy_spos = e->box.xy;
+    e->pruned_valid = false;   // (new slot order: nothing derived from the old one survives)
+    e->wbin_valid = false;
     e->nlist_valid = true;
     e->flag_pending = false;
     e->nlist_builds++;
@@ -869,8 +875,9 @@ static bool stale_from_bits(const pse_engine* e, uint32_t bits) {
 static int launch_disp_check(pse_engine* e, const float4* d_pos) {
     ProfScope ps(e, PH_REORDER);
     CK(cudaMemsetAsync(e->d_flag, 0, sizeof(uint32_t), e->stream));
-    max_disp_kernel<<<nblk(e->N, 256), 256, 0, e->stream>>>(d_pos, e->d_pos_build, e->N, e->box, e->d_flag); LAUNCHED(e);
-    words_copy_kernel<<<1, 32, 0, e->stream>>>(e->h_flag, e->d_flag, 2); LAUNCHED(e);
+    CK(cudaMemsetAsync(e->d_flag + 2, 0, sizeof(uint32_t), e->stream));
+    check_and_gather_kernel<<<nblk(e->N, 256), 256, 0, e->stream>>>(d_pos, e->d_perm, e->N, e->box, e->d_pos_build, e->d_spos, (float4*)e->d_px, e->d_flag); LAUNCHED(e);
+    words_copy_kernel<<<1, 32, 0, e->stream>>>(e->h_flag, e->d_flag, 3); LAUNCHED(e);
     CK(cudaEventRecord(e->flag_event, e->stream));
     e->flag_pending = true;
     return PSE_OK;
@@ -888,10 +895,13 @@ static int ensure_neighbors(pse_engine* e, const float4* d_pos) {
     }
     if (rebuild) {
         CKRC(pse_build_neighbors(e, d_pos));
-    } else {
-        ProfScope ps(e, PH_REORDER);
-        gather_pos_kernel<<<nblk(e->N, 256), 256, 0, e->stream>>>(d_pos, e->d_perm, e->N, e->d_spos, (float4*)e->d_px); LAUNCHED(e);
+    } else if (e->h_flag[2] == 0 && e->box.xy == e->xy_spos && e->reuse_static) {
+        // nobody moved and the box is the one of the previous call: the slot-ordered positions, the pruned list and the
+        // wave-space binning / factor rows of that call are still exact (the operator applied again at a fixed configuration)
+        return PSE_OK;
     }
+    // (no rebuild: the check above already brought the slot-ordered positions up to date)
+    e->xy_spos = e->box.xy;
     e->pruned_valid = false;
     e->wbin_valid = false;
     return PSE_OK;

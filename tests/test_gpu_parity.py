@@ -327,6 +327,33 @@ def test_pipelined_host_steps_match_device_steps(cuda):
     a.eng.close(); b.eng.close()
 
 
+def test_operator_reapplied_at_fixed_positions_reuses_static_work(cuda):
+    """M applied again at bit-identical positions keeps the pruned list / wave-space binning / factor rows of the previous call
+    (fewer launches), any movement - or a new tilt - redoes them; results equal the engine that never reuses (PSE_REUSE=0)."""
+    import os
+    import torch
+    s = System(20000, util.box_length(20000, 0.2), seed=6, lattice=True, want_ref=False)
+    G = torch.from_numpy(util.random_forces(s.N, 77)).cuda()
+    U1 = s.eng.mobility(s.pos, s.F).clone()
+    l0 = s.eng.stats()["kernel_launches"]
+    U2 = s.eng.mobility(s.pos, G).clone()
+    l1 = s.eng.stats()["kernel_launches"]
+    moved = s.pos.clone(); moved[5, 1] += 1e-4
+    U3 = s.eng.mobility(moved, G).clone()
+    l2 = s.eng.stats()["kernel_launches"]
+    assert l1 - l0 < l2 - l1                       # the second call skipped the position-only kernels, the third did not
+    os.environ["PSE_REUSE"] = "0"
+    try:
+        t = System(20000, s.L, seed=6, lattice=True, want_ref=False)
+    finally:
+        del os.environ["PSE_REUSE"]
+    close(U1, t.eng.mobility(s.pos, s.F), 2e-6); close(U2, t.eng.mobility(s.pos, G), 2e-6); close(U3, t.eng.mobility(moved, G), 2e-6)
+    s.eng.set_tilt(0.1)
+    t.eng.set_tilt(0.1)
+    close(s.eng.mobility(moved, G), t.eng.mobility(moved, G), 2e-6)   # same positions, new box: nothing may be reused
+    s.eng.close(); t.eng.close()
+
+
 def test_tiled_wave_path_is_bitwise_reproducible_and_matches_scatter_path(cuda):
     """The tile-owned spreading has a fixed summation order (no atomics): repeated runs are bitwise equal; the
     fallback scatter path (PSE_WAVE_TILED=0, used for tiny grids / P > 10) gives the same answer to round-off."""
