@@ -1,0 +1,100 @@
+"""Writes profiles/r2_summary.md and profiles/r2_scaling.md from the committed bench lines and ncu summaries of round 2."""
+import json, os
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def L(f):
+    p = os.path.join(HERE, f)
+    txt = open(p).read()
+    try:
+        return json.loads(txt)                       # a whole-file JSON document (ncu summaries, pretty-printed dicts)
+    except json.JSONDecodeError:
+        return json.loads([l for l in txt.splitlines() if l.startswith("{")][-1])   # torchrun chatter + one JSON line
+
+
+d, r, ls = L("r2_bench_ours.json"), L("r2_bench_ref.json"), L("r2_launch_shares.json")
+top = L("r2_top_kernels.json") + L("r2_fft_kernels.json")
+out = ["# Round 2 — measured on B200s (gpurun), config 3: N = 1,000,000, phi = 0.3, error 1e-3, xi = 0.5, kT = 1, dt = 1e-3\n",
+       "Files: `r2_bench_ours.json` / `r2_bench_ref.json` (the two `bench.py` arms at N = 1, NOT under a profiler), `r2_bench_ours_{2,4,8}gpu.json` "
+       "(`bench.py --gpus N` under torchrun), `r2_launches.csv` (ncu `--metrics gpu__time_duration.sum --clock-control none` of three steps) and its "
+       "per-kernel shares `r2_launch_shares.json`, `r2_top_kernels.json` / `r2_fft_kernels.json` (ncu `--set full`, key metrics), "
+       "`r2_sass_excerpt.txt`, `r2_sanitizer.txt`, `r2_shard8_config5.json`, `r2_scaling.md`, `r2_notes.md`; this file by `make_summary_r2.py`.\n"
+       "ncu times are cold-cache and serialised: compare SHARES with `phases` of the bench line, not absolutes.\n",
+       "## bench.py (CUDA events, no profiler)\n",
+       "| arm | steps/s (mean) | ms/step mean / median | end to end steps/s | Lanczos m |\n|---|---|---|---|---|",
+       f"| ours (engine RNG, r_buff 0.8, list rebuilt {d['nlist_builds_in_timed_region']}x in {d['steps']} steps) | {d['value']:.1f} | {d['ms_per_step']:.3f} / {d['ms_per_step_median']:.3f} | "
+       f"{d['e2e']['value']:.1f} pipelined ({d['e2e']['synchronous']['value']:.1f} synchronous) | {d['lanczos_m']} |",
+       f"| reference kernels (PSEv1/*.cu unmodified, sm_100a; neighbour list with HOOMD's default buffer, built outside the timed spans) | {r['value']:.1f} | "
+       f"{r['ms_per_step']:.2f} / {r['ms_per_step_median']:.2f} | {r['e2e']['value']:.1f} | {r['lanczos_m']} |\n",
+       f"Ratio ours / reference: {d['value'] / r['value']:.1f}x on the device, {d['e2e']['value'] / r['e2e']['value']:.1f}x end to end.  "
+       f"Deterministic M.F: {d['mf_us']:.0f} us with positions changing between calls, {d['mf_us_fixed_positions']:.0f} us re-applied at a fixed configuration.  "
+       f"Steady shear (tilt moving every step, eager launches): {d['sheared']['value']:.1f} steps/s.  "
+       f"CPU port ({d['cpu_baseline']['cores']} threads): {d['cpu_baseline']['value']:.3f} steps/s ({d['cpu_baseline']['sample']}).\n"]
+rf = d["roofline"]
+tr = f"{rf['traffic'] / 1e6:.0f} MB" if rf.get("traffic") else "n/a"
+out.append(f"Roofline (HBM, peak {rf['peak']} GB/s {rf['peak_source']}): dominant kernel {rf['kernel']}: {rf['us_per_launch']:.1f} us/launch, algorithmic "
+           f"{rf['algorithmic_bytes_per_launch'] / 1e6:.1f} MB -> {rf['achieved']:.0f} GB/s = {100 * rf['frac']:.1f}% of peak, {100 * rf['share_of_step']:.0f}% of the step "
+           f"(ncu DRAM traffic of the same launch: {tr}); whole step {rf['step']['algorithmic_bytes'] / 1e9:.2f} GB algorithmic -> {rf['step']['achieved']:.0f} GB/s = "
+           f"{100 * rf['step']['frac']:.1f}%; M.F {100 * rf['mf']['frac']:.1f}%.\n")
+out.append("## Per-kernel roofline table (bench.py `roofline.kernels`: algorithmic bytes / CUDA-event time) and the unit that actually binds\n")
+out.append("| phase | us | algorithmic MB | GB/s | fraction of HBM peak | bound by (ncu) |\n|---|---|---|---|---|---|")
+for k, v in rf["kernels"].items():
+    out.append(f"| {k} | {v['us']:.0f} | {v['algorithmic_MB']:.0f} | {v['GBps']:.0f} | {v['frac']:.3f} | {v['bound_by']} |")
+out.append("\n## Per-phase device time (bench.py `phases`, CUDA events on the engine stream, profiling mode = branches serial)\n")
+out.append("| phase | ms/step | launches/step | us/launch | share |\n|---|---|---|---|---|")
+for k, v in sorted(d["phases"].items(), key=lambda kv: -kv[1]["ms_per_step"]):
+    out.append(f"| {k} | {v['ms_per_step']:.3f} | {v['launches_per_step']:.1f} | {v['us_per_launch']:.1f} | {100 * v['ms_per_step'] / d['ms_per_step']:.1f}% |")
+out.append("\n(`wave_bin` = binning + W record headers + Gaussian factor rows (position-only part) and the force part; `scale` = x forward FFT + k-space scaling + "
+           "x inverse FFT in one kernel; `reorder` = displacement / moved check fused with the slot gather.)\n")
+out.append(f"## ncu launch list, one step with a list rebuild ({ls['launches']} launches, {ls['step_total_us_serialised']:.0f} us serialised)\n")
+out.append("| kernel | launches | total us | share |\n|---|---|---|---|")
+for k in ls["kernels"][:24]:
+    out.append(f"| `{k['kernel'][:70]}` | {k['launches']} | {k['total_us']:.1f} | {100 * k['share']:.1f}% |")
+out.append("\n## ncu --set full, top kernels (one launch each at N = 1M)\n")
+out.append("| kernel | us | DRAM r+w MB | DRAM % | issue active % | L1TEX % | L1 hit % | warps active % | regs | dyn smem KB | smem wavefronts (conflicts) M | warp instr M |\n|---|---|---|---|---|---|---|---|---|---|---|---|")
+seen = set()
+for k in top:
+    name = k["kernel"].split("(")[0]
+    if name in seen:
+        continue
+    seen.add(name)
+    g = lambda m, dflt=0.0: k.get(m, dflt)
+    out.append(f"| `{name[:52]}` | {g('gpu__time_duration.sum'):.1f} | {g('dram__bytes_read.sum') + g('dram__bytes_write.sum'):.0f} | "
+               f"{g('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'):.0f} | {g('smsp__issue_active.avg.pct_of_peak_sustained_active'):.0f} | "
+               f"{g('l1tex__throughput.avg.pct_of_peak_sustained_elapsed'):.0f} | {g('l1tex__t_sector_hit_rate.pct'):.0f} | "
+               f"{g('sm__warps_active.avg.pct_of_peak_sustained_active'):.0f} | {g('launch__registers_per_thread'):.0f} | {g('launch__shared_mem_per_block_dynamic'):.0f} | "
+               f"{g('l1tex__data_pipe_lsu_wavefronts_mem_shared.sum') / 1e6:.1f} ({g('l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum') / 1e6:.1f}) | {g('smsp__inst_executed.sum') / 1e6:.0f} |")
+open(os.path.join(HERE, "r2_summary.md"), "w").write("\n".join(out) + "\n")
+
+# ---- scaling
+rows = [(1, d)] + [(n, L(f"r2_bench_ours_{n}gpu.json")) for n in (2, 4, 8)]
+s = ["# Round 2 — strong scaling of ONE suspension over the GPUs of one node (bench.py --gpus N, max over ranks)\n",
+     "Config 3 (N = 1M, phi = 0.3, error 1e-3, 240^3, P = 6), slab-decomposed whole step (DESIGN.md §6), peer-memory transport.\n",
+     "| GPUs | steps/s | ms/step mean / median | speed-up | M.F us (moving / fixed positions) | M.F speed-up | e2e steps/s | replicas steps/s (side key, not scaling) | sync points / step | MB sent / rank / step |\n|---|---|---|---|---|---|---|---|---|---|"]
+v1, m1 = d["value"], d["mf_us"]
+for n, x in rows:
+    sh = x.get("shard", {})
+    s.append(f"| {n} | {x['value']:.1f} | {x['ms_per_step']:.3f} / {x['ms_per_step_median']:.3f} | {x['value'] / v1:.2f}x | {x['mf_us']:.0f} / {x['mf_us_fixed_positions']:.0f} | {m1 / x['mf_us']:.2f}x | "
+             f"{x['e2e']['value']:.1f} | {x.get('replicas', {}).get('value', float('nan')):.0f} | {sh.get('collectives_per_step', '-')} | "
+             f"{sh.get('bytes_sent_per_step_rank0', 0) / 1e6:.0f} |")
+s.append("\nPer-phase times on rank 0 (profiling mode: the two branches serial, so the sum exceeds the overlapped step), ms per step:\n")
+names = ["lanczos_spmv", "lanczos_vec", "prune", "nlist", "bin", "reorder", "wave_bin", "spread", "fft_r2c", "scale", "fft_c2r", "interp", "combine", "integrate",
+         "comm_transpose", "comm_grid_halo", "comm_vector_halo", "comm_allreduce", "comm_gather"]
+s.append("| phase | " + " | ".join(f"{n} GPU" for n, _ in rows) + " |\n|---|" + "---|" * len(rows))
+for nm in names:
+    s.append(f"| {nm} | " + " | ".join(f"{x['phases'].get(nm, {}).get('ms_per_step', 0):.3f}" for _, x in rows) + " |")
+c5 = rows[-1][1].get("config5", {})
+p5 = json.loads(open(os.path.join(HERE, "r2_shard8_config5.json")).read().splitlines()[0])
+s.append(f"\nThe `comm_*` rows include the wait for the slowest rank at each device-side barrier.  The largest exchange that is not overlapped with compute of the same "
+         f"branch is the pair of spectrum transposes; the vector halos and the three-word all-reduces are latency (5 iterations x ~20 us), not bandwidth.  "
+         f"NCCL (PSE_COMM=coll) for the same exchanges at 2 GPUs: 1.31 ms per step in collectives against 0.54 ms with the peer kernels (step 3.47 -> 2.82 ms before "
+         f"the two-stream overlap, 2.54 ms with it).  Push (remote stores) and pull variants of the transposes measure the same at 4 GPUs (154 vs 156 us).\n")
+s.append(f"## Config 5 (N = 8M, phi = 0.4, error 1e-4, xi = 0.45: 432^3, P = 8) on 8 GPUs\n\n"
+         f"`bench.py --gpus 8` config5 block: {c5.get('ms_per_step', 0):.2f} ms per step ({c5.get('steps_per_s', 0):.1f} steps/s), M.F {c5.get('mf_us', 0):.0f} us, Lanczos m = {c5.get('lanczos_m')}.\n"
+         f"`tests/sharded_check.py 8000000 0.4 0.45 1e-4` on 8 ranks against the single-GPU engine on the same inputs (`r2_shard8_config5.json`): M.F relative L2 {p5['mf_rel_l2']:.1e} "
+         f"(max {p5['mf_rel_max']:.1e}), full velocity with injected noise {p5['vel_rel_l2']:.1e} (max {p5['vel_rel_max']:.1e}), Lanczos m {p5['m']}, positions after three steps within "
+         f"{p5['pos_maxdiff_3steps']:.1e} (two units in the last place at a 438-wide box), images equal, identical bits on all ranks; M.F {p5['mf_us_single']:.0f} -> {p5['mf_us_sharded']:.0f} us "
+         f"({p5['mf_us_single'] / p5['mf_us_sharded']:.1f}x), step {p5['step_us_single']:.0f} -> {p5['step_us_sharded']:.0f} us ({p5['step_us_single'] / p5['step_us_sharded']:.1f}x).  "
+         f"The single-GPU engine at this size is itself checked against the reference's kernels in `test_config5_eight_million_properties`.\n")
+open(os.path.join(HERE, "r2_scaling.md"), "w").write("\n".join(s) + "\n")
+print("written")

@@ -83,7 +83,8 @@ for N, phi, xy in cases:
                           "images_equal": same_img, "identical_on_all_ranks": same, "mf_us_sharded": t_mf_sh, "mf_us_single": t_mf_1,
                           "step_us_sharded": t_st_sh, "step_us_single": t_st_1, "halo_planes": [info["halo_left"], info["halo_right"]],
                           "buffer_planes": info["buffer_planes"], "halo_layers": info["halo_layers"]}), flush=True)
-    ok &= e_mf[0] < 5e-6 and e_mf[1] < 1e-5 and e_v[0] < 5e-6 and e_v[1] < 1e-5 and dpos < 2e-5 and same_img and same and res["sharded"][2] == res["single"][2]
+    # positions: a few units in the last place of a coordinate of size L / 2 (1.5e-5 at the 438-wide box of config 5)
+    ok &= e_mf[0] < 5e-6 and e_mf[1] < 1e-5 and e_v[0] < 5e-6 and e_v[1] < 1e-5 and dpos < max(2e-5, 3e-7 * L) and same_img and same and res["sharded"][2] == res["single"][2]
     sh.close(); single.close()
     del sh, single, res
     torch.cuda.empty_cache()
