@@ -226,7 +226,7 @@ __global__ void nlist_kernel(const float4* __restrict__ spos, uint32_t N, PseBox
     uint32_t m = count;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(max_nn, m);
+    if ((threadIdx.x & 31) == 0 && m > __ldcg(max_nn)) atomicMax(max_nn, m);   // (look first: one word for the whole grid)
 }
 
 // sum of nn -> *total (uint64), for statistics only
@@ -270,8 +270,13 @@ __global__ void check_and_gather_kernel(const float4* __restrict__ pos, const ui
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) r2 = fmaxf(r2, __shfl_xor_sync(0xffffffffu, r2, o));
-    if ((threadIdx.x & 31) == 0 && r2 > 0.f) atomicMax(flags, __float_as_uint(r2));
-    if (__any_sync(0xffffffffu, moved) && (threadIdx.x & 31) == 0) flags[2] = 1u;
+    // one word each for the whole grid: look before touching it (tens of thousands of same-address atomics / stores serialise in L2)
+    const bool any_moved = __any_sync(0xffffffffu, moved);
+    if ((threadIdx.x & 31) == 0) {
+        const uint32_t bits = __float_as_uint(r2);
+        if (r2 > 0.f && bits > __ldcg(flags)) atomicMax(flags, bits);
+        if (any_moved && __ldcg(flags + 2) == 0u) flags[2] = 1u;
+    }
 }
 
 // ---- export in the reference layout (particle ids, rows ascending by id) --------------------
