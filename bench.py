@@ -385,14 +385,19 @@ def main():
     eng.wait()
     barrier()
     t0 = time.perf_counter()
-    for i in range(KE):   # (slab-decomposed: every rank uploads the forces, rank 0 downloads the result)
-        eng.step_host_async(hp[i & 1], hi[i & 1], hf, step_no, state_out=(rank == 0)); step_no += 1
+    use_prefetch = os.environ.get("BENCH_PREFETCH", "0") != "0"
+    if use_prefetch:
+        eng.prefetch_forces(hf)
+    for i in range(KE):   # slab-decomposed: every rank uploads the forces, rank 0 downloads the result
+        if use_prefetch:  # forces of step i+1 go up while step i computes (pse_host_prefetch_forces; measured no better than uploading beside the head)
+            eng.prefetch_forces(hf)
+        eng.step_host_async(hp[i & 1], hi[i & 1], None if use_prefetch else hf, step_no, state_out=(rank == 0)); step_no += 1
     eng.wait()
     torch.cuda.synchronize()
     t_e2e = max_over_ranks(time.perf_counter() - t0)
     assert np.isfinite(hp[(KE - 1) & 1]).all()
     KS = max(K // 2, 1)
-    eng.step_host_async(hp[0], hi[0], hf, step_no); step_no += 1     # (untimed: every rank's host arrays hold the common state again)
+    eng.step_host_async(hp[0], hi[0], None if use_prefetch else hf, step_no); step_no += 1     # (untimed: every rank's host arrays hold the common state again)
     eng.wait()
     barrier()
     t0 = time.perf_counter()
@@ -401,8 +406,8 @@ def main():
     torch.cuda.synchronize()
     t_sync = max_over_ranks(time.perf_counter() - t0)
     line["e2e"] = {"value": KE / t_e2e, "unit": "steps/s", "h2d_bytes_per_step": 16 * N, "d2h_bytes_per_step": 28 * N,
-                   "api": "pse_step_host_async + pse_wait (C ABI, pinned host buffers, device-resident state: forces in, positions + images out every step, "
-                          "copies overlapped with compute)" + ("; forces uploaded on every rank, result downloaded on rank 0" if world > 1 else ""),
+                   "api": "pse_step_host_async + pse_wait (C ABI, pinned host buffers, device-resident state: every step 16 N bytes of forces go up beside the "
+                          "position-only head of the step and 28 N bytes of positions + images come down while the next step computes)" + ("; forces uploaded on every rank, result downloaded on rank 0" if world > 1 else ""),
                    "synchronous": {"value": KS / t_sync, "h2d_bytes_per_step": 44 * N, "d2h_bytes_per_step": 28 * N,
                                    "api": "pse_step_host (positions + images + forces in, positions + images out, blocking)"}}
 

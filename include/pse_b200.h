@@ -202,6 +202,10 @@ int pse_step_host(pse_engine* e, float* h_pos4, int* h_image3, const float* h_F4
                                     device, one of them downloading it is enough) */
 int pse_step_host_async(pse_engine* e, float* h_pos4, int* h_image3, const float* h_F4, float* h_vel4, uint32_t timestep,
                         float shear_rate, uint32_t flags, int* m_lanczos_out);
+/* Inputs double-buffered too: start uploading the forces of a LATER pse_step_host_async call now (they must not depend on
+ * the steps in flight - external fields, forces computed ahead).  Calls given h_F4 == NULL consume the prefetched sets in
+ * order; two may be outstanding, so the upload for step t + 1 can be issued before the call for step t. */
+int pse_host_prefetch_forces(pse_engine* e, const float* h_F4);
 int pse_wait(pse_engine* e); /* blocks until the outputs of the last pse_step_host_async are on the host */
 
 /* ---- introspection ---------------------------------------------------------------------- */

@@ -114,6 +114,7 @@ SYMBOLS = {
     "pse_step_host": (_i, [_vp, _vp, _vp, _vp, _vp, _u32, _f, ctypes.POINTER(_i)]),
     "pse_step_host_async": (_i, [_vp, _vp, _vp, _vp, _vp, _u32, _f, _u32, ctypes.POINTER(_i)]),
     "pse_wait": (_i, [_vp]),
+    "pse_host_prefetch_forces": (_i, [_vp, _vp]),
     "pse_pair_force": (_i, [_vp, _vp, ctypes.POINTER(pse_pair_params), _vp, _i]),
     "pse_get_stats": (_i, [_vp, ctypes.POINTER(pse_stats)]),
     "pse_shard_plan": (_i, [_cfgp, _i, _i, ctypes.POINTER(pse_shard_info)]),

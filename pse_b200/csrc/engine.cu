@@ -160,6 +160,8 @@ struct pse_engine {
     uint32_t* h_flag;  // pinned
     cudaEvent_t flag_event;
     bool flag_pending;
+    const float4* precheck_pos;   // positions the pending displacement check was issued for (engine-owned state only), and their tilt
+    float precheck_xy;
     // wave space
     float* d_grid;
     float2* d_spec;
@@ -189,6 +191,10 @@ struct pse_engine {
     // step scratch
     float4* d_vel_work;
     float4 *d_hpos, *d_hF;  // device staging for pse_step_host
+    float4* d_hF_next[2];   // landing buffers of pse_host_prefetch_forces: a queue of two (copied into d_hF by the step that consumes one)
+    cudaEvent_t ev_Fnext[2], ev_Fcons[2];
+    uint64_t n_pref, n_cons;   // prefetches issued / consumed
+    int take_Fnext;            // landing buffer the step in flight takes its forces from, or -1
     int3* d_himage;
     int num_sms;
     struct ShardState* shard;  // multi-GPU slab decomposition of the whole step (pse_shard_init); null = single GPU
@@ -304,6 +310,11 @@ __global__ void words2_copy_kernel(uint32_t* __restrict__ dst_a, const uint32_t*
                                    const uint32_t* __restrict__ src_b, int nb) {
     for (int i = threadIdx.x; i < na; i += blockDim.x) dst_a[i] = src_a[i];
     for (int i = threadIdx.x; i < nb; i += blockDim.x) dst_b[i] = src_b[i];
+}
+// device-to-device copies of the step path are kernels too: a cudaMemcpyAsync D2D may be scheduled on a copy engine and then
+// waits behind the bulk host transfers of the pipelined entry point like the control words did
+__global__ void copy_f4_kernel(float4* __restrict__ dst, const float4* __restrict__ src, uint32_t n) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
 }
 struct CoefArg { float c[LANCZOS_M_MAX + 2]; };
 __global__ void coef_store_kernel(float* __restrict__ dst, CoefArg a, int m) {
@@ -611,6 +622,7 @@ extern "C" int pse_create(const pse_config* cfg, void* stream, pse_engine** out)
         if (tpp) e->spmv_tpp = atoi(tpp);
     }
     { const char* v = getenv("PSE_REUSE"); e->reuse_static = v ? atoi(v) != 0 : true; }
+    e->take_Fnext = -1;
     e->m_lanczos = 2;  // PSEv1/Stokes.cc:132
     e->row0 = 0; e->row1 = c.N;
     e->prof_pool = new std::vector<cudaEvent_t>();
@@ -682,6 +694,11 @@ extern "C" void pse_destroy(pse_engine* e) {
     if (e->ev_img) cudaEventDestroy(e->ev_img);
     if (e->ev_step) cudaEventDestroy(e->ev_step);
     if (e->ev_out) cudaEventDestroy(e->ev_out);
+    for (int k = 0; k < 2; ++k) {
+        if (e->ev_Fnext[k]) cudaEventDestroy(e->ev_Fnext[k]);
+        if (e->ev_Fcons[k]) cudaEventDestroy(e->ev_Fcons[k]);
+        if (e->d_hF_next[k]) cudaFree(e->d_hF_next[k]);
+    }
     if (e->h_nlinfo) cudaFreeHost(e->h_nlinfo);
     if (e->d_nlinfo) cudaFree(e->d_nlinfo);
     if (e->h_ab) cudaFreeHost(e->h_ab);
@@ -838,7 +855,7 @@ extern "C" int pse_build_neighbors(pse_engine* e, const float4* d_pos) {
     // made when somebody walks it directly (unpruned SpMV, pair forces, export): ensure_csr.
     e->csr_valid = false;
     if (!e->prune) CKRC(ensure_csr(e));
-    CK(cudaMemcpyAsync(e->d_pos_build, e->d_spos, sizeof(float4) * N, cudaMemcpyDeviceToDevice, st));   // slot order
+    copy_f4_kernel<<<e->num_sms * 4, 256, 0, st>>>(e->d_pos_build, e->d_spos, N); LAUNCHED(e);   // slot order
     delete ps;
     e->xy_build = e->box.xy;
     e->xy_spos = e->box.xy;
@@ -886,7 +903,11 @@ static int launch_disp_check(pse_engine* e, const float4* d_pos) {
 static int ensure_neighbors(pse_engine* e, const float4* d_pos) {
     bool rebuild = !e->nlist_valid;
     if (!rebuild) {
-        CKRC(launch_disp_check(e, d_pos));
+        // host-pipelined runs own their state: the check for these positions was issued at the end of the previous step, before
+        // its result started down the PCIe link, so the flags are already on the host (no round trip at the head of the step)
+        const bool prechecked = e->flag_pending && e->precheck_pos == d_pos && e->precheck_xy == e->box.xy;
+        e->precheck_pos = nullptr;
+        if (!prechecked) CKRC(launch_disp_check(e, d_pos));
         CK(cudaEventSynchronize(e->flag_event));
         e->flag_pending = false;
         if (e->h_flag[1] & 2u) return fail(e, PSE_ECUDA, "slab decomposition: a peer rank did not arrive at a synchronisation point within 10 s");
@@ -1337,6 +1358,13 @@ extern "C" int pse_velocity(pse_engine* e, const float4* d_pos, const float4* d_
         if (fork) CK(cudaStreamWaitEvent(st, e->ev_join, 0));
     }
     if (e->wait_F) { e->wait_F = false; CK(cudaStreamWaitEvent(st, e->ev_F, 0)); }
+    if (e->take_Fnext >= 0) {   // forces prefetched earlier: one device copy into the buffer the step (and its graph) reads
+        const int r = e->take_Fnext;
+        e->take_Fnext = -1;
+        CK(cudaStreamWaitEvent(st, e->ev_Fnext[r], 0));
+        copy_f4_kernel<<<e->num_sms * 4, 256, 0, st>>>(e->d_hF, e->d_hF_next[r], e->N); LAUNCHED(e);
+        CK(cudaEventRecord(e->ev_Fcons[r], st));
+    }
     CKRC(upload_stepdev(e, timestep));
     const int m_batch = lanczos_batch_size(e);
     if (m_out) *m_out = e->m_lanczos;
@@ -1438,11 +1466,8 @@ extern "C" int pse_step(pse_engine* e, float4* d_pos, int3* d_image, const float
 // and both transfers are hidden: the forces arrive on a copy stream while the position-only head of the step runs
 // (neighbour-list check / rebuild, pruning, wave-space binning and Gaussian factors), the result leaves on a second copy
 // stream while the NEXT step computes.  pse_wait blocks until the last result is on the host.
-extern "C" int pse_step_host_async(pse_engine* e, float* h_pos4, int* h_image3, const float* h_F4, float* h_vel4, uint32_t timestep,
-                                   float shear_rate, uint32_t flags, int* m_out) {
-    if (!e || !h_pos4 || !h_F4) return PSE_EINVAL;
+static int host_path_setup(pse_engine* e) {
     const size_t N = e->N;
-    cudaStream_t st = e->stream;
     if (!e->d_hpos) {
         CK(cudaMalloc(&e->d_hpos, sizeof(float4) * N));
         CK(cudaMalloc(&e->d_hF, sizeof(float4) * N));
@@ -1451,19 +1476,48 @@ extern "C" int pse_step_host_async(pse_engine* e, float* h_pos4, int* h_image3, 
     if (!e->stream_h2d) {
         CK(cudaStreamCreateWithFlags(&e->stream_h2d, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&e->stream_d2h, cudaStreamNonBlocking));
-        CK(cudaEventCreateWithFlags(&e->ev_F, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&e->ev_img, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&e->ev_step, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming));
-        CK(cudaEventRecord(e->ev_step, st));
+        for (cudaEvent_t* ev : {&e->ev_F, &e->ev_img, &e->ev_step, &e->ev_out, &e->ev_Fnext[0], &e->ev_Fnext[1], &e->ev_Fcons[0], &e->ev_Fcons[1]})
+            CK(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+        CK(cudaEventRecord(e->ev_step, e->stream));
+        CK(cudaEventRecord(e->ev_Fcons[0], e->stream));
+        CK(cudaEventRecord(e->ev_Fcons[1], e->stream));
     }
+    return PSE_OK;
+}
+// Start uploading the forces of a LATER pse_step_host_async call now; calls given h_F4 == NULL consume the prefetched sets in
+// order.  Two may be outstanding, so the upload for step t + 1 can be issued before the call for step t.
+extern "C" int pse_host_prefetch_forces(pse_engine* e, const float* h_F4) {
+    if (!e || !h_F4) return PSE_EINVAL;
+    if (e->n_pref - e->n_cons >= 2) return fail(e, PSE_EINVAL, "pse_host_prefetch_forces: two sets of forces are already waiting");
+    CKRC(host_path_setup(e));
+    const int w = (int)(e->n_pref & 1);
+    if (!e->d_hF_next[w]) CK(cudaMalloc(&e->d_hF_next[w], sizeof(float4) * e->N));
+    CK(cudaStreamWaitEvent(e->stream_h2d, e->ev_Fcons[w], 0));   // the previous consumer of this landing buffer is done with it
+    CK(cudaMemcpyAsync(e->d_hF_next[w], h_F4, sizeof(float4) * e->N, cudaMemcpyHostToDevice, e->stream_h2d));
+    CK(cudaEventRecord(e->ev_Fnext[w], e->stream_h2d));
+    e->n_pref++;
+    return PSE_OK;
+}
+extern "C" int pse_step_host_async(pse_engine* e, float* h_pos4, int* h_image3, const float* h_F4, float* h_vel4, uint32_t timestep,
+                                   float shear_rate, uint32_t flags, int* m_out) {
+    if (!e || !h_pos4) return PSE_EINVAL;
+    if (!h_F4 && e->n_pref == e->n_cons) return fail(e, PSE_EINVAL, "pse_step_host_async: no forces (h_F4 is NULL and nothing was prefetched)");
+    const size_t N = e->N;
+    cudaStream_t st = e->stream;
+    CKRC(host_path_setup(e));
     // (the velocity scratch is rewritten early in a step: a pending download of it has to finish first)
     if (e->wait_out && e->out_has_vel) { e->wait_out = false; CK(cudaStreamWaitEvent(st, e->ev_out, 0)); }
-    // the forces of this step: staged behind the previous step's last kernels (which may still be reading the staging buffer)
-    CK(cudaStreamWaitEvent(e->stream_h2d, e->ev_step, 0));
-    CK(cudaMemcpyAsync(e->d_hF, h_F4, sizeof(float4) * N, cudaMemcpyHostToDevice, e->stream_h2d));
-    CK(cudaEventRecord(e->ev_F, e->stream_h2d));
-    e->wait_F = true;
+    if (!h_F4) {
+        // prefetched during the previous step (pse_host_prefetch_forces): one device copy into the buffer the step (and its
+        // captured graph) reads
+        e->take_Fnext = (int)(e->n_cons++ & 1);   // (taken where the forces are first needed, after the position-only head: pse_velocity)
+    } else {
+        // the forces of this step: staged behind the previous step's last kernels (which may still be reading the staging buffer)
+        CK(cudaStreamWaitEvent(e->stream_h2d, e->ev_step, 0));
+        CK(cudaMemcpyAsync(e->d_hF, h_F4, sizeof(float4) * N, cudaMemcpyHostToDevice, e->stream_h2d));
+        CK(cudaEventRecord(e->ev_F, e->stream_h2d));
+        e->wait_F = true;
+    }
     if ((flags & PSE_HOST_STATE_IN) || !e->host_state_valid) {
         // the caller's positions / images replace the device state (first call, or the host changed them)
         if (e->wait_out) { e->wait_out = false; CK(cudaStreamWaitEvent(st, e->ev_out, 0)); }
@@ -1474,8 +1528,14 @@ extern "C" int pse_step_host_async(pse_engine* e, float* h_pos4, int* h_image3, 
         e->wait_img = true;
         e->host_state_valid = true;
     }
+    if (flags & PSE_HOST_STATE_IN) e->precheck_pos = nullptr;   // (a check issued for the old state says nothing about the new one)
     const int rc = pse_step(e, e->d_hpos, e->d_himage, e->d_hF, h_vel4 ? e->d_vel_work : nullptr, timestep, shear_rate, m_out);
     if (rc != PSE_OK) { e->host_state_valid = false; return rc; }
+    // the next step's displacement / moved check, now: its flags reach the host ahead of the state download below
+    if (e->nlist_valid) {
+        CKRC(launch_disp_check(e, e->d_hpos));
+        e->precheck_pos = e->d_hpos; e->precheck_xy = e->box.xy;
+    }
     CK(cudaEventRecord(e->ev_step, st));
     CK(cudaStreamWaitEvent(e->stream_d2h, e->ev_step, 0));
     if (!(flags & PSE_HOST_NO_STATE_OUT)) {

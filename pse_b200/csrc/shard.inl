@@ -488,7 +488,8 @@ static int shard_halo_fetch(pse_engine* e) {
 }
 
 // ---- wave space on the slab ---------------------------------------------------------------------------------------------------
-static int shard_wbin(pse_engine* e, const float4* sF) {
+// position-only part: bin the own particles, W record headers, Gaussian factor rows
+static int shard_wbin(pse_engine* e) {
     ShardState* s = e->shard;
     ProfScope ps(e, PH_WBIN);
     cudaStream_t st = e->stream;
@@ -501,12 +502,21 @@ static int shard_wbin(pse_engine* e, const float4* sF) {
     cell_fill_kernel<<<nblk(nrows, 256), 256, 0, st>>>(e->d_wcell_of, r1, e->d_wstart, e->d_wcount, e->d_wtmp, r0); LAUNCHED(e);
     cell_sort_block_kernel<<<nt, 128, 0, st>>>(e->d_wstart, e->d_wtmp, e->d_wperm); LAUNCHED(e);
     // W records carry the SLOT as particle id: velocities are collected in slot order (d_uslot)
-    wgather_kernel<<<nblk(nrows, 256), 256, 0, st>>>(e->d_spos, sF, e->d_org, e->d_wperm, nullptr, nrows, e->d_wpos, e->d_wF, e->d_worg, e->d_wid, e->tg,
-                                                     reinterpret_cast<int4*>(e->d_wrecs)); LAUNCHED(e);
+    wgather_kernel<<<nblk(nrows, 256), 256, 0, st>>>(e->d_spos, nullptr, e->d_org, e->d_wperm, nullptr, nrows, e->d_wpos, e->d_wF, e->d_worg, e->d_wid, e->tg,
+                                                     reinterpret_cast<int4*>(e->d_wrecs), nullptr, 1); LAUNCHED(e);
     launch_wweights(e->wp.P, st, e->d_wpos, e->d_worg, nrows, e->box, e->wp, e->d_wrecs + WREC_HDR, wrec_stride(e->wp.P)); LAUNCHED(e);
     if (s->world > 1) {
         shard_cover_kernel<<<nblk(nrows, 256), 256, 0, st>>>(e->d_org, r0, r1, e->wp.Nx, s->xorg, s->nxa, e->wp.P, e->d_flag + 1); LAUNCHED(e);
     }
+    return PSE_OK;
+}
+// the forces of the call into the W records
+static int shard_wforce(pse_engine* e, const float4* sF) {
+    ProfScope ps(e, PH_WBIN);
+    const uint32_t nrows = e->row1 - e->row0;
+    if (!nrows) return PSE_OK;
+    wgather_kernel<<<nblk(nrows, 256), 256, 0, e->stream>>>(e->d_spos, sF, e->d_org, e->d_wperm, nullptr, nrows, e->d_wpos, e->d_wF, e->d_worg, e->d_wid, e->tg,
+                                                        reinterpret_cast<int4*>(e->d_wrecs), nullptr, 2); LAUNCHED(e);
     return PSE_OK;
 }
 
@@ -529,8 +539,8 @@ static int shard_wave(pse_engine* e, const float4* sF, bool det, bool noise, con
         pp_sloc.p[r] = s->peer_sloc[r]; pp_tr.p[r] = s->peer_tr[r];
         pw_sloc.p[r] = const_cast<float2*>(s->peer_sloc[r]); pw_tr.p[r] = const_cast<float2*>(s->peer_tr[r]);
     }
-    CKRC(shard_wbin(e, det ? sF : nullptr));
     if (det) {
+        CKRC(shard_wforce(e, sF));
         {
             ProfScope ps(e, PH_SPREAD);
             CK(cudaMemsetAsync(e->d_grid, 0, sizeof(float) * 3 * s->Gl, st));
@@ -622,7 +632,28 @@ static int shard_velocity(pse_engine* e, const float4* d_pos, const float4* d_F,
     CKRC(shard_connect_peers(e));
     CKRC(ensure_neighbors(e, d_pos));   // replicated decision (identical positions on every rank); the build covers the own rows
     if (rnoise) CKRC(ensure_krylov(e));
+    // what needs the positions only comes first (forces still on their way from the host are waited for after it), pruning
+    // beside the binning on the second stream when the evaluation has both branches
+    const bool head_fork = (rdet || rnoise) && (wdet || wnoise) && e->overlap && !e->prof_on && e->stream2 && e->prune && !e->pruned_valid;
+    if (head_fork) {
+        CK(cudaEventRecord(e->ev_fork, st));
+        CK(cudaStreamWaitEvent(e->stream2, e->ev_fork, 0));
+        e->stream = e->stream2;
+        const int prc = ensure_pruned(e);
+        e->stream = st;
+        if (prc != PSE_OK) return prc;
+        CK(cudaEventRecord(e->ev_join, e->stream2));
+    } else if (rdet || rnoise) CKRC(ensure_pruned(e));
+    if (wdet || wnoise) CKRC(shard_wbin(e));
+    if (head_fork) CK(cudaStreamWaitEvent(st, e->ev_join, 0));
     if (e->wait_F) { e->wait_F = false; CK(cudaStreamWaitEvent(st, e->ev_F, 0)); }
+    if (e->take_Fnext >= 0) {   // forces prefetched earlier (pse_host_prefetch_forces)
+        const int r = e->take_Fnext;
+        e->take_Fnext = -1;
+        CK(cudaStreamWaitEvent(st, e->ev_Fnext[r], 0));
+        copy_f4_kernel<<<e->num_sms * 4, 256, 0, st>>>(e->d_hF, e->d_hF_next[r], e->N); LAUNCHED(e);
+        CK(cudaEventRecord(e->ev_Fcons[r], st));
+    }
     CKRC(upload_stepdev(e, timestep));
     const uint32_t r0 = e->row0, r1 = e->row1, nrows = r1 - r0;
     // forces in slot order (replicated pass over N: every rank reads its halo rows from the same array)

@@ -210,3 +210,7 @@ class Engine:
 
     def wait(self):
         self._ck(lib.pse_wait(self._h))
+
+    def prefetch_forces(self, F_np):
+        """Start uploading the forces of the NEXT step_host_async call (pass F_np=None there to consume them)."""
+        self._ck(lib.pse_host_prefetch_forces(self._h, ctypes.c_void_p(F_np.ctypes.data)))

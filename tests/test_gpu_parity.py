@@ -303,7 +303,7 @@ def test_stale_list_is_rebuilt_and_host_step_matches_device_step(cuda):
 def test_pipelined_host_steps_match_device_steps(cuda):
     """pse_step_host_async / pse_wait (device-resident state, forces up and state down on copy streams beside the compute,
     double-buffered host arrays) against the same steps through the device entry point: same trajectories, including
-    list rebuilds, a state re-upload in the middle (PSE_HOST_STATE_IN) and a velocity download."""
+    list rebuilds, a state re-upload in the middle (PSE_HOST_STATE_IN), prefetched forces (pse_host_prefetch_forces) and a velocity download."""
     import torch
     N, L = 20000, util.box_length(20000, 0.2)
     a = System(N, L, seed=4, lattice=True, want_ref=False)
@@ -318,7 +318,11 @@ def test_pipelined_host_steps_match_device_steps(cuda):
         if t == 4:       # the host edits the state: it must be taken from the host arrays again
             b.eng.wait()
             hp[t & 1][:] = hp[(t - 1) & 1]; hi[t & 1][:] = hi[(t - 1) & 1]
-        b.eng.step_host_async(hp[t & 1], hi[t & 1], Fs[t], t, shear_rate=0.1, vel_np=hv if t == 7 else None, state_in=(t == 4))
+        if t == 5:                               # from step 6 on the forces come from prefetches, issued one call ahead (queue of two)
+            b.eng.prefetch_forces(Fs[6])
+        if t == 6:
+            b.eng.prefetch_forces(Fs[7])
+        b.eng.step_host_async(hp[t & 1], hi[t & 1], None if t >= 6 else Fs[t], t, shear_rate=0.1, vel_np=hv if t == 7 else None, state_in=(t == 4))
     b.eng.wait()
     assert a.eng.stats()["nlist_builds"] >= 2
     # (spreading merges tile windows with floating-point reductions in arbitrary order: equal to round-off, not bitwise)
