@@ -1532,9 +1532,13 @@ extern "C" int pse_step_host_async(pse_engine* e, float* h_pos4, int* h_image3, 
     const int rc = pse_step(e, e->d_hpos, e->d_himage, e->d_hF, h_vel4 ? e->d_vel_work : nullptr, timestep, shear_rate, m_out);
     if (rc != PSE_OK) { e->host_state_valid = false; return rc; }
     // the next step's displacement / moved check, now: its flags reach the host ahead of the state download below
-    if (e->nlist_valid) {
+    static const bool precheck_on = !(getenv("PSE_PRECHECK") && getenv("PSE_PRECHECK")[0] == '0');
+    if (e->nlist_valid && precheck_on) {
         CKRC(launch_disp_check(e, e->d_hpos));
         e->precheck_pos = e->d_hpos; e->precheck_xy = e->box.xy;
+        // (the check moved the slot-ordered positions on to the new state: what was derived from the old one is stale even
+        // if a later call finds "nothing moved" relative to them)
+        e->pruned_valid = false; e->wbin_valid = false;
     }
     CK(cudaEventRecord(e->ev_step, st));
     CK(cudaStreamWaitEvent(e->stream_d2h, e->ev_step, 0));
