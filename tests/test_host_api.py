@@ -1,5 +1,5 @@
-"""Host-side mirror of the plugin API (no GPU): shear functions, variant, argument validation, and the
-multi-process replica logic over gloo (world_size 2)."""
+"""Host-side mirror of the plugin API (no GPU): shear functions, variant, argument validation, and the host logic of the
+slab-decomposed engine over gloo (world_size 2 and 3)."""
 import math
 import os
 import subprocess
@@ -10,6 +10,7 @@ import numpy as np
 import pytest
 
 import pse_b200 as PSEv1
+from tests import util
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -164,6 +165,25 @@ def test_shard_plan_all_to_all_is_consistent_world_3_gloo(tmp_path):
                           "--master-port", "29534", str(script)], capture_output=True, text=True, env=env, timeout=240)
     assert out.returncode == 0, out.stderr[-3000:]
     assert all((tmp_path / f"ok_{r}").exists() for r in range(3))
+
+
+def test_shard_plan_headline_configs_on_eight_ranks():
+    """The static decomposition of BASELINE.json configs[2] (240^3) and configs[4] (432^3, P = 8) over 8 ranks (host only): slabs tile the
+    grid, every rank's local real-space buffer is a fraction of the grid (no rank allocates a full one), the transposes balance."""
+    from pse_b200 import engine as E, sharded as S
+    for N, phi, xi, error, grid in ((1000000, 0.3, 0.5, 1e-3, 240), (8000000, 0.4, 0.45, 1e-4, 432)):
+        cfg = E.make_config(N, util.box_length(N, phi), xi=xi, error=error, r_buff=0.8)
+        infos = [S.plan(cfg, r, 8).as_dict() for r in range(8)]
+        assert infos[0]["x0"] == 0 and infos[-1]["x1"] == grid and infos[0]["y0"] == 0 and infos[-1]["y1"] == grid
+        for r in range(7):
+            assert infos[r]["x1"] == infos[r + 1]["x0"] and infos[r]["layer1"] == infos[r + 1]["layer0"]
+        for r, i in enumerate(infos):
+            nown = i["x1"] - i["x0"]
+            assert abs(nown - grid / 8) <= 0.15 * grid / 8 and nown >= max(i["halo_left"], i["halo_right"])   # whole layers of cells: 9 or 10 of 79
+            assert i["buffer_planes"] <= nown + i["halo_left"] + i["halo_right"] + 16 and i["buffer_planes"] < grid // 3
+            assert sum(i["a2a_send_bytes"]) == sum(infos[q]["a2a_recv_bytes"][r] for q in range(8))
+    with pytest.raises(E.PSEError):
+        S.plan(E.make_config(1000000, util.box_length(1000000, 0.3)), 0, 17)      # more ranks than the communicator supports
 
 
 def test_system_save_load_roundtrip_cpu(tmp_path):
