@@ -1041,11 +1041,13 @@ static int run_wbin(pse_engine* e) {
     // unordered fill into scratch (d_wcell_of is free again after the fill reads it), then rank sort per tile
     cell_fill_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_wcell_of, N, e->d_wstart, e->d_wcount, e->d_wtmp); LAUNCHED(e);
     cell_sort_block_kernel<<<nt, 128, 0, st>>>(e->d_wstart, e->d_wtmp, e->d_wperm); LAUNCHED(e);
-    wgather_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_spos, nullptr, e->d_org, e->d_wperm, e->d_perm, N, e->d_wpos, e->d_wF, e->d_worg, e->d_wid, e->tg,
-                                                 reinterpret_cast<int4*>(e->d_wrecs), nullptr, 1); LAUNCHED(e);
-    if (e->wave_v2) launch_wweights(e->wp.P, st, e->d_wpos, e->d_worg, N, e->box, e->wp, e->d_wrecs + WREC_HDR, wrec_stride(e->wp.P));
-    else launch_wweights(e->wp.P, st, e->d_wpos, e->d_worg, N, e->box, e->wp, e->d_wwt);
-    LAUNCHED(e);
+    if (e->wave_v2) {   // headers + factor rows of the W records in one kernel
+        launch_wrecords(e->wp.P, st, e->d_spos, e->d_org, e->d_wperm, e->d_perm, N, e->box, e->wp, e->tg, e->d_wrecs); LAUNCHED(e);
+    } else {
+        wgather_kernel<<<nblk(N, 256), 256, 0, st>>>(e->d_spos, nullptr, e->d_org, e->d_wperm, e->d_perm, N, e->d_wpos, e->d_wF, e->d_worg, e->d_wid, e->tg,
+                                                     nullptr, nullptr, 1); LAUNCHED(e);
+        launch_wweights(e->wp.P, st, e->d_wpos, e->d_worg, N, e->box, e->wp, e->d_wwt); LAUNCHED(e);
+    }
     e->wbin_valid = true;
     return PSE_OK;
 }

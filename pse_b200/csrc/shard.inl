@@ -502,9 +502,7 @@ static int shard_wbin(pse_engine* e) {
     cell_fill_kernel<<<nblk(nrows, 256), 256, 0, st>>>(e->d_wcell_of, r1, e->d_wstart, e->d_wcount, e->d_wtmp, r0); LAUNCHED(e);
     cell_sort_block_kernel<<<nt, 128, 0, st>>>(e->d_wstart, e->d_wtmp, e->d_wperm); LAUNCHED(e);
     // W records carry the SLOT as particle id: velocities are collected in slot order (d_uslot)
-    wgather_kernel<<<nblk(nrows, 256), 256, 0, st>>>(e->d_spos, nullptr, e->d_org, e->d_wperm, nullptr, nrows, e->d_wpos, e->d_wF, e->d_worg, e->d_wid, e->tg,
-                                                     reinterpret_cast<int4*>(e->d_wrecs), nullptr, 1); LAUNCHED(e);
-    launch_wweights(e->wp.P, st, e->d_wpos, e->d_worg, nrows, e->box, e->wp, e->d_wrecs + WREC_HDR, wrec_stride(e->wp.P)); LAUNCHED(e);
+    launch_wrecords(e->wp.P, st, e->d_spos, e->d_org, e->d_wperm, nullptr, nrows, e->box, e->wp, e->tg, e->d_wrecs); LAUNCHED(e);
     if (s->world > 1) {
         shard_cover_kernel<<<nblk(nrows, 256), 256, 0, st>>>(e->d_org, r0, r1, e->wp.Nx, s->xorg, s->nxa, e->wp.P, e->d_flag + 1); LAUNCHED(e);
     }

@@ -59,7 +59,87 @@ __device__ __forceinline__ void red_add(float* addr, float a) {
 // (wave_tiled.cuh) followed by the Gaussian factor row of wweights_kernel.  A record is a multiple of 16 bytes, so any run
 // of records is a legal bulk-copy source.
 #define WREC_HDR 12
+#define PSE_V2_SHAPES_FWD(X) X(6, 12, 12, 12) X(7, 15, 15, 12) X(8, 17, 17, 16)   // same list as PSE_V2_SHAPES below
 __host__ __device__ constexpr int wrec_stride(int P) { return WREC_HDR + wrow_stride(P); }
+
+// Position-only part of the W records in ONE kernel (the headers of wgather_kernel and the factor rows of wweights_kernel,
+// without the wpos / worg round trip between them): a block builds WW_PB whole records in shared memory and writes them as
+// one contiguous range.  The Gaussian factors are formed per axis first - P values of w_z per particle, and for an unsheared
+// box (xy = 0: x and y decouple) P of w_x and P of w_y, 3 P exponentials instead of P^2 + P; a sheared box keeps the coupled
+// w_xy(i, j) of weight_xy, one per thread.  Per-axis node positions and minimum-image displacements are formed operation by
+// operation as in weight_xy / weight_z; only exp(a + b) -> exp(a) exp(b) differs (1e-7).  The force words stay zero until
+// wgather_kernel's force part stores them.
+template <int P>
+__global__ void __launch_bounds__(256)
+wrecords_kernel(const float4* __restrict__ spos, const int4* __restrict__ org, const uint32_t* __restrict__ wperm,
+                const uint32_t* __restrict__ perm, uint32_t N, PseBox box, WaveParams wp, TileGrid tg, float* __restrict__ wrecs) {
+    constexpr int PP = P * P, NWD = PP + P, RS = wrec_stride(P);
+    __shared__ __align__(16) float rec[WW_PB * RS];
+    __shared__ float ax[WW_PB][3][P];
+    __shared__ float4 spp[WW_PB];
+    __shared__ int4 sorg[WW_PB];
+    const uint32_t w0 = blockIdx.x * WW_PB;
+    const int np = (int)min((uint32_t)WW_PB, N - w0);
+    if ((int)threadIdx.x < np) {
+        const int q = threadIdx.x;
+        const uint32_t s = wperm[w0 + q];
+        const float4 pp = __ldg(spos + s);
+        const int4 o = org[s];
+        spp[q] = pp; sorg[q] = o;
+        const uint32_t id = perm ? __ldg(perm + s) : s;
+        const int lx = o.x % tg.tx, ly = o.y % tg.ty, lz = o.z % tg.tz;
+        int4* h = reinterpret_cast<int4*>(rec + q * RS);
+        h[0] = make_int4(0, 0, 0, (int)id);
+        h[1] = make_int4((((lx / tg.cp) * tg.cy + ly / tg.cp) * tg.cz + lz / tg.cp) * tg.cs, lx % tg.cp, ly % tg.cp, lz % tg.cp);
+        h[2] = make_int4(lx, ly, lz, 0);
+    }
+    __syncthreads();
+    const bool sep = box.xy == 0.f;
+    for (int t = threadIdx.x; t < WW_PB * P; t += blockDim.x) {
+        const int q = t / P, i = t - q * P;
+        if (q >= np) break;
+        const float4 pp = spp[q];
+        const int4 o = sorg[q];
+        ax[q][2][i] = weight_z(box, wp, wrap_node(o.z + i, wp.Nz), pp.z);
+        if (sep) {
+            float rx = (wp.hx * (float)wrap_node(o.x + i, wp.Nx) - box.Lx * 0.5f) - pp.x;
+            rx = PSE_SUB(rx, PSE_MUL(box.Lx, rintf(PSE_MUL(rx, box.Lxinv))));
+            float ry = (wp.hy * (float)wrap_node(o.y + i, wp.Ny) - box.Ly * 0.5f) - pp.y;
+            ry = PSE_SUB(ry, PSE_MUL(box.Ly, rintf(PSE_MUL(ry, box.Lyinv))));
+            ax[q][0][i] = expf(-wp.expfac * (rx * rx));
+            ax[q][1][i] = expf(-wp.expfac * (ry * ry));
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < WW_PB * NWD; t += blockDim.x) {
+        const int q = t / NWD, r = t - q * NWD;
+        if (q >= np) break;
+        float v;
+        if (r >= PP) v = ax[q][2][r - PP];
+        else {
+            const int i = r / P, j = r - i * P;
+            if (sep) v = wp.prefac * (ax[q][0][i] * ax[q][1][j]);
+            else v = weight_xy(box, wp, wrap_node(sorg[q].x + i, wp.Nx), wrap_node(sorg[q].y + j, wp.Ny), spp[q].x, spp[q].y, wp.prefac);
+        }
+        rec[q * RS + WREC_HDR + r] = v;
+    }
+    if constexpr (RS > WREC_HDR + NWD) {
+        constexpr int PAD = RS - WREC_HDR - NWD;
+        for (int t = threadIdx.x; t < WW_PB * PAD; t += blockDim.x) rec[(t / PAD) * RS + WREC_HDR + NWD + t % PAD] = 0.f;
+    }
+    __syncthreads();
+    const float4* src = reinterpret_cast<const float4*>(rec);
+    float4* dst = reinterpret_cast<float4*>(wrecs + (size_t)w0 * RS);   // (a record is a multiple of 16 bytes)
+    for (int t = threadIdx.x; t < np * (RS / 4); t += blockDim.x) dst[t] = src[t];
+}
+static void launch_wrecords(int P, cudaStream_t st, const float4* spos, const int4* org, const uint32_t* wperm, const uint32_t* perm, uint32_t N,
+                            const PseBox& box, const WaveParams& wp, const TileGrid& tg, float* wrecs) {
+    if (!N) return;
+    const unsigned int nb = (N + WW_PB - 1) / WW_PB;
+#define X(p, a, b, c) if (P == p) { wrecords_kernel<p><<<nb, 256, 0, st>>>(spos, org, wperm, perm, N, box, wp, tg, wrecs); return; }
+    PSE_V2_SHAPES_FWD(X)
+#undef X
+}
 
 // Ring of shared-memory stages fed by bulk copies: one elected thread is the producer, every warp a consumer.
 // full[s] completes when the bytes of the chunk in stage s have landed; empty[s] when every warp has released it.
