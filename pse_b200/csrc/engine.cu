@@ -1180,10 +1180,14 @@ static int solve_coeffs(pse_engine* e, int m, const float* alpha, const float* b
 // U[perm] (+)= sqrt(2T/dt) * M_real^{1/2} psi, psi drawn per particle id (PSEv1/Brownian.cu:357-765).
 // lanczos_batch: everything up to the first host decision — psi, |psi|, the first m_in - 1 iterations and the
 // read-back of alpha/beta.  No host synchronisation inside, so it can be part of the captured step graph.
-static int lanczos_batch_size(const pse_engine* e) {
-    int m = e->m_lanczos - 1;  // PSEv1/Brownian.cu:465-466
+static int lanczos_first_m(const pse_engine* e) {
+    const int m = e->m_lanczos - 1;  // PSEv1/Brownian.cu:465-466
     return m < 1 ? 1 : m;
 }
+// The reference always takes at least one adaptive iteration after those m_in - 1 (its step norm starts at 1, :606-610), so
+// that iteration is issued with the batch: in the steady state (m unchanged from step to step) the whole solve needs ONE
+// host synchronisation instead of two, and all of its products sit inside the captured graph.
+static int lanczos_batch_size(const pse_engine* e) { return std::min(lanczos_first_m(e) + 1, LANCZOS_M_MAX); }
 static int lanczos_batch(pse_engine* e, const float* d_u_particles, int m, bool dual = false) {
     CKRC(ensure_pruned(e));
     const uint32_t N = e->N;
@@ -1202,11 +1206,13 @@ static int lanczos_batch(pse_engine* e, const float* d_u_particles, int m, bool 
 
 // host side: tridiagonal solves, adaptive iterations until the step norm drops below `error`, final combination
 // (slab-decomposed: U is the slot-ordered velocity buffer and `perm` is null)
-static int lanczos_finish(pse_engine* e, float4* U, int accumulate, int m, int* m_out, const float4* ydet, const uint32_t* perm) {
+static int lanczos_finish(pse_engine* e, float4* U, int accumulate, int m_have /* iterations lanczos_batch issued */, int* m_out, const float4* ydet,
+                          const uint32_t* perm) {
     cudaStream_t st = e->stream;
     float* alpha = e->h_ab;
     float* beta = e->h_ab + LANCZOS_M_MAX + 1;
     CK(cudaStreamSynchronize(st));
+    int m = std::min(lanczos_first_m(e), m_have);
     for (int j = 0; j < m; ++j)
         if (beta[j + 1] < 1e-8f) { m = j > 0 ? j : 1; break; }  // breakdown, PSEv1/Brownian.cu:507-510
     std::vector<double> c, c_prev;
@@ -1218,9 +1224,12 @@ static int lanczos_finish(pse_engine* e, float4* U, int accumulate, int m, int* 
     while (!broke && stepnorm > e->cfg.error && m < LANCZOS_M_MAX) {  // PSEv1/Brownian.cu:606-736
         ++m;
         const int j = m - 1;
-        CKRC(lanczos_iteration(e, j));
-        words2_copy_kernel<<<1, 32, 0, st>>>(WORDS(alpha + j), CWORDS(e->d_alpha + j), 1, WORDS(beta + j + 1), CWORDS(e->d_beta + j + 1), 1); LAUNCHED(e);
-        CK(cudaStreamSynchronize(st));
+        if (j >= m_have) {   // (the first adaptive iteration came with the batch)
+            CKRC(lanczos_iteration(e, j));
+            words2_copy_kernel<<<1, 32, 0, st>>>(WORDS(alpha + j), CWORDS(e->d_alpha + j), 1, WORDS(beta + j + 1), CWORDS(e->d_beta + j + 1), 1); LAUNCHED(e);
+            CK(cudaStreamSynchronize(st));
+            m_have = m;
+        }
         if (beta[j + 1] < 1e-8f) { m = j; break; }
         CKRC(solve_coeffs(e, m, alpha, beta, c));
         // ||V c_m - V c_{m-1}|| = ||c_m - [c_{m-1}; 0]|| for an orthonormal basis: no N-vector pass
