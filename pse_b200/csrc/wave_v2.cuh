@@ -111,17 +111,17 @@ wrecords_kernel(const float4* __restrict__ spos, const int4* __restrict__ org, c
         }
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < WW_PB * NWD; t += blockDim.x) {
-        const int q = t / NWD, r = t - q * NWD;
-        if (q >= np) break;
-        float v;
-        if (r >= PP) v = ax[q][2][r - PP];
-        else {
-            const int i = r / P, j = r - i * P;
-            if (sep) v = wp.prefac * (ax[q][0][i] * ax[q][1][j]);
-            else v = weight_xy(box, wp, wrap_node(sorg[q].x + i, wp.Nx), wrap_node(sorg[q].y + j, wp.Ny), spp[q].x, spp[q].y, wp.prefac);
-        }
-        rec[q * RS + WREC_HDR + r] = v;
+    {   // a thread keeps one factor index r = (i, j) or k for the whole block and walks the particles: no index arithmetic in the loop
+        constexpr int QP = 256 / NWD;                      // particles per pass
+        const int r = threadIdx.x % NWD, i = r / P, j = r - i * P;
+        if ((int)threadIdx.x < QP * NWD)
+            for (int q = threadIdx.x / NWD; q < np; q += QP) {
+                float v;
+                if (r >= PP) v = ax[q][2][r - PP];
+                else if (sep) v = wp.prefac * (ax[q][0][i] * ax[q][1][j]);
+                else v = weight_xy(box, wp, wrap_node(sorg[q].x + i, wp.Nx), wrap_node(sorg[q].y + j, wp.Ny), spp[q].x, spp[q].y, wp.prefac);
+                rec[q * RS + WREC_HDR + r] = v;
+            }
     }
     if constexpr (RS > WREC_HDR + NWD) {
         constexpr int PAD = RS - WREC_HDR - NWD;
