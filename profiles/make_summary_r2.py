@@ -13,11 +13,11 @@ def L(f):
 
 
 d, r, ls = L("r2_bench_ours.json"), L("r2_bench_ref.json"), L("r2_launch_shares.json")
-top = L("r2_top_kernels.json") + L("r2_fft_kernels.json")
+top = L("r2_top_kernels.json") + L("r2_fft_kernels.json") + L("r2_small_kernels.json")
 out = ["# Round 2 — measured on B200s (gpurun), config 3: N = 1,000,000, phi = 0.3, error 1e-3, xi = 0.5, kT = 1, dt = 1e-3\n",
        "Files: `r2_bench_ours.json` / `r2_bench_ref.json` (the two `bench.py` arms at N = 1, NOT under a profiler), `r2_bench_ours_{2,4,8}gpu.json` "
        "(`bench.py --gpus N` under torchrun), `r2_launches.csv` (ncu `--metrics gpu__time_duration.sum --clock-control none` of three steps) and its "
-       "per-kernel shares `r2_launch_shares.json`, `r2_top_kernels.json` / `r2_fft_kernels.json` (ncu `--set full`, key metrics), "
+       "per-kernel shares `r2_launch_shares.json`, `r2_top_kernels.json` / `r2_fft_kernels.json` / `r2_small_kernels.json` (ncu `--set full`, key metrics), "
        "`r2_sass_excerpt.txt`, `r2_sanitizer.txt`, `r2_shard8_config5.json`, `r2_scaling.md`, `r2_notes.md`; this file by `make_summary_r2.py`.\n"
        "ncu times are cold-cache and serialised: compare SHARES with `phases` of the bench line, not absolutes.\n",
        "## bench.py (CUDA events, no profiler)\n",
