@@ -186,6 +186,23 @@ def test_shard_plan_headline_configs_on_eight_ranks():
         S.plan(E.make_config(1000000, util.box_length(1000000, 0.3)), 0, 17)      # more ranks than the communicator supports
 
 
+def test_local_world_handles_and_abi_guards_without_gpu():
+    """Host-only pieces of the slab-decomposed ABI: the in-process world handle, and null / range checks that must not need a device."""
+    import ctypes
+    from pse_b200 import _lib
+    lib = _lib.lib
+    w = lib.pse_local_world_create(3)
+    assert w
+    lib.pse_local_world_destroy(w)
+    assert not lib.pse_local_world_create(0) and not lib.pse_local_world_create(17)
+    info = _lib.pse_shard_info()
+    assert lib.pse_shard_init(None, 0, 2, None, None) == _lib.PSE_EINVAL
+    assert lib.pse_shard_get_info(None, ctypes.byref(info)) == _lib.PSE_EINVAL
+    assert lib.pse_host_prefetch_forces(None, None) == _lib.PSE_EINVAL and lib.pse_wait(None) == _lib.PSE_EINVAL
+    cfg = PSEv1.engine.make_config(100000, util.box_length(100000, 0.2))
+    assert lib.pse_shard_plan(ctypes.byref(cfg), 3, 3, ctypes.byref(info)) == _lib.PSE_EINVAL      # rank outside the world
+
+
 def test_system_save_load_roundtrip_cpu(tmp_path):
     """Restart file: positions, images, step counter, box, forces survive a save/load (no GPU needed)."""
     from pse_b200 import system as S
